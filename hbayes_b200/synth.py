@@ -1,0 +1,189 @@
+"""Seeded synthetic networks and evidence for the BASELINE.json configs.
+
+PRNG = SplitMix64 everywhere (scalar for structure/CPTs, vectorised for evidence rows), so the same
+seeds give the same bytes on any box.  Networks are plain arrays in the reference's conventions
+(vertex id = index, CPT scope = [child, parents...], first variable slowest -- Bayes/Network.hs:69-79,
+Bayes/Factor/PrivateCPT.hs:315-320) and can be written as Hugin `.net` text in the dialect
+Bayes/ImportExport/HuginNet.hs accepts.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_M = (1 << 64) - 1
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & _M
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _M
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M
+        return z ^ (z >> 31)
+
+    def uniform(self):
+        return (self.next() >> 11) * (1.0 / (1 << 53))
+
+    def randint(self, lo, hi):
+        """inclusive bounds"""
+        return lo + self.next() % (hi - lo + 1)
+
+
+def splitmix64_array(seed, n):
+    """n consecutive SplitMix64 outputs as uint64 (identical to n calls of SplitMix64(seed).next())."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed & _M) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+class SynthNet:
+    """dims[v], parents[v] (CPT scope = [v] + parents[v]), values[v] in reference layout."""
+
+    def __init__(self, dims, parents, values, names=None):
+        self.dims = [int(d) for d in dims]
+        self.parents = [list(map(int, p)) for p in parents]
+        self.values = [np.asarray(v, np.float64) for v in values]
+        self.names = names or ["n%d" % i for i in range(len(dims))]
+
+    @property
+    def n(self):
+        return len(self.dims)
+
+    @property
+    def scopes(self):
+        return [[v] + self.parents[v] for v in range(self.n)]
+
+    def hugin_text(self):
+        """Hugin text: nodes in id order; `data` laid out parents-slowest / child-fastest (HuginNet.hs:139-147)."""
+        out = ["net\n{\n\tname = \"synthetic\";\n}\n"]
+        for v in range(self.n):
+            st = " ".join('"s%d"' % i for i in range(self.dims[v]))
+            out.append("node %s\n{\n\tstates = ( %s );\n}\n" % (self.names[v], st))
+        for v in range(self.n):
+            sc = self.scopes[v]
+            shape = [self.dims[x] for x in sc]
+            tab = self.values[v].reshape(shape)
+            hug = np.moveaxis(tab, 0, -1).reshape(-1)  # [parents..., child]
+            head = "potential ( %s | %s )" % (self.names[v], " ".join(self.names[p] for p in self.parents[v]))
+            data = " ".join(repr(float(x)) for x in hug)
+            out.append("%s\n{\n\tdata = ( %s );\n}\n" % (head, data))
+        return "".join(out)
+
+    def write_hugin(self, path):
+        with open(path, "w") as f:
+            f.write(self.hugin_text())
+        return path
+
+
+def _random_cpt(rng, dims, v, parents):
+    """u ~ U(0.05, 1) per state, normalised per parent configuration; reference layout (child slowest)."""
+    npar = 1
+    for p in parents:
+        npar *= dims[p]
+    d = dims[v]
+    tab = np.empty((d, npar), np.float64)
+    for j in range(npar):
+        u = [0.05 + 0.95 * rng.uniform() for _ in range(d)]
+        s = sum(u)
+        for i in range(d):
+            tab[i, j] = u[i] / s
+    return tab.reshape(-1)
+
+
+def random_dag_net(n, seed, states=(2, 4), max_parents=3, window=None):
+    """Random DAG, ids topological: node v draws k ~ U{0..max_parents} distinct parents from the
+    preceding `window` nodes (all predecessors when window is None)."""
+    rng = SplitMix64(seed)
+    dims = [rng.randint(states[0], states[1]) for _ in range(n)]
+    parents = []
+    for v in range(n):
+        lo = 0 if window is None else max(0, v - window)
+        cand = list(range(lo, v))
+        k = min(rng.randint(0, max_parents), len(cand))
+        ps = []
+        for _ in range(k):
+            j = rng.randint(0, len(cand) - 1)
+            ps.append(cand.pop(j))
+        parents.append(ps)
+    values = [_random_cpt(rng, dims, v, parents[v]) for v in range(n)]
+    return SynthNet(dims, parents, values)
+
+
+def grid_net(rows, cols, seed):
+    """rows x cols binary grid, node (i,j) has parents (i-1,j),(i,j-1); id = cols*i + j (config C5)."""
+    rng = SplitMix64(seed)
+    n = rows * cols
+    dims = [2] * n
+    parents = []
+    for i in range(rows):
+        for j in range(cols):
+            ps = []
+            if i > 0:
+                ps.append(cols * (i - 1) + j)
+            if j > 0:
+                ps.append(cols * i + j - 1)
+            parents.append(ps)
+    values = [_random_cpt(rng, dims, v, parents[v]) for v in range(n)]
+    return SynthNet(dims, parents, values)
+
+
+def ancestral_rows(net: SynthNet, n_rows, seed):
+    """n_rows ancestral samples as int8 [n_rows][n] (ids must be topological). Vectorised SplitMix64:
+    the uniform for (row r, variable v) is output number r*n + v + 1 of the stream."""
+    n = net.n
+    z = splitmix64_array(seed, n_rows * n).reshape(n_rows, n)
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+    rows = np.zeros((n_rows, n), np.int8)
+    for v in range(n):
+        ps = net.parents[v]
+        assert all(p < v for p in ps), "ancestral_rows needs topological ids"
+        d = net.dims[v]
+        tab = net.values[v].reshape([d] + [net.dims[p] for p in ps])
+        idx = tuple(rows[:, p].astype(np.int64) for p in ps)
+        probs = tab[(slice(None),) + idx] if ps else np.repeat(tab[:, None], n_rows, 1)  # [d, n_rows]
+        cdf = np.cumsum(probs, axis=0)
+        s = (u[:, v][None, :] >= cdf[:-1]).sum(axis=0)
+        rows[:, v] = s.astype(np.int8)
+    return rows
+
+
+def choose_observed(n, count, seed):
+    """`count` distinct variable ids (sorted)."""
+    rng = SplitMix64(seed)
+    cand = list(range(n))
+    out = []
+    for _ in range(count):
+        out.append(cand.pop(rng.randint(0, len(cand) - 1)))
+    return sorted(out)
+
+
+def evidence_matrix(net: SynthNet, n_rows, observed, seed):
+    """int8 [n_rows][n]: ancestral samples (so P(e) > 0) restricted to `observed`; -1 = unobserved."""
+    rows = ancestral_rows(net, n_rows, seed)
+    ev = np.full_like(rows, -1)
+    ev[:, observed] = rows[:, observed]
+    return ev
+
+
+# ---- named configurations of BASELINE.json ---------------------------------------------------
+
+
+def config_c2():
+    """Alarm-sized random DAG: 37 nodes, 2-4 states, <=3 parents (net seed 37001), 9 observed (seed 37002)."""
+    net = random_dag_net(37, 37001, states=(2, 4), max_parents=3)
+    observed = choose_observed(37, 9, 37002)
+    return net, observed
+
+
+def config_c2_evidence(net, observed, n_rows):
+    return evidence_matrix(net, n_rows, observed, 37003)
+
+
+def config_c5(rows=20, cols=20, seed=400001):
+    return grid_net(rows, cols, seed)
