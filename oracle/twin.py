@@ -209,7 +209,11 @@ def factor_scale(s, f):
 
 def factor_divide(f, d):
     """factorDivide (Factor.hs:171-172): scale by 1.0 / d."""
-    return factor_scale(1.0 / d, f)
+    if d == 0.0:  # Haskell: 1.0 / 0 = Infinity (then 0 * Infinity = NaN, PrivateCPT.hs:180-187)
+        inv = float("-inf") if str(d).startswith("-") else float("inf")
+    else:
+        inv = 1.0 / d
+    return factor_scale(inv, f)
 
 
 def factor_from_instantiation(dv, a):

@@ -1,0 +1,227 @@
+"""Pins the parity oracle (oracle/hbayes_oracle.cpp + oracle/twin.py) to the reference's own known answers.
+
+  * golden vectors of Bayes/Test/ReferencePatterns.hs:119-161 (cancer priors/posteriors, asia priors; abs tol 1e-4
+    as in :62-65)
+  * VE == JT on the sprinkler `example` (Bayes/Test/CompareEliminations.hs:67-84)
+  * the structure hand-traced in SURVEY Appendix B
+  * C++ oracle == independent pure-Python twin, bit for bit (values) and integer for integer (structure, op traces)
+  * brute-force joint enumeration on random networks, incl. children-before-parents ids (moralisation quirk A.6)
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import OracleJT, OracleNet, twin
+from hbayes_b200 import synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def jt_all(jt, n):
+    return [jt.posterior([v])[1] for v in range(n)]
+
+
+def test_cancer_structure_appendix_b():
+    net = OracleNet.load_hugin(os.path.join(G, "cancer.net"))
+    assert net.names == ["D", "E", "A", "C", "B"]
+    assert net.scopes == [[0, 3, 4], [1, 3], [2], [3, 2], [4, 2]]
+    assert net.values[0] == [.8, .8, .8, .05, .2, .2, .2, .95]
+    d = OracleJT(net).describe()
+    assert d["elim_order"] == [0, 1, 2, 4, 3]
+    assert d["clusters"] == [[2, 3, 4], [0, 3, 4], [1, 3]]
+    assert d["sep_vars"] == [[3, 4], [3]] and d["sep_child"] == [1, 2]
+    assert d["children"][0] == [2, 1]
+    assert d["factors"] == [[4, 3, 2], [0], [1]]
+
+
+# Bayes/Test/ReferencePatterns.hs:137-161 ; order of variables here: D E A C B
+CANCER_GOLD = {
+    (): {"A": [.2, .8], "B": [.32, .68], "C": [.08, .92], "D": [.32, .68], "E": [.616, .384]},
+    (("D", 0),): {"A": [.425, .575], "B": [.8, .2], "C": [.2, .8], "E": [.64, .36]},
+    (("D", 1),): {"A": [.0941, .9059], "B": [.0941, .9059], "C": [.0235, .9765], "E": [.6047, .3953]},
+}
+
+
+@pytest.mark.parametrize("ev", list(CANCER_GOLD))
+def test_cancer_goldens(ev):
+    net = OracleNet.load_hugin(os.path.join(G, "cancer.net"))
+    ids = {n: i for i, n in enumerate(net.names)}
+    jt = OracleJT(net)
+    jt.change_evidence([(ids[n], s) for n, s in ev])
+    for name, want in CANCER_GOLD[ev].items():
+        got = jt.posterior([ids[name]])[1]
+        assert np.abs(got - np.array(want)).max() < 1e-4, (name, got)
+        # VE gives the same
+        others = [v for v in range(net.n) if v != ids[name]]
+        _, ve = net.posterior_marginal(others, [ids[name]], [(ids[n], s) for n, s in ev])
+        assert np.abs(ve - np.array(want)).max() < 1e-4
+
+
+# Bayes/Test/ReferencePatterns.hs:119-131 (asia priors, state 0 = yes)
+ASIA_GOLD = {"A": .01, "S": .5, "T": .0104, "L": .055, "B": .45, "E": .0648, "X": .1103, "D": .4360}
+
+
+@pytest.mark.parametrize("fname", ["asia.net", "asia_rev.net"])
+def test_asia_goldens(fname):
+    net = OracleNet.load_hugin(os.path.join(G, fname))
+    ids = {n: i for i, n in enumerate(net.names)}
+    jt = OracleJT(net)
+    for name, want in ASIA_GOLD.items():
+        got = jt.posterior([ids[name]])[1]
+        assert abs(got[0] - want) < 1e-4 and abs(got[1] - (1 - want)) < 1e-4, (name, got)
+
+
+def test_sprinkler_ve_equals_jt():
+    """Bayes/Test/CompareEliminations.hs:67-84: priors of all variables, rain | wet, rain | wet, sprinkler."""
+    net = OracleNet.load_hugin(os.path.join(G, "sprinkler.net"))
+    jt = OracleJT(net)
+    d = jt.describe()
+    assert d["elim_order"] == [0, 2, 4, 5, 1, 3]
+    assert d["clusters"] == [[3, 4, 5], [0, 1, 3], [1, 2, 3]]
+    for evid in ([], [(2, 1)], [(2, 1), (1, 1)]):
+        jt.change_evidence(evid)
+        for v in range(net.n):
+            others = [x for x in range(net.n) if x != v]
+            _, ve = net.posterior_marginal(others, [v], evid)
+            got = jt.posterior([v])[1]
+            assert np.allclose(got, ve, rtol=2e-5, atol=0), (v, got, ve)
+    jt.change_evidence([])
+    assert np.allclose(jt.posterior([3])[1], [.48, .52], atol=1e-12)
+
+
+def same_bits(a, b):
+    """bit-identical, except that any NaN equals any NaN (zero-probability evidence)"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    nan = np.isnan(a)
+    return a.shape == b.shape and (nan == np.isnan(b)).all() and a[~nan].tobytes() == b[~nan].tobytes()
+
+
+def twin_net(onet):
+    return twin.Network.from_tables(onet.dims, [s[1:] for s in onet.scopes], onet.values, onet.names)
+
+
+def twin_describe(t):
+    nodes = sorted(t.factors.keys(), key=lambda c: t.node_vertex[c])
+    return [[dv[0] for dv in c] for c in nodes]
+
+
+NETS = ["cancer.net", "sprinkler.net", "asia.net", "asia_rev.net"]
+
+
+@pytest.mark.parametrize("fname", NETS)
+def test_cpp_equals_twin_bitwise(fname):
+    onet = OracleNet.load_hugin(os.path.join(G, fname))
+    tnet = twin.load_hugin(os.path.join(G, fname))
+    assert [f.vals for f in tnet.cpts] == onet.values
+    ojt = OracleJT(onet)
+    tjt = twin.create_junction_tree(tnet)
+    assert twin_describe(tjt) == ojt.describe()["clusters"]
+    rng = np.random.RandomState(7)
+    for trial in range(6):
+        k = rng.randint(0, min(4, onet.n))
+        vs = rng.permutation(onet.n)[:k].tolist()  # caller order is NOT sorted on purpose
+        ev = [(int(v), int(rng.randint(onet.dims[v]))) for v in vs]
+        ojt.change_evidence(ev)
+        twin.change_evidence(tjt, [(tnet.dv(v), s) for v, s in ev])
+        for v in range(onet.n):
+            a = ojt.posterior([v])[1]
+            b = twin.posterior(tjt, [tnet.dv(v)]).vals
+            assert same_bits(a, b), (fname, ev, v, a, b)
+            others = [x for x in range(onet.n) if x != v]
+            _, c = onet.posterior_marginal(others, [v], ev)
+            d = twin.posterior_marginal(tnet, [tnet.dv(x) for x in others], [tnet.dv(v)],
+                                        [(tnet.dv(x), s) for x, s in ev]).vals
+            assert same_bits(c, d)
+
+
+def random_small_net(seed, shuffle):
+    net = synth.random_dag_net(3 + seed % 6, 9000 + seed, states=(2, 3), max_parents=2)
+    if shuffle:  # relabel so children may precede parents
+        rng = np.random.RandomState(seed)
+        perm = rng.permutation(net.n)  # old id -> new id
+        inv = np.argsort(perm)
+        dims = [net.dims[inv[i]] for i in range(net.n)]
+        parents = [[int(perm[p]) for p in net.parents[inv[i]]] for i in range(net.n)]
+        values = [net.values[inv[i]] for i in range(net.n)]
+        net = synth.SynthNet(dims, parents, values)
+    return net
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_nets_vs_bruteforce_and_twin(seed):
+    net = random_small_net(seed, shuffle=seed % 2 == 1)
+    onet = OracleNet.from_arrays(net.dims, net.scopes, net.values)
+    tnet = twin.Network.from_tables(net.dims, net.parents, [v.tolist() for v in net.values])
+    ojt = OracleJT(onet)
+    tjt = twin.create_junction_tree(tnet)
+    assert twin_describe(tjt) == ojt.describe()["clusters"]
+    rng = np.random.RandomState(seed)
+    k = rng.randint(0, 3)
+    vs = rng.permutation(net.n)[:k].tolist()
+    ev = [(int(v), int(rng.randint(net.dims[v]))) for v in vs]
+    ojt.change_evidence(ev)
+    twin.change_evidence(tjt, [(tnet.dv(v), s) for v, s in ev])
+    for v in range(net.n):
+        a = ojt.posterior([v])[1]
+        b = np.array(twin.posterior(tjt, [tnet.dv(v)]).vals)
+        bf = np.array(twin.brute_force_posterior(tnet, v, dict(ev)))
+        assert a.tobytes() == b.tobytes()
+        assert np.abs(a - bf).max() < 1e-13
+        others = [x for x in range(net.n) if x != v]
+        _, c = onet.posterior_marginal(others, [v], ev)
+        assert np.abs(c - bf).max() < 1e-13
+
+
+def test_trace_cancer_d0_matches_appendix_b():
+    """The op trace the product's compiled schedule must reproduce (SURVEY Appendix B worked schedule)."""
+    net = OracleNet.load_hugin(os.path.join(G, "cancer.net"))
+    jt = OracleJT(net)
+    tr = jt.change_evidence([(0, 0)], trace=True)
+    kinds = [(m["kind"], m["cluster"], m["sep"]) for m in tr if m["kind"] != "posterior"]
+    assert kinds == [("up", 1, 1), ("up", 2, 2), ("down", 0, 2), ("down", 0, 1)]
+    up1 = tr[0]["steps"]
+    assert up1[0]["var"] == 0 and up1[0]["prod"] == [0, 3, 4] and up1[0]["out"] == [3, 4]
+    down_c = tr[2]["steps"]  # down {A,C,B} -> sep {C}: eliminate B then A
+    assert [s["var"] for s in down_c] == [4, 2, -1]
+    assert down_c[0]["prod"] == [4, 2, 3]
+    down_cb = tr[3]["steps"]  # message layout follows rule 5: scope [B,C]
+    assert down_cb[-1]["out"] == [4, 3]
+
+
+def test_ve_orders_grid():
+    """reference minFill semantics (no fill-in) on a grid starts 0, last, 1, cols, ..."""
+    g = synth.grid_net(4, 4, 1)
+    onet = OracleNet.from_arrays(g.dims, g.scopes, g.values)
+    tnet = twin.Network.from_tables(g.dims, g.parents, [v.tolist() for v in g.values])
+    for metric, tw in (("min_fill", twin.min_fill_order), ("min_degree", twin.min_degree_order)):
+        assert onet.ve_order(metric) == [dv[0] for dv in tw(tnet)]
+
+
+def test_factor_algebra_properties():
+    """The six QuickCheck properties of Bayes/Factor/CPT.hs:68-98 on the oracle's product / projectOut."""
+    rng = np.random.RandomState(3)
+    for _ in range(50):
+        def rand_factor(lo):
+            k = rng.randint(1, 4)
+            ids = (lo + rng.permutation(10)[:k]).tolist()
+            sc = [(int(i), int(rng.randint(2, 4))) for i in ids]
+            return sc, rng.rand(int(np.prod([d for _, d in sc])))
+        fa, fb = rand_factor(0), rand_factor(20)
+        # product then project the other factor's variables recovers factor * norm(other)
+        sc, vals = oracle.factor_product([fa, fb])
+        dims = dict(fa[0] + fb[0])
+        sc2, out = oracle.factor_project_out([(v, dims[v]) for v in sc], vals, [v for v, _ in fb[0]])
+        assert sc2 == [v for v, _ in fa[0]]
+        assert np.allclose(out, fa[1] * fb[1].sum(), rtol=1e-12)
+        # projection commutes
+        full = [(v, dims[v]) for v in sc]
+        a1 = oracle.factor_project_out(full, vals, [sc[0]])
+        a2 = oracle.factor_project_out([(v, dims[v]) for v in a1[0]], a1[1], [sc[-1]])
+        b1 = oracle.factor_project_out(full, vals, [sc[-1]])
+        b2 = oracle.factor_project_out([(v, dims[v]) for v in b1[0]], b1[1], [sc[0]])
+        assert a2[0] == b2[0] and np.allclose(a2[1], b2[1], rtol=1e-12)
+        # project all = norm
+        _, allout = oracle.factor_project_out(full, vals, sc)
+        assert np.allclose(allout, vals.sum(), rtol=1e-12)
