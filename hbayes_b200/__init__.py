@@ -1,0 +1,32 @@
+"""hbayes_b200 -- host-side mirror of hbayes' exact-inference API over libhbayes_cuda (B200, sm_100a).
+
+The names follow the reference (alpheccar/hbayes) so that its examples and tests read the same:
+
+    importBayesianGraph   Bayes/ImportExport/HuginNet.hs:160-167
+    createJunctionTree    Bayes/FactorElimination.hs:298-307
+    changeEvidence        Bayes/FactorElimination/JTree.hs:454-466
+    posterior             Bayes/FactorElimination.hs:314-327
+    priorMarginal         Bayes/VariableElimination.hs:134-147
+    posteriorMarginal     Bayes/VariableElimination.hs:116-130
+    minDegreeOrder / minFillOrder   Bayes/VariableElimination.hs:225-236
+
+plus the batched forms (one evidence row per query) that the GPU exists for.  All arithmetic happens in
+libhbayes_cuda.so; this package only marshals arrays.  It never imports `oracle/`.
+"""
+from .api import (  # noqa: F401
+    BayesianNetwork,
+    Factor,
+    JunctionTree,
+    VariableElimination,
+    changeEvidence,
+    createJunctionTree,
+    importBayesianGraph,
+    minDegreeOrder,
+    minFillOrder,
+    nodeComparisonForTriangulation,
+    numberOfAddedEdges,
+    posterior,
+    posteriorMarginal,
+    priorMarginal,
+)
+from ._lib import HbError, LIB_PATH  # noqa: F401

@@ -1,0 +1,85 @@
+"""ctypes binding of libhbayes_cuda.so (include/hbayes_cuda.h).  Plumbing only: the product is the library.
+
+The library must have been built in-tree (`make -C hbayes_b200/csrc` or `__graft_entry__.build()`); there is no
+fallback of any kind when it is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhbayes_cuda.so")
+
+HB_OK, HB_E_ARG, HB_E_NO_CLUSTER, HB_E_CUDA, HB_E_OOM, HB_E_IO, HB_E_UNSUPPORTED, HB_E_NCCL = 0, -1, -2, -3, -4, -5, -6, -7
+HB_STRUCTURE_ONLY = -1
+HB_HOST_PTRS, HB_DEVICE_PTRS = 0, 1
+
+vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+i32p, i64p, i8p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int8), C.POINTER(C.c_double)
+vpp, cpp = C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)
+
+# every symbol include/hbayes_cuda.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "hb_last_error": (C.c_char_p, []),
+    "hb_string_free": (None, [vp]),
+    "hb_device_count": (C.c_int, []),
+    "hb_net_create": (C.c_int, [i32, i32p, i64p, i32p, i64p, f64p, vpp]),
+    "hb_net_load_hugin": (C.c_int, [C.c_char_p, vpp]),
+    "hb_net_n_vars": (C.c_int, [vp]),
+    "hb_net_dims": (C.c_int, [vp, i32p]),
+    "hb_net_describe_json": (C.c_int, [vp, cpp]),
+    "hb_net_free": (None, [vp]),
+    "hb_ve_order": (C.c_int, [vp, i32, i32p, i32p]),
+    "hb_jt_compile": (C.c_int, [vp, i32, i32p, i32, vpp]),
+    "hb_jt_compile_with_order": (C.c_int, [vp, i32p, i32p, i32, vpp]),
+    "hb_jt_describe_json": (C.c_int, [vp, cpp]),
+    "hb_jt_program_json": (C.c_int, [vp, i32, i32p, cpp]),
+    "hb_jt_set_evidence": (C.c_int, [vp, i32, i32p, i32p]),
+    "hb_jt_posterior": (C.c_int, [vp, i32, i32p, i32p, f64p, i64, i64p]),
+    "hb_jt_posteriors_batch": (C.c_int, [vp, i64, vp, vp, i32]),
+    "hb_jt_set_stream": (C.c_int, [vp, vp]),
+    "hb_jt_set_workspace": (C.c_int, [vp, i64]),
+    "hb_jt_last_stats": (C.c_int, [vp, i64p]),
+    "hb_jt_set_timing": (C.c_int, [vp, i32]),
+    "hb_jt_last_timing": (C.c_int, [vp, f64p]),
+    "hb_jt_free": (None, [vp]),
+    "hb_ve_compile": (C.c_int, [vp, i32p, i32, i32p, i32, i32p, i32, vpp]),
+    "hb_ve_result_scope": (C.c_int, [vp, i32, i32p, i32p, i32p]),
+    "hb_ve_program_json": (C.c_int, [vp, i32, i32p, cpp]),
+    "hb_ve_posterior": (C.c_int, [vp, i32, i32p, i32p, i32p, f64p, i64, i64p]),
+    "hb_ve_posterior_batch": (C.c_int, [vp, i64, vp, vp, i32]),
+    "hb_ve_set_stream": (C.c_int, [vp, vp]),
+    "hb_ve_set_workspace": (C.c_int, [vp, i64]),
+    "hb_ve_last_stats": (C.c_int, [vp, i64p]),
+    "hb_ve_set_timing": (C.c_int, [vp, i32]),
+    "hb_ve_last_timing": (C.c_int, [vp, f64p]),
+    "hb_ve_free": (None, [vp]),
+}
+
+_LIB = None
+
+
+class HbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libhbayes_cuda error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Loads the library or raises: a missing build is an error, never a reason to compute elsewhere."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not built: run `make -C hbayes_b200/csrc` (or __graft_entry__.build())" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = L
+    return _LIB
+
+
+def check(code):
+    if code != HB_OK:
+        raise HbError(code, lib().hb_last_error().decode())

@@ -1,0 +1,293 @@
+"""Reference-shaped Python front-end over the C ABI (see package docstring for the file:line map)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (HB_DEVICE_PTRS, HB_E_NO_CLUSTER, HB_HOST_PTRS, HB_STRUCTURE_ONLY, HbError, check, f64p, i32p, i64p, lib)
+
+# the two comparators the reference exports for createJunctionTree (Bayes/FactorElimination.hs:71-111)
+nodeComparisonForTriangulation = 0
+numberOfAddedEdges = 1
+
+
+def _i32(xs):
+    a = np.ascontiguousarray(xs, dtype=np.int32)
+    return a, a.ctypes.data_as(i32p)
+
+
+def _take_json(ptr):
+    s = C.cast(ptr, C.c_char_p).value.decode()
+    lib().hb_string_free(ptr)
+    return json.loads(s)
+
+
+class Factor:
+    """A discrete factor as the reference's CPT shows it: variable order + flat values, first variable slowest
+    (Bayes/Factor/PrivateCPT.hs:67-72)."""
+
+    def __init__(self, variables: Sequence[int], dims: Sequence[int], values: np.ndarray):
+        self.variables = list(variables)
+        self.dims = list(dims)
+        self.values = np.asarray(values, np.float64)
+
+    def __repr__(self):
+        return "Factor(%s, %s)" % (self.variables, self.values.tolist())
+
+
+class BayesianNetwork:
+    """What `runBN` of a BNMonad yields (Bayes/BayesianNetwork.hs:211-212): an immutable hb_net handle."""
+
+    def __init__(self, handle):
+        self._h = handle
+        p = C.c_void_p()
+        check(lib().hb_net_describe_json(self._h, C.byref(p)))
+        d = _take_json(p)
+        self.names, self.dims, self.scopes, self.values = d["names"], d["dims"], d["scopes"], d["values"]
+        self.ids = {n: i for i, n in enumerate(self.names)}
+
+    @staticmethod
+    def from_tables(dims, scopes, values):
+        """CPT v: scope `scopes[v]` = [v, parents...], values in reference layout."""
+        n = len(dims)
+        da, dp = _i32(dims)
+        cpt_off = np.zeros(n + 1, np.int64)
+        val_off = np.zeros(n + 1, np.int64)
+        for v in range(n):
+            cpt_off[v + 1] = cpt_off[v] + len(scopes[v])
+            val_off[v + 1] = val_off[v] + len(values[v])
+        sa, sp = _i32(np.concatenate([np.asarray(s, np.int32) for s in scopes]))
+        vals = np.ascontiguousarray(np.concatenate([np.asarray(v, np.float64) for v in values]))
+        h = C.c_void_p()
+        check(lib().hb_net_create(n, dp, cpt_off.ctypes.data_as(i64p), sp, val_off.ctypes.data_as(i64p),
+                                  vals.ctypes.data_as(f64p), C.byref(h)))
+        return BayesianNetwork(h)
+
+    @property
+    def n(self):
+        return len(self.dims)
+
+    @property
+    def width(self):
+        return int(sum(self.dims))
+
+    def __del__(self):
+        try:
+            lib().hb_net_free(self._h)
+        except Exception:
+            pass
+
+
+def importBayesianGraph(path) -> BayesianNetwork | None:
+    """importBayesianGraph + runBN; returns None when the file does not parse (the reference's `Nothing`)."""
+    h = C.c_void_p()
+    code = lib().hb_net_load_hugin(str(path).encode(), C.byref(h))
+    if code != 0:
+        return None
+    return BayesianNetwork(h)
+
+
+def _order(net: BayesianNetwork, metric: int):
+    out = np.zeros(net.n, np.int32)
+    k = C.c_int32()
+    check(lib().hb_ve_order(net._h, metric, out.ctypes.data_as(i32p), C.byref(k)))
+    return out[: k.value].tolist()
+
+
+def minDegreeOrder(net):
+    return _order(net, 0)
+
+
+def minFillOrder(net):
+    return _order(net, 1)
+
+
+def _device_args(device):
+    if device is None:  # structure only: parity hooks work, compute calls fail loudly
+        return None, HB_STRUCTURE_ONLY, None
+    a, p = _i32([device])
+    return p, 1, a
+
+
+class _Batched:
+    """Shared by JunctionTree and VariableElimination: stream / workspace / stats plumbing."""
+
+    _prefix = ""
+
+    def _fn(self, name):
+        return getattr(lib(), self._prefix + name)
+
+    def set_stream(self, cuda_stream: int):
+        check(self._fn("set_stream")(self._h, C.c_void_p(cuda_stream)))
+
+    def set_workspace(self, nbytes: int):
+        check(self._fn("set_workspace")(self._h, int(nbytes)))
+
+    def set_timing(self, on: bool):
+        check(self._fn("set_timing")(self._h, 1 if on else 0))
+
+    def last_timing(self):
+        """CUDA-event milliseconds of the last batch call: prep / prodsum / output / total (set_timing(True) first)"""
+        out = np.zeros(4, np.float64)
+        check(self._fn("last_timing")(self._h, out.ctypes.data_as(f64p)))
+        return dict(zip(["prep_ms", "prodsum_ms", "output_ms", "total_ms"], out.tolist()))
+
+    def last_stats(self):
+        out = np.zeros(8, np.int64)
+        check(self._fn("last_stats")(self._h, out.ctypes.data_as(i64p)))
+        keys = ["launches", "tiles", "rows_per_tile", "arena_bytes", "row_entries", "prod_per_row", "row_read_per_row",
+                "row_write_per_row"]
+        return dict(zip(keys, out.tolist()))
+
+    def _run_matrix(self, fn, evidence, out, width):
+        """evidence/out: numpy arrays (host) or torch CUDA tensors (device pointers, no copies)."""
+        if isinstance(evidence, np.ndarray):
+            ev = np.ascontiguousarray(evidence, np.int8)
+            assert ev.ndim == 2 and ev.shape[1] == self.net.n
+            if out is None:
+                out = np.empty((ev.shape[0], width), np.float64)
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (ev.shape[0], width)
+            check(fn(self._h, ev.shape[0], ev.ctypes.data, out.ctypes.data, HB_HOST_PTRS))
+            return out
+        import torch  # device memory + streams only
+
+        assert evidence.dtype == torch.int8 and evidence.is_contiguous() and evidence.shape[1] == self.net.n
+        if evidence.is_cuda:
+            if out is None:
+                out = torch.empty((evidence.shape[0], width), dtype=torch.float64, device=evidence.device)
+            assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous()
+            check(fn(self._h, evidence.shape[0], evidence.data_ptr(), out.data_ptr(), HB_DEVICE_PTRS))
+        else:  # (pinned) host tensors
+            if out is None:
+                out = torch.empty((evidence.shape[0], width), dtype=torch.float64, pin_memory=evidence.is_pinned())
+            check(fn(self._h, evidence.shape[0], evidence.data_ptr(), out.data_ptr(), HB_HOST_PTRS))
+        return out
+
+
+class JunctionTree(_Batched):
+    """createJunctionTree's result.  `device=None` builds the structure only (no GPU needed, no compute possible)."""
+
+    _prefix = "hb_jt_"
+
+    def __init__(self, net: BayesianNetwork, cmp=nodeComparisonForTriangulation, order=None, device=0):
+        self.net = net
+        dp, nd, self._keep = _device_args(device)
+        h = C.c_void_p()
+        if order is not None:
+            oa, op = _i32(order)
+            check(lib().hb_jt_compile_with_order(net._h, op, dp, nd, C.byref(h)))
+        else:
+            check(lib().hb_jt_compile(net._h, int(cmp), dp, nd, C.byref(h)))
+        self._h = h
+
+    def describe(self):
+        p = C.c_void_p()
+        check(lib().hb_jt_describe_json(self._h, C.byref(p)))
+        return _take_json(p)
+
+    def program(self, observed: Iterable[int] = ()):
+        """parity hook: operation trace + physical steps compiled for changeEvidence on `observed` (in that order)"""
+        oa, op = _i32(list(observed))
+        p = C.c_void_p()
+        check(lib().hb_jt_program_json(self._h, len(oa), op, C.byref(p)))
+        return _take_json(p)
+
+    def changeEvidence(self, evidence: Sequence[tuple]):
+        """evidence = [(vertex, state)], order kept (it decides the reference's operation order)."""
+        va, vp_ = _i32([e[0] for e in evidence])
+        sa, sp = _i32([e[1] for e in evidence])
+        check(lib().hb_jt_set_evidence(self._h, len(evidence), vp_, sp))
+        return self
+
+    def posterior(self, variables: Sequence[int]):
+        qa, qp = _i32(list(variables))
+        size = int(np.prod([self.net.dims[v] for v in variables]))
+        out = np.zeros(size, np.float64)
+        scope = np.zeros(len(variables), np.int32)
+        n = C.c_int64()
+        code = lib().hb_jt_posterior(self._h, len(variables), qp, scope.ctypes.data_as(i32p), out.ctypes.data_as(f64p), size,
+                                     C.byref(n))
+        if code == HB_E_NO_CLUSTER:
+            return None  # the reference's `Nothing` (FactorElimination.hs:319)
+        check(code)
+        sc = scope.tolist()
+        return Factor(sc, [self.net.dims[v] for v in sc], out[: n.value])
+
+    def posteriors_batch(self, evidence, out=None):
+        """One query per row: changeEvidence row; posterior [v] for all v.  Returns [n_rows][sum dims]."""
+        return self._run_matrix(lib().hb_jt_posteriors_batch, evidence, out, self.net.width)
+
+    def __del__(self):
+        try:
+            lib().hb_jt_free(self._h)
+        except Exception:
+            pass
+
+
+class VariableElimination(_Batched):
+    """A (p, r) pair of posteriorMarginal compiled for replay over evidence rows."""
+
+    _prefix = "hb_ve_"
+
+    def __init__(self, net: BayesianNetwork, p: Sequence[int], r: Sequence[int], device=0):
+        self.net, self.p, self.r = net, list(p), list(r)
+        dp, nd, self._keep = _device_args(device)
+        pa, pp = _i32(self.p)
+        ra, rp = _i32(self.r)
+        h = C.c_void_p()
+        check(lib().hb_ve_compile(net._h, pp, len(self.p), rp, len(self.r), dp, nd, C.byref(h)))
+        self._h = h
+        self.width = int(np.prod([net.dims[v] for v in self.r]))
+
+    def program(self, observed: Iterable[int] = ()):
+        oa, op = _i32(list(observed))
+        p = C.c_void_p()
+        check(lib().hb_ve_program_json(self._h, len(oa), op, C.byref(p)))
+        return _take_json(p)
+
+    def posterior(self, assignment: Sequence[tuple] = ()):
+        va, vp_ = _i32([e[0] for e in assignment])
+        sa, sp = _i32([e[1] for e in assignment])
+        out = np.zeros(self.width, np.float64)
+        scope = np.zeros(len(self.r), np.int32)
+        n = C.c_int64()
+        check(lib().hb_ve_posterior(self._h, len(assignment), vp_, sp, scope.ctypes.data_as(i32p), out.ctypes.data_as(f64p),
+                                    self.width, C.byref(n)))
+        sc = scope.tolist()
+        return Factor(sc, [self.net.dims[v] for v in sc], out[: n.value])
+
+    def posterior_batch(self, evidence, out=None):
+        return self._run_matrix(lib().hb_ve_posterior_batch, evidence, out, self.width)
+
+    def __del__(self):
+        try:
+            lib().hb_ve_free(self._h)
+        except Exception:
+            pass
+
+
+# ---- the reference's function names -----------------------------------------------------------
+
+
+def createJunctionTree(cmp, net: BayesianNetwork, device=0) -> JunctionTree:
+    return JunctionTree(net, cmp=cmp, device=device)
+
+
+def changeEvidence(evidence, jt: JunctionTree) -> JunctionTree:
+    return jt.changeEvidence(evidence)
+
+
+def posterior(jt: JunctionTree, variables):
+    return jt.posterior(variables)
+
+
+def posteriorMarginal(net: BayesianNetwork, p, r, assignment, device=0) -> Factor:
+    return VariableElimination(net, p, r, device=device).posterior(assignment)
+
+
+def priorMarginal(net: BayesianNetwork, ea, eb, device=0) -> Factor:
+    return VariableElimination(net, ea, eb, device=device).posterior([])

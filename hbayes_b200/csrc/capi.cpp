@@ -1,0 +1,509 @@
+// capi.cpp -- the C ABI of libhbayes_cuda (include/hbayes_cuda.h): handle management, program cache,
+// host<->device staging.  No arithmetic happens here.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/hbayes_cuda.h"
+#include "engine.hpp"
+#include "model.hpp"
+
+using namespace hb;
+
+namespace {
+
+thread_local std::string g_error;
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return HB_OK;
+  } catch (const Error& e) {
+    g_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_error = "host allocation failed";
+    return HB_E_OOM;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return HB_E_ARG;
+  }
+}
+
+char* dup_json(const std::string& s) {
+  char* p = (char*)malloc(s.size() + 1);
+  if (!p) throw std::bad_alloc();
+  memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+void cuda_ok(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw Error(e == cudaErrorMemoryAllocation ? HB_E_OOM : HB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int pick_device(const int32_t* devices, int32_t n_devices) {
+  if (!devices && n_devices == HB_STRUCTURE_ONLY) return -1;  // host structure only: every compute call fails
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    throw Error(HB_E_CUDA, "no CUDA device: libhbayes_cuda has no CPU fallback");
+  int dev = 0;
+  if (devices && n_devices > 0) dev = devices[0];
+  if (dev < 0 || dev >= count) throw Error(HB_E_ARG, "device ordinal out of range");
+  return dev;
+}
+
+struct Compiled {
+  std::unique_ptr<Program> prog;
+  Executor* ex = nullptr;
+  ~Compiled() {
+    if (ex) executor_destroy(ex);
+  }
+};
+
+// What a junction-tree handle and a variable-elimination handle share: the network, the GPU, the cache
+// of compiled programs (one per observed-variable list) and grow-only staging buffers.
+struct Session {
+  Network net;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t workspace = 0;
+  std::map<std::vector<int>, std::unique_ptr<Compiled>> cache;
+  int8_t* d_ev = nullptr;
+  double* d_out = nullptr;
+  size_t ev_cap = 0, out_cap = 0;
+  int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool timing = false;
+  Executor* last_ex = nullptr;  // executor of the last batch call (for hb_*_last_timing)
+
+  ~Session() {
+    if (device >= 0) cudaSetDevice(device);
+    cache.clear();
+    if (d_ev) cudaFree(d_ev);
+    if (d_out) cudaFree(d_out);
+  }
+  // the device-resident form of a compiled program, created on first use
+  Executor* executor(Compiled& c) {
+    if (device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
+    if (!c.ex) c.ex = executor_create(*c.prog, device, workspace);
+    executor_set_timing(c.ex, timing);
+    last_ex = c.ex;
+    return c.ex;
+  }
+  void reserve(size_t ev_bytes, size_t out_bytes) {
+    if (device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
+    cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+    if (ev_bytes > ev_cap) {
+      if (d_ev) cudaFree(d_ev), d_ev = nullptr;
+      cuda_ok(cudaMalloc(&d_ev, ev_bytes), "cudaMalloc(evidence staging)");
+      ev_cap = ev_bytes;
+    }
+    if (out_bytes > out_cap) {
+      if (d_out) cudaFree(d_out), d_out = nullptr;
+      cuda_ok(cudaMalloc(&d_out, out_bytes), "cudaMalloc(output staging)");
+      out_cap = out_bytes;
+    }
+  }
+  void note(const Compiled& c, const RunStats& rs, bool accumulate) {
+    if (!accumulate) memset(stats, 0, sizeof stats);
+    stats[0] += rs.launches;
+    stats[1] += rs.tiles;
+    stats[2] = rs.rows_per_tile;
+    stats[3] = rs.arena_bytes;
+    stats[4] = c.prog->row_entries;
+    stats[5] = c.prog->stat_prod;
+    stats[6] = c.prog->stat_row_read;
+    stats[7] = c.prog->stat_row_write;
+  }
+};
+
+std::vector<int> observed_of_row(const int8_t* row, int n_vars) {
+  std::vector<int> obs;
+  for (int v = 0; v < n_vars; ++v)
+    if (row[v] >= 0) obs.push_back(v);
+  return obs;
+}
+
+// Runs `get(observed)`'s program over an evidence matrix.  Host buffers: rows are assumed to share the
+// observed set of row 0 (the device checks every row); if they do not, they are grouped by observed set
+// on the host and each group runs with its own program.
+template <class GetProgram>
+void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags) {
+  if (n_rows < 0 || (n_rows > 0 && (!evidence || !out))) throw Error(HB_E_ARG, "null evidence or output buffer");
+  if (n_rows == 0) return;
+  const int n_vars = s.net.n();
+  if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
+  cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+  RunStats rs;
+  if (flags & HB_DEVICE_PTRS) {
+    std::vector<int8_t> first(n_vars);
+    cuda_ok(cudaMemcpyAsync(first.data(), evidence, n_vars, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(first row)");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    Compiled& c = get(observed_of_row(first.data(), n_vars));
+    executor_run(s.executor(c), n_rows, evidence, out, s.stream, &rs);
+    s.note(c, rs, false);
+    executor_check(s.executor(c), s.stream);
+    return;
+  }
+  Compiled& c0 = get(observed_of_row(evidence, n_vars));
+  const int64_t width = c0.prog->out_width;
+  s.reserve((size_t)n_rows * n_vars, (size_t)n_rows * width * sizeof(double));
+  cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)n_rows * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+  executor_run(s.executor(c0), n_rows, s.d_ev, s.d_out, s.stream, &rs);
+  s.note(c0, rs, false);
+  bool uniform = true;
+  try {
+    executor_check(s.executor(c0), s.stream);
+  } catch (const Error& e) {
+    if (e.code != HB_E_ARG) throw;
+    uniform = false;
+  }
+  if (uniform) {
+    cuda_ok(cudaMemcpyAsync(out, s.d_out, (size_t)n_rows * width * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    return;
+  }
+  // mixed observed sets: group rows on the host
+  std::map<std::vector<int>, std::vector<int64_t>> groups;
+  for (int64_t r = 0; r < n_rows; ++r) groups[observed_of_row(evidence + r * n_vars, n_vars)].push_back(r);
+  std::vector<int8_t> ev;
+  std::vector<double> res;
+  bool first = true;
+  for (auto& kv : groups) {
+    Compiled& c = get(kv.first);
+    const int64_t m = (int64_t)kv.second.size();
+    ev.resize((size_t)m * n_vars);
+    for (int64_t i = 0; i < m; ++i) memcpy(ev.data() + i * n_vars, evidence + kv.second[i] * n_vars, n_vars);
+    cuda_ok(cudaMemcpyAsync(s.d_ev, ev.data(), ev.size(), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+    executor_run(s.executor(c), m, s.d_ev, s.d_out, s.stream, &rs);
+    s.note(c, rs, !first);
+    first = false;
+    executor_check(s.executor(c), s.stream);  // states out of range -> HB_E_ARG
+    res.resize((size_t)m * width);
+    cuda_ok(cudaMemcpyAsync(res.data(), s.d_out, res.size() * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    for (int64_t i = 0; i < m; ++i) memcpy(out + kv.second[i] * width, res.data() + i * width, width * sizeof(double));
+  }
+}
+
+}  // namespace
+
+struct hb_net {
+  Network net;
+};
+
+struct hb_jt {
+  Session s;
+  std::unique_ptr<Tree> tree;
+  std::vector<int> ev_vars, ev_states;  // current changeEvidence list
+  std::vector<double> posts;            // posterior [v] for every v under the current evidence
+  std::vector<int64_t> post_off;
+
+  // program for changeEvidence `observed` (in that order) + the given queries (empty = posterior [v] for all v)
+  Compiled& program(const std::vector<int>& observed, const std::vector<int>& query) {
+    std::vector<int> key = observed;
+    key.push_back(-1);
+    key.insert(key.end(), query.begin(), query.end());
+    auto it = s.cache.find(key);
+    if (it != s.cache.end()) return *it->second;
+    std::vector<Query> qs;
+    if (query.empty())
+      for (int v = 0; v < s.net.n(); ++v) qs.push_back(Query{{v}});
+    else
+      qs.push_back(Query{query});
+    auto c = std::make_unique<Compiled>();
+    c->prog.reset(compile_jt(s.net, *tree, observed, qs));
+    return *(s.cache[key] = std::move(c));
+  }
+  void run_one(Compiled& c, std::vector<double>& out) {
+    std::vector<int8_t> row(s.net.n(), -1);
+    for (size_t i = 0; i < ev_vars.size(); ++i) row[ev_vars[i]] = (int8_t)ev_states[i];
+    out.assign((size_t)c.prog->out_width, 0.0);
+    s.reserve(row.size(), out.size() * sizeof(double));
+    cuda_ok(cudaMemcpyAsync(s.d_ev, row.data(), row.size(), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+    RunStats rs;
+    executor_run(s.executor(c), 1, s.d_ev, s.d_out, s.stream, &rs);
+    s.note(c, rs, false);
+    executor_check(s.executor(c), s.stream);
+    cuda_ok(cudaMemcpyAsync(out.data(), s.d_out, out.size() * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+  }
+};
+
+struct hb_ve {
+  Session s;
+  std::vector<int> p, r;
+  Compiled& program(const std::vector<int>& observed) {
+    auto it = s.cache.find(observed);
+    if (it != s.cache.end()) return *it->second;
+    auto c = std::make_unique<Compiled>();
+    c->prog.reset(compile_ve(s.net, p, r, observed));
+    return *(s.cache[observed] = std::move(c));
+  }
+};
+
+static void check_evidence_list(const Network& net, int32_t n, const int32_t* vars, const int32_t* states) {
+  if (n < 0 || (n > 0 && (!vars || !states))) throw Error(HB_E_ARG, "null evidence list");
+  for (int i = 0; i < n; ++i) {
+    if (vars[i] < 0 || vars[i] >= net.n()) throw Error(HB_E_ARG, "evidence on unknown vertex");
+    if (states[i] < 0 || states[i] >= net.dims[vars[i]]) throw Error(HB_E_ARG, "evidence state out of range");
+  }
+}
+
+extern "C" {
+
+const char* hb_last_error(void) { return g_error.c_str(); }
+void hb_string_free(char* s) { free(s); }
+int hb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int hb_net_create(int32_t n_vars, const int32_t* dims, const int64_t* cpt_off, const int32_t* cpt_scope,
+                  const int64_t* val_off, const double* cpt_vals, hb_net** out) {
+  return guarded([&] {
+    if (!out) throw Error(HB_E_ARG, "null out");
+    std::unique_ptr<Network> n(network_create(n_vars, dims, cpt_off, cpt_scope, val_off, cpt_vals));
+    *out = new hb_net{std::move(*n)};
+  });
+}
+int hb_net_load_hugin(const char* path, hb_net** out) {
+  return guarded([&] {
+    if (!out) throw Error(HB_E_ARG, "null out");
+    std::unique_ptr<Network> n(network_load_hugin(path));
+    *out = new hb_net{std::move(*n)};
+  });
+}
+int hb_net_n_vars(const hb_net* net) { return net ? net->net.n() : HB_E_ARG; }
+int hb_net_dims(const hb_net* net, int32_t* dims_out) {
+  return guarded([&] {
+    if (!net || !dims_out) throw Error(HB_E_ARG, "null argument");
+    for (int v = 0; v < net->net.n(); ++v) dims_out[v] = net->net.dims[v];
+  });
+}
+int hb_net_describe_json(const hb_net* net, char** out_json) {
+  return guarded([&] {
+    if (!net || !out_json) throw Error(HB_E_ARG, "null argument");
+    *out_json = dup_json(describe_network(net->net));
+  });
+}
+void hb_net_free(hb_net* net) { delete net; }
+
+int hb_ve_order(const hb_net* net, int32_t metric, int32_t* order_out, int32_t* n_out) {
+  return guarded([&] {
+    if (!net || !order_out || !n_out) throw Error(HB_E_ARG, "null argument");
+    std::vector<int> o = ve_elimination_order(net->net, metric);
+    for (size_t i = 0; i < o.size(); ++i) order_out[i] = o[i];
+    *n_out = (int32_t)o.size();
+  });
+}
+
+static int jt_compile(const hb_net* net, int32_t cmp, const int32_t* order, const int32_t* devices, int32_t n_devices, hb_jt** out) {
+  return guarded([&] {
+    if (!net || !out) throw Error(HB_E_ARG, "null argument");
+    auto jt = std::make_unique<hb_jt>();
+    jt->s.net = net->net;
+    jt->tree.reset(tree_build(jt->s.net, cmp, order));  // host work first: structure errors surface without a GPU
+    jt->s.device = pick_device(devices, n_devices);
+    jt->post_off.assign(1, 0);
+    for (int d : jt->s.net.dims) jt->post_off.push_back(jt->post_off.back() + d);
+    Compiled& prior = jt->program({}, {});
+    if (jt->s.device >= 0) jt->run_one(prior, jt->posts);  // createJunctionTree calibrates the tree (distribute . collect)
+    *out = jt.release();
+  });
+}
+int hb_jt_compile(const hb_net* net, int32_t cmp, const int32_t* devices, int32_t n_devices, hb_jt** out) {
+  return jt_compile(net, cmp, nullptr, devices, n_devices, out);
+}
+int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const int32_t* devices, int32_t n_devices, hb_jt** out) {
+  if (!elim_order) {
+    g_error = "null elimination order";
+    return HB_E_ARG;
+  }
+  return jt_compile(net, 0, elim_order, devices, n_devices, out);
+}
+int hb_jt_describe_json(const hb_jt* jt, char** out_json) {
+  return guarded([&] {
+    if (!jt || !out_json) throw Error(HB_E_ARG, "null argument");
+    *out_json = dup_json(describe_tree(*jt->tree));
+  });
+}
+int hb_jt_program_json(hb_jt* jt, int32_t n, const int32_t* vars, char** out_json) {
+  return guarded([&] {
+    if (!jt || !out_json || n < 0 || (n > 0 && !vars)) throw Error(HB_E_ARG, "null argument");
+    *out_json = dup_json(describe_program(*jt->program(std::vector<int>(vars, vars + n), {}).prog));
+  });
+}
+int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states) {
+  return guarded([&] {
+    if (!jt) throw Error(HB_E_ARG, "null handle");
+    check_evidence_list(jt->s.net, n, vars, states);
+    std::vector<int> v(vars, vars + n), st(states, states + n);
+    Compiled& c = jt->program(v, {});
+    jt->ev_vars = v;
+    jt->ev_states = st;
+    jt->run_one(c, jt->posts);
+  });
+}
+int hb_jt_posterior(hb_jt* jt, int32_t n_q, const int32_t* q_vars, int32_t* out_scope, double* out, int64_t out_len,
+                    int64_t* n_written) {
+  return guarded([&] {
+    if (!jt || n_q <= 0 || !q_vars || !out) throw Error(HB_E_ARG, "null or empty query");
+    const Network& net = jt->s.net;
+    if (n_q == 1) {
+      const int v = q_vars[0];
+      if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "query on unknown vertex");
+      if (out_len < net.dims[v]) throw Error(HB_E_ARG, "output buffer too small");
+      for (int i = 0; i < net.dims[v]; ++i) out[i] = jt->posts[jt->post_off[v] + i];
+      if (out_scope) out_scope[0] = v;
+      if (n_written) *n_written = net.dims[v];
+      return;
+    }
+    Compiled& c = jt->program(jt->ev_vars, std::vector<int>(q_vars, q_vars + n_q));
+    if (out_len < c.prog->out_width) throw Error(HB_E_ARG, "output buffer too small");
+    std::vector<double> res;
+    jt->run_one(c, res);
+    std::copy(res.begin(), res.end(), out);
+    const Group& g = c.prog->groups.back();
+    if (out_scope)
+      for (size_t i = 0; i < g.out_scope.size(); ++i) out_scope[i] = g.out_scope[i];
+    if (n_written) *n_written = c.prog->out_width;
+  });
+}
+int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags) {
+  return guarded([&] {
+    if (!jt) throw Error(HB_E_ARG, "null handle");
+    run_matrix(jt->s, [&](const std::vector<int>& obs) -> Compiled& { return jt->program(obs, {}); }, n_rows, evidence, out, flags);
+  });
+}
+int hb_jt_set_stream(hb_jt* jt, void* cuda_stream) {
+  if (!jt) return HB_E_ARG;
+  jt->s.stream = (cudaStream_t)cuda_stream;
+  return HB_OK;
+}
+int hb_jt_set_workspace(hb_jt* jt, int64_t bytes) {
+  if (!jt || bytes < 0) return HB_E_ARG;
+  jt->s.workspace = bytes;
+  jt->s.cache.clear();
+  jt->s.last_ex = nullptr;
+  return HB_OK;
+}
+int hb_jt_set_timing(hb_jt* jt, int32_t on) {
+  if (!jt) return HB_E_ARG;
+  jt->s.timing = on != 0;
+  return HB_OK;
+}
+int hb_jt_last_timing(hb_jt* jt, double* out4) {
+  return guarded([&] {
+    if (!jt || !out4 || !jt->s.last_ex) throw Error(HB_E_ARG, "no timed run");
+    executor_last_timing(jt->s.last_ex, jt->s.stream, out4);
+  });
+}
+int hb_jt_last_stats(const hb_jt* jt, int64_t* out8) {
+  if (!jt || !out8) return HB_E_ARG;
+  memcpy(out8, jt->s.stats, sizeof jt->s.stats);
+  return HB_OK;
+}
+void hb_jt_free(hb_jt* jt) { delete jt; }
+
+int hb_ve_compile(const hb_net* net, const int32_t* p, int32_t np, const int32_t* r, int32_t nr, const int32_t* devices,
+                  int32_t n_devices, hb_ve** out) {
+  return guarded([&] {
+    if (!net || !out || np < 0 || nr <= 0 || (np > 0 && !p) || !r) throw Error(HB_E_ARG, "null or empty argument");
+    auto ve = std::make_unique<hb_ve>();
+    ve->s.net = net->net;
+    ve->p.assign(p, p + np);
+    ve->r.assign(r, r + nr);
+    for (int v : ve->p)
+      if (v < 0 || v >= net->net.n()) throw Error(HB_E_ARG, "elimination order mentions an unknown vertex");
+    for (int v : ve->r)
+      if (v < 0 || v >= net->net.n()) throw Error(HB_E_ARG, "query mentions an unknown vertex");
+    ve->s.device = pick_device(devices, n_devices);
+    *out = ve.release();
+  });
+}
+int hb_ve_result_scope(hb_ve* ve, int32_t n_obs, const int32_t* observed, int32_t* scope_out, int32_t* n_out) {
+  return guarded([&] {
+    if (!ve || !scope_out || !n_out || n_obs < 0 || (n_obs > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
+    const Group& g = ve->program(std::vector<int>(observed, observed + n_obs)).prog->groups.back();
+    for (size_t i = 0; i < g.out_scope.size(); ++i) scope_out[i] = g.out_scope[i];
+    *n_out = (int32_t)g.out_scope.size();
+  });
+}
+int hb_ve_program_json(hb_ve* ve, int32_t n_obs, const int32_t* observed, char** out_json) {
+  return guarded([&] {
+    if (!ve || !out_json || n_obs < 0 || (n_obs > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
+    *out_json = dup_json(describe_program(*ve->program(std::vector<int>(observed, observed + n_obs)).prog));
+  });
+}
+int hb_ve_posterior(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* states, int32_t* out_scope, double* out,
+                    int64_t out_len, int64_t* n_written) {
+  return guarded([&] {
+    if (!ve || !out) throw Error(HB_E_ARG, "null argument");
+    check_evidence_list(ve->s.net, n, vars, states);
+    Compiled& c = ve->program(std::vector<int>(vars, vars + n));
+    if (out_len < c.prog->out_width) throw Error(HB_E_ARG, "output buffer too small");
+    Session& s = ve->s;
+    std::vector<int8_t> row(s.net.n(), -1);
+    for (int i = 0; i < n; ++i) row[vars[i]] = (int8_t)states[i];
+    s.reserve(row.size(), (size_t)c.prog->out_width * sizeof(double));
+    cuda_ok(cudaMemcpyAsync(s.d_ev, row.data(), row.size(), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+    RunStats rs;
+    executor_run(s.executor(c), 1, s.d_ev, s.d_out, s.stream, &rs);
+    s.note(c, rs, false);
+    executor_check(s.executor(c), s.stream);
+    cuda_ok(cudaMemcpyAsync(out, s.d_out, (size_t)c.prog->out_width * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    const Group& g = c.prog->groups.back();
+    if (out_scope)
+      for (size_t i = 0; i < g.out_scope.size(); ++i) out_scope[i] = g.out_scope[i];
+    if (n_written) *n_written = c.prog->out_width;
+  });
+}
+int hb_ve_posterior_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags) {
+  return guarded([&] {
+    if (!ve) throw Error(HB_E_ARG, "null handle");
+    run_matrix(ve->s, [&](const std::vector<int>& obs) -> Compiled& { return ve->program(obs); }, n_rows, evidence, out, flags);
+  });
+}
+int hb_ve_set_stream(hb_ve* ve, void* cuda_stream) {
+  if (!ve) return HB_E_ARG;
+  ve->s.stream = (cudaStream_t)cuda_stream;
+  return HB_OK;
+}
+int hb_ve_set_workspace(hb_ve* ve, int64_t bytes) {
+  if (!ve || bytes < 0) return HB_E_ARG;
+  ve->s.workspace = bytes;
+  ve->s.cache.clear();
+  ve->s.last_ex = nullptr;
+  return HB_OK;
+}
+int hb_ve_set_timing(hb_ve* ve, int32_t on) {
+  if (!ve) return HB_E_ARG;
+  ve->s.timing = on != 0;
+  return HB_OK;
+}
+int hb_ve_last_timing(hb_ve* ve, double* out4) {
+  return guarded([&] {
+    if (!ve || !out4 || !ve->s.last_ex) throw Error(HB_E_ARG, "no timed run");
+    executor_last_timing(ve->s.last_ex, ve->s.stream, out4);
+  });
+}
+int hb_ve_last_stats(const hb_ve* ve, int64_t* out8) {
+  if (!ve || !out8) return HB_E_ARG;
+  memcpy(out8, ve->s.stats, sizeof ve->s.stats);
+  return HB_OK;
+}
+void hb_ve_free(hb_ve* ve) { delete ve; }
+
+}  // extern "C"

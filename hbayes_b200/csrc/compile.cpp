@@ -1,0 +1,597 @@
+// compile.cpp -- the schedule compiler: runs the reference's bucket elimination SYMBOLICALLY, once per
+// (network, observed-variable list), and emits a flat list of fused product/sum-out steps with index
+// maps.  The GPU replays that list for every evidence row (engine.cu).
+//
+// What is reproduced from the reference, operation for operation:
+//   marginal / createBuckets / addBucket / updateBucket / marginalizeOneVariable
+//       (Bayes/VariableElimination.hs:56-73, Bayes/VariableElimination/Buckets.hs:47-111)
+//   product scope = foldr1 union, value = ps * (v1 * (v2 * ...)), scalars folded into ps
+//       (Bayes/Factor/PrivateCPT.hs:215-238)
+//   sum-out keeps the remaining variables in their order, adds terms in ascending state from 0
+//       (Bayes/Factor/PrivateCPT.hs:243-266, Bayes/Factor/CPT.hs:140-141)
+//   newMessage input order f ++ e ++ input, collect / distribute (Bayes/FactorElimination/JTree.hs:288-369,485-491)
+//   changeEvidence: indicators in the caller's order, each prepended to its cluster (JTree.hs:424-466)
+//   posterior input order d : u ++ f ++ e (Bayes/FactorElimination.hs:314-327)
+//
+// What is different (and why it is value-identical): an observed variable is never
+// enumerated.  Its indicator is the constant 1.0 at the observed state and every table is only
+// stored at that state ("evidence slicing"): x * 1.0 == x and 0 + x + 0 == x exactly, and entries at
+// the other states are exactly 0 in the reference and never reach a result.  Requires finite table
+// values (0 * inf would be NaN in the reference).
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <sstream>
+
+#include "model.hpp"
+
+namespace hb {
+namespace {
+
+bool contains(const std::vector<int>& xs, int x) { return std::find(xs.begin(), xs.end(), x) != xs.end(); }
+
+// Data.List.union on duplicate-free lists (Bayes/PrivateTypes.hs:118-128)
+std::vector<int> list_union(const std::vector<int>& xs, const std::vector<int>& ys) {
+  std::vector<int> out = xs;
+  for (int y : ys)
+    if (!contains(out, y)) out.push_back(y);
+  return out;
+}
+
+struct Compiler {
+  const Network& net;
+  Program& P;
+  int one = -1;  // the `Scalar 1.0` table
+
+  Compiler(const Network& n, Program& p, const std::vector<int>& observed) : net(n), P(p) {
+    P.net = &net;
+    P.observed = observed;
+    P.is_observed.assign(net.n(), 0);
+    for (int v : observed) {
+      if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "evidence on unknown vertex " + std::to_string(v));
+      if (P.is_observed[v]) throw Error(HB_E_ARG, "vertex " + std::to_string(v) + " observed twice");
+      P.is_observed[v] = 1;
+    }
+    P.pot_off.assign(net.n(), 0);
+    for (int v = 0; v < net.n(); ++v) P.pot_off[v] = P.pot_entries, P.pot_entries += (int64_t)net.values[v].size();
+    Table t;
+    t.kind = T_ONE;
+    t.scalar = true;
+    one = add(t);
+  }
+
+  int add(const Table& t) {
+    P.tables.push_back(t);
+    return (int)P.tables.size() - 1;
+  }
+  const Table& T(int id) const { return P.tables[id]; }
+  int resolve(int id) const {
+    while (P.tables[id].alias_of >= 0) id = P.tables[id].alias_of;
+    return id;
+  }
+
+  void set_physical(Table& t) {  // row-major over the unobserved variables of the structural scope
+    t.pscope.clear();
+    for (int v : t.scope)
+      if (!P.is_observed[v]) t.pscope.push_back(v);
+    t.pstride.assign(t.pscope.size(), 1);
+    t.size = 1;
+    for (int i = (int)t.pscope.size() - 1; i >= 0; --i) t.pstride[i] = t.size, t.size *= net.dims[t.pscope[i]];
+  }
+
+  // CPT of vertex v as it sits in the potential pool (Bayes/Network.hs:69-79): strides of the FULL table,
+  // observed variables selected per row through a slice offset.
+  int potential(int v) {
+    Table t;
+    t.kind = T_POT;
+    t.pot = v;
+    t.scope = net.scope[v];
+    t.off = P.pot_off[v];
+    std::vector<int64_t> full(t.scope.size(), 1);
+    for (int i = (int)t.scope.size() - 2; i >= 0; --i) full[i] = full[i + 1] * net.dims[t.scope[i + 1]];
+    Slice sl;
+    sl.pot = v;
+    t.size = 1;
+    for (size_t i = 0; i < t.scope.size(); ++i) {
+      if (P.is_observed[t.scope[i]])
+        sl.vars.push_back(t.scope[i]), sl.strides.push_back(full[i]);
+      else
+        t.pscope.push_back(t.scope[i]), t.pstride.push_back(full[i]), t.size *= net.dims[t.scope[i]];
+    }
+    if (!sl.vars.empty()) {
+      t.slice_slot = (int)P.slices.size();
+      P.slices.push_back(sl);
+    }
+    return add(t);
+  }
+
+  // factorFromInstantiation (Bayes/Factor.hs:90-94) of an observed variable: 1.0 at the row's state.
+  int indicator(int v) {
+    Table t;
+    t.kind = T_ONE;
+    t.scope = {v};
+    return add(t);
+  }
+
+  bool batch_invariant(int id) const {
+    const Table& t = T(resolve(id));
+    return t.kind == T_ONE || t.kind == T_SHARED || (t.kind == T_POT && t.slice_slot < 0);
+  }
+
+  // One reference operation: itemProduct of `inputs` followed (sum_var >= 0) by itemProjectOut sum_var.
+  int product_sumout(const std::vector<int>& inputs, int sum_var, Group& g) {
+    Group::TraceStep tr;
+    tr.var = sum_var;
+    for (int id : inputs) tr.inputs.push_back(T(id).scope);
+    if (inputs.empty()) {  // _factorProduct [] = Scalar 1.0; projectOut of a Scalar is the Scalar
+      g.trace.push_back(tr);
+      return one;
+    }
+    std::vector<int> naked = T(inputs.back()).scope;
+    for (int i = (int)inputs.size() - 2; i >= 0; --i) naked = list_union(T(inputs[i]).scope, naked);
+    std::vector<int> chain, scalars;  // structural partition isScalarFactor (PrivateCPT.hs:223)
+    for (int id : inputs) (T(id).scalar ? scalars : chain).push_back(id);
+    Table out;
+    out.scalar = true;
+    if (!chain.empty()) {
+      for (int v : naked)
+        if (v != sum_var) out.scope.push_back(v);
+      out.scalar = out.scope.empty();  // createCPTWithDims [] = Scalar
+    }
+    tr.prod = chain.empty() ? std::vector<int>{} : naked;
+    tr.out = out.scope;
+    g.trace.push_back(tr);
+
+    // ---- physical lowering ----
+    Step st;
+    st.group = (int)P.groups.size();
+    st.sum_var = sum_var;
+    bool shared = true;
+    for (int id : scalars)
+      if (T(resolve(id)).kind != T_ONE) st.scalars.push_back(resolve(id)), shared = shared && batch_invariant(id);
+    std::vector<int> real;
+    for (int id : chain)
+      if (T(resolve(id)).kind != T_ONE) real.push_back(resolve(id)), shared = shared && batch_invariant(id);
+    if (real.empty() && st.scalars.empty()) {  // only ones: the constant 1.0
+      out.kind = T_ONE;
+      return add(out);
+    }
+    const bool sums = sum_var >= 0 && !P.is_observed[sum_var] && contains(naked, sum_var) && !chain.empty();
+    if (!sums && st.scalars.empty() && real.size() == 1) {  // 1.0 * v (and 0 + v): the table itself
+      out.alias_of = real[0];
+      out.kind = T(real[0]).kind;
+      set_physical(out);
+      return add(out);
+    }
+    if (real.empty() && st.scalars.size() == 1) {
+      out.alias_of = st.scalars[0];
+      out.kind = T(st.scalars[0]).kind;
+      return add(out);
+    }
+    out.kind = shared ? T_SHARED : T_ROW;
+    set_physical(out);
+    st.shared = shared;
+    st.d = sums ? net.dims[sum_var] : 1;
+    st.n_out = out.size;
+    // split the output index: trailing variables with product C go into `lo`, the rest into `hi`
+    const int nk = (int)out.pscope.size();
+    int split = nk;
+    int64_t C = 1;
+    while (split > 0 && C * C < st.n_out && C * net.dims[out.pscope[split - 1]] <= 4096) C *= net.dims[out.pscope[--split]];
+    st.C = C;
+    st.n_hi = st.n_out / C;
+    for (int id : real) {
+      const Table& t = T(id);
+      StepInput in;
+      in.table = id;
+      auto stride_of = [&](int v) -> int64_t {
+        for (size_t i = 0; i < t.pscope.size(); ++i)
+          if (t.pscope[i] == v) return t.pstride[i];
+        return 0;
+      };
+      in.sstride = sums ? stride_of(sum_var) : 0;
+      in.hi.assign((size_t)st.n_hi, 0);
+      in.lo.assign((size_t)C, 0);
+      auto fill = [&](std::vector<int32_t>& dst, int from, int to) {
+        std::vector<int> digit(nk, 0);
+        int64_t off = 0;
+        for (size_t e = 0; e < dst.size(); ++e) {
+          dst[e] = (int32_t)off;
+          for (int j = to - 1; j >= from; --j) {
+            int64_t s = stride_of(out.pscope[j]);
+            if (++digit[j] < net.dims[out.pscope[j]]) {
+              off += s;
+              break;
+            }
+            off -= s * (digit[j] - 1);
+            digit[j] = 0;
+          }
+        }
+      };
+      fill(in.hi, 0, split);
+      fill(in.lo, split, nk);
+      st.in.push_back(std::move(in));
+      P.stat_reads += st.n_out * st.d;
+      if (t.kind == T_ROW) P.stat_row_read += std::min<int64_t>(t.size, st.n_out * st.d);
+    }
+    if (!shared) {
+      P.stat_prod += st.n_out * st.d;
+      P.stat_row_write += st.n_out;
+      P.stat_max_table = std::max(P.stat_max_table, st.n_out * st.d);
+    }
+    st.trace_inputs = tr.inputs;
+    st.trace_prod = tr.prod;
+    st.trace_out = tr.out;
+    int id = add(out);
+    st.out = id;
+    P.tables[id].def_step = (int)P.steps.size();
+    P.steps.push_back(std::move(st));
+    return id;
+  }
+
+  // marginal (VariableElimination.hs:56-73) over symbolic factors; `assignment` = indicator tables.
+  int marginal(const std::vector<int>& lf, const std::vector<int>& p, const std::vector<int>& r,
+               const std::vector<int>& assignment, Group& g) {
+    std::vector<int> order = p;
+    order.insert(order.end(), r.begin(), r.end());
+    std::map<int, std::vector<int>> buckets;  // Data.Map DV [f]; DV order = vertex id
+    std::vector<int> rest = lf;
+    for (int dv : order) {  // createBuckets (Buckets.hs:47-65)
+      std::vector<int> fk, others;
+      for (int id : rest) (contains(T(id).scope, dv) ? fk : others).push_back(id);
+      rest.swap(others);
+      buckets[dv] = fk;
+    }
+    size_t head = 0;  // order[head..] = variables still to process
+    auto add_bucket = [&](int id) {  // addBucket (Buckets.hs:92-98): prepend
+      for (size_t i = head; i < order.size(); ++i)
+        if (contains(T(id).scope, order[i])) {
+          auto& b = buckets[order[i]];
+          b.insert(b.begin(), id);
+          return;
+        }
+    };
+    for (int id : assignment) add_bucket(id);
+    for (int dv : p) {  // marginalizeOneVariable + updateBucket (Buckets.hs:74-89,105-111)
+      std::vector<int> fk = buckets.at(dv);
+      int f2 = product_sumout(fk, dv, g);
+      if (head < order.size()) ++head;
+      if (T(f2).scalar)
+        buckets[dv] = {f2};
+      else {
+        buckets.erase(dv);
+        add_bucket(f2);
+      }
+    }
+    std::vector<int> fin;
+    for (auto& kv : buckets) fin.insert(fin.end(), kv.second.begin(), kv.second.end());
+    return product_sumout(fin, -1, g);
+  }
+
+  std::vector<int> first_appearance(const std::vector<int>& factors) const {  // nub . concatMap factorVariables
+    std::vector<int> seen;
+    for (int id : factors)
+      for (int v : T(id).scope)
+        if (!contains(seen, v)) seen.push_back(v);
+    return seen;
+  }
+
+  // Normalisation + expansion of a query result (factorNorm / factorDivide, Factor.hs:171-172,
+  // PrivateCPT.hs:167-187): norm = left fold over the layout order, every entry times 1.0 / norm.
+  void emit_output(int result, Group& g) {
+    Step st;
+    st.kind = STEP_OUTPUT;
+    st.group = (int)P.groups.size();
+    const int rid = resolve(result);
+    const Table& t = T(result);
+    StepInput in;
+    in.table = rid;
+    st.in.push_back(in);
+    g.out_scope = t.scope;
+    g.result = result;
+    const int nq = (int)t.scope.size();
+    std::vector<int64_t> fstride(nq, 1);
+    st.n_full = 1;
+    for (int i = nq - 1; i >= 0; --i) fstride[i] = st.n_full, st.n_full *= net.dims[t.scope[i]];
+    // physical strides of the stored table (an alias shares its target's layout)
+    const Table& stored = T(rid);
+    st.full_map.assign((size_t)st.n_full, 0);
+    std::vector<int> digit(nq, 0);
+    for (int64_t e = 0; e < st.n_full; ++e) {
+      int64_t off = 0;
+      for (int i = 0; i < nq; ++i)
+        for (size_t j = 0; j < stored.pscope.size(); ++j)
+          if (stored.pscope[j] == t.scope[i]) off += stored.pstride[j] * digit[i];
+      st.full_map[e] = (int32_t)off;
+      for (int i = nq - 1; i >= 0; --i) {
+        if (++digit[i] < net.dims[t.scope[i]]) break;
+        digit[i] = 0;
+      }
+    }
+    for (int i = 0; i < nq; ++i)
+      if (P.is_observed[t.scope[i]]) {
+        st.obs_var.push_back(t.scope[i]);
+        st.obs_stride.push_back(fstride[i]);
+        st.obs_dim.push_back(net.dims[t.scope[i]]);
+      }
+    st.n_out = stored.size;
+    st.out_col = P.out_width;
+    P.out_width += st.n_full;
+    P.steps.push_back(std::move(st));
+  }
+
+  // Dead steps (messages no requested query needs) are dropped; liveness-based placement of the
+  // per-row tables in the row arena; shared tables get their own arena.
+  void finish() {
+    const int ns = (int)P.steps.size();
+    std::vector<char> live_t(P.tables.size(), 0), live_s(ns, 0);
+    for (int s = ns - 1; s >= 0; --s) {
+      Step& st = P.steps[s];
+      if (st.kind == STEP_OUTPUT || live_t[st.out]) {
+        live_s[s] = 1;
+        for (auto& in : st.in) live_t[in.table] = 1;
+        for (int id : st.scalars) live_t[id] = 1;
+      }
+    }
+    std::vector<Step> kept;
+    std::vector<int> remap_group_first;
+    for (int s = 0; s < ns; ++s)
+      if (live_s[s]) kept.push_back(std::move(P.steps[s]));
+    P.steps.swap(kept);
+    for (auto& t : P.tables) t.def_step = t.last_use = -1;
+    for (int s = 0; s < (int)P.steps.size(); ++s) {
+      Step& st = P.steps[s];
+      if (st.kind == STEP_PRODSUM) P.tables[st.out].def_step = s;
+      for (auto& in : st.in) P.tables[in.table].last_use = s;
+      for (int id : st.scalars) P.tables[id].last_use = s;
+    }
+    // shared arena: no reuse (computed once, read by every row)
+    for (auto& t : P.tables)
+      if (t.kind == T_SHARED && t.alias_of < 0 && t.def_step >= 0) t.off = P.shared_entries, P.shared_entries += t.size;
+    // row arena: first-fit over a free list, tables released after their last reader
+    std::vector<std::pair<int64_t, int64_t>> free_list;  // (offset, size), sorted by offset
+    int64_t top = 0;
+    std::vector<std::vector<int>> dies_at(P.steps.size());
+    for (size_t id = 0; id < P.tables.size(); ++id) {
+      const Table& t = P.tables[id];
+      if (t.kind == T_ROW && t.alias_of < 0 && t.def_step >= 0 && t.last_use >= 0) dies_at[t.last_use].push_back((int)id);
+    }
+    auto release = [&](int64_t off, int64_t size) {
+      auto it = std::lower_bound(free_list.begin(), free_list.end(), std::make_pair(off, (int64_t)0));
+      it = free_list.insert(it, {off, size});
+      if (it + 1 != free_list.end() && it->first + it->second == (it + 1)->first) it->second += (it + 1)->second, free_list.erase(it + 1);
+      if (it != free_list.begin() && (it - 1)->first + (it - 1)->second == it->first) (it - 1)->second += it->second, it = free_list.erase(it), --it;
+      if (it->first + it->second == top) top = it->first, free_list.erase(it);
+    };
+    for (int s = 0; s < (int)P.steps.size(); ++s) {
+      Step& st = P.steps[s];
+      if (st.kind == STEP_PRODSUM && !st.shared) {
+        Table& t = P.tables[st.out];
+        bool placed = false;
+        for (size_t i = 0; i < free_list.size(); ++i)
+          if (free_list[i].second >= t.size) {
+            t.off = free_list[i].first;
+            free_list[i].first += t.size, free_list[i].second -= t.size;
+            if (free_list[i].second == 0) free_list.erase(free_list.begin() + i);
+            placed = true;
+            break;
+          }
+        if (!placed) t.off = top, top += t.size;
+        P.row_entries = std::max(P.row_entries, top);
+        if (t.last_use < 0) release(t.off, t.size);  // cannot happen after dead-step removal; kept for safety
+      }
+      for (int id : dies_at[s]) release(P.tables[id].off, P.tables[id].size);
+    }
+  }
+};
+
+void js_list(std::ostringstream& o, const std::vector<int>& v) {
+  o << "[";
+  for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << v[i];
+  o << "]";
+}
+template <class V>
+void js_nums(std::ostringstream& o, const V& v) {
+  o << "[";
+  for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << (long long)v[i];
+  o << "]";
+}
+
+}  // namespace
+
+// createJunctionTree's calibration / changeEvidence (JTree.hs:454-466) followed by `posterior q` for
+// every requested query, as one program.
+Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>& observed,
+                    const std::vector<Query>& queries) {
+  auto prog = std::make_unique<Program>();
+  Compiler C(net, *prog, observed);
+  const int nc = (int)tree.clusters.size(), nsep = tree.n_seps();
+  std::vector<int> pot(net.n());
+  for (int v = 0; v < net.n(); ++v) pot[v] = C.potential(v);
+  std::vector<std::vector<int>> f(nc), e(nc);
+  for (int c = 0; c < nc; ++c)
+    for (int v : tree.factors[c]) f[c].push_back(pot[v]);
+  // updateTreeValues changeEvidence (JTree.hs:424-440,459-460): caller's order, each PREPENDED
+  for (int v : observed) {
+    int c = tree_covering_cluster(net, tree, {v});
+    e[c].insert(e[c].begin(), C.indicator(v));
+  }
+  std::vector<int> up(nsep + 1, -1), down(nsep + 1, -1);
+  auto message = [&](int kind, int cluster, int sep, const std::vector<int>& incoming) {  // newMessage (JTree.hs:485-491)
+    Group g;
+    g.kind = kind;
+    g.cluster = cluster;
+    g.sep = sep;
+    std::vector<int> all = f[cluster];
+    all.insert(all.end(), e[cluster].begin(), e[cluster].end());
+    all.insert(all.end(), incoming.begin(), incoming.end());
+    const std::vector<int>& keep = tree.sep_vars[sep - 1];
+    std::vector<int> remove;
+    for (int v : C.first_appearance(all))
+      if (!contains(keep, v)) remove.push_back(v);
+    int res = C.marginal(all, remove, keep, {}, g);
+    g.out_scope = C.T(res).scope;
+    g.result = res;
+    prog->groups.push_back(std::move(g));
+    return res;
+  };
+  // collect (JTree.hs:329-348): level-synchronous sweep from the leaves; an up message is a pure function
+  // of the subtree below it, so it is emitted once, the first time the sweep finds its inputs ready.
+  {
+    std::vector<int> level;
+    for (int c : tree.by_rank)
+      if (tree.children[c].empty()) level.push_back(c);
+    std::vector<int> rank(nc);
+    for (int i = 0; i < nc; ++i) rank[tree.by_rank[i]] = i;
+    while (!level.empty()) {
+      for (int h : level) {
+        int ps = tree.parent_sep[h];
+        if (ps < 0 || up[ps] >= 0) continue;
+        bool ready = true;
+        std::vector<int> inc;
+        for (int s : tree.children[h]) {
+          if (up[s] < 0) ready = false;
+          inc.push_back(up[s]);
+        }
+        if (ready) up[ps] = message(0, h, ps, inc);
+      }
+      std::vector<int> next;
+      for (int h : level)
+        if (tree.parent_sep[h] >= 0) next.push_back(tree.sep_parent[tree.parent_sep[h] - 1]);
+      std::sort(next.begin(), next.end(), [&](int a, int b) { return rank[a] < rank[b]; });
+      next.erase(std::unique(next.begin(), next.end()), next.end());
+      level.swap(next);
+    }
+  }
+  // distribute (JTree.hs:350-369): all down messages of a node (children newest first), then recurse.
+  {
+    std::vector<int> stack = {tree.root};
+    while (!stack.empty()) {
+      int node = stack.back();
+      stack.pop_back();
+      for (int child : tree.children[node]) {
+        std::vector<int> inc;  // [down from parent] ++ [up of the other children]  (JTree.hs:307-322)
+        if (tree.parent_sep[node] >= 0) inc.push_back(down[tree.parent_sep[node]]);
+        for (int s : tree.children[node])
+          if (s != child) inc.push_back(up[s]);
+        down[child] = message(1, node, child, inc);
+      }
+      for (auto it = tree.children[node].rbegin(); it != tree.children[node].rend(); ++it) stack.push_back(tree.sep_child[*it - 1]);
+    }
+  }
+  // posterior (FactorElimination.hs:314-327)
+  for (const Query& q : queries) {
+    if (q.vars.empty()) throw Error(HB_E_ARG, "empty posterior query");
+    for (size_t i = 0; i < q.vars.size(); ++i) {
+      if (q.vars[i] < 0 || q.vars[i] >= net.n()) throw Error(HB_E_ARG, "query on unknown vertex");
+      for (size_t j = 0; j < i; ++j)
+        if (q.vars[i] == q.vars[j]) throw Error(HB_E_ARG, "query repeats a vertex");
+    }
+    int c = tree_find_cluster(tree, q.vars);
+    if (c < 0) throw Error(HB_E_NO_CLUSTER, "no cluster holds all query variables");
+    Group g;
+    g.kind = 2;
+    g.cluster = c;
+    g.query = q.vars;
+    std::vector<int> all;
+    all.push_back(tree.parent_sep[c] >= 0 ? down[tree.parent_sep[c]] : C.one);
+    for (int s : tree.children[c]) all.push_back(up[s]);
+    all.insert(all.end(), f[c].begin(), f[c].end());
+    all.insert(all.end(), e[c].begin(), e[c].end());
+    std::vector<int> remove;
+    for (int v : C.first_appearance(all))
+      if (!contains(q.vars, v)) remove.push_back(v);
+    int res = C.marginal(all, remove, q.vars, {}, g);
+    C.emit_output(res, g);
+    prog->groups.push_back(std::move(g));
+  }
+  C.finish();
+  return prog.release();
+}
+
+// posteriorMarginal g p r assignment (VariableElimination.hs:116-130): all CPTs in ascending vertex id,
+// indicators added with addBucket in the caller's order.
+Program* compile_ve(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
+                    const std::vector<int>& observed) {
+  auto prog = std::make_unique<Program>();
+  Compiler C(net, *prog, observed);
+  for (int v : p)
+    if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "elimination order mentions an unknown vertex");
+  for (int v : r)
+    if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "query mentions an unknown vertex");
+  std::vector<int> lf, asg;
+  for (int v = 0; v < net.n(); ++v) lf.push_back(C.potential(v));
+  for (int v : observed) asg.push_back(C.indicator(v));
+  Group g;
+  g.kind = 3;
+  g.query = r;
+  int res = C.marginal(lf, p, r, asg, g);
+  C.emit_output(res, g);
+  prog->groups.push_back(std::move(g));
+  C.finish();
+  return prog.release();
+}
+
+// Parity hook (hb_jt_describe_json / hb_ve_describe_json): the reference-level operation trace of every
+// message and query, plus the physical step list with its index maps.
+std::string describe_program(const Program& P) {
+  std::ostringstream o;
+  o << "{\"observed\":";
+  js_list(o, P.observed);
+  o << ",\"row_entries\":" << P.row_entries << ",\"shared_entries\":" << P.shared_entries << ",\"out_width\":" << P.out_width
+    << ",\"stats\":{\"prod\":" << P.stat_prod << ",\"reads\":" << P.stat_reads << ",\"row_read\":" << P.stat_row_read
+    << ",\"row_write\":" << P.stat_row_write << ",\"max_table\":" << P.stat_max_table << ",\"steps\":" << P.steps.size() << "}";
+  o << ",\"groups\":[";
+  const char* kinds[] = {"up", "down", "posterior", "ve"};
+  for (size_t i = 0; i < P.groups.size(); ++i) {
+    const Group& g = P.groups[i];
+    o << (i ? "," : "") << "{\"kind\":\"" << kinds[g.kind] << "\",\"cluster\":" << g.cluster << ",\"sep\":" << g.sep << ",\"query\":";
+    js_list(o, g.query);
+    o << ",\"out_scope\":";
+    js_list(o, g.out_scope);
+    o << ",\"steps\":[";
+    for (size_t j = 0; j < g.trace.size(); ++j) {
+      const auto& t = g.trace[j];
+      o << (j ? "," : "") << "{\"kind\":\"" << (t.var >= 0 ? "elim" : "final") << "\",\"var\":" << t.var << ",\"inputs\":[";
+      for (size_t k = 0; k < t.inputs.size(); ++k) {
+        o << (k ? "," : "");
+        js_list(o, t.inputs[k]);
+      }
+      o << "],\"prod\":";
+      js_list(o, t.prod);
+      o << ",\"out\":";
+      js_list(o, t.out);
+      o << "}";
+    }
+    o << "]}";
+  }
+  o << "],\"physical\":[";
+  for (size_t i = 0; i < P.steps.size(); ++i) {
+    const Step& s = P.steps[i];
+    o << (i ? "," : "") << "{\"kind\":" << s.kind << ",\"shared\":" << (s.shared ? 1 : 0) << ",\"group\":" << s.group
+      << ",\"sum_var\":" << s.sum_var << ",\"d\":" << s.d << ",\"n_out\":" << s.n_out << ",\"C\":" << s.C << ",\"out\":" << s.out;
+    if (s.kind == STEP_PRODSUM) {
+      o << ",\"out_scope\":";
+      js_list(o, P.tables[s.out].pscope);
+      o << ",\"out_off\":" << P.tables[s.out].off;
+    } else
+      o << ",\"out_col\":" << s.out_col << ",\"n_full\":" << s.n_full;
+    o << ",\"scalars\":";
+    js_list(o, s.scalars);
+    o << ",\"in\":[";
+    for (size_t k = 0; k < s.in.size(); ++k) {
+      const Table& t = P.tables[s.in[k].table];
+      o << (k ? "," : "") << "{\"table\":" << s.in[k].table << ",\"kind\":" << t.kind << ",\"pot\":" << t.pot << ",\"off\":" << t.off
+        << ",\"size\":" << t.size << ",\"sstride\":" << s.in[k].sstride << ",\"scope\":";
+      js_list(o, t.pscope);
+      o << ",\"strides\":";
+      js_nums(o, t.pstride);
+      o << "}";
+    }
+    o << "]}";
+  }
+  o << "]}";
+  return o.str();
+}
+
+}  // namespace hb

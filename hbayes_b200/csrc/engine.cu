@@ -1,0 +1,629 @@
+// engine.cu -- sm_100a kernels and the row-tiled replay of a compiled Program.
+//
+// Data layout in HBM
+//   potential pool   double[pot_entries]            all CPTs, reference layout, batch-invariant
+//   shared arena     double[shared_entries]         evidence-independent derived tables (computed once)
+//   row arena        double[row_entries][RT]        per-row derived tables, ROW-FASTEST: entry e of row r
+//                                                   of a tile sits at (off + e) * RT + r, so the 32 lanes
+//                                                   of a warp (32 consecutive rows, same entry) read and
+//                                                   write 256 contiguous bytes
+//   slice offsets    int32[n_slices][RT]            entry offset of each sliced CPT for each row
+//   evidence         int8[n_rows][n_vars]           caller's matrix, -1 = unobserved
+//   output           double[n_rows][out_width]      caller's matrix
+//
+// Kernels
+//   prep_rows_kernel     evidence -> slice offsets + consistency check          (Bayes/Factor.hs:90-94)
+//   prodsum_kernel<K>    fused factor product + sum-out of one variable + evidence slicing
+//                        (marginalizeOneVariable = _factorProduct + cptFactorProjectOutWith,
+//                         Buckets.hs:105-111, PrivateCPT.hs:215-266)
+//   output_kernel        factorNorm + factorDivide + expansion to the query scope
+//                        (PrivateCPT.hs:167-187, Factor.hs:171-172)
+// All arithmetic is binary64 with explicit round-to-nearest multiply/add (no FMA contraction), in the
+// reference's association order: ps * (v1 * (v2 * ...)) and 0 + t0 + t1 + ...
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace hb {
+
+#define HB_CUDA(call)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess)                                                                                 \
+      throw Error(e_ == cudaErrorMemoryAllocation ? HB_E_OOM : HB_E_CUDA,                                  \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                     \
+  } while (0)
+
+namespace {
+
+constexpr int MAXK = 8;       // chain inputs handled by the templated kernel
+constexpr int MAXS = 4;       // structural scalars per step
+constexpr int MAXOBS = 8;     // observed variables inside one query
+constexpr int BLOCK = 256;
+
+// A table as a kernel sees it: element (e, row) lives at base[e * mult + rowterm(row)].
+struct TabRef {
+  const double* base;     // pool + table offset (row tables: arena + off * RT)
+  const int32_t* rowoff;  // sliced potential: per-row entry offset for this tile, else nullptr
+  int is_row;             // 1: per-row table (mult = RT, rowterm = row)
+  int is_one;             // 1: the constant 1.0
+};
+
+struct InArg {
+  TabRef t;
+  const int32_t* hi;
+  const int32_t* lo;
+  long long sstride;      // stride of the summed variable, in entries
+};
+
+template <int K>
+struct StepArgs {
+  InArg in[K > 0 ? K : 1];
+  TabRef sc[MAXS];
+  int n_sc;
+  int d;                  // terms per output entry
+  int C;                  // o = hiI * C + loI
+  long long n_out;
+  double* out;            // arena + off * RT (row) or shared + off
+  int out_is_row;
+  int nr;                 // rows in this tile
+  long long RT;           // row stride of the arena
+};
+
+struct GenericArgs {      // any number of inputs / scalars, descriptors in global memory
+  const InArg* in;
+  const TabRef* sc;
+  int k, n_sc, d, C;
+  long long n_out;
+  double* out;
+  int out_is_row, nr;
+  long long RT;
+};
+
+__device__ __forceinline__ const double* row_ptr(const TabRef& t, int row) {
+  return t.base + (t.is_row ? (long long)row : (t.rowoff ? (long long)__ldg(t.rowoff + row) : 0ll));
+}
+
+// ps = s1 * (s2 * (... * sn))   (elementProduct over the scalars, PrivateCPT.hs:225-227)
+__device__ __forceinline__ double fold_scalars(const TabRef* sc, int n, int row) {
+  double ps = *row_ptr(sc[n - 1], row);
+  for (int i = n - 2; i >= 0; --i) ps = __dmul_rn(*row_ptr(sc[i], row), ps);
+  return ps;
+}
+
+// One thread = one evidence row (threadIdx.x) walking a strip of output entries (threadIdx.y / blockIdx.x).
+// All lanes of a warp share the output entry, so index-map loads are broadcasts and every table access
+// of the warp is one contiguous 256-byte segment (row tables) or a handful of addresses (potentials).
+template <int K>
+__global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ StepArgs<K> a) {
+  const int row = blockIdx.y * blockDim.x + threadIdx.x;
+  if (row >= a.nr) return;
+  const double* p[K > 0 ? K : 1];
+  long long m[K > 0 ? K : 1], ss[K > 0 ? K : 1];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    p[i] = row_ptr(a.in[i].t, row);
+    m[i] = a.in[i].t.is_row ? a.RT : 1;
+    ss[i] = a.in[i].sstride * m[i];
+  }
+  const bool has_ps = a.n_sc > 0;
+  const double ps = has_ps ? fold_scalars(a.sc, a.n_sc, row) : 1.0;
+  double* outp = a.out + (a.out_is_row ? row : 0);
+  const long long om = a.out_is_row ? a.RT : 1;
+  const long long step = (long long)gridDim.x * blockDim.y;
+  for (long long o = (long long)blockIdx.x * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
+    const unsigned hiI = (unsigned)o / (unsigned)a.C, loI = (unsigned)o - hiI * (unsigned)a.C;  // n_out < 2^31
+    long long off[K > 0 ? K : 1];
+#pragma unroll
+    for (int i = 0; i < K; ++i) off[i] = (long long)(__ldg(a.in[i].hi + hiI) + __ldg(a.in[i].lo + loI)) * m[i];
+    double acc = 0.0;
+#pragma unroll 4
+    for (int s = 0; s < a.d; ++s) {
+      double c;
+      if (K == 0) {
+        c = ps;
+      } else {
+        c = p[K - 1][off[K - 1]];
+#pragma unroll
+        for (int i = K - 2; i >= 0; --i) c = __dmul_rn(p[i][off[i]], c);
+        if (has_ps) c = __dmul_rn(ps, c);
+      }
+      acc = __dadd_rn(acc, c);
+#pragma unroll
+      for (int i = 0; i < K; ++i) off[i] += ss[i];
+    }
+    outp[o * om] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArgs a) {
+  const int row = blockIdx.y * blockDim.x + threadIdx.x;
+  if (row >= a.nr) return;
+  const double ps = a.n_sc > 0 ? fold_scalars(a.sc, a.n_sc, row) : 1.0;
+  double* outp = a.out + (a.out_is_row ? row : 0);
+  const long long om = a.out_is_row ? a.RT : 1;
+  const long long step = (long long)gridDim.x * blockDim.y;
+  for (long long o = (long long)blockIdx.x * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
+    const unsigned hiI = (unsigned)(o / a.C), loI = (unsigned)(o - (long long)hiI * a.C);
+    double acc = 0.0;
+    for (int s = 0; s < a.d; ++s) {
+      double c = ps;
+      for (int i = a.k - 1; i >= 0; --i) {
+        const InArg& in = a.in[i];
+        const long long mm = in.t.is_row ? a.RT : 1;
+        const long long off = ((long long)(__ldg(in.hi + hiI) + __ldg(in.lo + loI)) + s * in.sstride) * mm;
+        const double v = row_ptr(in.t, row)[off];
+        c = (i == a.k - 1) ? v : __dmul_rn(v, c);
+      }
+      if (a.k > 0 && a.n_sc > 0) c = __dmul_rn(ps, c);
+      acc = __dadd_rn(acc, c);
+    }
+    outp[o * om] = acc;
+  }
+}
+
+// ---- evidence -> slice offsets, and the consistency check -------------------------------------
+struct PrepArgs {
+  const int8_t* ev;        // [nr][n_vars] for this tile
+  int nr, n_vars, n_slices;
+  long long RT;
+  const int8_t* observed;  // [n_vars] 0/1
+  const int32_t* dims;     // [n_vars]
+  const int32_t* sl_begin; // [n_slices + 1]
+  const int32_t* sl_var;
+  const int32_t* sl_stride;
+  int32_t* rowoff;         // [n_slices][RT]
+  int* flag;
+};
+
+__global__ void __launch_bounds__(BLOCK) prep_rows_kernel(const PrepArgs a) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.nr) return;
+  const int8_t* e = a.ev + (long long)row * a.n_vars;
+  bool bad = false;
+  for (int v = 0; v < a.n_vars; ++v) {
+    const int s = e[v];
+    const bool obs = a.observed[v] != 0;
+    bad |= obs ? (s < 0 || s >= a.dims[v]) : (s >= 0);
+  }
+  if (bad) atomicOr(a.flag, 1);
+  for (int j = 0; j < a.n_slices; ++j) {
+    int off = 0;
+    for (int t = a.sl_begin[j]; t < a.sl_begin[j + 1]; ++t) {
+      int s = e[a.sl_var[t]];
+      s = s < 0 ? 0 : (s >= a.dims[a.sl_var[t]] ? 0 : s);  // keep reads in bounds for flagged rows
+      off += a.sl_stride[t] * s;
+    }
+    a.rowoff[(long long)j * a.RT + row] = off;
+  }
+}
+
+// ---- normalise + expand ------------------------------------------------------------------------
+struct OutDesc {
+  TabRef t;                // rowoff is rebased per tile at launch
+  long long off_entries;   // (unused on device; kept for debugging)
+  int slice;               // slice slot or -1
+  int n_phys, n_full;
+  long long out_col;
+  int map_off, order_off;  // into the int32 map pool
+  int n_obs;
+  int obs_var[MAXOBS], obs_stride[MAXOBS], obs_dim[MAXOBS];
+};
+
+struct OutArgs {
+  const OutDesc* desc;
+  int n_desc;
+  const int32_t* maps;
+  const int32_t* rowoff;   // [n_slices][RT]
+  const double* arena;
+  const int8_t* ev;        // this tile
+  double* out;             // this tile: [nr][width]
+  int nr, n_vars;
+  long long RT, width;
+};
+
+// thread = (row, query).  norm = 0 + x0 + x1 + ... over the result's layout order; every entry of the
+// full table is (1.0 / norm) * value, where the value of an entry that contradicts the evidence is 0.0
+// (so zero-probability evidence gives NaN exactly as 0 * (1/0) does in the reference).
+__global__ void __launch_bounds__(BLOCK) output_kernel(const OutArgs a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (int)(gid % a.nr);
+  const int q = (int)(gid / a.nr);
+  if (q >= a.n_desc) return;
+  const OutDesc& d = a.desc[q];
+  const double* p = nullptr;
+  long long m = 1;
+  if (!d.t.is_one) {
+    if (d.t.is_row) {
+      p = d.t.base + row;
+      m = a.RT;
+    } else
+      p = d.t.base + (d.slice >= 0 ? (long long)a.rowoff[(long long)d.slice * a.RT + row] : 0ll);
+  }
+  const int32_t* order = a.maps + d.order_off;
+  const int32_t* fmap = a.maps + d.map_off;
+  double norm = 0.0;
+  for (int j = 0; j < d.n_phys; ++j) norm = __dadd_rn(norm, p ? p[(long long)order[j] * m] : 1.0);
+  const double inv = __ddiv_rn(1.0, norm);
+  const int8_t* e = a.ev + (long long)row * a.n_vars;
+  int st[MAXOBS];
+  for (int j = 0; j < d.n_obs; ++j) st[j] = e[d.obs_var[j]];
+  double* o = a.out + (long long)row * a.width + d.out_col;
+  for (int f = 0; f < d.n_full; ++f) {
+    bool match = true;
+    for (int j = 0; j < d.n_obs; ++j) match &= ((f / d.obs_stride[j]) % d.obs_dim[j]) == st[j];
+    const double v = match ? (p ? p[(long long)fmap[f] * m] : 1.0) : 0.0;
+    o[f] = __dmul_rn(inv, v);
+  }
+}
+
+}  // namespace
+
+// ================================ host side =====================================================
+struct Executor {
+  const Program* P = nullptr;
+  int device = 0;
+  int64_t workspace = 0;
+  double *d_pots = nullptr, *d_shared = nullptr, *d_arena = nullptr;
+  int32_t *d_maps = nullptr, *d_rowoff = nullptr;
+  int8_t* d_observed = nullptr;
+  int32_t *d_dims = nullptr, *d_sl_begin = nullptr, *d_sl_var = nullptr, *d_sl_stride = nullptr;
+  OutDesc* d_out_desc = nullptr;
+  InArg* d_gen_in = nullptr;     // descriptors of the generic-path steps (rebuilt when RT changes)
+  TabRef* d_gen_sc = nullptr;
+  int* d_flag = nullptr;
+  int64_t RT = 0;                // current arena row stride
+  std::vector<int64_t> hi_off, lo_off;  // per (step, input): offsets into the map pool
+  std::vector<int64_t> in_base;         // first (step,input) index of each step
+  std::vector<OutDesc> out_desc;
+  std::vector<int> out_steps;
+  int64_t gen_in_total = 0, gen_sc_total = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> events;  // 4 per tile of the last run when timing is on
+  size_t events_used = 0;
+  cudaEvent_t next_event() {
+    if (events_used == events.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) throw Error(HB_E_CUDA, "cudaEventCreate failed");
+      events.push_back(e);
+    }
+    return events[events_used++];
+  }
+  ~Executor() {
+    cudaSetDevice(device);
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_rowoff, (void*)d_observed, (void*)d_dims,
+                    (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_gen_in, (void*)d_gen_sc, (void*)d_flag})
+      if (p) cudaFree(p);
+  }
+};
+
+namespace {
+
+template <class T>
+T* upload(const std::vector<T>& v) {
+  T* d = nullptr;
+  HB_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) HB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+template <class T>
+void free_dev(T*& p) {
+  if (p) HB_CUDA(cudaFree(p));
+  p = nullptr;
+}
+
+TabRef tab_ref(const Executor& ex, const Table& t, int64_t RT, const int32_t* rowoff_tile) {
+  TabRef r{nullptr, nullptr, 0, 0};
+  switch (t.kind) {
+    case T_ONE: r.is_one = 1; break;
+    case T_POT:
+      r.base = ex.d_pots + t.off;
+      if (t.slice_slot >= 0) r.rowoff = rowoff_tile + (int64_t)t.slice_slot * RT;
+      break;
+    case T_SHARED: r.base = ex.d_shared + t.off; break;
+    case T_ROW: r.base = ex.d_arena + t.off * RT, r.is_row = 1; break;
+  }
+  return r;
+}
+
+// threads of a block along the row axis: the smallest power of two covering the tile, at most BLOCK
+int block_rows(int nr) {
+  int bx = 1;
+  while (bx < nr && bx < BLOCK) bx <<= 1;
+  return bx;
+}
+
+template <int K>
+void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, bool shared_pass, cudaStream_t stream) {
+  const Program& P = *ex.P;
+  StepArgs<K> a;
+  memset(&a, 0, sizeof a);
+  for (int i = 0; i < K; ++i) {
+    a.in[i].t = tab_ref(ex, P.tables[st.in[i].table], RT, ex.d_rowoff);
+    a.in[i].hi = ex.d_maps + ex.hi_off[ex.in_base[si] + i];
+    a.in[i].lo = ex.d_maps + ex.lo_off[ex.in_base[si] + i];
+    a.in[i].sstride = st.in[i].sstride;
+  }
+  a.n_sc = (int)st.scalars.size();
+  for (int i = 0; i < a.n_sc; ++i) a.sc[i] = tab_ref(ex, P.tables[st.scalars[i]], RT, ex.d_rowoff);
+  a.d = st.d;
+  a.C = (int)st.C;
+  a.n_out = st.n_out;
+  const Table& out = P.tables[st.out];
+  a.out_is_row = out.kind == T_ROW;
+  a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
+  a.nr = nr;
+  a.RT = RT;
+  const int bx = block_rows(nr);
+  const int by = BLOCK / bx;
+  dim3 block(bx, by), grid;
+  grid.y = (nr + bx - 1) / bx;
+  const int64_t max_x = (st.n_out + by - 1) / by;
+  const int64_t want = (148 * 8 * 4 + grid.y - 1) / grid.y;
+  grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_x, want));
+  prodsum_kernel<K><<<grid, block, 0, stream>>>(a);
+  (void)shared_pass;
+}
+
+}  // namespace
+
+static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream, int64_t gen_in_at,
+                           int64_t gen_sc_at) {
+  const int k = (int)st.in.size(), s = (int)st.scalars.size();
+  if (k <= MAXK && s <= MAXS) {
+    switch (k) {
+      case 0: launch_k<0>(ex, st, si, RT, nr, false, stream); break;
+      case 1: launch_k<1>(ex, st, si, RT, nr, false, stream); break;
+      case 2: launch_k<2>(ex, st, si, RT, nr, false, stream); break;
+      case 3: launch_k<3>(ex, st, si, RT, nr, false, stream); break;
+      case 4: launch_k<4>(ex, st, si, RT, nr, false, stream); break;
+      case 5: launch_k<5>(ex, st, si, RT, nr, false, stream); break;
+      case 6: launch_k<6>(ex, st, si, RT, nr, false, stream); break;
+      case 7: launch_k<7>(ex, st, si, RT, nr, false, stream); break;
+      default: launch_k<8>(ex, st, si, RT, nr, false, stream); break;
+    }
+  } else {
+    const Program& P = *ex.P;
+    GenericArgs a;
+    a.in = ex.d_gen_in + gen_in_at;
+    a.sc = ex.d_gen_sc + gen_sc_at;
+    a.k = k;
+    a.n_sc = s;
+    a.d = st.d;
+    a.C = (int)st.C;
+    a.n_out = st.n_out;
+    const Table& out = P.tables[st.out];
+    a.out_is_row = out.kind == T_ROW;
+    a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
+    a.nr = nr;
+    a.RT = RT;
+    const int bx = block_rows(nr);
+    const int by = BLOCK / bx;
+    dim3 block(bx, by), grid;
+    grid.y = (nr + bx - 1) / bx;
+    const int64_t max_x = (st.n_out + by - 1) / by;
+    const int64_t want = (148 * 8 * 4 + grid.y - 1) / grid.y;
+    grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_x, want));
+    prodsum_generic_kernel<<<grid, block, 0, stream>>>(a);
+  }
+}
+
+// (Re)builds everything that depends on the arena row stride RT: the arena itself, the slice-offset
+// table, the generic-path descriptors and the output descriptors.
+static void set_row_stride(Executor& ex, int64_t RT) {
+  if (RT == ex.RT) return;
+  const Program& P = *ex.P;
+  free_dev(ex.d_arena);
+  free_dev(ex.d_rowoff);
+  HB_CUDA(cudaMalloc(&ex.d_arena, std::max<int64_t>(P.row_entries, 1) * RT * sizeof(double)));
+  HB_CUDA(cudaMalloc(&ex.d_rowoff, std::max<int64_t>((int64_t)P.slices.size(), 1) * RT * sizeof(int32_t)));
+  ex.RT = RT;
+  std::vector<InArg> gin;
+  std::vector<TabRef> gsc;
+  for (size_t si = 0; si < P.steps.size(); ++si) {
+    const Step& st = P.steps[si];
+    if (st.kind != STEP_PRODSUM || ((int)st.in.size() <= MAXK && (int)st.scalars.size() <= MAXS)) continue;
+    for (size_t i = 0; i < st.in.size(); ++i) {
+      InArg a;
+      a.t = tab_ref(ex, P.tables[st.in[i].table], RT, ex.d_rowoff);
+      a.hi = ex.d_maps + ex.hi_off[ex.in_base[si] + i];
+      a.lo = ex.d_maps + ex.lo_off[ex.in_base[si] + i];
+      a.sstride = st.in[i].sstride;
+      gin.push_back(a);
+    }
+    for (int id : st.scalars) gsc.push_back(tab_ref(ex, P.tables[id], RT, ex.d_rowoff));
+  }
+  free_dev(ex.d_gen_in);
+  free_dev(ex.d_gen_sc);
+  ex.d_gen_in = upload(gin);
+  ex.d_gen_sc = upload(gsc);
+  for (size_t j = 0; j < ex.out_steps.size(); ++j) {
+    const Step& st = P.steps[ex.out_steps[j]];
+    const Table& t = P.tables[st.in[0].table];
+    ex.out_desc[j].t = tab_ref(ex, t, RT, ex.d_rowoff);
+    ex.out_desc[j].slice = t.kind == T_POT ? t.slice_slot : -1;
+  }
+  free_dev(ex.d_out_desc);
+  ex.d_out_desc = upload(ex.out_desc);
+}
+
+Executor* executor_create(const Program& P, int device, int64_t workspace_bytes) {
+  HB_CUDA(cudaSetDevice(device));
+  auto ex = std::make_unique<Executor>();
+  ex->P = &P;
+  ex->device = device;
+  const Network& net = *P.net;
+  // potential pool
+  std::vector<double> pots((size_t)P.pot_entries);
+  for (int v = 0; v < net.n(); ++v) std::copy(net.values[v].begin(), net.values[v].end(), pots.begin() + P.pot_off[v]);
+  ex->d_pots = upload(pots);
+  HB_CUDA(cudaMalloc(&ex->d_shared, std::max<int64_t>(P.shared_entries, 1) * sizeof(double)));
+  // index-map pool
+  std::vector<int32_t> maps;
+  for (size_t si = 0; si < P.steps.size(); ++si) {
+    const Step& st = P.steps[si];
+    ex->in_base.push_back((int64_t)ex->hi_off.size());
+    if (st.kind == STEP_PRODSUM) {
+      for (const StepInput& in : st.in) {
+        ex->hi_off.push_back((int64_t)maps.size());
+        maps.insert(maps.end(), in.hi.begin(), in.hi.end());
+        ex->lo_off.push_back((int64_t)maps.size());
+        maps.insert(maps.end(), in.lo.begin(), in.lo.end());
+      }
+    } else {
+      if ((int)st.obs_var.size() > MAXOBS) throw Error(HB_E_UNSUPPORTED, "more than 8 observed variables in one query");
+      OutDesc d;
+      memset(&d, 0, sizeof d);
+      d.n_full = (int)st.n_full;
+      d.out_col = st.out_col;
+      d.map_off = (int)maps.size();
+      maps.insert(maps.end(), st.full_map.begin(), st.full_map.end());
+      // the stored entries in the order the full layout visits them (norm is a left fold over that order)
+      d.order_off = (int)maps.size();
+      int n_phys = 0;
+      for (int64_t f = 0; f < st.n_full; ++f) {
+        bool first_state = true;
+        for (size_t j = 0; j < st.obs_var.size(); ++j) first_state &= ((f / st.obs_stride[j]) % st.obs_dim[j]) == 0;
+        if (first_state) maps.push_back(st.full_map[f]), ++n_phys;
+      }
+      d.n_phys = n_phys;
+      d.n_obs = (int)st.obs_var.size();
+      for (int j = 0; j < d.n_obs; ++j) d.obs_var[j] = st.obs_var[j], d.obs_stride[j] = (int)st.obs_stride[j], d.obs_dim[j] = (int)st.obs_dim[j];
+      ex->out_desc.push_back(d);
+      ex->out_steps.push_back((int)si);
+    }
+  }
+  ex->d_maps = upload(maps);
+  // evidence preparation tables
+  std::vector<int8_t> obs(P.is_observed.begin(), P.is_observed.end());
+  std::vector<int32_t> dims(net.dims.begin(), net.dims.end()), sl_begin = {0}, sl_var, sl_stride;
+  for (const Slice& s : P.slices) {
+    for (size_t j = 0; j < s.vars.size(); ++j) sl_var.push_back(s.vars[j]), sl_stride.push_back((int32_t)s.strides[j]);
+    sl_begin.push_back((int32_t)sl_var.size());
+  }
+  ex->d_observed = upload(obs);
+  ex->d_dims = upload(dims);
+  ex->d_sl_begin = upload(sl_begin);
+  ex->d_sl_var = upload(sl_var);
+  ex->d_sl_stride = upload(sl_stride);
+  HB_CUDA(cudaMalloc(&ex->d_flag, sizeof(int)));
+  HB_CUDA(cudaMemset(ex->d_flag, 0, sizeof(int)));
+  if (workspace_bytes <= 0) {
+    size_t free_b = 0, total_b = 0;
+    HB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    workspace_bytes = std::min<int64_t>((int64_t)(free_b * 0.6), (int64_t)24 << 30);
+  }
+  ex->workspace = workspace_bytes;
+  // batch-invariant steps: evaluated once, here, with a single pseudo-row
+  set_row_stride(*ex, 32);
+  int64_t gi = 0, gs = 0;
+  for (size_t si = 0; si < P.steps.size(); ++si) {
+    const Step& st = P.steps[si];
+    if (st.kind != STEP_PRODSUM) continue;
+    const bool generic = (int)st.in.size() > MAXK || (int)st.scalars.size() > MAXS;
+    if (st.shared) launch_prodsum(*ex, st, (int)si, 32, 1, 0, gi, gs);
+    if (generic) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
+  }
+  HB_CUDA(cudaGetLastError());
+  HB_CUDA(cudaDeviceSynchronize());
+  return ex.release();
+}
+
+void executor_destroy(Executor* ex) { delete ex; }
+int executor_device(const Executor* ex) { return ex->device; }
+
+void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream_, RunStats* stats) {
+  if (n_rows <= 0) return;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const Program& P = *ex->P;
+  HB_CUDA(cudaSetDevice(ex->device));
+  const int n_vars = P.net->n();
+  // rows per tile: as many as the workspace allows, in multiples of 32 (one warp of rows)
+  const int64_t per_row = std::max<int64_t>(P.row_entries, 1) * 8 + (int64_t)P.slices.size() * 4;
+  int64_t cap = ex->workspace / per_row / 32 * 32;
+  if (cap < 32) throw Error(HB_E_OOM, "row arena of one 32-row tile (" + std::to_string(per_row * 32) + " bytes) exceeds the workspace");
+  cap = std::min<int64_t>(cap, (int64_t)1 << 22);
+  const int64_t RT = std::min<int64_t>(cap, (n_rows + 31) / 32 * 32);
+  if (RT > ex->RT || ex->RT > 4 * RT) {
+    HB_CUDA(cudaStreamSynchronize(stream));
+    set_row_stride(*ex, RT);
+  }
+  const int64_t stride = ex->RT;
+  int64_t launches = 0, tiles = 0;
+  ex->events_used = 0;
+  auto mark = [&]() {
+    if (ex->timing) HB_CUDA(cudaEventRecord(ex->next_event(), stream));
+  };
+  for (int64_t r0 = 0; r0 < n_rows; r0 += stride, ++tiles) {
+    const int nr = (int)std::min<int64_t>(stride, n_rows - r0);
+    mark();
+    PrepArgs pa{d_evidence + r0 * n_vars, nr, n_vars, (int)P.slices.size(), stride, ex->d_observed, ex->d_dims,
+                ex->d_sl_begin, ex->d_sl_var, ex->d_sl_stride, ex->d_rowoff, ex->d_flag};
+    prep_rows_kernel<<<(nr + BLOCK - 1) / BLOCK, BLOCK, 0, stream>>>(pa);
+    ++launches;
+    mark();
+    int64_t gi = 0, gs = 0;
+    for (size_t si = 0; si < P.steps.size(); ++si) {
+      const Step& st = P.steps[si];
+      if (st.kind != STEP_PRODSUM) continue;
+      const bool generic = (int)st.in.size() > MAXK || (int)st.scalars.size() > MAXS;
+      if (!st.shared) launch_prodsum(*ex, st, (int)si, stride, nr, stream, gi, gs), ++launches;
+      if (generic) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
+    }
+    mark();
+    if (!ex->out_desc.empty()) {
+      OutArgs oa{ex->d_out_desc, (int)ex->out_desc.size(), ex->d_maps, ex->d_rowoff, ex->d_arena, d_evidence + r0 * n_vars,
+                 d_out + r0 * P.out_width, nr, n_vars, stride, P.out_width};
+      const int64_t threads = (int64_t)nr * (int64_t)ex->out_desc.size();
+      output_kernel<<<(unsigned)((threads + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>(oa);
+      ++launches;
+    }
+    mark();
+  }
+  HB_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->launches = launches;
+    stats->tiles = tiles;
+    stats->rows_per_tile = stride;
+    stats->arena_bytes = std::max<int64_t>(P.row_entries, 1) * stride * 8;
+  }
+}
+
+void executor_set_timing(Executor* ex, bool on) { ex->timing = on; }
+
+void executor_last_timing(Executor* ex, void* stream, double out4[4]) {
+  HB_CUDA(cudaSetDevice(ex->device));
+  HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+  for (size_t i = 0; i + 3 < ex->events_used; i += 4) {
+    float ms = 0;
+    for (int j = 0; j < 3; ++j) {
+      HB_CUDA(cudaEventElapsedTime(&ms, ex->events[i + j], ex->events[i + j + 1]));
+      out4[j] += ms;
+    }
+    HB_CUDA(cudaEventElapsedTime(&ms, ex->events[i], ex->events[i + 3]));
+    out4[3] += ms;
+  }
+}
+
+void executor_check(Executor* ex, void* stream) {
+  HB_CUDA(cudaSetDevice(ex->device));
+  int flag = 0;
+  HB_CUDA(cudaMemcpyAsync(&flag, ex->d_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag) {
+    HB_CUDA(cudaMemsetAsync(ex->d_flag, 0, sizeof(int), (cudaStream_t)stream));
+    throw Error(HB_E_ARG, "evidence row inconsistent with the compiled observed set (or state out of range)");
+  }
+}
+
+}  // namespace hb

@@ -1,0 +1,40 @@
+// engine.hpp -- device side of libhbayes_cuda: a compiled Program resident on one GPU.
+#pragma once
+#include <cstdint>
+
+#include "model.hpp"
+
+namespace hb {
+
+struct Executor;
+
+struct RunStats {          // filled by executor_run (host-side counts, no device sync)
+  int64_t launches = 0;    // kernels launched
+  int64_t tiles = 0;       // row tiles
+  int64_t rows_per_tile = 0;
+  int64_t arena_bytes = 0;
+};
+
+// Uploads potentials, index maps and step descriptors to `device` and evaluates the batch-invariant
+// (shared) steps once.  `workspace_bytes` caps the per-row arena (0 = default: 60 % of free memory, at most 24 GiB).
+Executor* executor_create(const Program& P, int device, int64_t workspace_bytes);
+void executor_destroy(Executor* ex);
+
+// One pass of the program over n_rows evidence rows.  d_evidence: int8 [n_rows][n_vars] (-1 = unobserved),
+// d_out: double [n_rows][out_width]; both DEVICE pointers.  Asynchronous on `stream` (a cudaStream_t).
+// A row whose observed set differs from the program's, or whose state is out of range, raises the
+// executor's error flag (see executor_check).
+void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream, RunStats* stats);
+
+// Synchronises `stream` and throws HB_E_ARG if a row of an earlier run was inconsistent with the program.
+void executor_check(Executor* ex, void* stream);
+
+int executor_device(const Executor* ex);
+
+// CUDA-event timing of the kernel groups on the launching stream (off by default).  After a run,
+// executor_last_timing synchronises the stream and returns milliseconds summed over the row tiles:
+// [0] prep_rows_kernel, [1] all prodsum kernels, [2] output_kernel, [3] whole pass.
+void executor_set_timing(Executor* ex, bool on);
+void executor_last_timing(Executor* ex, void* stream, double out4[4]);
+
+}  // namespace hb

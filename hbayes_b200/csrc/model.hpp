@@ -1,19 +1,23 @@
 // model.hpp -- host-side structures of libhbayes_cuda: network, junction tree, compiled program.
 //
-// Everything here is integer/graph work done once per network (SURVEY 8a rows a5,a6,a9-a15); the
-// floating-point work it schedules runs in engine.cu.  Reference semantics are cited per function
-// in the .cpp files (paths relative to the hbayes tree, e.g. Bayes/FactorElimination.hs:130-143).
+// Everything here is integer/graph work done once per (network, observed-variable list)
+// (SURVEY 8a rows a5,a6,a9-a15).  The floating-point work it schedules runs in engine.cu.
+// Reference semantics are cited per function in the .cpp files (paths relative to the hbayes
+// tree, e.g. Bayes/FactorElimination.hs:130-143).
 #pragma once
 #include <cstdint>
-#include <map>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "../../include/hbayes_cuda.h"  // status codes HB_OK, HB_E_*
+
 namespace hb {
 
-struct Error {
+
+struct Error : std::runtime_error {
   int code;
-  std::string msg;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
 // ---- Bayesian network: what runBN / importBayesianGraph yield (Bayes/Network.hs:69-79) ----------
@@ -23,7 +27,7 @@ struct Network {
   std::vector<std::vector<double>> values;  // reference layout: first variable slowest
   std::vector<std::string> names;
   int n() const { return (int)dims.size(); }
-  int64_t width() const {  // sum_v dims[v]: doubles per JT query
+  int64_t width() const {  // sum_v dims[v]: doubles per junction-tree query
     int64_t w = 0;
     for (int d : dims) w += d;
     return w;
@@ -41,86 +45,112 @@ struct Tree {
   std::vector<int> parent_sep;              // cluster -> separator number (1-based) or -1 for the root
   std::vector<int> sep_parent, sep_child;   // separator (index sep-1) -> cluster
   std::vector<std::vector<int>> sep_vars;   // separator (index sep-1) -> ascending vertex ids
-  std::vector<std::vector<int>> children;   // cluster -> separators, newest first
+  std::vector<std::vector<int>> children;   // cluster -> separator numbers, newest first
   std::vector<std::vector<int>> factors;    // cluster -> CPT vertex ids in list order (last assigned first)
   std::vector<int> by_rank;                 // cluster ids in ascending `Cluster` (lexicographic) order
+  int n_seps() const { return (int)sep_parent.size(); }
 };
-// cmp: 0 = nodeComparisonForTriangulation (weightedEdges), 1 = numberOfAddedEdges; order overrides cmp.
+// cmp: 0 = nodeComparisonForTriangulation (weightedEdges), 1 = numberOfAddedEdges; `order` overrides cmp.
 Tree* tree_build(const Network& net, int cmp, const int32_t* order);
+// first minimal-state-space cluster covering `vars`, scanning clusters in ascending Cluster order
 int tree_covering_cluster(const Network& net, const Tree& t, const std::vector<int>& vars);
-// top-most cluster holding all q vars (traverseTree findClusterFor), -1 if none
+// last top-most cluster (pre-order) holding all q vars (traverseTree findClusterFor), -1 if none
 int tree_find_cluster(const Tree& t, const std::vector<int>& q);
 
 std::vector<int> ve_elimination_order(const Network& net, int metric /*0 minDegree, 1 minFill*/);
 
 // ---- Compiled program: flat step list replayed per evidence row --------------------------------
-enum Loc : int32_t { LOC_ARENA = 0, LOC_POT = 1, LOC_ONE = 2 };
-enum StepKind : int32_t { STEP_PRODSUM = 0, STEP_OUTPUT = 1 };
+//
+// A *table* is a symbolic factor.  Its structural scope is the reference's variable list; its
+// physical scope drops the observed variables: a table is only ever stored at the observed states
+// of the row (evidence slicing -- value-identical to multiplying by the 0/1 indicator).
+enum TableKind : int32_t {
+  T_ONE = 0,     // the constant 1.0: an indicator read at its observed state, the product of an empty
+                 // bucket, posterior's `Scalar 1.0`.  Never stored, never multiplied (x*1.0 is exact).
+  T_POT = 1,     // a CPT of the network, in the potential pool (batch-invariant; sliced per row when it
+                 // mentions an observed variable)
+  T_SHARED = 2,  // derived table that does not depend on the evidence states: computed once per program
+  T_ROW = 3,     // derived per-row table, lives in the row arena [entry][row]
+};
 
-struct Table {           // a symbolic factor
-  bool scalar = false;   // structural Scalar (PrivateCPT.hs:67-72)
-  bool is_one = false;   // physically the constant 1.0 (evidence indicator at its observed state, empty bucket)
-  bool is_evidence = false;
-  int pot = -1;          // vertex id when this is a CPT (LOC_POT) or an evidence indicator
-  std::vector<int> scope;   // structural scope, reference order
-  std::vector<int> pscope;  // physical scope: scope minus sliced (observed) variables
-  std::vector<int64_t> pstride;  // stride of each pscope variable in the physical layout
-  int64_t size = 1;         // physical entries
-  int32_t loc = LOC_ARENA;
-  int64_t off = 0;          // arena entry offset / offset into the potential pool
-  int alias_of = -1;
+struct Table {
+  int32_t kind = T_ROW;
+  bool scalar = false;           // structural `Scalar` (PrivateCPT.hs:67-72): empty structural scope
+  int pot = -1;                  // vertex id for T_POT
+  std::vector<int> scope;        // structural scope, reference order
+  std::vector<int> pscope;       // physical scope = scope minus observed variables (same order)
+  std::vector<int64_t> pstride;  // stride of each pscope variable in the stored layout
+  int64_t size = 1;              // physical entries
+  int64_t off = 0;               // entry offset in its pool (potential pool / shared arena / row arena)
+  int slice_slot = -1;           // T_POT mentioning observed variables: index into Program::slices
+  int alias_of = -1;             // a final product of a single table is that table
   int def_step = -1, last_use = -1;
 };
 
 struct StepInput {
-  int table;
-  int64_t sstride;                 // stride of the summed variable in this input (0 if absent / sliced)
-  std::vector<int32_t> hi, lo;     // off(o) = hi[o / C] + lo[o % C]
+  int table = -1;
+  int64_t sstride = 0;          // stride of the summed variable in this input (0 if absent)
+  std::vector<int32_t> hi, lo;  // entry offset of output index o: hi[o / C] + lo[o % C]
 };
+
+enum StepKind : int32_t { STEP_PRODSUM = 0, STEP_OUTPUT = 1 };
 
 struct Step {
   int32_t kind = STEP_PRODSUM;
-  int sum_var = -1;                // eliminated vertex, -1 for a final product
-  int d = 1;                       // physical terms per output (1 if no sum / summed variable observed)
-  std::vector<StepInput> in;       // physical table inputs, chain order v1*(v2*(...*vk))
-  std::vector<int> scalars;        // structural scalars s1*(s2*...), multiplied as ps * chain
-  int out = -1;                    // output table
+  bool shared = false;          // all inputs batch-invariant: runs once at upload time, not per row
+  int sum_var = -1;             // eliminated vertex, -1 for a final product
+  int d = 1;                    // physical terms per output (1 when nothing is summed or the variable is observed)
+  std::vector<StepInput> in;    // chain inputs in reference order: v1 * (v2 * (... * vk))
+  std::vector<int> scalars;     // structural scalars, ps = s1 * (s2 * ...), applied as ps * chain
+  int out = -1;                 // output table
   int64_t n_out = 1, C = 1, n_hi = 1;
-  // STEP_OUTPUT: normalise `in[0]` and expand to the full query scope
+  // STEP_OUTPUT: normalise table `in[0]` and expand it to the full query scope
   int64_t out_col = 0, n_full = 1;
-  std::vector<int32_t> full_map;               // full entry -> physical entry
-  std::vector<int> obs_slot;                   // observed query variables: evidence slot,
-  std::vector<int64_t> obs_stride, obs_dim;    //   stride and dim in the full layout
-  // provenance, for hb_*_describe_json (the parity hook)
+  std::vector<int32_t> full_map;               // full entry -> physical entry of in[0] (ignoring observed vars)
+  std::vector<int> obs_var;                    // observed query variables ...
+  std::vector<int64_t> obs_stride, obs_dim;    // ... their stride and dimension in the full layout
+  // provenance, for hb_*_describe_json (the parity hook): the reference-level operation
   int group = -1;
   std::vector<std::vector<int>> trace_inputs;  // structural scopes of ALL reference inputs (incl. indicators)
   std::vector<int> trace_prod, trace_out;
 };
 
 struct Group {  // one reference-level `marginal` call: a message or a posterior
-  int kind;     // 0 up, 1 down, 2 posterior, 3 ve
+  int kind;     // 0 up, 1 down, 2 posterior, 3 variable elimination
   int cluster = -1, sep = -1;
   std::vector<int> query;
   std::vector<int> out_scope;  // result variable order (rule A.5 / A.10)
-  int first_step = 0, n_steps = 0;
+  int result = -1;             // table id
+  // the reference-level trace (what the oracle's interpreter does for the same evidence list)
+  struct TraceStep {
+    int var;  // eliminated vertex, -1 = final product
+    std::vector<std::vector<int>> inputs;
+    std::vector<int> prod, out;
+  };
+  std::vector<TraceStep> trace;
+};
+
+struct Slice {  // per-row entry offset of a sliced potential: sum_j stride_j * state(var_j)
+  int pot;
+  std::vector<int> vars;
+  std::vector<int64_t> strides;
 };
 
 struct Program {
   const Network* net = nullptr;
-  std::vector<int> observed;        // ordered as given by the caller (changeEvidence list order)
-  std::vector<int> slot_of_var;     // vertex -> evidence slot or -1
+  std::vector<int> observed;     // in the caller's order (changeEvidence list order)
+  std::vector<char> is_observed; // per vertex
   std::vector<Table> tables;
-  std::vector<Step> steps;
+  std::vector<Step> steps;       // shared steps and per-row steps interleaved in dependency order
   std::vector<Group> groups;
-  int64_t arena_entries = 0;        // per-row arena size
-  int64_t out_width = 0;            // doubles written per row
-  // sliced potentials: evoff[slot][row] = sum stride * state
-  std::vector<int> sliced_pots;                        // vertex ids with >=1 observed variable in scope
-  std::vector<int> pot_slice_slot;                     // vertex -> index into sliced_pots or -1
-  std::vector<std::vector<std::pair<int, int64_t>>> pot_slice_terms;  // per sliced pot: (evidence slot, stride)
-  std::vector<int64_t> pot_off;                        // vertex -> offset into the potential pool
-  int64_t pot_pool = 0;
-  int64_t max_table = 0, total_prod = 0, total_reads = 0, total_out = 0;
+  std::vector<Slice> slices;
+  std::vector<int64_t> pot_off;  // vertex -> entry offset in the potential pool
+  int64_t pot_entries = 0;
+  int64_t shared_entries = 0;    // shared arena size
+  int64_t row_entries = 0;       // per-row arena size (after liveness reuse)
+  int64_t out_width = 0;         // doubles written per row
+  // statistics (per row, physical)
+  int64_t stat_prod = 0, stat_reads = 0, stat_row_read = 0, stat_row_write = 0, stat_max_table = 0;
 };
 
 struct Query {

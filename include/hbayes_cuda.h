@@ -1,0 +1,135 @@
+/* hbayes_cuda.h -- C ABI of libhbayes_cuda, the B200 engine behind hbayes' exact-inference hot path.
+ *
+ * The reference (alpheccar/hbayes, pure Haskell) has no FFI of its own; these entry points are what a
+ * Haskell `foreign import ccall` module would bind to replace, for this path only, the functions cited
+ * beside each declaration (paths relative to the hbayes source tree).  INTEGRATION.md shows that
+ * binding.  Plain pointers and sizes only; no C++ or torch types; no callbacks.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, negative = error class below; hb_last_error()
+ *     returns a thread-local message valid until the next call on the same thread.  Nothing throws or
+ *     aborts across this boundary.
+ *   - the caller owns every input and output buffer; the library copies what it keeps.
+ *   - handles are opaque and released by hb_*_free (usable as Haskell ForeignPtr finalizers).
+ *   - vertices are dense ids 0..n_vars-1 (the reference's Vertex ids); a CPT's scope is
+ *     [child, parents in `ingoing` order] and its values are laid out with the FIRST variable slowest
+ *     (Bayes/Network.hs:69-79, Bayes/Factor/PrivateCPT.hs:315-320).
+ *   - evidence matrices are int8 [n_rows][n_vars], -1 = unobserved; a row stands for
+ *     changeEvidence [v =: s | v <- ascending vertex id, observed].
+ *   - zero-probability evidence yields NaN rows exactly as the reference does (1.0 / 0 * 0); not an error.
+ *   - there is no CPU fallback: without a CUDA device every compile call fails with HB_E_CUDA.
+ */
+#ifndef HBAYES_CUDA_H
+#define HBAYES_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_E_ARG (-1)         /* bad argument, inconsistent CPT, evidence row not matching */
+#define HB_E_NO_CLUSTER (-2)  /* query variables not inside one cluster: Haskell `Nothing` (FactorElimination.hs:319) */
+#define HB_E_CUDA (-3)
+#define HB_E_OOM (-4)
+#define HB_E_IO (-5)
+#define HB_E_UNSUPPORTED (-6)
+#define HB_E_NCCL (-7)
+
+/* pass devices = NULL, n_devices = HB_STRUCTURE_ONLY to a compile call to get a handle that only answers the
+ * describe/program_json parity hooks (host graph work); every compute call on it fails with HB_E_CUDA. */
+#define HB_STRUCTURE_ONLY (-1)
+
+#define HB_HOST_PTRS 0    /* evidence / out are host buffers: copies are part of the call */
+#define HB_DEVICE_PTRS 1  /* evidence / out are device buffers on the handle's GPU */
+
+typedef struct hb_net hb_net;
+typedef struct hb_jt hb_jt;
+typedef struct hb_ve hb_ve;
+
+const char* hb_last_error(void);
+void hb_string_free(char* s);
+/* number of visible CUDA devices (0 when there is none); never fails */
+int hb_device_count(void);
+
+/* ---- network ------------------------------------------------------------------------------- */
+/* runBN of a BNMonad (Bayes/BayesianNetwork.hs:211-212): CPT v has scope cpt_scope[cpt_off[v]..cpt_off[v+1])
+ * (child first) and values cpt_vals[val_off[v]..val_off[v+1]). */
+int hb_net_create(int32_t n_vars, const int32_t* dims, const int64_t* cpt_off, const int32_t* cpt_scope,
+                  const int64_t* val_off, const double* cpt_vals, hb_net** out);
+/* importBayesianGraph + runBN (Bayes/ImportExport/HuginNet.hs:160-195), dialect of SURVEY Appendix C */
+int hb_net_load_hugin(const char* path, hb_net** out);
+int hb_net_n_vars(const hb_net* net);
+int hb_net_dims(const hb_net* net, int32_t* dims_out /* n_vars */);
+/* {"names","dims","scopes","values"}; free with hb_string_free */
+int hb_net_describe_json(const hb_net* net, char** out_json);
+void hb_net_free(hb_net* net);
+
+/* minDegreeOrder (metric 0) / minFillOrder (metric 1) (Bayes/VariableElimination.hs:210-236);
+ * order_out has room for n_vars ids, *n_out receives how many were written */
+int hb_ve_order(const hb_net* net, int32_t metric, int32_t* order_out, int32_t* n_out);
+
+/* ---- junction tree ------------------------------------------------------------------------- */
+/* createJunctionTree cmp g (Bayes/FactorElimination.hs:298-307).  cmp: 0 = nodeComparisonForTriangulation
+ * (weightedEdges, :71-111), 1 = numberOfAddedEdges.  devices: CUDA ordinals; this build uses devices[0]
+ * (one process per GPU; rows are sharded by the caller). The tree is calibrated without evidence. */
+int hb_jt_compile(const hb_net* net, int32_t cmp, const int32_t* devices, int32_t n_devices, hb_jt** out);
+/* same, with the vertex elimination order of the triangulation given explicitly (any other `cmp` closure
+ * is evaluated on the Haskell side: the metric is static) */
+int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const int32_t* devices, int32_t n_devices,
+                             hb_jt** out);
+/* parity hook: {"elim_order","clusters","root","parent_sep","sep_parent","sep_child","sep_vars","children","factors"} */
+int hb_jt_describe_json(const hb_jt* jt, char** out_json);
+/* parity hook: the operation trace (every message and every single-variable posterior, with product scopes)
+ * and the physical step list compiled for changeEvidence [vars[0], vars[1], ...] */
+int hb_jt_program_json(hb_jt* jt, int32_t n, const int32_t* vars, char** out_json);
+/* changeEvidence (Bayes/FactorElimination/JTree.hs:454-466); list order is preserved */
+int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states);
+/* posterior jt q_vars (Bayes/FactorElimination.hs:314-327).  out_scope receives the variable order of the
+ * result (n_q ids), out its values (first variable of out_scope slowest); *n_written the number of values. */
+int hb_jt_posterior(hb_jt* jt, int32_t n_q, const int32_t* q_vars, int32_t* out_scope, double* out, int64_t out_len,
+                    int64_t* n_written);
+/* one junction-tree query per row: changeEvidence row, then posterior [v] for every v.
+ * out: double [n_rows][sum_v dims[v]], variables in ascending id.  Rows of one call may have different
+ * observed sets with HB_HOST_PTRS (grouped internally); with HB_DEVICE_PTRS all rows must share one. */
+int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags);
+/* CUDA stream (a cudaStream_t) the handle launches on; NULL = the default stream */
+int hb_jt_set_stream(hb_jt* jt, void* cuda_stream);
+/* bytes of device workspace the row arena may use (0 = default) */
+int hb_jt_set_workspace(hb_jt* jt, int64_t bytes);
+/* counters of the last batch call: [0] kernels launched, [1] row tiles, [2] rows per tile, [3] arena bytes,
+ * [4] per-row arena entries, [5] product entries per row, [6] per-row table entries read per row,
+ * [7] per-row table entries written per row */
+int hb_jt_last_stats(const hb_jt* jt, int64_t* out8);
+/* CUDA-event timing of the kernel groups on the handle's stream (off by default).  hb_jt_last_timing
+ * synchronises the stream; out4 = milliseconds of the last batch call summed over its row tiles:
+ * [0] evidence preparation kernel, [1] all product/sum-out kernels, [2] normalise/expand kernel, [3] whole pass */
+int hb_jt_set_timing(hb_jt* jt, int32_t on);
+int hb_jt_last_timing(hb_jt* jt, double* out4);
+void hb_jt_free(hb_jt* jt);
+
+/* ---- variable elimination ------------------------------------------------------------------ */
+/* posteriorMarginal g p r (Bayes/VariableElimination.hs:116-130): p = variables to eliminate, in order,
+ * r = remaining (query) variables.  priorMarginal is the same with no evidence. */
+int hb_ve_compile(const hb_net* net, const int32_t* p, int32_t np, const int32_t* r, int32_t nr,
+                  const int32_t* devices, int32_t n_devices, hb_ve** out);
+/* result variable order (depends on the observed set: rule A.5); scope_out has room for nr ids */
+int hb_ve_result_scope(hb_ve* ve, int32_t n_obs, const int32_t* observed, int32_t* scope_out, int32_t* n_out);
+int hb_ve_program_json(hb_ve* ve, int32_t n_obs, const int32_t* observed, char** out_json);
+/* assignment in the caller's order (posteriorMarginal's [DVI] argument); out has prod_r dims[r] doubles */
+int hb_ve_posterior(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* states, int32_t* out_scope, double* out,
+                    int64_t out_len, int64_t* n_written);
+/* one posteriorMarginal per row (assignment = observed entries in ascending vertex id); out: [n_rows][prod_r dims[r]] */
+int hb_ve_posterior_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags);
+int hb_ve_set_stream(hb_ve* ve, void* cuda_stream);
+int hb_ve_set_workspace(hb_ve* ve, int64_t bytes);
+int hb_ve_last_stats(const hb_ve* ve, int64_t* out8);
+int hb_ve_set_timing(hb_ve* ve, int32_t on);
+int hb_ve_last_timing(hb_ve* ve, double* out4);
+void hb_ve_free(hb_ve* ve);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBAYES_CUDA_H */

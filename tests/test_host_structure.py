@@ -1,0 +1,127 @@
+"""CPU tests of the product's host side (no GPU, no compute): the C-ABI library loads and exports every
+declared symbol, and the compiled structures equal the oracle's integer for integer -- junction tree
+(elimination order, clusters, separators, factor assignment), per-message bucket-elimination traces
+("clique index maps and elimination order bit-exact"), VE orders and traces."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hbayes_b200 as hb
+from hbayes_b200 import _lib, synth
+from oracle import OracleJT, OracleNet
+from helpers import G, GOLDEN_NETS, oracle_traces, product_traces, random_evidence_list, random_net
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hbayes_cuda.h")).read()
+    declared = set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_cpu_fallback():
+    """Without a device a compile call fails with HB_E_CUDA; a structure-only handle refuses to compute."""
+    net = hb.importBayesianGraph(os.path.join(G, "cancer.net"))
+    jt = hb.JunctionTree(net, device=None)
+    with pytest.raises(hb.HbError) as e:
+        jt.posteriors_batch(np.full((2, net.n), -1, np.int8))
+    assert e.value.code == _lib.HB_E_CUDA
+    if _lib.lib().hb_device_count() == 0:
+        with pytest.raises(hb.HbError) as e:
+            hb.JunctionTree(net, device=0)
+        assert e.value.code == _lib.HB_E_CUDA
+
+
+def test_hugin_loader_matches_oracle():
+    for f in GOLDEN_NETS:
+        a = hb.importBayesianGraph(os.path.join(G, f))
+        b = OracleNet.load_hugin(os.path.join(G, f))
+        assert (a.names, a.dims, a.scopes, a.values) == (b.names, b.dims, b.scopes, b.values)
+    assert hb.importBayesianGraph(os.path.join(G, "missing.net")) is None
+
+
+def test_bad_arguments_are_status_codes():
+    with pytest.raises(hb.HbError) as e:
+        hb.BayesianNetwork.from_tables([2, 2], [[0], [1, 0]], [[0.5, 0.5], [0.1, 0.9, 0.3]])
+    assert e.value.code == _lib.HB_E_ARG
+    net = hb.importBayesianGraph(os.path.join(G, "asia.net"))
+    jt = hb.JunctionTree(net, device=None)
+    with pytest.raises(hb.HbError):
+        jt.program([0, 0])  # observed twice
+    with pytest.raises(hb.HbError):
+        jt.program([99])
+
+
+def check_tree_and_traces(pnet, onet, rng, trials, max_obs):
+    pjt = hb.JunctionTree(pnet, device=None)
+    ojt = OracleJT(onet)
+    assert pjt.describe() == ojt.describe()
+    for _ in range(trials):
+        ev = random_evidence_list(rng, onet.dims, max_obs)
+        want = oracle_traces(ojt, ev)
+        prog = pjt.program([v for v, _ in ev])
+        got = product_traces(prog)
+        assert got.keys() == want.keys()
+        for k in want:
+            assert got[k] == want[k], (ev, k)
+
+
+@pytest.mark.parametrize("fname", GOLDEN_NETS)
+def test_golden_nets_structure_and_traces(fname):
+    pnet = hb.importBayesianGraph(os.path.join(G, fname))
+    onet = OracleNet.load_hugin(os.path.join(G, fname))
+    check_tree_and_traces(pnet, onet, np.random.RandomState(1), trials=8, max_obs=4)
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_random_nets_structure_and_traces(seed):
+    net = random_net(seed, n=4 + seed % 12, states=(2, 4), max_parents=3, shuffle=seed % 2 == 1)
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    onet = OracleNet.from_arrays(net.dims, net.scopes, net.values)
+    check_tree_and_traces(pnet, onet, np.random.RandomState(seed), trials=4, max_obs=5)
+
+
+def test_added_edges_comparator_and_explicit_order():
+    net = random_net(5, n=12, states=(2, 3), max_parents=3)
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    onet = OracleNet.from_arrays(net.dims, net.scopes, net.values)
+    assert hb.JunctionTree(pnet, cmp=hb.numberOfAddedEdges, device=None).describe() == OracleJT(onet, cmp="added").describe()
+    order = np.random.RandomState(3).permutation(net.n).tolist()
+    assert hb.JunctionTree(pnet, order=order, device=None).describe() == OracleJT(onet, order=order).describe()
+
+
+def test_c2_structure_matches_oracle():
+    net, observed = synth.config_c2()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    onet = OracleNet.from_arrays(net.dims, net.scopes, net.values)
+    pjt = hb.JunctionTree(pnet, device=None)
+    ojt = OracleJT(onet)
+    assert pjt.describe() == ojt.describe()
+    ev = [(v, 0) for v in observed]
+    assert product_traces(pjt.program(observed)) == oracle_traces(ojt, ev)
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (4, 5), (6, 6)])
+def test_ve_orders_and_traces(shape):
+    g = synth.grid_net(shape[0], shape[1], 11)
+    pnet = hb.BayesianNetwork.from_tables(g.dims, g.scopes, g.values)
+    onet = OracleNet.from_arrays(g.dims, g.scopes, g.values)
+    assert hb.minFillOrder(pnet) == onet.ve_order("min_fill")
+    assert hb.minDegreeOrder(pnet) == onet.ve_order("min_degree")
+    r = [g.n - 1]
+    p = [v for v in hb.minFillOrder(pnet) if v not in r]
+    ve = hb.VariableElimination(pnet, p, r, device=None)
+    rng = np.random.RandomState(0)
+    for _ in range(4):
+        ev = random_evidence_list(rng, g.dims, 4)
+        ev = [(v, s) for v, s in ev if v not in r]
+        _, _, want = onet.posterior_marginal(p, r, ev, trace=True)
+        got = ve.program([v for v, _ in ev])["groups"][0]["steps"]
+        assert got == want
