@@ -342,8 +342,9 @@ struct Compiler {
     for (int s = 0; s < (int)P.steps.size(); ++s) {
       Step& st = P.steps[s];
       if (st.kind == STEP_PRODSUM) P.tables[st.out].def_step = s;
-      for (auto& in : st.in) P.tables[in.table].last_use = s;
-      for (int id : st.scalars) P.tables[id].last_use = s;
+      // query results are read by ONE normalise/expand kernel after the last step: they live to the end
+      for (auto& in : st.in) P.tables[in.table].last_use = st.kind == STEP_OUTPUT ? (int)P.steps.size() - 1 : std::max(P.tables[in.table].last_use, s);
+      for (int id : st.scalars) P.tables[id].last_use = std::max(P.tables[id].last_use, s);
     }
     // shared arena: no reuse (computed once, read by every row)
     for (auto& t : P.tables)
