@@ -127,6 +127,34 @@ struct Compiler {
       g.trace.push_back(tr);
       return one;
     }
+    // Common subexpressions: the same operation on the same tables (e.g. the first eliminations of two
+    // posteriors of one cluster) is the same sequence of floating-point operations; emit it once.
+    std::vector<int> key;
+    for (int id : inputs) {  // an alias stands for its target when both have the same structural scope
+      const int r = resolve(id);
+      key.push_back(T(id).scope == T(r).scope ? r : id);
+    }
+    key.push_back(-2 - sum_var);
+    auto memo = cse.find(key);
+    if (memo != cse.end()) {
+      tr.prod = memo->second.prod;
+      tr.out = T(memo->second.table).scope;
+      g.trace.push_back(tr);
+      return memo->second.table;
+    }
+    const int result = product_sumout_new(inputs, sum_var, tr);
+    g.trace.push_back(tr);
+    cse[key] = Memo{result, tr.prod};
+    return result;
+  }
+
+  struct Memo {
+    int table;
+    std::vector<int> prod;
+  };
+  std::map<std::vector<int>, Memo> cse;
+
+  int product_sumout_new(const std::vector<int>& inputs, int sum_var, Group::TraceStep& tr) {
     std::vector<int> naked = T(inputs.back()).scope;
     for (int i = (int)inputs.size() - 2; i >= 0; --i) naked = list_union(T(inputs[i]).scope, naked);
     std::vector<int> chain, scalars;  // structural partition isScalarFactor (PrivateCPT.hs:223)
@@ -140,7 +168,6 @@ struct Compiler {
     }
     tr.prod = chain.empty() ? std::vector<int>{} : naked;
     tr.out = out.scope;
-    g.trace.push_back(tr);
 
     // ---- physical lowering ----
     Step st;

@@ -43,7 +43,7 @@ namespace hb {
 
 namespace {
 
-constexpr int MAXK = 8;       // chain inputs handled by the templated kernel
+constexpr int MAXK = 6;       // chain inputs handled by the templated kernel
 constexpr int MAXS = 4;       // structural scalars per step
 constexpr int MAXOBS = 8;     // observed variables inside one query
 constexpr int BLOCK = 256;
@@ -56,11 +56,13 @@ struct TabRef {
   int is_one;             // 1: the constant 1.0
 };
 
+// Index maps are stored PRE-MULTIPLIED by the table's element stride (RT for row tables, 1 otherwise),
+// so the offset of output entry o in an input is just hi[o / C] + lo[o % C] (uint32 elements).
 struct InArg {
   TabRef t;
-  const int32_t* hi;
-  const int32_t* lo;
-  long long sstride;      // stride of the summed variable, in entries
+  const uint32_t* hi;
+  const uint32_t* lo;
+  unsigned sstride;       // stride of the summed variable, in elements (pre-multiplied like the maps)
 };
 
 template <int K>
@@ -69,8 +71,8 @@ struct StepArgs {
   TabRef sc[MAXS];
   int n_sc;
   int d;                  // terms per output entry
-  int C;                  // o = hiI * C + loI
-  long long n_out;
+  unsigned C;             // o = hiI * C + loI
+  unsigned n_out;
   double* out;            // arena + off * RT (row) or shared + off
   int out_is_row;
   int nr;                 // rows in this tile
@@ -80,8 +82,8 @@ struct StepArgs {
 struct GenericArgs {      // any number of inputs / scalars, descriptors in global memory
   const InArg* in;
   const TabRef* sc;
-  int k, n_sc, d, C;
-  long long n_out;
+  int k, n_sc, d;
+  unsigned C, n_out;
   double* out;
   int out_is_row, nr;
   long long RT;
@@ -98,74 +100,140 @@ __device__ __forceinline__ double fold_scalars(const TabRef* sc, int n, int row)
   return ps;
 }
 
-// One thread = one evidence row (threadIdx.x) walking a strip of output entries (threadIdx.y / blockIdx.x).
-// All lanes of a warp share the output entry, so index-map loads are broadcasts and every table access
-// of the warp is one contiguous 256-byte segment (row tables) or a handful of addresses (potentials).
-template <int K>
+// V rows per thread: a pair of adjacent rows of a row table is one 16-byte access.
+template <int V>
+struct Rows;
+template <>
+struct Rows<1> {
+  double x;
+  __device__ __forceinline__ static Rows load(const double* p0, const double*, bool, unsigned off) { return {p0[off]}; }
+  __device__ __forceinline__ static Rows splat(double a, double) { return {a}; }
+  __device__ __forceinline__ Rows mul(const Rows& o) const { return {__dmul_rn(x, o.x)}; }
+  __device__ __forceinline__ Rows add(const Rows& o) const { return {__dadd_rn(x, o.x)}; }
+  __device__ __forceinline__ void store(double* p) const { *p = x; }
+};
+template <>
+struct Rows<2> {
+  double x, y;
+  __device__ __forceinline__ static Rows load(const double* p0, const double* p1, bool is_row, unsigned off) {
+    if (is_row) {
+      const double2 v = *reinterpret_cast<const double2*>(p0 + off);
+      return {v.x, v.y};
+    }
+    return {p0[off], p1[off]};
+  }
+  __device__ __forceinline__ static Rows splat(double a, double b) { return {a, b}; }
+  __device__ __forceinline__ Rows mul(const Rows& o) const { return {__dmul_rn(x, o.x), __dmul_rn(y, o.y)}; }
+  __device__ __forceinline__ Rows add(const Rows& o) const { return {__dadd_rn(x, o.x), __dadd_rn(y, o.y)}; }
+  __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+};
+
+// The fused clique-message kernel: out[o] = 0 + sum_s ps * (in1[o,s] * (in2[o,s] * (... * inK[o,s]))).
+// One thread owns V adjacent evidence rows (threadIdx.x) and walks a contiguous strip of output entries
+// (threadIdx.y / blockIdx.x), U entries per iteration so that U*K*D independent loads are in flight.
+// All lanes of a warp share the output entry: index-map loads are broadcasts, and every row-table access
+// of the warp is one contiguous 256*V-byte segment.  D = terms per entry (0: run-time count).
+template <int K, int V, int D>
 __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ StepArgs<K> a) {
-  const int row = blockIdx.y * blockDim.x + threadIdx.x;
-  if (row >= a.nr) return;
-  const double* p[K > 0 ? K : 1];
-  long long m[K > 0 ? K : 1], ss[K > 0 ? K : 1];
+  constexpr int U = 2;
+  typedef Rows<V> R;
+  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (row >= a.nr) return;  // V == 2: the pad row after an odd tile exists in the arena and in rowoff
+  const double* p0[K];
+  const double* p1[K];
+  bool isrow[K];
+  unsigned ss[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) {
-    p[i] = row_ptr(a.in[i].t, row);
-    m[i] = a.in[i].t.is_row ? a.RT : 1;
-    ss[i] = a.in[i].sstride * m[i];
+    isrow[i] = a.in[i].t.is_row != 0;
+    p0[i] = row_ptr(a.in[i].t, row);
+    p1[i] = (V == 2 && !isrow[i]) ? row_ptr(a.in[i].t, row + 1) : p0[i];
+    ss[i] = a.in[i].sstride;
   }
   const bool has_ps = a.n_sc > 0;
-  const double ps = has_ps ? fold_scalars(a.sc, a.n_sc, row) : 1.0;
+  R ps = R::splat(1.0, 1.0);
+  if (has_ps) ps = R::splat(fold_scalars(a.sc, a.n_sc, row), V == 2 ? fold_scalars(a.sc, a.n_sc, row + 1) : 0.0);
   double* outp = a.out + (a.out_is_row ? row : 0);
-  const long long om = a.out_is_row ? a.RT : 1;
-  const long long step = (long long)gridDim.x * blockDim.y;
-  for (long long o = (long long)blockIdx.x * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
-    const unsigned hiI = (unsigned)o / (unsigned)a.C, loI = (unsigned)o - hiI * (unsigned)a.C;  // n_out < 2^31
-    long long off[K > 0 ? K : 1];
+  const size_t om = a.out_is_row ? (size_t)a.RT : 1;
+  const int d = D > 0 ? D : a.d;
+  // contiguous strip of output entries for this (blockIdx.x, threadIdx.y)
+  const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;
+  const unsigned per = (a.n_out + lanes - 1) / lanes;
+  unsigned o = lane * per;
+  const unsigned o_end = min(a.n_out, o + per);
+  if (o >= o_end) return;
+  unsigned hiI = o / a.C, loI = o - hiI * a.C;
+  while (o < o_end) {
+    unsigned off[U][K];
+    const int nu = (o + 1 < o_end) ? U : 1;
 #pragma unroll
-    for (int i = 0; i < K; ++i) off[i] = (long long)(__ldg(a.in[i].hi + hiI) + __ldg(a.in[i].lo + loI)) * m[i];
-    double acc = 0.0;
-#pragma unroll 4
-    for (int s = 0; s < a.d; ++s) {
-      double c;
-      if (K == 0) {
-        c = ps;
+    for (int u = 0; u < U; ++u) {
+      if (u < nu) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) off[u][i] = __ldg(a.in[i].hi + hiI) + __ldg(a.in[i].lo + loI);
+        if (++loI == a.C) loI = 0, ++hiI;
       } else {
-        c = p[K - 1][off[K - 1]];
 #pragma unroll
-        for (int i = K - 2; i >= 0; --i) c = __dmul_rn(p[i][off[i]], c);
-        if (has_ps) c = __dmul_rn(ps, c);
+        for (int i = 0; i < K; ++i) off[u][i] = off[0][i];  // tail: recompute entry 0, never stored
       }
-      acc = __dadd_rn(acc, c);
-#pragma unroll
-      for (int i = 0; i < K; ++i) off[i] += ss[i];
     }
-    outp[o * om] = acc;
+    R acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = R::splat(0.0, 0.0);
+    if (D > 0) {
+#pragma unroll
+      for (int s = 0; s < (D > 0 ? D : 1); ++s) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], off[u][K - 1] + s * ss[K - 1]);
+#pragma unroll
+          for (int i = K - 2; i >= 0; --i) c = R::load(p0[i], p1[i], isrow[i], off[u][i] + s * ss[i]).mul(c);
+          if (has_ps) c = ps.mul(c);
+          acc[u] = acc[u].add(c);
+        }
+      }
+    } else {
+      for (int s = 0; s < d; ++s) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], off[u][K - 1] + s * ss[K - 1]);
+#pragma unroll
+          for (int i = K - 2; i >= 0; --i) c = R::load(p0[i], p1[i], isrow[i], off[u][i] + s * ss[i]).mul(c);
+          if (has_ps) c = ps.mul(c);
+          acc[u] = acc[u].add(c);
+        }
+      }
+    }
+    acc[0].store(outp + (size_t)o * om);
+    if (nu > 1) acc[1].store(outp + (size_t)(o + 1) * om);
+    o += nu;
   }
 }
 
+// Any number of inputs and scalars (descriptors in global memory), one row per thread.  Rare: buckets
+// with more than MAXK tables, or steps made of scalars only.
 __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArgs a) {
   const int row = blockIdx.y * blockDim.x + threadIdx.x;
   if (row >= a.nr) return;
   const double ps = a.n_sc > 0 ? fold_scalars(a.sc, a.n_sc, row) : 1.0;
   double* outp = a.out + (a.out_is_row ? row : 0);
-  const long long om = a.out_is_row ? a.RT : 1;
-  const long long step = (long long)gridDim.x * blockDim.y;
-  for (long long o = (long long)blockIdx.x * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
-    const unsigned hiI = (unsigned)(o / a.C), loI = (unsigned)(o - (long long)hiI * a.C);
+  const size_t om = a.out_is_row ? (size_t)a.RT : 1;
+  const unsigned step = gridDim.x * blockDim.y;
+  for (unsigned o = blockIdx.x * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
+    const unsigned hiI = o / a.C, loI = o - hiI * a.C;
     double acc = 0.0;
     for (int s = 0; s < a.d; ++s) {
       double c = ps;
       for (int i = a.k - 1; i >= 0; --i) {
         const InArg& in = a.in[i];
-        const long long mm = in.t.is_row ? a.RT : 1;
-        const long long off = ((long long)(__ldg(in.hi + hiI) + __ldg(in.lo + loI)) + s * in.sstride) * mm;
+        const unsigned off = __ldg(in.hi + hiI) + __ldg(in.lo + loI) + s * in.sstride;
         const double v = row_ptr(in.t, row)[off];
         c = (i == a.k - 1) ? v : __dmul_rn(v, c);
       }
       if (a.k > 0 && a.n_sc > 0) c = __dmul_rn(ps, c);
       acc = __dadd_rn(acc, c);
     }
-    outp[o * om] = acc;
+    outp[(size_t)o * om] = acc;
   }
 }
 
@@ -185,7 +253,11 @@ struct PrepArgs {
 
 __global__ void __launch_bounds__(BLOCK) prep_rows_kernel(const PrepArgs a) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= a.nr) return;
+  if (row >= a.nr) {  // pad rows up to the next multiple of 32 read slice 0 (their results are never used)
+    if (row < ((a.nr + 31) & ~31))
+      for (int j = 0; j < a.n_slices; ++j) a.rowoff[(long long)j * a.RT + row] = 0;
+    return;
+  }
   const int8_t* e = a.ev + (long long)row * a.n_vars;
   bool bad = false;
   for (int v = 0; v < a.n_vars; ++v) {
@@ -220,7 +292,7 @@ struct OutDesc {
 struct OutArgs {
   const OutDesc* desc;
   int n_desc;
-  const int32_t* maps;
+  const uint32_t* maps;
   const int32_t* rowoff;   // [n_slices][RT]
   const double* arena;
   const int8_t* ev;        // this tile
@@ -247,8 +319,8 @@ __global__ void __launch_bounds__(BLOCK) output_kernel(const OutArgs a) {
     } else
       p = d.t.base + (d.slice >= 0 ? (long long)a.rowoff[(long long)d.slice * a.RT + row] : 0ll);
   }
-  const int32_t* order = a.maps + d.order_off;
-  const int32_t* fmap = a.maps + d.map_off;
+  const uint32_t* order = a.maps + d.order_off;
+  const uint32_t* fmap = a.maps + d.map_off;
   double norm = 0.0;
   for (int j = 0; j < d.n_phys; ++j) norm = __dadd_rn(norm, p ? p[(long long)order[j] * m] : 1.0);
   const double inv = __ddiv_rn(1.0, norm);
@@ -272,7 +344,9 @@ struct Executor {
   int device = 0;
   int64_t workspace = 0;
   double *d_pots = nullptr, *d_shared = nullptr, *d_arena = nullptr;
-  int32_t *d_maps = nullptr, *d_rowoff = nullptr;
+  uint32_t *d_maps = nullptr;     // index maps, element stride 1 (potentials, shared tables, output maps)
+  uint32_t *d_maps_rt = nullptr;  // the same maps multiplied by RT (row tables)
+  int32_t* d_rowoff = nullptr;
   int8_t* d_observed = nullptr;
   int32_t *d_dims = nullptr, *d_sl_begin = nullptr, *d_sl_var = nullptr, *d_sl_stride = nullptr;
   OutDesc* d_out_desc = nullptr;
@@ -280,11 +354,12 @@ struct Executor {
   TabRef* d_gen_sc = nullptr;
   int* d_flag = nullptr;
   int64_t RT = 0;                // current arena row stride
+  int64_t max_row_table = 1;     // largest per-row table (entries): bounds RT so that offsets fit 32 bits
+  std::vector<uint32_t> maps;    // host copy of the stride-1 maps
   std::vector<int64_t> hi_off, lo_off;  // per (step, input): offsets into the map pool
   std::vector<int64_t> in_base;         // first (step,input) index of each step
   std::vector<OutDesc> out_desc;
   std::vector<int> out_steps;
-  int64_t gen_in_total = 0, gen_sc_total = 0;
   bool timing = false;
   std::vector<cudaEvent_t> events;  // 4 per tile of the last run when timing is on
   size_t events_used = 0;
@@ -299,8 +374,9 @@ struct Executor {
   ~Executor() {
     cudaSetDevice(device);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
-    for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_rowoff, (void*)d_observed, (void*)d_dims,
-                    (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_gen_in, (void*)d_gen_sc, (void*)d_flag})
+    for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
+                    (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_gen_in,
+                    (void*)d_gen_sc, (void*)d_flag})
       if (p) cudaFree(p);
   }
 };
@@ -321,13 +397,13 @@ void free_dev(T*& p) {
   p = nullptr;
 }
 
-TabRef tab_ref(const Executor& ex, const Table& t, int64_t RT, const int32_t* rowoff_tile) {
+TabRef tab_ref(const Executor& ex, const Table& t, int64_t RT) {
   TabRef r{nullptr, nullptr, 0, 0};
   switch (t.kind) {
     case T_ONE: r.is_one = 1; break;
     case T_POT:
       r.base = ex.d_pots + t.off;
-      if (t.slice_slot >= 0) r.rowoff = rowoff_tile + (int64_t)t.slice_slot * RT;
+      if (t.slice_slot >= 0) r.rowoff = ex.d_rowoff + (int64_t)t.slice_slot * RT;
       break;
     case T_SHARED: r.base = ex.d_shared + t.off; break;
     case T_ROW: r.base = ex.d_arena + t.off * RT, r.is_row = 1; break;
@@ -335,43 +411,67 @@ TabRef tab_ref(const Executor& ex, const Table& t, int64_t RT, const int32_t* ro
   return r;
 }
 
-// threads of a block along the row axis: the smallest power of two covering the tile, at most BLOCK
-int block_rows(int nr) {
+InArg in_arg(const Executor& ex, const Step& st, int si, int i, int64_t RT) {
+  const Table& t = ex.P->tables[st.in[i].table];
+  InArg a;
+  a.t = tab_ref(ex, t, RT);
+  const uint32_t* pool = t.kind == T_ROW ? ex.d_maps_rt : ex.d_maps;
+  a.hi = pool + ex.hi_off[ex.in_base[si] + i];
+  a.lo = pool + ex.lo_off[ex.in_base[si] + i];
+  a.sstride = (unsigned)(st.in[i].sstride * (t.kind == T_ROW ? RT : 1));
+  return a;
+}
+
+struct LaunchShape {
+  dim3 grid, block;
+};
+// threads along the row axis: the smallest power of two covering the tile's row-threads, at most BLOCK;
+// the rest of the block and grid.x split the output entries into contiguous strips.
+LaunchShape launch_shape(int row_threads, int64_t n_out) {
   int bx = 1;
-  while (bx < nr && bx < BLOCK) bx <<= 1;
-  return bx;
+  while (bx < row_threads && bx < BLOCK) bx <<= 1;
+  const int by = BLOCK / bx;
+  LaunchShape s;
+  s.block = dim3(bx, by);
+  s.grid.y = (row_threads + bx - 1) / bx;
+  const int64_t max_x = (n_out + 2 * by - 1) / (2 * by);  // at least two entries per thread (U = 2)
+  const int64_t want = (148 * 8 * 2 + s.grid.y - 1) / s.grid.y;
+  s.grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_x, want));
+  return s;
+}
+
+template <int K, int V>
+void launch_kv(const StepArgs<K>& a, int d, const LaunchShape& sh, cudaStream_t stream) {
+  switch (d) {
+    case 1: prodsum_kernel<K, V, 1><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    case 2: prodsum_kernel<K, V, 2><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    case 3: prodsum_kernel<K, V, 3><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    case 4: prodsum_kernel<K, V, 4><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    default: prodsum_kernel<K, V, 0><<<sh.grid, sh.block, 0, stream>>>(a); break;
+  }
 }
 
 template <int K>
-void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, bool shared_pass, cudaStream_t stream) {
+void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
   const Program& P = *ex.P;
   StepArgs<K> a;
   memset(&a, 0, sizeof a);
-  for (int i = 0; i < K; ++i) {
-    a.in[i].t = tab_ref(ex, P.tables[st.in[i].table], RT, ex.d_rowoff);
-    a.in[i].hi = ex.d_maps + ex.hi_off[ex.in_base[si] + i];
-    a.in[i].lo = ex.d_maps + ex.lo_off[ex.in_base[si] + i];
-    a.in[i].sstride = st.in[i].sstride;
-  }
+  for (int i = 0; i < K; ++i) a.in[i] = in_arg(ex, st, si, i, RT);
   a.n_sc = (int)st.scalars.size();
-  for (int i = 0; i < a.n_sc; ++i) a.sc[i] = tab_ref(ex, P.tables[st.scalars[i]], RT, ex.d_rowoff);
+  for (int i = 0; i < a.n_sc; ++i) a.sc[i] = tab_ref(ex, P.tables[st.scalars[i]], RT);
   a.d = st.d;
-  a.C = (int)st.C;
-  a.n_out = st.n_out;
+  a.C = (unsigned)st.C;
+  a.n_out = (unsigned)st.n_out;
   const Table& out = P.tables[st.out];
   a.out_is_row = out.kind == T_ROW;
   a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
   a.nr = nr;
   a.RT = RT;
-  const int bx = block_rows(nr);
-  const int by = BLOCK / bx;
-  dim3 block(bx, by), grid;
-  grid.y = (nr + bx - 1) / bx;
-  const int64_t max_x = (st.n_out + by - 1) / by;
-  const int64_t want = (148 * 8 * 4 + grid.y - 1) / grid.y;
-  grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_x, want));
-  prodsum_kernel<K><<<grid, block, 0, stream>>>(a);
-  (void)shared_pass;
+  // two rows per thread (16-byte accesses) as soon as a tile has a full warp of row pairs
+  if (nr >= 64)
+    launch_kv<K, 2>(a, st.d, launch_shape((nr + 1) / 2, st.n_out), stream);
+  else
+    launch_kv<K, 1>(a, st.d, launch_shape(nr, st.n_out), stream);
 }
 
 }  // namespace
@@ -379,17 +479,14 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, bo
 static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream, int64_t gen_in_at,
                            int64_t gen_sc_at) {
   const int k = (int)st.in.size(), s = (int)st.scalars.size();
-  if (k <= MAXK && s <= MAXS) {
+  if (k >= 1 && k <= MAXK && s <= MAXS) {
     switch (k) {
-      case 0: launch_k<0>(ex, st, si, RT, nr, false, stream); break;
-      case 1: launch_k<1>(ex, st, si, RT, nr, false, stream); break;
-      case 2: launch_k<2>(ex, st, si, RT, nr, false, stream); break;
-      case 3: launch_k<3>(ex, st, si, RT, nr, false, stream); break;
-      case 4: launch_k<4>(ex, st, si, RT, nr, false, stream); break;
-      case 5: launch_k<5>(ex, st, si, RT, nr, false, stream); break;
-      case 6: launch_k<6>(ex, st, si, RT, nr, false, stream); break;
-      case 7: launch_k<7>(ex, st, si, RT, nr, false, stream); break;
-      default: launch_k<8>(ex, st, si, RT, nr, false, stream); break;
+      case 1: launch_k<1>(ex, st, si, RT, nr, stream); break;
+      case 2: launch_k<2>(ex, st, si, RT, nr, stream); break;
+      case 3: launch_k<3>(ex, st, si, RT, nr, stream); break;
+      case 4: launch_k<4>(ex, st, si, RT, nr, stream); break;
+      case 5: launch_k<5>(ex, st, si, RT, nr, stream); break;
+      default: launch_k<6>(ex, st, si, RT, nr, stream); break;
     }
   } else {
     const Program& P = *ex.P;
@@ -399,48 +496,44 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
     a.k = k;
     a.n_sc = s;
     a.d = st.d;
-    a.C = (int)st.C;
-    a.n_out = st.n_out;
+    a.C = (unsigned)st.C;
+    a.n_out = (unsigned)st.n_out;
     const Table& out = P.tables[st.out];
     a.out_is_row = out.kind == T_ROW;
     a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
     a.nr = nr;
     a.RT = RT;
-    const int bx = block_rows(nr);
-    const int by = BLOCK / bx;
-    dim3 block(bx, by), grid;
-    grid.y = (nr + bx - 1) / bx;
-    const int64_t max_x = (st.n_out + by - 1) / by;
-    const int64_t want = (148 * 8 * 4 + grid.y - 1) / grid.y;
-    grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_x, want));
-    prodsum_generic_kernel<<<grid, block, 0, stream>>>(a);
+    LaunchShape sh = launch_shape(nr, st.n_out);
+    prodsum_generic_kernel<<<sh.grid, sh.block, 0, stream>>>(a);
   }
 }
 
+static bool is_generic(const Step& st) {
+  const int k = (int)st.in.size(), s = (int)st.scalars.size();
+  return !(k >= 1 && k <= MAXK && s <= MAXS);
+}
+
 // (Re)builds everything that depends on the arena row stride RT: the arena itself, the slice-offset
-// table, the generic-path descriptors and the output descriptors.
+// table, the RT-multiplied index maps, the generic-path descriptors and the output descriptors.
 static void set_row_stride(Executor& ex, int64_t RT) {
   if (RT == ex.RT) return;
   const Program& P = *ex.P;
   free_dev(ex.d_arena);
   free_dev(ex.d_rowoff);
+  free_dev(ex.d_maps_rt);
   HB_CUDA(cudaMalloc(&ex.d_arena, std::max<int64_t>(P.row_entries, 1) * RT * sizeof(double)));
   HB_CUDA(cudaMalloc(&ex.d_rowoff, std::max<int64_t>((int64_t)P.slices.size(), 1) * RT * sizeof(int32_t)));
   ex.RT = RT;
+  std::vector<uint32_t> scaled(ex.maps.size());
+  for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = (uint32_t)((uint64_t)ex.maps[i] * (uint64_t)RT);  // only row-table maps are read from this copy
+  ex.d_maps_rt = upload(scaled);
   std::vector<InArg> gin;
   std::vector<TabRef> gsc;
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
-    if (st.kind != STEP_PRODSUM || ((int)st.in.size() <= MAXK && (int)st.scalars.size() <= MAXS)) continue;
-    for (size_t i = 0; i < st.in.size(); ++i) {
-      InArg a;
-      a.t = tab_ref(ex, P.tables[st.in[i].table], RT, ex.d_rowoff);
-      a.hi = ex.d_maps + ex.hi_off[ex.in_base[si] + i];
-      a.lo = ex.d_maps + ex.lo_off[ex.in_base[si] + i];
-      a.sstride = st.in[i].sstride;
-      gin.push_back(a);
-    }
-    for (int id : st.scalars) gsc.push_back(tab_ref(ex, P.tables[id], RT, ex.d_rowoff));
+    if (st.kind != STEP_PRODSUM || !is_generic(st)) continue;
+    for (size_t i = 0; i < st.in.size(); ++i) gin.push_back(in_arg(ex, st, (int)si, (int)i, RT));
+    for (int id : st.scalars) gsc.push_back(tab_ref(ex, P.tables[id], RT));
   }
   free_dev(ex.d_gen_in);
   free_dev(ex.d_gen_sc);
@@ -449,7 +542,7 @@ static void set_row_stride(Executor& ex, int64_t RT) {
   for (size_t j = 0; j < ex.out_steps.size(); ++j) {
     const Step& st = P.steps[ex.out_steps[j]];
     const Table& t = P.tables[st.in[0].table];
-    ex.out_desc[j].t = tab_ref(ex, t, RT, ex.d_rowoff);
+    ex.out_desc[j].t = tab_ref(ex, t, RT);
     ex.out_desc[j].slice = t.kind == T_POT ? t.slice_slot : -1;
   }
   free_dev(ex.d_out_desc);
@@ -468,16 +561,19 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
   ex->d_pots = upload(pots);
   HB_CUDA(cudaMalloc(&ex->d_shared, std::max<int64_t>(P.shared_entries, 1) * sizeof(double)));
   // index-map pool
-  std::vector<int32_t> maps;
+  std::vector<uint32_t>& maps = ex->maps;
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
     ex->in_base.push_back((int64_t)ex->hi_off.size());
     if (st.kind == STEP_PRODSUM) {
+      if (st.n_out >= ((int64_t)1 << 31)) throw Error(HB_E_UNSUPPORTED, "a table with 2^31 or more entries");
       for (const StepInput& in : st.in) {
         ex->hi_off.push_back((int64_t)maps.size());
         maps.insert(maps.end(), in.hi.begin(), in.hi.end());
         ex->lo_off.push_back((int64_t)maps.size());
         maps.insert(maps.end(), in.lo.begin(), in.lo.end());
+        const Table& t = P.tables[in.table];
+        if (t.kind == T_ROW) ex->max_row_table = std::max(ex->max_row_table, t.size);
       }
     } else {
       if ((int)st.obs_var.size() > MAXOBS) throw Error(HB_E_UNSUPPORTED, "more than 8 observed variables in one query");
@@ -493,7 +589,7 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
       for (int64_t f = 0; f < st.n_full; ++f) {
         bool first_state = true;
         for (size_t j = 0; j < st.obs_var.size(); ++j) first_state &= ((f / st.obs_stride[j]) % st.obs_dim[j]) == 0;
-        if (first_state) maps.push_back(st.full_map[f]), ++n_phys;
+        if (first_state) maps.push_back((uint32_t)st.full_map[f]), ++n_phys;
       }
       d.n_phys = n_phys;
       d.n_obs = (int)st.obs_var.size();
@@ -529,9 +625,8 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
     if (st.kind != STEP_PRODSUM) continue;
-    const bool generic = (int)st.in.size() > MAXK || (int)st.scalars.size() > MAXS;
     if (st.shared) launch_prodsum(*ex, st, (int)si, 32, 1, 0, gi, gs);
-    if (generic) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
+    if (is_generic(st)) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
   }
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaDeviceSynchronize());
@@ -547,11 +642,14 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
   const Program& P = *ex->P;
   HB_CUDA(cudaSetDevice(ex->device));
   const int n_vars = P.net->n();
-  // rows per tile: as many as the workspace allows, in multiples of 32 (one warp of rows)
+  // rows per tile: as many as the workspace allows, in multiples of 32 (one warp of rows), and few enough
+  // that every row-table offset (entry * RT + row) fits 32 bits
   const int64_t per_row = std::max<int64_t>(P.row_entries, 1) * 8 + (int64_t)P.slices.size() * 4;
   int64_t cap = ex->workspace / per_row / 32 * 32;
   if (cap < 32) throw Error(HB_E_OOM, "row arena of one 32-row tile (" + std::to_string(per_row * 32) + " bytes) exceeds the workspace");
+  cap = std::min<int64_t>(cap, (((int64_t)1 << 32) - 1) / (ex->max_row_table + 1) / 32 * 32);
   cap = std::min<int64_t>(cap, (int64_t)1 << 22);
+  if (cap < 32) throw Error(HB_E_UNSUPPORTED, "per-row table too large for 32-bit offsets");
   const int64_t RT = std::min<int64_t>(cap, (n_rows + 31) / 32 * 32);
   if (RT > ex->RT || ex->RT > 4 * RT) {
     HB_CUDA(cudaStreamSynchronize(stream));
@@ -568,16 +666,15 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     mark();
     PrepArgs pa{d_evidence + r0 * n_vars, nr, n_vars, (int)P.slices.size(), stride, ex->d_observed, ex->d_dims,
                 ex->d_sl_begin, ex->d_sl_var, ex->d_sl_stride, ex->d_rowoff, ex->d_flag};
-    prep_rows_kernel<<<(nr + BLOCK - 1) / BLOCK, BLOCK, 0, stream>>>(pa);
+    prep_rows_kernel<<<(((nr + 31) & ~31) + BLOCK - 1) / BLOCK, BLOCK, 0, stream>>>(pa);
     ++launches;
     mark();
     int64_t gi = 0, gs = 0;
     for (size_t si = 0; si < P.steps.size(); ++si) {
       const Step& st = P.steps[si];
       if (st.kind != STEP_PRODSUM) continue;
-      const bool generic = (int)st.in.size() > MAXK || (int)st.scalars.size() > MAXS;
       if (!st.shared) launch_prodsum(*ex, st, (int)si, stride, nr, stream, gi, gs), ++launches;
-      if (generic) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
+      if (is_generic(st)) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
     }
     mark();
     if (!ex->out_desc.empty()) {

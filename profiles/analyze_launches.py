@@ -1,0 +1,51 @@
+"""Joins an ncu launch list (gpu__time_duration.sum per launch) of `bench.py --rows R` with the compiled C2
+program: per-launch algorithmic bytes, achieved GB/s and time shares.  usage: analyze_launches.py launches.csv R"""
+import collections
+import csv
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import hbayes_b200 as hb
+from hbayes_b200 import synth
+
+path, R = sys.argv[1], int(sys.argv[2])
+rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+names = [r[4] for r in rows]
+dur = [float(r[-1]) for r in rows]
+grid = [r[8] for r in rows]
+blk = [r[7] for r in rows]
+idx = [i for i, n in enumerate(names) if "prep_rows" in n]
+s, e = idx[-2], idx[-1]
+net, observed = synth.config_c2()
+pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+p = hb.JunctionTree(pnet, device=None).program(observed)
+steps = [x for x in p["physical"] if x["kind"] == 0 and not x["shared"]]
+L = [i for i in range(s + 1, e) if "prodsum" in names[i]]
+assert len(L) == len(steps), (len(L), len(steps))
+tot = totb = 0
+recs = []
+for li, st in zip(L, steps):
+    rd = sum(min(i["size"], st["n_out"] * st["d"]) for i in st["in"] if i["kind"] == 3)
+    b = 8 * (rd + st["n_out"]) * R
+    recs.append((dur[li], b / dur[li], st["n_out"], st["d"], len(st["in"]), sum(1 for i in st["in"] if i["kind"] == 3), grid[li], blk[li]))
+    tot += dur[li]
+    totb += b
+others = sum(dur[i] for i in range(s, e) if "prodsum" not in names[i])
+print("pass: %d prodsum launches %.1f us (%.1f%% of pass), other kernels %.1f us; prodsum algorithmic %.0f GB/s (cold-cache, serialised)"
+      % (len(L), tot / 1e3, 100 * tot / (tot + others), others / 1e3, totb / tot))
+recs.sort(reverse=True)
+print("top launches:")
+for r in recs[:20]:
+    print("  %8.0f ns %6.0f GB/s n_out=%5d d=%d k=%d row_inputs=%d grid=%s block=%s" % r)
+b = collections.defaultdict(lambda: [0, 0, 0])
+for (d_, bw, n, dd, k, ri, _, _) in recs:
+    b[(k, ri)][0] += d_
+    b[(k, ri)][1] += bw * d_
+    b[(k, ri)][2] += 1
+print("by (k inputs, per-row inputs): launches, time share, mean GB/s")
+for k in sorted(b):
+    print("  ", k, b[k][2], "%.3f" % (b[k][0] / tot), "%.0f" % (b[k][1] / b[k][0]))
+for i in range(s, e):
+    if "prodsum" not in names[i]:
+        print("  other:", names[i][-60:], dur[i], "ns")
