@@ -172,7 +172,6 @@ struct Compiler {
     // ---- physical lowering ----
     Step st;
     st.group = (int)P.groups.size();
-    st.sum_var = sum_var;
     bool shared = true;
     for (int id : scalars)
       if (T(resolve(id)).kind != T_ONE) st.scalars.push_back(resolve(id)), shared = shared && batch_invariant(id);
@@ -198,60 +197,18 @@ struct Compiler {
     out.kind = shared ? T_SHARED : T_ROW;
     set_physical(out);
     st.shared = shared;
-    st.d = sums ? net.dims[sum_var] : 1;
-    st.n_out = out.size;
-    // split the output index: trailing variables with product C go into `lo`, the rest into `hi`
-    const int nk = (int)out.pscope.size();
-    int split = nk;
-    int64_t C = 1;
-    while (split > 0 && C * C < st.n_out && C * net.dims[out.pscope[split - 1]] <= 4096) C *= net.dims[out.pscope[--split]];
-    st.C = C;
-    st.n_hi = st.n_out / C;
+    Level lv;
+    lv.sum_var = sums ? sum_var : -1;
+    lv.d = sums ? net.dims[sum_var] : 1;
     for (int id : real) {
-      const Table& t = T(id);
       StepInput in;
       in.table = id;
-      auto stride_of = [&](int v) -> int64_t {
-        for (size_t i = 0; i < t.pscope.size(); ++i)
-          if (t.pscope[i] == v) return t.pstride[i];
-        return 0;
-      };
-      in.sstride = sums ? stride_of(sum_var) : 0;
-      in.hi.assign((size_t)st.n_hi, 0);
-      in.lo.assign((size_t)C, 0);
-      auto fill = [&](std::vector<int32_t>& dst, int from, int to) {
-        std::vector<int> digit(nk, 0);
-        int64_t off = 0;
-        for (size_t e = 0; e < dst.size(); ++e) {
-          dst[e] = (int32_t)off;
-          for (int j = to - 1; j >= from; --j) {
-            int64_t s = stride_of(out.pscope[j]);
-            if (++digit[j] < net.dims[out.pscope[j]]) {
-              off += s;
-              break;
-            }
-            off -= s * (digit[j] - 1);
-            digit[j] = 0;
-          }
-        }
-      };
-      fill(in.hi, 0, split);
-      fill(in.lo, split, nk);
-      st.in.push_back(std::move(in));
-      P.stat_reads += st.n_out * st.d;
-      if (t.kind == T_ROW) P.stat_row_read += std::min<int64_t>(t.size, st.n_out * st.d);
+      lv.in.push_back(in);
     }
-    if (!shared) {
-      P.stat_prod += st.n_out * st.d;
-      P.stat_row_write += st.n_out;
-      P.stat_max_table = std::max(P.stat_max_table, st.n_out * st.d);
-    }
-    st.trace_inputs = tr.inputs;
-    st.trace_prod = tr.prod;
-    st.trace_out = tr.out;
+    st.levels.push_back(std::move(lv));
+    st.n_out = out.size;
     int id = add(out);
     st.out = id;
-    P.tables[id].def_step = (int)P.steps.size();
     P.steps.push_back(std::move(st));
     return id;
   }
@@ -311,9 +268,7 @@ struct Compiler {
     st.group = (int)P.groups.size();
     const int rid = resolve(result);
     const Table& t = T(result);
-    StepInput in;
-    in.table = rid;
-    st.in.push_back(in);
+    st.result = rid;
     g.out_scope = t.scope;
     g.result = result;
     const int nq = (int)t.scope.size();
@@ -347,31 +302,135 @@ struct Compiler {
     P.steps.push_back(std::move(st));
   }
 
-  // Dead steps (messages no requested query needs) are dropped; liveness-based placement of the
-  // per-row tables in the row arena; shared tables get their own arena.
-  void finish() {
-    const int ns = (int)P.steps.size();
-    std::vector<char> live_t(P.tables.size(), 0), live_s(ns, 0);
-    for (int s = ns - 1; s >= 0; --s) {
-      Step& st = P.steps[s];
-      if (st.kind == STEP_OUTPUT || live_t[st.out]) {
-        live_s[s] = 1;
-        for (auto& in : st.in) live_t[in.table] = 1;
-        for (int id : st.scalars) live_t[id] = 1;
+  template <class F>
+  static void for_each_input(const Step& st, F&& f) {
+    if (st.kind == STEP_OUTPUT) {
+      f(st.result);
+      return;
+    }
+    for (const Level& l : st.levels)
+      for (const StepInput& in : l.in) f(in.table);
+    for (int id : st.scalars) f(id);
+  }
+
+  // After the symbolic run: drop dead steps (messages no requested query needs), fuse producer/consumer
+  // chains, build the index maps, place the per-row tables in the row arena by liveness.
+  void finish(const CompileOptions& opt) {
+    // ---- 1. dead steps ----
+    {
+      const int ns = (int)P.steps.size();
+      std::vector<char> live_t(P.tables.size(), 0), live_s(ns, 0);
+      for (int s = ns - 1; s >= 0; --s) {
+        const Step& st = P.steps[s];
+        if (st.kind == STEP_OUTPUT || live_t[st.out]) {
+          live_s[s] = 1;
+          for_each_input(st, [&](int id) { live_t[id] = 1; });
+        }
+      }
+      std::vector<Step> kept;
+      for (int s = 0; s < ns; ++s)
+        if (live_s[s]) kept.push_back(std::move(P.steps[s]));
+      P.steps.swap(kept);
+    }
+    for (const Step& st : P.steps)
+      if (st.kind == STEP_PRODSUM && !st.shared) ++P.stat_ops;
+    // ---- 2. fusion ----
+    // Consumer S whose FIRST chain input T is produced by step Q, read by nobody else, and whose scope is
+    // exactly S's product scope (every entry of T is used once): Q's levels are appended below S's and T
+    // disappears.  The inner value is complete before it is multiplied, so the FP sequence is unchanged.
+    if (opt.fuse) {
+      std::vector<int> uses(P.tables.size(), 0), producer(P.tables.size(), -1);
+      for (const Step& st : P.steps) for_each_input(st, [&](int id) { ++uses[id]; });
+      for (int s = 0; s < (int)P.steps.size(); ++s)
+        if (P.steps[s].kind == STEP_PRODSUM) producer[P.steps[s].out] = s;
+      std::vector<char> dead(P.steps.size(), 0);
+      for (int s = 0; s < (int)P.steps.size(); ++s) {
+        Step& S = P.steps[s];
+        if (S.kind != STEP_PRODSUM || !S.scalars.empty() || S.levels[0].in.empty()) continue;
+        const int tid = S.levels[0].in[0].table;
+        const int q = producer[tid];
+        if (q < 0 || uses[tid] != 1) continue;
+        const Step& Q = P.steps[q];
+        if (Q.shared != S.shared || !Q.scalars.empty()) continue;
+        if ((int)(S.levels.size() + Q.levels.size()) > opt.max_levels || S.n_inputs() - 1 + Q.n_inputs() > opt.max_inputs) continue;
+        std::vector<int> want = P.tables[S.out].pscope;  // S's physical product scope
+        if (S.levels[0].sum_var >= 0) want.push_back(S.levels[0].sum_var);
+        std::vector<int> have = P.tables[tid].pscope;
+        std::sort(want.begin(), want.end());
+        std::sort(have.begin(), have.end());
+        if (want != have) continue;
+        S.levels[0].in.erase(S.levels[0].in.begin());
+        for (const Level& l : Q.levels) S.levels.push_back(l);
+        dead[q] = 1;
+        producer[tid] = -1;
+      }
+      std::vector<Step> kept;
+      for (size_t s = 0; s < P.steps.size(); ++s)
+        if (!dead[s]) kept.push_back(std::move(P.steps[s]));
+      P.steps.swap(kept);
+    }
+    // ---- 3. index maps and statistics ----
+    for (Step& st : P.steps) {
+      if (st.kind != STEP_PRODSUM) continue;
+      const Table& out = P.tables[st.out];
+      const int nk = (int)out.pscope.size();
+      // split the output index: trailing variables with product C go into `lo`, the rest into `hi`
+      int split = nk;
+      int64_t C = 1;
+      while (split > 0 && C * C < st.n_out && C * net.dims[out.pscope[split - 1]] <= 4096) C *= net.dims[out.pscope[--split]];
+      st.C = C;
+      st.n_hi = st.n_out / C;
+      int64_t terms = 1;
+      for (size_t l = 0; l < st.levels.size(); ++l) {
+        terms *= st.levels[l].d;
+        for (StepInput& in : st.levels[l].in) {
+          const Table& t = P.tables[in.table];
+          auto stride_of = [&](int v) -> int64_t {
+            for (size_t i = 0; i < t.pscope.size(); ++i)
+              if (t.pscope[i] == v) return t.pstride[i];
+            return 0;
+          };
+          in.lstride.clear();
+          for (size_t m = 0; m <= l; ++m) in.lstride.push_back(st.levels[m].sum_var >= 0 ? stride_of(st.levels[m].sum_var) : 0);
+          auto fill = [&](std::vector<uint32_t>& dst, size_t count, int from, int to) {
+            dst.assign(count, 0);
+            std::vector<int> digit(nk, 0);
+            int64_t off = 0;
+            for (size_t e = 0; e < count; ++e) {
+              dst[e] = (uint32_t)off;
+              for (int j = to - 1; j >= from; --j) {
+                const int64_t sj = stride_of(out.pscope[j]);
+                if (++digit[j] < net.dims[out.pscope[j]]) {
+                  off += sj;
+                  break;
+                }
+                off -= sj * (digit[j] - 1);
+                digit[j] = 0;
+              }
+            }
+          };
+          fill(in.hi, (size_t)st.n_hi, 0, split);
+          fill(in.lo, (size_t)C, split, nk);
+          if (!st.shared) {
+            P.stat_reads += st.n_out * terms;
+            if (t.kind == T_ROW) P.stat_row_read += std::min<int64_t>(t.size, st.n_out * terms);
+          }
+        }
+        if (!st.shared) P.stat_prod += st.n_out * terms;
+      }
+      if (!st.shared) {
+        P.stat_row_write += st.n_out;
+        P.stat_max_table = std::max(P.stat_max_table, st.n_out * terms);
       }
     }
-    std::vector<Step> kept;
-    std::vector<int> remap_group_first;
-    for (int s = 0; s < ns; ++s)
-      if (live_s[s]) kept.push_back(std::move(P.steps[s]));
-    P.steps.swap(kept);
+    // ---- 4. liveness and arena placement ----
     for (auto& t : P.tables) t.def_step = t.last_use = -1;
-    for (int s = 0; s < (int)P.steps.size(); ++s) {
-      Step& st = P.steps[s];
+    const int last = (int)P.steps.size() - 1;
+    for (int s = 0; s <= last; ++s) {
+      const Step& st = P.steps[s];
       if (st.kind == STEP_PRODSUM) P.tables[st.out].def_step = s;
       // query results are read by ONE normalise/expand kernel after the last step: they live to the end
-      for (auto& in : st.in) P.tables[in.table].last_use = st.kind == STEP_OUTPUT ? (int)P.steps.size() - 1 : std::max(P.tables[in.table].last_use, s);
-      for (int id : st.scalars) P.tables[id].last_use = std::max(P.tables[id].last_use, s);
+      for_each_input(st, [&](int id) { P.tables[id].last_use = st.kind == STEP_OUTPUT ? last : std::max(P.tables[id].last_use, s); });
     }
     // shared arena: no reuse (computed once, read by every row)
     for (auto& t : P.tables)
@@ -391,7 +450,7 @@ struct Compiler {
       if (it != free_list.begin() && (it - 1)->first + (it - 1)->second == it->first) (it - 1)->second += it->second, it = free_list.erase(it), --it;
       if (it->first + it->second == top) top = it->first, free_list.erase(it);
     };
-    for (int s = 0; s < (int)P.steps.size(); ++s) {
+    for (int s = 0; s <= last; ++s) {
       Step& st = P.steps[s];
       if (st.kind == STEP_PRODSUM && !st.shared) {
         Table& t = P.tables[st.out];
@@ -406,7 +465,6 @@ struct Compiler {
           }
         if (!placed) t.off = top, top += t.size;
         P.row_entries = std::max(P.row_entries, top);
-        if (t.last_use < 0) release(t.off, t.size);  // cannot happen after dead-step removal; kept for safety
       }
       for (int id : dies_at[s]) release(P.tables[id].off, P.tables[id].size);
     }
@@ -430,7 +488,7 @@ void js_nums(std::ostringstream& o, const V& v) {
 // createJunctionTree's calibration / changeEvidence (JTree.hs:454-466) followed by `posterior q` for
 // every requested query, as one program.
 Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>& observed,
-                    const std::vector<Query>& queries) {
+                    const std::vector<Query>& queries, const CompileOptions& opt) {
   auto prog = std::make_unique<Program>();
   Compiler C(net, *prog, observed);
   const int nc = (int)tree.clusters.size(), nsep = tree.n_seps();
@@ -533,14 +591,14 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
     C.emit_output(res, g);
     prog->groups.push_back(std::move(g));
   }
-  C.finish();
+  C.finish(opt);
   return prog.release();
 }
 
 // posteriorMarginal g p r assignment (VariableElimination.hs:116-130): all CPTs in ascending vertex id,
 // indicators added with addBucket in the caller's order.
 Program* compile_ve(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
-                    const std::vector<int>& observed) {
+                    const std::vector<int>& observed, const CompileOptions& opt) {
   auto prog = std::make_unique<Program>();
   Compiler C(net, *prog, observed);
   for (int v : p)
@@ -556,7 +614,7 @@ Program* compile_ve(const Network& net, const std::vector<int>& p, const std::ve
   int res = C.marginal(lf, p, r, asg, g);
   C.emit_output(res, g);
   prog->groups.push_back(std::move(g));
-  C.finish();
+  C.finish(opt);
   return prog.release();
 }
 
@@ -568,7 +626,7 @@ std::string describe_program(const Program& P) {
   js_list(o, P.observed);
   o << ",\"row_entries\":" << P.row_entries << ",\"shared_entries\":" << P.shared_entries << ",\"out_width\":" << P.out_width
     << ",\"stats\":{\"prod\":" << P.stat_prod << ",\"reads\":" << P.stat_reads << ",\"row_read\":" << P.stat_row_read
-    << ",\"row_write\":" << P.stat_row_write << ",\"max_table\":" << P.stat_max_table << ",\"steps\":" << P.steps.size() << "}";
+    << ",\"row_write\":" << P.stat_row_write << ",\"max_table\":" << P.stat_max_table << ",\"steps\":" << P.steps.size() << ",\"ops\":" << P.stat_ops << "}";
   o << ",\"groups\":[";
   const char* kinds[] = {"up", "down", "posterior", "ve"};
   for (size_t i = 0; i < P.groups.size(); ++i) {
@@ -596,27 +654,34 @@ std::string describe_program(const Program& P) {
   o << "],\"physical\":[";
   for (size_t i = 0; i < P.steps.size(); ++i) {
     const Step& s = P.steps[i];
-    o << (i ? "," : "") << "{\"kind\":" << s.kind << ",\"shared\":" << (s.shared ? 1 : 0) << ",\"group\":" << s.group
-      << ",\"sum_var\":" << s.sum_var << ",\"d\":" << s.d << ",\"n_out\":" << s.n_out << ",\"C\":" << s.C << ",\"out\":" << s.out;
+    o << (i ? "," : "") << "{\"kind\":" << s.kind << ",\"shared\":" << (s.shared ? 1 : 0) << ",\"group\":" << s.group << ",\"n_out\":" << s.n_out
+      << ",\"C\":" << s.C << ",\"out\":" << s.out;
     if (s.kind == STEP_PRODSUM) {
       o << ",\"out_scope\":";
       js_list(o, P.tables[s.out].pscope);
-      o << ",\"out_off\":" << P.tables[s.out].off;
+      o << ",\"out_off\":" << P.tables[s.out].off << ",\"scalars\":";
+      js_list(o, s.scalars);
+      o << ",\"levels\":[";
+      for (size_t l = 0; l < s.levels.size(); ++l) {
+        const Level& lv = s.levels[l];
+        o << (l ? "," : "") << "{\"sum_var\":" << lv.sum_var << ",\"d\":" << lv.d << ",\"in\":[";
+        for (size_t k = 0; k < lv.in.size(); ++k) {
+          const Table& t = P.tables[lv.in[k].table];
+          o << (k ? "," : "") << "{\"table\":" << lv.in[k].table << ",\"kind\":" << t.kind << ",\"pot\":" << t.pot << ",\"off\":" << t.off
+            << ",\"size\":" << t.size << ",\"lstride\":";
+          js_nums(o, lv.in[k].lstride);
+          o << ",\"scope\":";
+          js_list(o, t.pscope);
+          o << ",\"strides\":";
+          js_nums(o, t.pstride);
+          o << "}";
+        }
+        o << "]}";
+      }
+      o << "]";
     } else
-      o << ",\"out_col\":" << s.out_col << ",\"n_full\":" << s.n_full;
-    o << ",\"scalars\":";
-    js_list(o, s.scalars);
-    o << ",\"in\":[";
-    for (size_t k = 0; k < s.in.size(); ++k) {
-      const Table& t = P.tables[s.in[k].table];
-      o << (k ? "," : "") << "{\"table\":" << s.in[k].table << ",\"kind\":" << t.kind << ",\"pot\":" << t.pot << ",\"off\":" << t.off
-        << ",\"size\":" << t.size << ",\"sstride\":" << s.in[k].sstride << ",\"scope\":";
-      js_list(o, t.pscope);
-      o << ",\"strides\":";
-      js_nums(o, t.pstride);
-      o << "}";
-    }
-    o << "]}";
+      o << ",\"result\":" << s.result << ",\"out_col\":" << s.out_col << ",\"n_full\":" << s.n_full;
+    o << "}";
   }
   o << "]}";
   return o.str();

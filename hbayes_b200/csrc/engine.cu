@@ -45,6 +45,7 @@ namespace {
 
 constexpr int MAXK = 6;       // chain inputs handled by the templated kernel
 constexpr int MAXS = 4;       // structural scalars per step
+constexpr int MAXL = 4;       // levels of a fused chain
 constexpr int MAXOBS = 8;     // observed variables inside one query
 constexpr int BLOCK = 256;
 
@@ -207,6 +208,87 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
     acc[0].store(outp + (size_t)o * om);
     if (nu > 1) acc[1].store(outp + (size_t)(o + 1) * om);
     o += nu;
+  }
+}
+
+// ---- fused chains (Step::levels.size() > 1) ----------------------------------------------------
+// value_l = 0 + sum_{s_l} value_{l+1} * (in_1 * (in_2 * ...)); the inner value is a register, the table it
+// stands for never exists.  Inputs are flattened level 0 first; input i belongs to level lvl[i] and moves
+// by st[i][m] entries per state of the summed variable of level m <= lvl[i].
+template <int K>
+struct FusedArgs {
+  InArg in[K];
+  unsigned st[K][MAXL];
+  int lvl[K];
+  int L;
+  int d[MAXL];
+  unsigned C, n_out;
+  double* out;
+  int out_is_row, nr;
+  long long RT;
+};
+
+template <int K, int V, int LVL>
+__device__ __forceinline__ Rows<V> eval_level(const FusedArgs<K>& a, const double* const (&p0)[K], const double* const (&p1)[K],
+                                               const bool (&isrow)[K], const unsigned (&off)[K]) {
+  typedef Rows<V> R;
+  R acc = R::splat(0.0, 0.0);
+  const int d = a.d[LVL];
+#pragma unroll 2
+  for (int s = 0; s < d; ++s) {
+    unsigned o2[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) o2[i] = off[i] + s * a.st[i][LVL];
+    R c = R::splat(1.0, 1.0);
+    bool have = false;
+#pragma unroll
+    for (int i = K - 1; i >= 0; --i) {
+      if (a.lvl[i] == LVL) {
+        const R x = R::load(p0[i], p1[i], isrow[i], o2[i]);
+        c = have ? x.mul(c) : x;
+        have = true;
+      }
+    }
+    if constexpr (LVL + 1 < MAXL) {
+      if (LVL + 1 < a.L) {
+        const R v = eval_level<K, V, LVL + 1>(a, p0, p1, isrow, o2);
+        c = have ? v.mul(c) : v;
+      }
+    }
+    acc = acc.add(c);
+  }
+  return acc;
+}
+
+template <int K, int V>
+__global__ void __launch_bounds__(BLOCK) fused_kernel(const __grid_constant__ FusedArgs<K> a) {
+  typedef Rows<V> R;
+  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  if (row >= a.nr) return;
+  const double* p0[K];
+  const double* p1[K];
+  bool isrow[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    isrow[i] = a.in[i].t.is_row != 0;
+    p0[i] = row_ptr(a.in[i].t, row);
+    p1[i] = (V == 2 && !isrow[i]) ? row_ptr(a.in[i].t, row + 1) : p0[i];
+  }
+  double* outp = a.out + (a.out_is_row ? row : 0);
+  const size_t om = a.out_is_row ? (size_t)a.RT : 1;
+  const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;
+  const unsigned per = (a.n_out + lanes - 1) / lanes;
+  unsigned o = lane * per;
+  const unsigned o_end = min(a.n_out, o + per);
+  if (o >= o_end) return;
+  unsigned hiI = o / a.C, loI = o - hiI * a.C;
+  for (; o < o_end; ++o) {
+    unsigned off[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) off[i] = __ldg(a.in[i].hi + hiI) + __ldg(a.in[i].lo + loI);
+    if (++loI == a.C) loI = 0, ++hiI;
+    const R v = eval_level<K, V, 0>(a, p0, p1, isrow, off);
+    v.store(outp + (size_t)o * om);
   }
 }
 
@@ -411,14 +493,28 @@ TabRef tab_ref(const Executor& ex, const Table& t, int64_t RT) {
   return r;
 }
 
+// input number `i` of a step, counting level 0 first
+const StepInput& flat_input(const Step& st, int i, int* level = nullptr) {
+  for (size_t l = 0; l < st.levels.size(); ++l) {
+    if (i < (int)st.levels[l].in.size()) {
+      if (level) *level = (int)l;
+      return st.levels[l].in[i];
+    }
+    i -= (int)st.levels[l].in.size();
+  }
+  throw Error(HB_E_ARG, "input index out of range");
+}
+
 InArg in_arg(const Executor& ex, const Step& st, int si, int i, int64_t RT) {
-  const Table& t = ex.P->tables[st.in[i].table];
+  int level = 0;
+  const StepInput& in = flat_input(st, i, &level);
+  const Table& t = ex.P->tables[in.table];
   InArg a;
   a.t = tab_ref(ex, t, RT);
   const uint32_t* pool = t.kind == T_ROW ? ex.d_maps_rt : ex.d_maps;
   a.hi = pool + ex.hi_off[ex.in_base[si] + i];
   a.lo = pool + ex.lo_off[ex.in_base[si] + i];
-  a.sstride = (unsigned)(st.in[i].sstride * (t.kind == T_ROW ? RT : 1));
+  a.sstride = (unsigned)(in.lstride[level] * (t.kind == T_ROW ? RT : 1));
   return a;
 }
 
@@ -459,7 +555,7 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   for (int i = 0; i < K; ++i) a.in[i] = in_arg(ex, st, si, i, RT);
   a.n_sc = (int)st.scalars.size();
   for (int i = 0; i < a.n_sc; ++i) a.sc[i] = tab_ref(ex, P.tables[st.scalars[i]], RT);
-  a.d = st.d;
+  a.d = st.levels[0].d;
   a.C = (unsigned)st.C;
   a.n_out = (unsigned)st.n_out;
   const Table& out = P.tables[st.out];
@@ -469,17 +565,64 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   a.RT = RT;
   // two rows per thread (16-byte accesses) as soon as a tile has a full warp of row pairs
   if (nr >= 64)
-    launch_kv<K, 2>(a, st.d, launch_shape((nr + 1) / 2, st.n_out), stream);
+    launch_kv<K, 2>(a, a.d, launch_shape((nr + 1) / 2, st.n_out), stream);
   else
-    launch_kv<K, 1>(a, st.d, launch_shape(nr, st.n_out), stream);
+    launch_kv<K, 1>(a, a.d, launch_shape(nr, st.n_out), stream);
+}
+
+template <int K>
+void launch_fused(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
+  const Program& P = *ex.P;
+  FusedArgs<K> a;
+  memset(&a, 0, sizeof a);
+  a.L = (int)st.levels.size();
+  for (int l = 0; l < a.L; ++l) a.d[l] = st.levels[l].d;
+  for (int i = 0; i < K; ++i) {
+    int level = 0;
+    const StepInput& in = flat_input(st, i, &level);
+    a.in[i] = in_arg(ex, st, si, i, RT);
+    a.lvl[i] = level;
+    const int64_t mult = P.tables[in.table].kind == T_ROW ? RT : 1;
+    for (int m = 0; m <= level; ++m) a.st[i][m] = (unsigned)(in.lstride[m] * mult);
+  }
+  a.C = (unsigned)st.C;
+  a.n_out = (unsigned)st.n_out;
+  const Table& out = P.tables[st.out];
+  a.out_is_row = out.kind == T_ROW;
+  a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
+  a.nr = nr;
+  a.RT = RT;
+  if (nr >= 64) {
+    LaunchShape sh = launch_shape((nr + 1) / 2, 2 * st.n_out);
+    fused_kernel<K, 2><<<sh.grid, sh.block, 0, stream>>>(a);
+  } else {
+    LaunchShape sh = launch_shape(nr, 2 * st.n_out);
+    fused_kernel<K, 1><<<sh.grid, sh.block, 0, stream>>>(a);
+  }
 }
 
 }  // namespace
 
+static bool is_generic(const Step& st) {
+  const int k = st.n_inputs(), s = (int)st.scalars.size();
+  if (st.levels.size() > 1) return false;  // the compiler only fuses within MAXL levels / MAXK inputs, without scalars
+  return !(k >= 1 && k <= MAXK && s <= MAXS);
+}
+
 static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream, int64_t gen_in_at,
                            int64_t gen_sc_at) {
-  const int k = (int)st.in.size(), s = (int)st.scalars.size();
-  if (k >= 1 && k <= MAXK && s <= MAXS) {
+  const int k = st.n_inputs(), s = (int)st.scalars.size();
+  if (st.levels.size() > 1) {
+    if ((int)st.levels.size() > MAXL || k < 1 || k > MAXK || s) throw Error(HB_E_UNSUPPORTED, "fused step exceeds the kernel limits");
+    switch (k) {
+      case 1: launch_fused<1>(ex, st, si, RT, nr, stream); break;
+      case 2: launch_fused<2>(ex, st, si, RT, nr, stream); break;
+      case 3: launch_fused<3>(ex, st, si, RT, nr, stream); break;
+      case 4: launch_fused<4>(ex, st, si, RT, nr, stream); break;
+      case 5: launch_fused<5>(ex, st, si, RT, nr, stream); break;
+      default: launch_fused<6>(ex, st, si, RT, nr, stream); break;
+    }
+  } else if (!is_generic(st)) {
     switch (k) {
       case 1: launch_k<1>(ex, st, si, RT, nr, stream); break;
       case 2: launch_k<2>(ex, st, si, RT, nr, stream); break;
@@ -495,7 +638,7 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
     a.sc = ex.d_gen_sc + gen_sc_at;
     a.k = k;
     a.n_sc = s;
-    a.d = st.d;
+    a.d = st.levels[0].d;
     a.C = (unsigned)st.C;
     a.n_out = (unsigned)st.n_out;
     const Table& out = P.tables[st.out];
@@ -506,11 +649,6 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
     LaunchShape sh = launch_shape(nr, st.n_out);
     prodsum_generic_kernel<<<sh.grid, sh.block, 0, stream>>>(a);
   }
-}
-
-static bool is_generic(const Step& st) {
-  const int k = (int)st.in.size(), s = (int)st.scalars.size();
-  return !(k >= 1 && k <= MAXK && s <= MAXS);
 }
 
 // (Re)builds everything that depends on the arena row stride RT: the arena itself, the slice-offset
@@ -532,7 +670,7 @@ static void set_row_stride(Executor& ex, int64_t RT) {
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
     if (st.kind != STEP_PRODSUM || !is_generic(st)) continue;
-    for (size_t i = 0; i < st.in.size(); ++i) gin.push_back(in_arg(ex, st, (int)si, (int)i, RT));
+    for (int i = 0; i < st.n_inputs(); ++i) gin.push_back(in_arg(ex, st, (int)si, i, RT));
     for (int id : st.scalars) gsc.push_back(tab_ref(ex, P.tables[id], RT));
   }
   free_dev(ex.d_gen_in);
@@ -541,7 +679,7 @@ static void set_row_stride(Executor& ex, int64_t RT) {
   ex.d_gen_sc = upload(gsc);
   for (size_t j = 0; j < ex.out_steps.size(); ++j) {
     const Step& st = P.steps[ex.out_steps[j]];
-    const Table& t = P.tables[st.in[0].table];
+    const Table& t = P.tables[st.result];
     ex.out_desc[j].t = tab_ref(ex, t, RT);
     ex.out_desc[j].slice = t.kind == T_POT ? t.slice_slot : -1;
   }
@@ -567,7 +705,8 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     ex->in_base.push_back((int64_t)ex->hi_off.size());
     if (st.kind == STEP_PRODSUM) {
       if (st.n_out >= ((int64_t)1 << 31)) throw Error(HB_E_UNSUPPORTED, "a table with 2^31 or more entries");
-      for (const StepInput& in : st.in) {
+      for (int i = 0; i < st.n_inputs(); ++i) {
+        const StepInput& in = flat_input(st, i);
         ex->hi_off.push_back((int64_t)maps.size());
         maps.insert(maps.end(), in.hi.begin(), in.hi.end());
         ex->lo_off.push_back((int64_t)maps.size());
@@ -626,7 +765,7 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     const Step& st = P.steps[si];
     if (st.kind != STEP_PRODSUM) continue;
     if (st.shared) launch_prodsum(*ex, st, (int)si, 32, 1, 0, gi, gs);
-    if (is_generic(st)) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
+    if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
   }
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaDeviceSynchronize());
@@ -674,7 +813,7 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
       const Step& st = P.steps[si];
       if (st.kind != STEP_PRODSUM) continue;
       if (!st.shared) launch_prodsum(*ex, st, (int)si, stride, nr, stream, gi, gs), ++launches;
-      if (is_generic(st)) gi += (int64_t)st.in.size(), gs += (int64_t)st.scalars.size();
+      if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
     }
     mark();
     if (!ex->out_desc.empty()) {

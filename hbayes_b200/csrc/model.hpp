@@ -89,8 +89,18 @@ struct Table {
 
 struct StepInput {
   int table = -1;
-  int64_t sstride = 0;          // stride of the summed variable in this input (0 if absent)
-  std::vector<int32_t> hi, lo;  // entry offset of output index o: hi[o / C] + lo[o % C]
+  std::vector<int64_t> lstride;  // stride (entries) along the summed variable of level 0..own level (0 if absent)
+  std::vector<uint32_t> hi, lo;  // entry offset of output index o: hi[o / C] + lo[o % C]
+};
+
+// One reference operation (itemProduct of a bucket + itemProjectOut of one variable).  A step holds a
+// chain of them, level 0 outermost: the table a level produces is consumed only by the level above it,
+// as the FIRST factor of that level's product, so it never has to exist in memory:
+//   value_l = 0 + sum_{s_l} value_{l+1} * (in_1 * (in_2 * ...))      (value_{L} absent for the innermost level)
+struct Level {
+  int sum_var = -1;  // eliminated vertex, -1 for a final product
+  int d = 1;         // physical terms (1 when nothing is summed or the variable is observed)
+  std::vector<StepInput> in;  // stored inputs in reference chain order (after the fused inner value)
 };
 
 enum StepKind : int32_t { STEP_PRODSUM = 0, STEP_OUTPUT = 1 };
@@ -98,21 +108,22 @@ enum StepKind : int32_t { STEP_PRODSUM = 0, STEP_OUTPUT = 1 };
 struct Step {
   int32_t kind = STEP_PRODSUM;
   bool shared = false;          // all inputs batch-invariant: runs once at upload time, not per row
-  int sum_var = -1;             // eliminated vertex, -1 for a final product
-  int d = 1;                    // physical terms per output (1 when nothing is summed or the variable is observed)
-  std::vector<StepInput> in;    // chain inputs in reference order: v1 * (v2 * (... * vk))
-  std::vector<int> scalars;     // structural scalars, ps = s1 * (s2 * ...), applied as ps * chain
+  std::vector<Level> levels;    // STEP_PRODSUM: >= 1 level
+  std::vector<int> scalars;     // structural scalars of level 0, ps = s1 * (s2 * ...), applied as ps * chain (never fused)
   int out = -1;                 // output table
   int64_t n_out = 1, C = 1, n_hi = 1;
-  // STEP_OUTPUT: normalise table `in[0]` and expand it to the full query scope
+  // STEP_OUTPUT: normalise table `result` and expand it to the full query scope
+  int result = -1;
   int64_t out_col = 0, n_full = 1;
-  std::vector<int32_t> full_map;               // full entry -> physical entry of in[0] (ignoring observed vars)
+  std::vector<int32_t> full_map;               // full entry -> physical entry of `result` (ignoring observed vars)
   std::vector<int> obs_var;                    // observed query variables ...
   std::vector<int64_t> obs_stride, obs_dim;    // ... their stride and dimension in the full layout
-  // provenance, for hb_*_describe_json (the parity hook): the reference-level operation
-  int group = -1;
-  std::vector<std::vector<int>> trace_inputs;  // structural scopes of ALL reference inputs (incl. indicators)
-  std::vector<int> trace_prod, trace_out;
+  int group = -1;                              // provenance: index into Program::groups (first emitter)
+  int n_inputs() const {
+    int n = 0;
+    for (const Level& l : levels) n += (int)l.in.size();
+    return n;
+  }
 };
 
 struct Group {  // one reference-level `marginal` call: a message or a posterior
@@ -151,15 +162,21 @@ struct Program {
   int64_t out_width = 0;         // doubles written per row
   // statistics (per row, physical)
   int64_t stat_prod = 0, stat_reads = 0, stat_row_read = 0, stat_row_write = 0, stat_max_table = 0;
+  int64_t stat_ops = 0;          // reference-level product/sum-out operations behind the per-row steps
 };
 
 struct Query {
   std::vector<int> vars;
 };
+struct CompileOptions {
+  bool fuse = true;    // chain a step into its only consumer (the intermediate table stays in registers)
+  int max_levels = 4;  // levels per fused step
+  int max_inputs = 6;  // stored inputs per fused step
+};
 Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>& observed,
-                    const std::vector<Query>& queries);
+                    const std::vector<Query>& queries, const CompileOptions& opt = CompileOptions());
 Program* compile_ve(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
-                    const std::vector<int>& observed);
+                    const std::vector<int>& observed, const CompileOptions& opt = CompileOptions());
 
 std::string describe_network(const Network& net);
 std::string describe_tree(const Tree& t);
