@@ -21,31 +21,35 @@ net, observed = synth.config_c2()
 pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
 p = hb.JunctionTree(pnet, device=None).program(observed)
 steps = [x for x in p["physical"] if x["kind"] == 0 and not x["shared"]]
-L = [i for i in range(s + 1, e) if "prodsum" in names[i]]
+L = [i for i in range(s + 1, e) if "prodsum" in names[i] or "fused" in names[i] or "staged" in names[i]]
 assert len(L) == len(steps), (len(L), len(steps))
 tot = totb = 0
 recs = []
 for li, st in zip(L, steps):
-    rd = sum(min(i["size"], st["n_out"] * st["d"]) for i in st["in"] if i["kind"] == 3)
+    rd = loads = potloads = 0
+    terms = 1
+    for lv in st["levels"]:
+        terms *= lv["d"]
+        for i in lv["in"]:
+            loads += st["n_out"] * terms
+            if i["kind"] == 3:
+                rd += min(i["size"], st["n_out"] * terms)
+            elif i["kind"] == 1:
+                potloads += st["n_out"] * terms
     b = 8 * (rd + st["n_out"]) * R
-    recs.append((dur[li], b / dur[li], st["n_out"], st["d"], len(st["in"]), sum(1 for i in st["in"] if i["kind"] == 3), grid[li], blk[li]))
+    k = sum(len(lv["in"]) for lv in st["levels"])
+    recs.append((dur[li], b / dur[li], st["n_out"], len(st["levels"]), k, loads, potloads, 1e3 * dur[li] / R / max(loads, 1), grid[li]))
     tot += dur[li]
     totb += b
-others = sum(dur[i] for i in range(s, e) if "prodsum" not in names[i])
-print("pass: %d prodsum launches %.1f us (%.1f%% of pass), other kernels %.1f us; prodsum algorithmic %.0f GB/s (cold-cache, serialised)"
+others = sum(dur[i] for i in range(s, e) if "prodsum" not in names[i] and "fused" not in names[i] and "staged" not in names[i])
+print("pass: %d product/sum-out launches %.1f us (%.1f%% of pass), other kernels %.1f us; algorithmic %.0f GB/s (cold-cache, serialised)"
       % (len(L), tot / 1e3, 100 * tot / (tot + others), others / 1e3, totb / tot))
 recs.sort(reverse=True)
 print("top launches:")
-for r in recs[:20]:
-    print("  %8.0f ns %6.0f GB/s n_out=%5d d=%d k=%d row_inputs=%d grid=%s block=%s" % r)
-b = collections.defaultdict(lambda: [0, 0, 0])
-for (d_, bw, n, dd, k, ri, _, _) in recs:
-    b[(k, ri)][0] += d_
-    b[(k, ri)][1] += bw * d_
-    b[(k, ri)][2] += 1
-print("by (k inputs, per-row inputs): launches, time share, mean GB/s")
-for k in sorted(b):
-    print("  ", k, b[k][2], "%.3f" % (b[k][0] / tot), "%.0f" % (b[k][1] / b[k][0]))
+for r in recs[:25]:
+    print("  %8.0f ns %6.0f GB/s n_out=%5d levels=%d k=%d loads/row=%5d (pot %5d)  %.3f ps/load/row grid=%s" % r)
+tl = sum(r[5] for r in recs)
+print("loads per row %d, potential loads %d; mean %.3f ps per load per row" % (tl, sum(r[6] for r in recs), 1e3 * tot / R / tl))
 for i in range(s, e):
-    if "prodsum" not in names[i]:
+    if "prodsum" not in names[i] and "fused" not in names[i] and "staged" not in names[i]:
         print("  other:", names[i][-60:], dur[i], "ns")
