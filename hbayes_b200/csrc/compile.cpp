@@ -352,7 +352,10 @@ struct Compiler {
         if (q < 0 || uses[tid] != 1) continue;
         const Step& Q = P.steps[q];
         if (Q.shared != S.shared || !Q.scalars.empty()) continue;
-        if ((int)(S.levels.size() + Q.levels.size()) > opt.max_levels || S.n_inputs() - 1 + Q.n_inputs() > opt.max_inputs) continue;
+        const int q_inner = (int)Q.levels.back().in.size();
+        if ((int)(S.levels.size() + Q.levels.size()) > opt.max_levels || q_inner < 1 || q_inner > opt.max_inner ||
+            S.n_inputs() - 1 + Q.n_inputs() - q_inner > opt.max_outer)
+          continue;
         std::vector<int> want = P.tables[S.out].pscope;  // S's physical product scope
         if (S.levels[0].sum_var >= 0) want.push_back(S.levels[0].sum_var);
         std::vector<int> have = P.tables[tid].pscope;

@@ -231,96 +231,14 @@ struct FusedArgs {
 
 constexpr int FU = 2;  // output entries evaluated in lock-step by one thread of the fused kernel
 
-// right fold of the stored inputs of level `level` at the current offsets (+ s * stride of that level):
-// r = in_1 * (in_2 * (...)); returns false when the level has no stored input.
-template <int K, int V>
-__device__ __forceinline__ bool level_chain(const FusedArgs<K>& a, const double* const (&p0)[K], const double* const (&p1)[K],
-                                            const bool (&isrow)[K], const unsigned (&cur)[FU][K], int level, int s, Rows<V> (&r)[FU]) {
-  typedef Rows<V> R;
-  bool have = false;
-#pragma unroll
-  for (int i = K - 1; i >= 0; --i) {
-    if (a.lvl[i] == level) {
-      const unsigned ds = s * a.st[i][level];
-#pragma unroll
-      for (int u = 0; u < FU; ++u) {
-        const R x = R::load(p0[i], p1[i], isrow[i], cur[u][i] + ds);
-        r[u] = have ? x.mul(r[u]) : x;
-      }
-      have = true;
-    }
-  }
-  return have;
-}
-
-// The nest of sums is walked as an odometer over the outer levels; the innermost level (where most of
-// the loads are) is unrolled four terms at a time so that 4 * k * FU loads are in flight per thread.
-// `cur` holds the entry offsets of the FU output entries in every input; v receives their values.
-template <int K, int V>
-__device__ __forceinline__ void eval_entries(const FusedArgs<K>& a, const double* const (&p0)[K], const double* const (&p1)[K],
-                                              const bool (&isrow)[K], unsigned (&cur)[FU][K], Rows<V> (&v)[FU]) {
-  typedef Rows<V> R;
-  const int inner = a.L - 1, d_inner = a.d[inner];
-  R acc[MAXL][FU];
-  int digit[MAXL];
-#pragma unroll
-  for (int l = 0; l < MAXL; ++l) {
-    digit[l] = 0;
-#pragma unroll
-    for (int u = 0; u < FU; ++u) acc[l][u] = R::splat(0.0, 0.0);
-  }
-  for (;;) {
-    // innermost level: value = 0 + sum_s chain(s)
-#pragma unroll
-    for (int u = 0; u < FU; ++u) v[u] = R::splat(0.0, 0.0);
-    for (int s0 = 0; s0 < d_inner; s0 += 4) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (s0 + q < d_inner) {
-          R c[FU];
-          level_chain<K, V>(a, p0, p1, isrow, cur, inner, s0 + q, c);
-#pragma unroll
-          for (int u = 0; u < FU; ++u) v[u] = v[u].add(c[u]);
-        }
-      }
-    }
-    // carry the finished value up through the outer levels
-    int l = inner - 1;
-#pragma unroll
-    for (int ll = MAXL - 2; ll >= 0; --ll) {
-      if (ll == l) {
-        R r[FU];
-        const bool have = level_chain<K, V>(a, p0, p1, isrow, cur, ll, 0, r);
-#pragma unroll
-        for (int u = 0; u < FU; ++u) acc[ll][u] = acc[ll][u].add(have ? v[u].mul(r[u]) : v[u]);
-        if (++digit[ll] < a.d[ll]) {
-#pragma unroll
-          for (int u = 0; u < FU; ++u)
-#pragma unroll
-            for (int i = 0; i < K; ++i) cur[u][i] += a.st[i][ll];
-          l = -2;  // next term of this level: back to the innermost loop
-        } else {
-          const unsigned back = (unsigned)(a.d[ll] - 1);
-#pragma unroll
-          for (int u = 0; u < FU; ++u) {
-#pragma unroll
-            for (int i = 0; i < K; ++i) cur[u][i] -= back * a.st[i][ll];
-            v[u] = acc[ll][u];
-            acc[ll][u] = R::splat(0.0, 0.0);
-          }
-          digit[ll] = 0;
-          l = ll - 1;
-        }
-      }
-    }
-    if (l == -1) break;  // level 0 finished: v is the output entry
-  }
-}
-
-// Streaming form: inputs are read from global memory (row tables: one coalesced 512-byte segment per warp
-// access).  Used when the inputs of a step are too large to stage or are read only once anyway.
-template <int K, int V>
-__global__ void __launch_bounds__(BLOCK) fused_kernel(const __grid_constant__ FusedArgs<K> a) {
+// Fused chain kernel.  Template: KO = stored inputs of the outer levels (flattened first, level from
+// lvl[]), KI = stored inputs of the innermost level (the last KI inputs), DI = terms of the innermost
+// sum (0: run-time count).  The innermost level is where the loads are: it is fully static, so all its
+// FU * DI * KI loads are issued back to back.  The outer levels are walked as an odometer (run-time
+// uniform control flow, executed once per finished inner sum).
+template <int KO, int KI, int V, int DI>
+__global__ void __launch_bounds__(BLOCK, 2) fused_kernel(const __grid_constant__ FusedArgs<KO + KI> a) {
+  constexpr int K = KO + KI;
   typedef Rows<V> R;
   const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (row >= a.nr) return;
@@ -341,6 +259,11 @@ __global__ void __launch_bounds__(BLOCK) fused_kernel(const __grid_constant__ Fu
   const unsigned o_end = min(a.n_out, o + per);
   if (o >= o_end) return;
   unsigned hiI = o / a.C, loI = o - hiI * a.C;
+  const int inner = a.L - 1;
+  const int d_inner = DI > 0 ? DI : a.d[inner];
+  unsigned sti[KI];  // stride of the innermost summed variable in the innermost inputs
+#pragma unroll
+  for (int i = 0; i < KI; ++i) sti[i] = a.st[KO + i][inner];
   while (o < o_end) {
     unsigned cur[FU][K];
     const int nu = min((unsigned)FU, o_end - o);
@@ -355,82 +278,86 @@ __global__ void __launch_bounds__(BLOCK) fused_kernel(const __grid_constant__ Fu
         for (int i = 0; i < K; ++i) cur[u][i] = cur[0][i];  // tail: entry 0 again, never stored
       }
     }
-    R v[FU];
-    eval_entries<K, V>(a, p0, p1, isrow, cur, v);
+    R acc[MAXL - 1][FU], v[FU];
+    int digit[MAXL - 1];
+#pragma unroll
+    for (int l = 0; l < MAXL - 1; ++l) {
+      digit[l] = 0;
+#pragma unroll
+      for (int u = 0; u < FU; ++u) acc[l][u] = R::splat(0.0, 0.0);
+    }
+    for (;;) {
+      // ---- innermost level: v = 0 + sum_s in_1 * (in_2 * ...), static shape ----
+#pragma unroll
+      for (int u = 0; u < FU; ++u) v[u] = R::splat(0.0, 0.0);
+      if (DI > 0) {
+#pragma unroll
+        for (int q = 0; q < (DI > 0 ? DI : 1); ++q) {
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], cur[u][K - 1] + q * sti[KI - 1]);
+#pragma unroll
+            for (int i = KI - 2; i >= 0; --i) c = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur[u][KO + i] + q * sti[i]).mul(c);
+            v[u] = v[u].add(c);
+          }
+        }
+      } else {
+        for (int q = 0; q < d_inner; ++q) {
+#pragma unroll
+          for (int u = 0; u < FU; ++u) {
+            R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], cur[u][K - 1] + q * sti[KI - 1]);
+#pragma unroll
+            for (int i = KI - 2; i >= 0; --i) c = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur[u][KO + i] + q * sti[i]).mul(c);
+            v[u] = v[u].add(c);
+          }
+        }
+      }
+      // ---- carry the finished value up through the outer levels ----
+      int l = inner - 1;
+#pragma unroll
+      for (int ll = MAXL - 2; ll >= 0; --ll) {
+        if (ll == l) {
+          R r[FU];
+          bool have = false;
+#pragma unroll
+          for (int i = KO - 1; i >= 0; --i) {
+            if (a.lvl[i] == ll) {
+#pragma unroll
+              for (int u = 0; u < FU; ++u) {
+                const R x = R::load(p0[i], p1[i], isrow[i], cur[u][i]);
+                r[u] = have ? x.mul(r[u]) : x;
+              }
+              have = true;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < FU; ++u) acc[ll][u] = acc[ll][u].add(have ? v[u].mul(r[u]) : v[u]);
+          if (++digit[ll] < a.d[ll]) {
+#pragma unroll
+            for (int u = 0; u < FU; ++u)
+#pragma unroll
+              for (int i = 0; i < K; ++i) cur[u][i] += a.st[i][ll];
+            l = -2;  // next term of this level: back to the innermost sum
+          } else {
+            const unsigned back = (unsigned)(a.d[ll] - 1);
+#pragma unroll
+            for (int u = 0; u < FU; ++u) {
+#pragma unroll
+              for (int i = 0; i < K; ++i) cur[u][i] -= back * a.st[i][ll];
+              v[u] = acc[ll][u];
+              acc[ll][u] = R::splat(0.0, 0.0);
+            }
+            digit[ll] = 0;
+            l = ll - 1;
+          }
+        }
+      }
+      if (l == -1) break;  // level 0 finished (or there is no outer level): v is the output entry
+    }
 #pragma unroll
     for (int u = 0; u < FU; ++u)
       if (u < nu) v[u].store(outp + (size_t)(o + u) * om);
     o += nu;
-  }
-}
-
-// Staged form (the clique-message kernel proper): a CTA owns a tile of TR = 2 * blockDim.x evidence rows
-// and ALL output entries of the step.  It first copies its rows of every per-row input table into shared
-// memory (each entry read from HBM exactly once, 16-byte coalesced), then evaluates the outputs from
-// shared memory: the joint table of a bucket is enumerated many times over small inputs, so the re-reads
-// are shared-memory hits instead of L2 round trips.  Index maps are the unscaled ones (times TR here);
-// the strides in `st` arrive pre-multiplied by TR.
-template <int K>
-struct StagedArgs {
-  FusedArgs<K> f;
-  int sm_off[K];  // entry offset of each staged input inside the staging area
-  int size[K];    // entries of each staged input
-};
-
-template <int K>
-__global__ void __launch_bounds__(BLOCK) staged_kernel(const __grid_constant__ StagedArgs<K> sa) {
-  constexpr int V = 2;
-  typedef Rows<V> R;
-  const FusedArgs<K>& a = sa.f;
-  extern __shared__ double2 staging[];
-  const int TRt = blockDim.x, TR = TRt * V;
-  const int row0 = blockIdx.x * TR;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    if (a.in[i].t.is_row) {
-      const double* g = a.in[i].t.base + row0 + threadIdx.x * V;
-      double2* s2 = staging + (size_t)sa.sm_off[i] * TRt + threadIdx.x;
-      const int n = sa.size[i];
-#pragma unroll 4
-      for (int e = threadIdx.y; e < n; e += blockDim.y) s2[(size_t)e * TRt] = *reinterpret_cast<const double2*>(g + (size_t)e * a.RT);
-    }
-  }
-  __syncthreads();
-  const int row = row0 + threadIdx.x * V;
-  if (row >= a.nr) return;
-  const double* p0[K];
-  const double* p1[K];
-  bool isrow[K];
-  unsigned mul[K];
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    isrow[i] = a.in[i].t.is_row != 0;
-    if (isrow[i]) {
-      p0[i] = p1[i] = reinterpret_cast<const double*>(staging + (size_t)sa.sm_off[i] * TRt + threadIdx.x);
-      mul[i] = TR;
-    } else {
-      p0[i] = row_ptr(a.in[i].t, row);
-      p1[i] = row_ptr(a.in[i].t, row + 1);
-      mul[i] = 1;
-    }
-  }
-  double* outp = a.out + (a.out_is_row ? row : 0);
-  const size_t om = a.out_is_row ? (size_t)a.RT : 1;
-  for (unsigned o = threadIdx.y * FU; o < a.n_out; o += blockDim.y * FU) {
-    unsigned cur[FU][K];
-    const int nu = min((unsigned)FU, a.n_out - o);
-#pragma unroll
-    for (int u = 0; u < FU; ++u) {
-      const unsigned ou = u < nu ? o + u : o;
-      const unsigned hiI = ou / a.C, loI = ou - hiI * a.C;
-#pragma unroll
-      for (int i = 0; i < K; ++i) cur[u][i] = (__ldg(a.in[i].hi + hiI) + __ldg(a.in[i].lo + loI)) * mul[i];
-    }
-    R v[FU];
-    eval_entries<K, V>(a, p0, p1, isrow, cur, v);
-#pragma unroll
-    for (int u = 0; u < FU; ++u)
-      if (u < nu) v[u].store(outp + (size_t)(o + u) * om);
   }
 }
 
@@ -712,45 +639,32 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
     launch_kv<K, 1>(a, a.d, launch_shape(nr, st.n_out), stream);
 }
 
-constexpr int STAGE_BYTES = 100 * 1024;  // staging area per CTA: two CTAs per SM
+constexpr int MAX_KO = 4, MAX_KI = 3;  // the same limits the compiler's fusion pass uses (CompileOptions)
 
-template <int K>
+template <int KO, int KI, int V>
+void launch_fused_d(const FusedArgs<KO + KI>& a, int di, const LaunchShape& sh, cudaStream_t stream) {
+  switch (di) {
+    case 2: fused_kernel<KO, KI, V, 2><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    case 3: fused_kernel<KO, KI, V, 3><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    case 4: fused_kernel<KO, KI, V, 4><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    default: fused_kernel<KO, KI, V, 0><<<sh.grid, sh.block, 0, stream>>>(a); break;
+  }
+}
+
+template <int KO, int KI>
 void launch_fused(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
+  constexpr int K = KO + KI;
   const Program& P = *ex.P;
-  StagedArgs<K> sa;
-  memset(&sa, 0, sizeof sa);
-  FusedArgs<K>& a = sa.f;
+  FusedArgs<K> a;
+  memset(&a, 0, sizeof a);
   a.L = (int)st.levels.size();
   for (int l = 0; l < a.L; ++l) a.d[l] = st.levels[l].d;
-  // staging pays when the per-row inputs are small and enumerated several times
-  int64_t row_entries = 0, row_loads = 0, terms = 1;
-  for (int l = 0, i = 0; l < a.L; ++l) {
-    terms *= st.levels[l].d;
-    for (const StepInput& in : st.levels[l].in) {
-      const Table& t = P.tables[in.table];
-      if (t.kind == T_ROW) sa.sm_off[i] = (int)row_entries, sa.size[i] = (int)t.size, row_entries += t.size, row_loads += st.n_out * terms;
-      ++i;
-    }
-  }
-  int TR = 0;
-  static const bool stage_enabled = getenv("HB_STAGE") && atoi(getenv("HB_STAGE")) != 0;  // experimental: slower than streaming so far
-  if (stage_enabled && nr >= 64 && row_entries > 0 && 2 * row_loads >= 3 * row_entries)
-    for (int cand : {64, 32, 16})
-      if (row_entries * cand * 8 <= STAGE_BYTES) {
-        TR = cand;
-        break;
-      }
   for (int i = 0; i < K; ++i) {
     int level = 0;
     const StepInput& in = flat_input(st, i, &level);
-    const Table& t = P.tables[in.table];
     a.in[i] = in_arg(ex, st, si, i, RT);
-    if (TR && t.kind == T_ROW) {  // unscaled maps; the kernel multiplies by TR
-      a.in[i].hi = ex.d_maps + ex.hi_off[ex.in_base[si] + i];
-      a.in[i].lo = ex.d_maps + ex.lo_off[ex.in_base[si] + i];
-    }
     a.lvl[i] = level;
-    const int64_t mult = t.kind == T_ROW ? (TR ? TR : RT) : 1;
+    const int64_t mult = P.tables[in.table].kind == T_ROW ? RT : 1;
     for (int m = 0; m <= level; ++m) a.st[i][m] = (unsigned)(in.lstride[m] * mult);
   }
   a.C = (unsigned)st.C;
@@ -760,24 +674,21 @@ void launch_fused(const Executor& ex, const Step& st, int si, int64_t RT, int nr
   a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
   a.nr = nr;
   a.RT = RT;
-  if (!TR && a.L == 1) return launch_k<K>(ex, st, si, RT, nr, stream);  // plain streaming step: the specialised kernel
-  if (TR) {
-    const int bx = TR / 2;
-    const int by = (int)std::max<int64_t>(1, std::min<int64_t>(BLOCK / bx, (st.n_out + FU - 1) / FU));
-    dim3 block(bx, by), grid((nr + TR - 1) / TR, 1);
-    staged_kernel<K><<<grid, block, (size_t)row_entries * TR * 8, stream>>>(sa);
-  } else if (nr >= 64) {
-    LaunchShape sh = launch_shape((nr + 1) / 2, st.n_out);
-    fused_kernel<K, 2><<<sh.grid, sh.block, 0, stream>>>(a);
-  } else {
-    LaunchShape sh = launch_shape(nr, st.n_out);
-    fused_kernel<K, 1><<<sh.grid, sh.block, 0, stream>>>(a);
-  }
+  const int di = st.levels.back().d;
+  if (nr >= 64)
+    launch_fused_d<KO, KI, 2>(a, di, launch_shape((nr + 1) / 2, st.n_out), stream);
+  else
+    launch_fused_d<KO, KI, 1>(a, 0, launch_shape(nr, st.n_out), stream);  // tiny batches: the run-time-count form
 }
 
-template <int K>
-void allow_staging() {
-  HB_CUDA(cudaFuncSetAttribute(staged_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+template <int KO>
+void launch_fused_ki(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
+  switch ((int)st.levels.back().in.size()) {
+    case 1: launch_fused<KO, 1>(ex, st, si, RT, nr, stream); break;
+    case 2: launch_fused<KO, 2>(ex, st, si, RT, nr, stream); break;
+    case 3: launch_fused<KO, 3>(ex, st, si, RT, nr, stream); break;
+    default: throw Error(HB_E_UNSUPPORTED, "fused step: innermost level has 0 or more than 3 stored inputs");
+  }
 }
 
 }  // namespace
@@ -791,16 +702,16 @@ static bool is_generic(const Step& st) {
 static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream, int64_t gen_in_at,
                            int64_t gen_sc_at) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
-  static const bool stage_l1 = getenv("HB_STAGE") && atoi(getenv("HB_STAGE")) != 0;
-  if (st.levels.size() > 1 || (stage_l1 && s == 0 && k >= 1 && k <= MAXK && nr >= 64)) {
-    if ((int)st.levels.size() > MAXL || k < 1 || k > MAXK || s) throw Error(HB_E_UNSUPPORTED, "fused step exceeds the kernel limits");
-    switch (k) {
-      case 1: launch_fused<1>(ex, st, si, RT, nr, stream); break;
-      case 2: launch_fused<2>(ex, st, si, RT, nr, stream); break;
-      case 3: launch_fused<3>(ex, st, si, RT, nr, stream); break;
-      case 4: launch_fused<4>(ex, st, si, RT, nr, stream); break;
-      case 5: launch_fused<5>(ex, st, si, RT, nr, stream); break;
-      default: launch_fused<6>(ex, st, si, RT, nr, stream); break;
+  if (st.levels.size() > 1) {
+    const int ki = (int)st.levels.back().in.size();
+    if ((int)st.levels.size() > MAXL || s) throw Error(HB_E_UNSUPPORTED, "fused step exceeds the kernel limits");
+    switch (k - ki) {
+      case 0: launch_fused_ki<0>(ex, st, si, RT, nr, stream); break;
+      case 1: launch_fused_ki<1>(ex, st, si, RT, nr, stream); break;
+      case 2: launch_fused_ki<2>(ex, st, si, RT, nr, stream); break;
+      case 3: launch_fused_ki<3>(ex, st, si, RT, nr, stream); break;
+      case 4: launch_fused_ki<4>(ex, st, si, RT, nr, stream); break;
+      default: throw Error(HB_E_UNSUPPORTED, "fused step: more than 4 stored inputs in the outer levels");
     }
   } else if (!is_generic(st)) {
     switch (k) {
@@ -939,7 +850,6 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
   }
   ex->workspace = workspace_bytes;
   // batch-invariant steps: evaluated once, here, with a single pseudo-row
-  allow_staging<1>(), allow_staging<2>(), allow_staging<3>(), allow_staging<4>(), allow_staging<5>(), allow_staging<6>();
   set_row_stride(*ex, 64);
   int64_t gi = 0, gs = 0;
   for (size_t si = 0; si < P.steps.size(); ++si) {

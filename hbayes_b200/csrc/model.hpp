@@ -171,7 +171,8 @@ struct Query {
 struct CompileOptions {
   bool fuse = true;    // chain a step into its only consumer (the intermediate table stays in registers)
   int max_levels = 4;  // levels per fused step
-  int max_inputs = 6;  // stored inputs per fused step
+  int max_outer = 4;   // stored inputs of the outer levels of a fused step
+  int max_inner = 3;   // stored inputs of its innermost level
 };
 Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>& observed,
                     const std::vector<Query>& queries, const CompileOptions& opt = CompileOptions());
