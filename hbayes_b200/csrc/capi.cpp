@@ -2,6 +2,7 @@
 // host<->device staging.  No arithmetic happens here.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -81,12 +82,19 @@ struct Session {
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool timing = false;
   Executor* last_ex = nullptr;  // executor of the last batch call (for hb_*_last_timing)
+  // host-buffer batches are cut into chunks: the device->host copy of chunk i (copy_stream) overlaps the
+  // kernels of chunk i+1 (stream)
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_done;
+  int64_t chunk_rows = 1 << 18;
 
   ~Session() {
     if (device >= 0) cudaSetDevice(device);
     cache.clear();
     if (d_ev) cudaFree(d_ev);
     if (d_out) cudaFree(d_out);
+    for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
   // the device-resident form of a compiled program, created on first use
   Executor* executor(Compiled& c) {
@@ -154,21 +162,37 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
   Compiled& c0 = get(observed_of_row(evidence, n_vars));
   const int64_t width = c0.prog->out_width;
   s.reserve((size_t)n_rows * n_vars, (size_t)n_rows * width * sizeof(double));
+  if (!s.copy_stream) cuda_ok(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)n_rows * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
-  executor_run(s.executor(c0), n_rows, s.d_ev, s.d_out, s.stream, &rs);
-  s.note(c0, rs, false);
+  if (const char* env = getenv("HB_CHUNK_ROWS")) s.chunk_rows = std::max<int64_t>(64, atoll(env));
+  const int64_t n_chunks = std::max<int64_t>(1, (n_rows + s.chunk_rows - 1) / s.chunk_rows);
+  const int64_t per = ((n_rows + n_chunks - 1) / n_chunks + 63) / 64 * 64;
+  Executor* ex0 = s.executor(c0);
+  bool first_chunk = true;
+  for (int64_t r0 = 0, c = 0; r0 < n_rows; r0 += per, ++c) {
+    const int64_t m = std::min<int64_t>(per, n_rows - r0);
+    executor_run(ex0, m, s.d_ev + r0 * n_vars, s.d_out + r0 * width, s.stream, &rs);
+    s.note(c0, rs, !first_chunk);
+    first_chunk = false;
+    if ((int64_t)s.chunk_done.size() <= c) {
+      cudaEvent_t e;
+      cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+      s.chunk_done.push_back(e);
+    }
+    cuda_ok(cudaEventRecord(s.chunk_done[c], s.stream), "cudaEventRecord");
+    cuda_ok(cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c], 0), "cudaStreamWaitEvent");
+    cuda_ok(cudaMemcpyAsync(out + r0 * width, s.d_out + r0 * width, (size_t)m * width * sizeof(double), cudaMemcpyDeviceToHost, s.copy_stream),
+            "cudaMemcpy(out)");
+  }
   bool uniform = true;
   try {
-    executor_check(s.executor(c0), s.stream);
+    executor_check(ex0, s.stream);
   } catch (const Error& e) {
     if (e.code != HB_E_ARG) throw;
     uniform = false;
   }
-  if (uniform) {
-    cuda_ok(cudaMemcpyAsync(out, s.d_out, (size_t)n_rows * width * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
-    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
-    return;
-  }
+  cuda_ok(cudaStreamSynchronize(s.copy_stream), "cudaStreamSynchronize");
+  if (uniform) return;
   // mixed observed sets: group rows on the host
   std::map<std::vector<int>, std::vector<int64_t>> groups;
   for (int64_t r = 0; r < n_rows; ++r) groups[observed_of_row(evidence + r * n_vars, n_vars)].push_back(r);

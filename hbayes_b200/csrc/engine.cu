@@ -440,50 +440,72 @@ struct OutDesc {
   int obs_var[MAXOBS], obs_stride[MAXOBS], obs_dim[MAXOBS];
 };
 
+struct OutChunk {           // a run of consecutive queries whose columns fit one shared-memory tile
+  int desc_begin, desc_end;
+  int col_begin, width;
+  int direct;               // a single very wide query: written straight to the caller's matrix, no tile
+};
+
 struct OutArgs {
   const OutDesc* desc;
-  int n_desc;
+  const OutChunk* chunks;
   const uint32_t* maps;
   const int32_t* rowoff;   // [n_slices][RT]
-  const double* arena;
   const int8_t* ev;        // this tile
   double* out;             // this tile: [nr][width]
   int nr, n_vars;
   long long RT, width;
 };
 
-// thread = (row, query).  norm = 0 + x0 + x1 + ... over the result's layout order; every entry of the
-// full table is (1.0 / norm) * value, where the value of an entry that contradicts the evidence is 0.0
-// (so zero-probability evidence gives NaN exactly as 0 * (1/0) does in the reference).
+constexpr int OUT_ROWS = 64;     // evidence rows per CTA
+constexpr int OUT_COLS = 128;    // at most this many output columns per chunk (a single wider query gets its own chunk)
+
+// CTA = 64 rows x one column chunk.  Phase 1: thread = (row, query) -- norm = 0 + x0 + x1 + ... over the
+// result's layout order, every entry of the full table is (1.0 / norm) * value, where an entry that
+// contradicts the evidence has the value 0.0 (zero-probability evidence gives NaN exactly as 0 * (1/0)
+// does in the reference); arena reads are coalesced along the rows, the tile goes to shared memory.
+// Phase 2: the tile is written out row by row, 256-byte coalesced segments of the caller's matrix.
 __global__ void __launch_bounds__(BLOCK) output_kernel(const OutArgs a) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = (int)(gid % a.nr);
-  const int q = (int)(gid / a.nr);
-  if (q >= a.n_desc) return;
-  const OutDesc& d = a.desc[q];
-  const double* p = nullptr;
-  long long m = 1;
-  if (!d.t.is_one) {
-    if (d.t.is_row) {
-      p = d.t.base + row;
-      m = a.RT;
-    } else
-      p = d.t.base + (d.slice >= 0 ? (long long)a.rowoff[(long long)d.slice * a.RT + row] : 0ll);
+  extern __shared__ double tile[];  // [OUT_ROWS][width + 1]
+  const OutChunk ch = a.chunks[blockIdx.y];
+  const int row0 = blockIdx.x * OUT_ROWS;
+  const int pitch = ch.width + 1;
+  const int r = threadIdx.x % OUT_ROWS, row = row0 + r;
+  if (row < a.nr) {
+    const int8_t* e = a.ev + (long long)row * a.n_vars;
+    for (int q = ch.desc_begin + threadIdx.x / OUT_ROWS; q < ch.desc_end; q += BLOCK / OUT_ROWS) {
+      const OutDesc& d = a.desc[q];
+      const double* p = nullptr;
+      long long m = 1;
+      if (!d.t.is_one) {
+        if (d.t.is_row) {
+          p = d.t.base + row;
+          m = a.RT;
+        } else
+          p = d.t.base + (d.slice >= 0 ? (long long)a.rowoff[(long long)d.slice * a.RT + row] : 0ll);
+      }
+      const uint32_t* order = a.maps + d.order_off;
+      const uint32_t* fmap = a.maps + d.map_off;
+      double norm = 0.0;
+      for (int j = 0; j < d.n_phys; ++j) norm = __dadd_rn(norm, p ? p[(long long)order[j] * m] : 1.0);
+      const double inv = __ddiv_rn(1.0, norm);
+      int st[MAXOBS];
+      for (int j = 0; j < d.n_obs; ++j) st[j] = e[d.obs_var[j]];
+      double* o = ch.direct ? a.out + (long long)row * a.width + d.out_col : tile + r * pitch + (int)(d.out_col - ch.col_begin);
+      for (int f = 0; f < d.n_full; ++f) {
+        bool match = true;
+        for (int j = 0; j < d.n_obs; ++j) match &= ((f / d.obs_stride[j]) % d.obs_dim[j]) == st[j];
+        const double v = match ? (p ? p[(long long)fmap[f] * m] : 1.0) : 0.0;
+        o[f] = __dmul_rn(inv, v);
+      }
+    }
   }
-  const uint32_t* order = a.maps + d.order_off;
-  const uint32_t* fmap = a.maps + d.map_off;
-  double norm = 0.0;
-  for (int j = 0; j < d.n_phys; ++j) norm = __dadd_rn(norm, p ? p[(long long)order[j] * m] : 1.0);
-  const double inv = __ddiv_rn(1.0, norm);
-  const int8_t* e = a.ev + (long long)row * a.n_vars;
-  int st[MAXOBS];
-  for (int j = 0; j < d.n_obs; ++j) st[j] = e[d.obs_var[j]];
-  double* o = a.out + (long long)row * a.width + d.out_col;
-  for (int f = 0; f < d.n_full; ++f) {
-    bool match = true;
-    for (int j = 0; j < d.n_obs; ++j) match &= ((f / d.obs_stride[j]) % d.obs_dim[j]) == st[j];
-    const double v = match ? (p ? p[(long long)fmap[f] * m] : 1.0) : 0.0;
-    o[f] = __dmul_rn(inv, v);
+  if (ch.direct) return;
+  __syncthreads();
+  const int rows = min(OUT_ROWS, a.nr - row0);
+  for (int idx = threadIdx.x; idx < rows * ch.width; idx += BLOCK) {
+    const int rr = idx / ch.width, c = idx - rr * ch.width;
+    a.out[(long long)(row0 + rr) * a.width + ch.col_begin + c] = tile[rr * pitch + c];
   }
 }
 
@@ -501,6 +523,9 @@ struct Executor {
   int8_t* d_observed = nullptr;
   int32_t *d_dims = nullptr, *d_sl_begin = nullptr, *d_sl_var = nullptr, *d_sl_stride = nullptr;
   OutDesc* d_out_desc = nullptr;
+  OutChunk* d_out_chunks = nullptr;
+  std::vector<OutChunk> out_chunks;
+  int out_tile_bytes = 0;
   InArg* d_gen_in = nullptr;     // descriptors of the generic-path steps (rebuilt when RT changes)
   TabRef* d_gen_sc = nullptr;
   int* d_flag = nullptr;
@@ -526,7 +551,7 @@ struct Executor {
     cudaSetDevice(device);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
-                    (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_gen_in,
+                    (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_out_chunks, (void*)d_gen_in,
                     (void*)d_gen_sc, (void*)d_flag})
       if (p) cudaFree(p);
   }
@@ -829,6 +854,23 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     }
   }
   ex->d_maps = upload(maps);
+  // column chunks of the normalise/expand kernel
+  {
+    int max_w = 1;
+    constexpr int MAX_TILE_COLS = 200 * 1024 / (OUT_ROWS * 8) - 1;
+    for (size_t j = 0; j < ex->out_desc.size(); ++j) {
+      const OutDesc& d = ex->out_desc[j];
+      const bool wide = d.n_full > MAX_TILE_COLS;
+      if (wide || ex->out_chunks.empty() || ex->out_chunks.back().direct || ex->out_chunks.back().width + d.n_full > OUT_COLS)
+        ex->out_chunks.push_back(OutChunk{(int)j, (int)j, (int)d.out_col, 0, wide ? 1 : 0});
+      ex->out_chunks.back().desc_end = (int)j + 1;
+      ex->out_chunks.back().width += d.n_full;
+      if (!wide) max_w = std::max(max_w, ex->out_chunks.back().width);
+    }
+    ex->out_tile_bytes = OUT_ROWS * (max_w + 1) * (int)sizeof(double);
+    HB_CUDA(cudaFuncSetAttribute(output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ex->d_out_chunks = upload(ex->out_chunks);
+  }
   // evidence preparation tables
   std::vector<int8_t> obs(P.is_observed.begin(), P.is_observed.end());
   std::vector<int32_t> dims(net.dims.begin(), net.dims.end()), sl_begin = {0}, sl_var, sl_stride;
@@ -908,10 +950,10 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     }
     mark();
     if (!ex->out_desc.empty()) {
-      OutArgs oa{ex->d_out_desc, (int)ex->out_desc.size(), ex->d_maps, ex->d_rowoff, ex->d_arena, d_evidence + r0 * n_vars,
+      OutArgs oa{ex->d_out_desc, ex->d_out_chunks, ex->d_maps, ex->d_rowoff, d_evidence + r0 * n_vars,
                  d_out + r0 * P.out_width, nr, n_vars, stride, P.out_width};
-      const int64_t threads = (int64_t)nr * (int64_t)ex->out_desc.size();
-      output_kernel<<<(unsigned)((threads + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>(oa);
+      dim3 grid((nr + OUT_ROWS - 1) / OUT_ROWS, (unsigned)ex->out_chunks.size());
+      output_kernel<<<grid, BLOCK, ex->out_tile_bytes, stream>>>(oa);
       ++launches;
     }
     mark();
