@@ -153,6 +153,7 @@ def main():
 
     import hbayes_b200 as hb
     from hbayes_b200 import synth
+    from hbayes_b200.dist import max_over_ranks, whole_job_rate
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,10 +194,7 @@ def main():
             fn()
         e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1), device="cuda")
 
     dev_step = lambda: jt.posteriors_batch(d_ev, d_out)
     e2e_step = lambda: jt.posteriors_batch(ev_pinned, out_pinned)
@@ -218,8 +216,8 @@ def main():
     ms_e2e = timed(e2e_step, e2e_steps)
 
     if rank == 0:
-        value = world * rows * args.steps / (ms / 1e3)
-        e2e_value = world * rows * e2e_steps / (ms_e2e / 1e3)
+        value = whole_job_rate([rows] * world, args.steps, ms)
+        e2e_value = whole_job_rate([rows] * world, e2e_steps, ms_e2e)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

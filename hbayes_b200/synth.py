@@ -187,3 +187,24 @@ def config_c2_evidence(net, observed, n_rows):
 
 def config_c5(rows=20, cols=20, seed=400001):
     return grid_net(rows, cols, seed)
+
+
+def config_c3():
+    """500-node random DAG, 2-4 states, <=3 parents from a window of 4 predecessors; net seed 500003 is the
+    first of 500001.. whose maximal cluster under the REFERENCE triangulation (static weightedEdges metric,
+    SURVEY A.7) lands in [2^19.5, 2^20.5] state combinations (2^20.2); 125 observed variables (seed 500004)."""
+    net = random_dag_net(500, 500003, states=(2, 4), max_parents=3, window=4)
+    observed = choose_observed(500, 125, 500004)
+    return net, observed
+
+
+def config_c3_evidence(net, observed, n_rows):
+    return evidence_matrix(net, n_rows, observed, 500005)
+
+
+def config_c5_query(net, metric_order):
+    """r = [last node], p = reference minFillOrder minus r, 10 % of the other variables observed (seed 400002)."""
+    r = [net.n - 1]
+    p = [v for v in metric_order if v not in r]
+    observed = choose_observed(net.n - 1, max(1, net.n // 10), 400002)
+    return p, r, observed
