@@ -55,7 +55,7 @@ def config_dict(n_gpus, rows_per_gpu):
         "n_vars": 37,
         "out_doubles_per_row": 107,
         "sharding": "rows x%d, no collective" % n_gpus,
-        "l2_policy": "working set per step >> L2 (row arena ~18 GB, output 0.9 GB per GPU): no flush needed",
+        "l2_policy": "working set per step >> L2 (row arena 13.9 GB, output 0.9 GB per GPU): no flush needed",
     }
 
 
@@ -227,6 +227,13 @@ def main():
         algo_bytes = 8.0 * (stats["row_read_per_row"] + stats["row_write_per_row"]) * rows
         achieved = algo_bytes / (tm["prodsum_ms"] / 1e3) / 1e9
         n_prodsum = stats["launches"] - 2 * stats["tiles"]
+        traffic, traffic_note = None, "no ncu capture for this row count"
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches (ncu, profiles/r1_traffic.json)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if rows == ROWS_PER_GPU and abs(tj["algorithmic_bytes"] - algo_bytes) < 1e-6 * algo_bytes:
+                traffic, traffic_note = tj["traffic_bytes"], tj["source"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -236,10 +243,13 @@ def main():
             "gpu_launches": int(stats["launches"]) * args.steps,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "prodsum_kernel<K> (all %d fused product/sum-out launches of one pass)" % n_prodsum,
+                "bound": "hbm",
+                "kernel": "the %d fused product/sum-out launches of one pass (prodsum_kernel<K,V,D> + fused_kernel<KO,KI,V,DI>, "
+                          "95%% of the pass; aggregated: one launch = one schedule step over all rows)" % n_prodsum,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_pass": algo_bytes, "prodsum_ms_per_pass": tm["prodsum_ms"], "traffic": None,
+                "algorithmic_bytes_per_pass": algo_bytes, "prodsum_ms_per_pass": tm["prodsum_ms"], "traffic": traffic,
+                "traffic_note": traffic_note,
                 "per_row": {"entries_read": stats["row_read_per_row"], "entries_written": stats["row_write_per_row"],
                             "product_entries": stats["prod_per_row"], "arena_entries": stats["row_entries"]},
                 "pass_ms": tm,
