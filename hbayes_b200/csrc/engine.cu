@@ -132,14 +132,14 @@ struct Rows<2> {
 
 // The fused clique-message kernel: out[o] = 0 + sum_s ps * (in1[o,s] * (in2[o,s] * (... * inK[o,s]))).
 // One thread owns V adjacent evidence rows (threadIdx.x) and walks a contiguous strip of output entries
-// (threadIdx.y / blockIdx.x), U entries per iteration so that U*K*D independent loads are in flight.
+// (threadIdx.y / blockIdx.y), U entries per iteration so that U*K*D independent loads are in flight.
 // All lanes of a warp share the output entry: index-map loads are broadcasts, and every row-table access
 // of the warp is one contiguous 256*V-byte segment.  D = terms per entry (0: run-time count).
 template <int K, int V, int D>
 __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ StepArgs<K> a) {
   constexpr int U = 2;
   typedef Rows<V> R;
-  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (row >= a.nr) return;  // V == 2: the pad row after an odd tile exists in the arena and in rowoff
   const double* p0[K];
   const double* p1[K];
@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
   double* outp = a.out + (a.out_is_row ? row : 0);
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
   const int d = D > 0 ? D : a.d;
-  // contiguous strip of output entries for this (blockIdx.x, threadIdx.y)
-  const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;
+  // contiguous strip of output entries for this (blockIdx.y, threadIdx.y)
+  const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;
   const unsigned per = (a.n_out + lanes - 1) / lanes;
   unsigned o = lane * per;
   const unsigned o_end = min(a.n_out, o + per);
@@ -240,7 +240,7 @@ template <int KO, int KI, int V, int DI>
 __global__ void __launch_bounds__(BLOCK, 2) fused_kernel(const __grid_constant__ FusedArgs<KO + KI> a) {
   constexpr int K = KO + KI;
   typedef Rows<V> R;
-  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (row >= a.nr) return;
   const double* p0[K];
   const double* p1[K];
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(BLOCK, 2) fused_kernel(const __grid_constant__
   }
   double* outp = a.out + (a.out_is_row ? row : 0);
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
-  const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;
+  const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;
   const unsigned per = (a.n_out + lanes - 1) / lanes;
   unsigned o = lane * per;
   const unsigned o_end = min(a.n_out, o + per);
@@ -364,13 +364,13 @@ __global__ void __launch_bounds__(BLOCK, 2) fused_kernel(const __grid_constant__
 // Any number of inputs and scalars (descriptors in global memory), one row per thread.  Rare: buckets
 // with more than MAXK tables, or steps made of scalars only.
 __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArgs a) {
-  const int row = blockIdx.y * blockDim.x + threadIdx.x;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= a.nr) return;
   const double ps = a.n_sc > 0 ? fold_scalars(a.sc, a.n_sc, row) : 1.0;
   double* outp = a.out + (a.out_is_row ? row : 0);
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
-  const unsigned step = gridDim.x * blockDim.y;
-  for (unsigned o = blockIdx.x * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
+  const unsigned step = gridDim.y * blockDim.y;
+  for (unsigned o = blockIdx.y * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
     const unsigned hiI = o / a.C, loI = o - hiI * a.C;
     double acc = 0.0;
     for (int s = 0; s < a.d; ++s) {
@@ -615,19 +615,46 @@ InArg in_arg(const Executor& ex, const Step& st, int si, int i, int64_t RT) {
 struct LaunchShape {
   dim3 grid, block;
 };
-// threads along the row axis: the smallest power of two covering the tile's row-threads, at most BLOCK;
-// the rest of the block and grid.x split the output entries into contiguous strips.
-LaunchShape launch_shape(int row_threads, int64_t n_out) {
+// Launch shapes.  Rows run along x (blocks of up to BLOCK row-threads), output entries are cut into
+// contiguous strips along threadIdx.y / blockIdx.y.
+//  * streaming shape: a block is as wide in rows as possible; strips only to fill the machine.
+//  * reuse shape: when a step enumerates small per-row inputs many times, a block owns just 32 row-threads
+//    (one warp wide) and ALL output entries, so the rows of its inputs (`tile_bytes`) stay in L1 while the
+//    block sweeps the entries -- the re-reads stop going to L2.
+struct Reuse {
+  int64_t row_entries = 0;  // entries of all per-row inputs
+  int64_t row_loads = 0;    // loads of per-row inputs per row
+};
+LaunchShape launch_shape(int row_threads, int rows_per_thread, int64_t n_out, const Reuse& reuse = Reuse()) {
+  LaunchShape s;
+  static const bool reuse_on = !(getenv("HB_REUSE_TILE") && atoi(getenv("HB_REUSE_TILE")) == 0);
+  const int64_t tile_bytes = reuse.row_entries * 32 * rows_per_thread * 8;
+  if (reuse_on && row_threads >= 64 && n_out >= 32 && reuse.row_entries > 0 && reuse.row_loads >= 3 * reuse.row_entries &&
+      tile_bytes <= 96 * 1024) {
+    s.block = dim3(32, BLOCK / 32);
+    s.grid = dim3((row_threads + 31) / 32, 1);
+    return s;
+  }
   int bx = 1;
   while (bx < row_threads && bx < BLOCK) bx <<= 1;
   const int by = BLOCK / bx;
-  LaunchShape s;
   s.block = dim3(bx, by);
-  s.grid.y = (row_threads + bx - 1) / bx;
-  const int64_t max_x = (n_out + 2 * by - 1) / (2 * by);  // at least two entries per thread (U = 2)
-  const int64_t want = (148 * 8 * 2 + s.grid.y - 1) / s.grid.y;
-  s.grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_x, want));
+  s.grid.x = (row_threads + bx - 1) / bx;
+  const int64_t max_y = (n_out + 2 * by - 1) / (2 * by);  // at least two entries per thread (U = 2)
+  const int64_t want = (148 * 8 * 2 + s.grid.x - 1) / s.grid.x;
+  s.grid.y = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_y, want), 65535));
   return s;
+}
+
+Reuse reuse_of(const Program& P, const Step& st) {
+  Reuse r;
+  int64_t terms = 1;
+  for (const Level& l : st.levels) {
+    terms *= l.d;
+    for (const StepInput& in : l.in)
+      if (P.tables[in.table].kind == T_ROW) r.row_entries += P.tables[in.table].size, r.row_loads += st.n_out * terms;
+  }
+  return r;
 }
 
 template <int K, int V>
@@ -659,9 +686,9 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   a.RT = RT;
   // two rows per thread (16-byte accesses) as soon as a tile has a full warp of row pairs
   if (nr >= 64)
-    launch_kv<K, 2>(a, a.d, launch_shape((nr + 1) / 2, st.n_out), stream);
+    launch_kv<K, 2>(a, a.d, launch_shape((nr + 1) / 2, 2, st.n_out, reuse_of(P, st)), stream);
   else
-    launch_kv<K, 1>(a, a.d, launch_shape(nr, st.n_out), stream);
+    launch_kv<K, 1>(a, a.d, launch_shape(nr, 1, st.n_out), stream);
 }
 
 constexpr int MAX_KO = 4, MAX_KI = 3;  // the same limits the compiler's fusion pass uses (CompileOptions)
@@ -701,9 +728,9 @@ void launch_fused(const Executor& ex, const Step& st, int si, int64_t RT, int nr
   a.RT = RT;
   const int di = st.levels.back().d;
   if (nr >= 64)
-    launch_fused_d<KO, KI, 2>(a, di, launch_shape((nr + 1) / 2, st.n_out), stream);
+    launch_fused_d<KO, KI, 2>(a, di, launch_shape((nr + 1) / 2, 2, st.n_out, reuse_of(P, st)), stream);
   else
-    launch_fused_d<KO, KI, 1>(a, 0, launch_shape(nr, st.n_out), stream);  // tiny batches: the run-time-count form
+    launch_fused_d<KO, KI, 1>(a, 0, launch_shape(nr, 1, st.n_out), stream);  // tiny batches: the run-time-count form
 }
 
 template <int KO>
@@ -762,7 +789,7 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
     a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
     a.nr = nr;
     a.RT = RT;
-    LaunchShape sh = launch_shape(nr, st.n_out);
+    LaunchShape sh = launch_shape(nr, 1, st.n_out);
     prodsum_generic_kernel<<<sh.grid, sh.block, 0, stream>>>(a);
   }
 }
