@@ -25,6 +25,8 @@ SIGNATURES = {
     "hb_string_free": (None, [vp]),
     "hb_device_count": (C.c_int, []),
     "hb_net_create": (C.c_int, [i32, i32p, i64p, i32p, i64p, f64p, vpp]),
+    "hb_net_create_procedural": (C.c_int, [i32, i32p, i64p, i32p, i64p, f64p, C.POINTER(C.c_uint64), vpp]),
+    "hb_net_cpt_values": (C.c_int, [vp, i32, i64, i64, f64p]),
     "hb_net_load_hugin": (C.c_int, [C.c_char_p, vpp]),
     "hb_net_n_vars": (C.c_int, [vp]),
     "hb_net_dims": (C.c_int, [vp, i32p]),
@@ -33,11 +35,14 @@ SIGNATURES = {
     "hb_ve_order": (C.c_int, [vp, i32, i32p, i32p]),
     "hb_jt_compile": (C.c_int, [vp, i32, i32p, i32, vpp]),
     "hb_jt_compile_with_order": (C.c_int, [vp, i32p, i32p, i32, vpp]),
+    "hb_jt_compile_split": (C.c_int, [vp, i32, i32p, i32, i32, i32p, i32p, vpp]),
     "hb_jt_describe_json": (C.c_int, [vp, cpp]),
     "hb_jt_program_json": (C.c_int, [vp, i32, i32p, cpp]),
     "hb_jt_set_evidence": (C.c_int, [vp, i32, i32p, i32p]),
     "hb_jt_posterior": (C.c_int, [vp, i32, i32p, i32p, f64p, i64, i64p]),
     "hb_jt_posteriors_batch": (C.c_int, [vp, i64, vp, vp, i32]),
+    "hb_jt_set_split": (C.c_int, [vp, i32, i32p, i32p]),
+    "hb_jt_normalise_batch": (C.c_int, [vp, i64, vp, i32]),
     "hb_jt_set_stream": (C.c_int, [vp, vp]),
     "hb_jt_set_workspace": (C.c_int, [vp, i64]),
     "hb_jt_last_stats": (C.c_int, [vp, i64p]),

@@ -67,6 +67,32 @@ class BayesianNetwork:
                                   vals.ctypes.data_as(f64p), C.byref(h)))
         return BayesianNetwork(h)
 
+    @staticmethod
+    def from_tables_procedural(dims, scopes, values, proc_seed):
+        """like from_tables; CPT v with proc_seed[v] != 0 is procedural (values[v] must be empty)"""
+        n = len(dims)
+        da, dp = _i32(dims)
+        cpt_off = np.zeros(n + 1, np.int64)
+        val_off = np.zeros(n + 1, np.int64)
+        for v in range(n):
+            cpt_off[v + 1] = cpt_off[v] + len(scopes[v])
+            val_off[v + 1] = val_off[v] + len(values[v])
+        sa, sp = _i32(np.concatenate([np.asarray(s, np.int32) for s in scopes]))
+        vals = np.ascontiguousarray(np.concatenate([np.asarray(v, np.float64) for v in values] + [np.zeros(1)]))
+        seeds = np.ascontiguousarray(proc_seed, np.uint64)
+        h = C.c_void_p()
+        check(lib().hb_net_create_procedural(n, dp, cpt_off.ctypes.data_as(i64p), sp, val_off.ctypes.data_as(i64p),
+                                             vals.ctypes.data_as(f64p), seeds.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(h)))
+        return BayesianNetwork(h)
+
+    def cpt_values(self, v, offset=0, count=None):
+        """entries of CPT v in reference layout (works for procedural CPTs too)"""
+        if count is None:
+            count = int(np.prod([self.dims[x] for x in self.scopes[v]])) - offset
+        out = np.zeros(count, np.float64)
+        check(lib().hb_net_cpt_values(self._h, v, offset, count, out.ctypes.data_as(f64p)))
+        return out
+
     @property
     def n(self):
         return len(self.dims)
@@ -173,11 +199,15 @@ class JunctionTree(_Batched):
 
     _prefix = "hb_jt_"
 
-    def __init__(self, net: BayesianNetwork, cmp=nodeComparisonForTriangulation, order=None, device=0):
+    def __init__(self, net: BayesianNetwork, cmp=nodeComparisonForTriangulation, order=None, device=0, split=None):
         self.net = net
         dp, nd, self._keep = _device_args(device)
         h = C.c_void_p()
-        if order is not None:
+        if split is not None:  # one slice of a split clique: [(vertex, state)], no calibration
+            va, vp_ = _i32([e[0] for e in split])
+            sa, sp = _i32([e[1] for e in split])
+            check(lib().hb_jt_compile_split(net._h, int(cmp), dp, nd, len(split), vp_, sp, C.byref(h)))
+        elif order is not None:
             oa, op = _i32(order)
             check(lib().hb_jt_compile_with_order(net._h, op, dp, nd, C.byref(h)))
         else:
@@ -220,6 +250,22 @@ class JunctionTree(_Batched):
     def posteriors_batch(self, evidence, out=None):
         """One query per row: changeEvidence row; posterior [v] for all v.  Returns [n_rows][sum dims]."""
         return self._run_matrix(lib().hb_jt_posteriors_batch, evidence, out, self.net.width)
+
+    def set_split(self, fixed: Sequence[tuple]):
+        """split clique: this handle owns the slice `fixed` = [(vertex, state)]; batch results become unnormalised"""
+        va, vp_ = _i32([e[0] for e in fixed])
+        sa, sp = _i32([e[1] for e in fixed])
+        check(lib().hb_jt_set_split(self._h, len(fixed), vp_, sp))
+
+    def normalise_batch(self, out):
+        """in place: per row and per variable, x * (1.0 / sum x)  (after the slices' results have been summed)"""
+        if isinstance(out, np.ndarray):
+            assert out.dtype == np.float64 and out.flags.c_contiguous
+            check(lib().hb_jt_normalise_batch(self._h, out.shape[0], out.ctypes.data, HB_HOST_PTRS))
+        else:
+            assert out.is_cuda and out.is_contiguous()
+            check(lib().hb_jt_normalise_batch(self._h, out.shape[0], out.data_ptr(), HB_DEVICE_PTRS))
+        return out
 
     def __del__(self):
         try:

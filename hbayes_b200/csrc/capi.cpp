@@ -87,6 +87,8 @@ struct Session {
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_done;
   int64_t chunk_rows = 1 << 18;
+  // split clique: variables fixed to this handle's slice; batch results are then left unnormalised
+  std::vector<std::pair<int, int>> fixed;
 
   ~Session() {
     if (device >= 0) cudaSetDevice(device);
@@ -154,7 +156,7 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
     cuda_ok(cudaMemcpyAsync(first.data(), evidence, n_vars, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(first row)");
     cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
     Compiled& c = get(observed_of_row(first.data(), n_vars));
-    executor_run(s.executor(c), n_rows, evidence, out, s.stream, &rs);
+    executor_run(s.executor(c), n_rows, evidence, out, s.stream, &rs, s.fixed.empty());
     s.note(c, rs, false);
     executor_check(s.executor(c), s.stream);
     return;
@@ -171,7 +173,7 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
   bool first_chunk = true;
   for (int64_t r0 = 0, c = 0; r0 < n_rows; r0 += per, ++c) {
     const int64_t m = std::min<int64_t>(per, n_rows - r0);
-    executor_run(ex0, m, s.d_ev + r0 * n_vars, s.d_out + r0 * width, s.stream, &rs);
+    executor_run(ex0, m, s.d_ev + r0 * n_vars, s.d_out + r0 * width, s.stream, &rs, s.fixed.empty());
     s.note(c0, rs, !first_chunk);
     first_chunk = false;
     if ((int64_t)s.chunk_done.size() <= c) {
@@ -205,7 +207,7 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
     ev.resize((size_t)m * n_vars);
     for (int64_t i = 0; i < m; ++i) memcpy(ev.data() + i * n_vars, evidence + kv.second[i] * n_vars, n_vars);
     cuda_ok(cudaMemcpyAsync(s.d_ev, ev.data(), ev.size(), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
-    executor_run(s.executor(c), m, s.d_ev, s.d_out, s.stream, &rs);
+    executor_run(s.executor(c), m, s.d_ev, s.d_out, s.stream, &rs, s.fixed.empty());
     s.note(c, rs, !first);
     first = false;
     executor_check(s.executor(c), s.stream);  // states out of range -> HB_E_ARG
@@ -234,6 +236,8 @@ struct hb_jt {
     std::vector<int> key = observed;
     key.push_back(-1);
     key.insert(key.end(), query.begin(), query.end());
+    key.push_back(-1);
+    for (auto& f : s.fixed) key.push_back(f.first), key.push_back(f.second);
     auto it = s.cache.find(key);
     if (it != s.cache.end()) return *it->second;
     std::vector<Query> qs;
@@ -242,10 +246,13 @@ struct hb_jt {
     else
       qs.push_back(Query{query});
     auto c = std::make_unique<Compiled>();
-    c->prog.reset(compile_jt(s.net, *tree, observed, qs));
+    CompileOptions opt;
+    opt.fixed = s.fixed;
+    c->prog.reset(compile_jt(s.net, *tree, observed, qs, opt));
     return *(s.cache[key] = std::move(c));
   }
   void run_one(Compiled& c, std::vector<double>& out) {
+    if (!s.fixed.empty()) throw Error(HB_E_UNSUPPORTED, "the single-row calls are not available on a split handle: use the batch call");
     std::vector<int8_t> row(s.net.n(), -1);
     for (size_t i = 0; i < ev_vars.size(); ++i) row[ev_vars[i]] = (int8_t)ev_states[i];
     out.assign((size_t)c.prog->out_width, 0.0);
@@ -301,6 +308,21 @@ int hb_net_create(int32_t n_vars, const int32_t* dims, const int64_t* cpt_off, c
     *out = new hb_net{std::move(*n)};
   });
 }
+int hb_net_create_procedural(int32_t n_vars, const int32_t* dims, const int64_t* cpt_off, const int32_t* cpt_scope,
+                             const int64_t* val_off, const double* cpt_vals, const uint64_t* proc_seed, hb_net** out) {
+  return guarded([&] {
+    if (!out || !proc_seed) throw Error(HB_E_ARG, "null argument");
+    std::unique_ptr<Network> n(network_create(n_vars, dims, cpt_off, cpt_scope, val_off, cpt_vals, proc_seed));
+    *out = new hb_net{std::move(*n)};
+  });
+}
+int hb_net_cpt_values(const hb_net* net, int32_t v, int64_t offset, int64_t count, double* out) {
+  return guarded([&] {
+    if (!net || !out || v < 0 || v >= net->net.n() || offset < 0 || count < 0 || offset + count > net->net.cpt_entries(v))
+      throw Error(HB_E_ARG, "bad CPT range");
+    for (int64_t i = 0; i < count; ++i) out[i] = net->net.cpt_value(v, offset + i);
+  });
+}
 int hb_net_load_hugin(const char* path, hb_net** out) {
   return guarded([&] {
     if (!out) throw Error(HB_E_ARG, "null out");
@@ -348,6 +370,21 @@ static int jt_compile(const hb_net* net, int32_t cmp, const int32_t* order, cons
 }
 int hb_jt_compile(const hb_net* net, int32_t cmp, const int32_t* devices, int32_t n_devices, hb_jt** out) {
   return jt_compile(net, cmp, nullptr, devices, n_devices, out);
+}
+int hb_jt_compile_split(const hb_net* net, int32_t cmp, const int32_t* devices, int32_t n_devices, int32_t n_fixed,
+                        const int32_t* vars, const int32_t* states, hb_jt** out) {
+  return guarded([&] {
+    if (!net || !out) throw Error(HB_E_ARG, "null argument");
+    check_evidence_list(net->net, n_fixed, vars, states);
+    auto jt = std::make_unique<hb_jt>();
+    jt->s.net = net->net;
+    jt->tree.reset(tree_build(jt->s.net, cmp, nullptr));
+    jt->s.device = pick_device(devices, n_devices);
+    jt->post_off.assign(1, 0);
+    for (int d : jt->s.net.dims) jt->post_off.push_back(jt->post_off.back() + d);
+    for (int i = 0; i < n_fixed; ++i) jt->s.fixed.push_back({vars[i], states[i]});
+    *out = jt.release();  // no calibration: the unsplit tables may not fit one GPU
+  });
 }
 int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const int32_t* devices, int32_t n_devices, hb_jt** out) {
   if (!elim_order) {
@@ -408,6 +445,33 @@ int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, do
   return guarded([&] {
     if (!jt) throw Error(HB_E_ARG, "null handle");
     run_matrix(jt->s, [&](const std::vector<int>& obs) -> Compiled& { return jt->program(obs, {}); }, n_rows, evidence, out, flags);
+  });
+}
+int hb_jt_set_split(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states) {
+  return guarded([&] {
+    if (!jt) throw Error(HB_E_ARG, "null handle");
+    check_evidence_list(jt->s.net, n, vars, states);
+    jt->s.fixed.clear();
+    for (int i = 0; i < n; ++i) jt->s.fixed.push_back({vars[i], states[i]});
+    jt->s.cache.clear();
+    jt->s.last_ex = nullptr;
+  });
+}
+int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags) {
+  return guarded([&] {
+    if (!jt || !out || n_rows < 0) throw Error(HB_E_ARG, "null argument");
+    Session& s = jt->s;
+    if (!s.last_ex) throw Error(HB_E_ARG, "no batch has run on this handle yet");
+    const int64_t width = s.net.width();
+    if (flags & HB_DEVICE_PTRS) {
+      executor_normalise(s.last_ex, n_rows, out, s.stream);
+      return;
+    }
+    s.reserve(0, (size_t)n_rows * width * sizeof(double));
+    cuda_ok(cudaMemcpyAsync(s.d_out, out, (size_t)n_rows * width * sizeof(double), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy");
+    executor_normalise(s.last_ex, n_rows, s.d_out, s.stream);
+    cuda_ok(cudaMemcpyAsync(out, s.d_out, (size_t)n_rows * width * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
   });
 }
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream) {

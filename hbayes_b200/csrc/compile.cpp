@@ -43,17 +43,30 @@ struct Compiler {
   Program& P;
   int one = -1;  // the `Scalar 1.0` table
 
-  Compiler(const Network& n, Program& p, const std::vector<int>& observed) : net(n), P(p) {
+  Compiler(const Network& n, Program& p, const std::vector<int>& observed, const CompileOptions& opt) : net(n), P(p) {
     P.net = &net;
     P.observed = observed;
     P.is_observed.assign(net.n(), 0);
+    P.fixed_state.assign(net.n(), -1);
+    for (auto& f : opt.fixed) {
+      if (f.first < 0 || f.first >= net.n() || f.second < 0 || f.second >= net.dims[f.first]) throw Error(HB_E_ARG, "bad fixed (split) variable or state");
+      P.fixed_state[f.first] = f.second;
+    }
     for (int v : observed) {
       if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "evidence on unknown vertex " + std::to_string(v));
       if (P.is_observed[v]) throw Error(HB_E_ARG, "vertex " + std::to_string(v) + " observed twice");
       P.is_observed[v] = 1;
     }
+    for (int v = 0; v < net.n(); ++v)
+      if (P.fixed_state[v] >= 0 && !P.is_observed[v]) throw Error(HB_E_ARG, "a fixed (split) variable must be listed as observed");
+    // potential pool: a CPT is stored whole, except that variables with a compile-time state are restricted away
     P.pot_off.assign(net.n(), 0);
-    for (int v = 0; v < net.n(); ++v) P.pot_off[v] = P.pot_entries, P.pot_entries += (int64_t)net.values[v].size();
+    for (int v = 0; v < net.n(); ++v) {
+      int64_t entries = 1;
+      for (int x : net.scope[v])
+        if (P.fixed_state[x] < 0) entries *= net.dims[x];
+      P.pot_off[v] = P.pot_entries, P.pot_entries += entries;
+    }
     Table t;
     t.kind = T_ONE;
     t.scalar = true;
@@ -87,17 +100,28 @@ struct Compiler {
     t.pot = v;
     t.scope = net.scope[v];
     t.off = P.pot_off[v];
-    std::vector<int64_t> full(t.scope.size(), 1);
-    for (int i = (int)t.scope.size() - 2; i >= 0; --i) full[i] = full[i + 1] * net.dims[t.scope[i + 1]];
+    const int ns = (int)t.scope.size();
+    std::vector<int64_t> full(ns, 1), stored(ns, 0);
+    for (int i = ns - 2; i >= 0; --i) full[i] = full[i + 1] * net.dims[t.scope[i + 1]];
+    int64_t acc = 1;  // stored layout: the reference layout with the fixed variables removed
+    for (int i = ns - 1; i >= 0; --i)
+      if (P.fixed_state[t.scope[i]] < 0) stored[i] = acc, acc *= net.dims[t.scope[i]];
     Slice sl;
     sl.pot = v;
     t.size = 1;
-    for (size_t i = 0; i < t.scope.size(); ++i) {
-      if (P.is_observed[t.scope[i]])
-        sl.vars.push_back(t.scope[i]), sl.strides.push_back(full[i]);
+    for (int i = 0; i < ns; ++i) {
+      const int x = t.scope[i];
+      if (P.fixed_state[x] >= 0)
+        t.full_base += full[i] * P.fixed_state[x];
+      else if (P.is_observed[x])
+        sl.vars.push_back(x), sl.strides.push_back(stored[i]);
       else
-        t.pscope.push_back(t.scope[i]), t.pstride.push_back(full[i]), t.size *= net.dims[t.scope[i]];
+        t.pscope.push_back(x), t.pstride.push_back(stored[i]), t.full_stride.push_back(full[i]), t.size *= net.dims[x];
     }
+    // the observed (per-row) variables keep their place in the stored layout: remember their full strides too
+    for (int i = 0; i < ns; ++i)
+      if (P.fixed_state[t.scope[i]] < 0 && P.is_observed[t.scope[i]]) sl.full_strides.push_back(full[i]);
+    sl.stored_entries = acc;
     if (!sl.vars.empty()) {
       t.slice_slot = (int)P.slices.size();
       P.slices.push_back(sl);
@@ -493,7 +517,7 @@ void js_nums(std::ostringstream& o, const V& v) {
 Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>& observed,
                     const std::vector<Query>& queries, const CompileOptions& opt) {
   auto prog = std::make_unique<Program>();
-  Compiler C(net, *prog, observed);
+  Compiler C(net, *prog, observed, opt);
   const int nc = (int)tree.clusters.size(), nsep = tree.n_seps();
   std::vector<int> pot(net.n());
   for (int v = 0; v < net.n(); ++v) pot[v] = C.potential(v);
@@ -603,7 +627,7 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
 Program* compile_ve(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
                     const std::vector<int>& observed, const CompileOptions& opt) {
   auto prog = std::make_unique<Program>();
-  Compiler C(net, *prog, observed);
+  Compiler C(net, *prog, observed, opt);
   for (int v : p)
     if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "elimination order mentions an unknown vertex");
   for (int v : r)

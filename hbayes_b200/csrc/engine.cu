@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "procedural.hpp"
 
 namespace hb {
 
@@ -388,12 +389,34 @@ __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArg
   }
 }
 
+// ---- potential pool: procedural CPTs are generated in place (restricted to the fixed states) ------
+struct ProcFillArgs {
+  double* dst;          // pool + pot_off[v]
+  long long entries;    // stored entries
+  unsigned long long seed, npar, full_base;
+  int d, n_free;        // child states, number of non-fixed scope variables (slowest first)
+  int dim[40];
+  unsigned long long full_stride[40];
+};
+
+__global__ void __launch_bounds__(BLOCK) proc_fill_kernel(const ProcFillArgs a) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a.entries; e += (long long)gridDim.x * blockDim.x) {
+    unsigned long long idx = a.full_base, rest = (unsigned long long)e;
+    for (int j = a.n_free - 1; j >= 0; --j) {
+      const unsigned long long dj = (unsigned long long)a.dim[j];
+      idx += (rest % dj) * a.full_stride[j];
+      rest /= dj;
+    }
+    a.dst[e] = proc_cpt_value(a.seed, a.d, a.npar, idx);
+  }
+}
+
 // ---- evidence -> slice offsets, and the consistency check -------------------------------------
 struct PrepArgs {
   const int8_t* ev;        // [nr][n_vars] for this tile
   int nr, n_vars, n_slices;
   long long RT;
-  const int8_t* observed;  // [n_vars] 0/1
+  const int8_t* observed;  // [n_vars] 0 = unobserved, 1 = observed per row, 2 + s = fixed at state s
   const int32_t* dims;     // [n_vars]
   const int32_t* sl_begin; // [n_slices + 1]
   const int32_t* sl_var;
@@ -405,7 +428,7 @@ struct PrepArgs {
 __global__ void __launch_bounds__(BLOCK) prep_rows_kernel(const PrepArgs a) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= a.nr) {  // pad rows up to the next multiple of 64 read slice 0 (their results are never used)
-    if (row < ((a.nr + 63) & ~63))
+    if (row < ((a.nr + 63) & ~63) && row < a.RT)
       for (int j = 0; j < a.n_slices; ++j) a.rowoff[(long long)j * a.RT + row] = 0;
     return;
   }
@@ -413,8 +436,8 @@ __global__ void __launch_bounds__(BLOCK) prep_rows_kernel(const PrepArgs a) {
   bool bad = false;
   for (int v = 0; v < a.n_vars; ++v) {
     const int s = e[v];
-    const bool obs = a.observed[v] != 0;
-    bad |= obs ? (s < 0 || s >= a.dims[v]) : (s >= 0);
+    const int o = a.observed[v];
+    bad |= o == 0 ? (s >= 0) : (o == 1 ? (s < 0 || s >= a.dims[v]) : (s != o - 2));
   }
   if (bad) atomicOr(a.flag, 1);
   for (int j = 0; j < a.n_slices; ++j) {
@@ -455,6 +478,7 @@ struct OutArgs {
   double* out;             // this tile: [nr][width]
   int nr, n_vars;
   long long RT, width;
+  int normalise;           // 0: leave the query results unnormalised (partial sums of a split clique)
 };
 
 constexpr int OUT_ROWS = 64;     // evidence rows per CTA
@@ -488,7 +512,7 @@ __global__ void __launch_bounds__(BLOCK) output_kernel(const OutArgs a) {
       const uint32_t* fmap = a.maps + d.map_off;
       double norm = 0.0;
       for (int j = 0; j < d.n_phys; ++j) norm = __dadd_rn(norm, p ? p[(long long)order[j] * m] : 1.0);
-      const double inv = __ddiv_rn(1.0, norm);
+      const double inv = a.normalise ? __ddiv_rn(1.0, norm) : 1.0;
       int st[MAXOBS];
       for (int j = 0; j < d.n_obs; ++j) st[j] = e[d.obs_var[j]];
       double* o = ch.direct ? a.out + (long long)row * a.width + d.out_col : tile + r * pitch + (int)(d.out_col - ch.col_begin);
@@ -509,6 +533,26 @@ __global__ void __launch_bounds__(BLOCK) output_kernel(const OutArgs a) {
   }
 }
 
+// factorNorm + factorDivide of an already expanded, unnormalised result matrix (the sum over the slices of
+// a split clique): per row and per query block, norm = 0 + x0 + x1 + ..., x_i *= 1.0 / norm.
+struct NormArgs {
+  double* out;
+  const int* col_begin;  // [n_blocks + 1]
+  int n_blocks;
+  long long n_rows, width;
+};
+__global__ void __launch_bounds__(BLOCK) normalise_kernel(const NormArgs a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.n_rows * a.n_blocks) return;
+  const long long row = gid / a.n_blocks;
+  const int b = (int)(gid % a.n_blocks);
+  double* p = a.out + row * a.width;
+  double norm = 0.0;
+  for (int c = a.col_begin[b]; c < a.col_begin[b + 1]; ++c) norm = __dadd_rn(norm, p[c]);
+  const double inv = __ddiv_rn(1.0, norm);
+  for (int c = a.col_begin[b]; c < a.col_begin[b + 1]; ++c) p[c] = __dmul_rn(inv, p[c]);
+}
+
 }  // namespace
 
 // ================================ host side =====================================================
@@ -524,6 +568,7 @@ struct Executor {
   int32_t *d_dims = nullptr, *d_sl_begin = nullptr, *d_sl_var = nullptr, *d_sl_stride = nullptr;
   OutDesc* d_out_desc = nullptr;
   OutChunk* d_out_chunks = nullptr;
+  int* d_norm_cols = nullptr;
   std::vector<OutChunk> out_chunks;
   int out_tile_bytes = 0;
   InArg* d_gen_in = nullptr;     // descriptors of the generic-path steps (rebuilt when RT changes)
@@ -551,7 +596,7 @@ struct Executor {
     cudaSetDevice(device);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
-                    (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_out_chunks, (void*)d_gen_in,
+                    (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_out_chunks, (void*)d_norm_cols, (void*)d_gen_in,
                     (void*)d_gen_sc, (void*)d_flag})
       if (p) cudaFree(p);
   }
@@ -837,9 +882,56 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
   ex->device = device;
   const Network& net = *P.net;
   // potential pool
-  std::vector<double> pots((size_t)P.pot_entries);
-  for (int v = 0; v < net.n(); ++v) std::copy(net.values[v].begin(), net.values[v].end(), pots.begin() + P.pot_off[v]);
-  ex->d_pots = upload(pots);
+  // potential pool: every CPT restricted to the fixed (split) states; stored ones are gathered on the host,
+  // procedural ones are generated on the device
+  HB_CUDA(cudaMalloc(&ex->d_pots, std::max<int64_t>(P.pot_entries, 1) * sizeof(double)));
+  {
+    std::vector<double> staged;
+    for (int v = 0; v < net.n(); ++v) {
+      const std::vector<int>& sc = net.scope[v];
+      std::vector<int> dim;
+      std::vector<int64_t> fstride;
+      int64_t full = 1, base = 0, entries = 1;
+      for (int i = (int)sc.size() - 1; i >= 0; --i) {
+        if (P.fixed_state[sc[i]] >= 0)
+          base += full * P.fixed_state[sc[i]];
+        else
+          dim.insert(dim.begin(), net.dims[sc[i]]), fstride.insert(fstride.begin(), full), entries *= net.dims[sc[i]];
+        full *= net.dims[sc[i]];
+      }
+      if (net.procedural(v)) {
+        if (dim.size() > 40) throw Error(HB_E_UNSUPPORTED, "procedural CPT with more than 40 free variables");
+        ProcFillArgs a;
+        memset(&a, 0, sizeof a);
+        a.dst = ex->d_pots + P.pot_off[v];
+        a.entries = entries;
+        a.seed = net.proc_seed[v];
+        a.npar = (unsigned long long)(net.cpt_entries(v) / net.dims[v]);
+        a.full_base = (unsigned long long)base;
+        a.d = net.dims[v];
+        a.n_free = (int)dim.size();
+        for (size_t j = 0; j < dim.size(); ++j) a.dim[j] = dim[j], a.full_stride[j] = (unsigned long long)fstride[j];
+        proc_fill_kernel<<<(unsigned)std::min<int64_t>((entries + BLOCK - 1) / BLOCK, 148 * 16), BLOCK>>>(a);
+      } else {
+        staged.resize((size_t)entries);
+        std::vector<int> digit(dim.size(), 0);
+        int64_t src = base;
+        for (int64_t e = 0; e < entries; ++e) {
+          staged[(size_t)e] = net.values[v][(size_t)src];
+          for (int j = (int)dim.size() - 1; j >= 0; --j) {
+            if (++digit[j] < dim[j]) {
+              src += fstride[j];
+              break;
+            }
+            src -= fstride[j] * (digit[j] - 1);
+            digit[j] = 0;
+          }
+        }
+        HB_CUDA(cudaMemcpy(ex->d_pots + P.pot_off[v], staged.data(), (size_t)entries * sizeof(double), cudaMemcpyHostToDevice));
+      }
+    }
+    HB_CUDA(cudaGetLastError());
+  }
   HB_CUDA(cudaMalloc(&ex->d_shared, std::max<int64_t>(P.shared_entries, 1) * sizeof(double)));
   // index-map pool
   std::vector<uint32_t>& maps = ex->maps;
@@ -900,6 +992,8 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
   }
   // evidence preparation tables
   std::vector<int8_t> obs(P.is_observed.begin(), P.is_observed.end());
+  for (int v = 0; v < net.n(); ++v)
+    if (P.fixed_state[v] >= 0) obs[v] = (int8_t)(2 + P.fixed_state[v]);
   std::vector<int32_t> dims(net.dims.begin(), net.dims.end()), sl_begin = {0}, sl_var, sl_stride;
   for (const Slice& s : P.slices) {
     for (size_t j = 0; j < s.vars.size(); ++j) sl_var.push_back(s.vars[j]), sl_stride.push_back((int32_t)s.strides[j]);
@@ -935,7 +1029,7 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
 void executor_destroy(Executor* ex) { delete ex; }
 int executor_device(const Executor* ex) { return ex->device; }
 
-void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream_, RunStats* stats) {
+void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream_, RunStats* stats, bool normalise) {
   if (n_rows <= 0) return;
   cudaStream_t stream = (cudaStream_t)stream_;
   const Program& P = *ex->P;
@@ -944,12 +1038,13 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
   // rows per tile: as many as the workspace allows, in multiples of 32 (one warp of rows), and few enough
   // that every row-table offset (entry * RT + row) fits 32 bits
   const int64_t per_row = std::max<int64_t>(P.row_entries, 1) * 8 + (int64_t)P.slices.size() * 4;
-  int64_t cap = ex->workspace / per_row / 64 * 64;
-  if (cap < 64) throw Error(HB_E_OOM, "row arena of one 64-row tile (" + std::to_string(per_row * 64) + " bytes) exceeds the workspace");
-  cap = std::min<int64_t>(cap, (((int64_t)1 << 32) - 1) / (ex->max_row_table + 1) / 64 * 64);
+  // tiles are multiples of 64 rows; a batch smaller than that (huge per-row tables, few rows) gets an even stride
+  auto round_rows = [](int64_t r) { return r >= 64 ? r / 64 * 64 : r / 2 * 2; };
+  int64_t cap = round_rows(ex->workspace / per_row);
+  cap = std::min<int64_t>(cap, round_rows((((int64_t)1 << 32) - 1) / (ex->max_row_table + 1)));
   cap = std::min<int64_t>(cap, (int64_t)1 << 22);
-  if (cap < 64) throw Error(HB_E_UNSUPPORTED, "per-row table too large for 32-bit offsets");
-  const int64_t RT = std::min<int64_t>(cap, (n_rows + 63) / 64 * 64);
+  if (cap < 2) throw Error(HB_E_OOM, "the row arena of two rows (" + std::to_string(per_row * 2) + " bytes) exceeds the workspace or 32-bit offsets");
+  const int64_t RT = std::min<int64_t>(cap, n_rows >= 64 ? (n_rows + 63) / 64 * 64 : (n_rows + 1) / 2 * 2);
   if (RT > ex->RT || ex->RT > 4 * RT) {
     HB_CUDA(cudaStreamSynchronize(stream));
     set_row_stride(*ex, RT);
@@ -978,7 +1073,7 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     mark();
     if (!ex->out_desc.empty()) {
       OutArgs oa{ex->d_out_desc, ex->d_out_chunks, ex->d_maps, ex->d_rowoff, d_evidence + r0 * n_vars,
-                 d_out + r0 * P.out_width, nr, n_vars, stride, P.out_width};
+                 d_out + r0 * P.out_width, nr, n_vars, stride, P.out_width, normalise ? 1 : 0};
       dim3 grid((nr + OUT_ROWS - 1) / OUT_ROWS, (unsigned)ex->out_chunks.size());
       output_kernel<<<grid, BLOCK, ex->out_tile_bytes, stream>>>(oa);
       ++launches;
@@ -992,6 +1087,22 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     stats->rows_per_tile = stride;
     stats->arena_bytes = std::max<int64_t>(P.row_entries, 1) * stride * 8;
   }
+}
+
+void executor_normalise(Executor* ex, int64_t n_rows, double* d_out, void* stream_) {
+  if (n_rows <= 0) return;
+  HB_CUDA(cudaSetDevice(ex->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!ex->d_norm_cols) {
+    std::vector<int> cols;
+    for (const OutDesc& d : ex->out_desc) cols.push_back((int)d.out_col);
+    cols.push_back((int)ex->P->out_width);
+    ex->d_norm_cols = upload(cols);
+  }
+  NormArgs a{d_out, ex->d_norm_cols, (int)ex->out_desc.size(), n_rows, ex->P->out_width};
+  const int64_t threads = n_rows * a.n_blocks;
+  normalise_kernel<<<(unsigned)((threads + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>(a);
+  HB_CUDA(cudaGetLastError());
 }
 
 void executor_set_timing(Executor* ex, bool on) { ex->timing = on; }

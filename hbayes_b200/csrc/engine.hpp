@@ -24,7 +24,12 @@ void executor_destroy(Executor* ex);
 // d_out: double [n_rows][out_width]; both DEVICE pointers.  Asynchronous on `stream` (a cudaStream_t).
 // A row whose observed set differs from the program's, or whose state is out of range, raises the
 // executor's error flag (see executor_check).
-void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream, RunStats* stats);
+void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream, RunStats* stats,
+                  bool normalise = true);
+
+// factorNorm + factorDivide of an expanded, UNNORMALISED result matrix (device pointer), per row and per
+// query: the last step of a split-clique query after the partial results of the slices have been summed.
+void executor_normalise(Executor* ex, int64_t n_rows, double* d_out, void* stream);
 
 // Synchronises `stream` and throws HB_E_ARG if a row of an earlier run was inconsistent with the program.
 void executor_check(Executor* ex, void* stream);

@@ -63,7 +63,7 @@ u128 triangulation_metric(const Network& net, const BitMatrix& moral, int v, int
   u128 tot = 0;
   for (int x : nb)
     for (int y : nb)
-      if (x != y && !moral.get(x, y)) tot += cmp == 0 ? (u128)net.values[x].size() * (u128)net.values[y].size() : (u128)1;
+      if (x != y && !moral.get(x, y)) tot += cmp == 0 ? (u128)net.cpt_entries(x) * (u128)net.cpt_entries(y) : (u128)1;
   return tot;
 }
 

@@ -24,9 +24,17 @@ struct Error : std::runtime_error {
 struct Network {
   std::vector<int> dims;                    // vertex id = index
   std::vector<std::vector<int>> scope;      // scope[v] = [v, parents in `ingoing` order]
-  std::vector<std::vector<double>> values;  // reference layout: first variable slowest
+  std::vector<std::vector<double>> values;  // reference layout: first variable slowest (empty for a procedural CPT)
+  std::vector<uint64_t> proc_seed;          // != 0: CPT v is procedural (procedural.hpp), values[v] is empty
   std::vector<std::string> names;
   int n() const { return (int)dims.size(); }
+  bool procedural(int v) const { return !proc_seed.empty() && proc_seed[v] != 0; }
+  int64_t cpt_entries(int v) const {  // factorDimension of CPT v
+    int64_t p = 1;
+    for (int x : scope[v]) p *= dims[x];
+    return p;
+  }
+  double cpt_value(int v, int64_t idx) const;  // entry idx of CPT v, stored or procedural
   int64_t width() const {  // sum_v dims[v]: doubles per junction-tree query
     int64_t w = 0;
     for (int d : dims) w += d;
@@ -34,7 +42,7 @@ struct Network {
   }
 };
 Network* network_create(int n_vars, const int32_t* dims, const int64_t* cpt_off, const int32_t* cpt_scope,
-                        const int64_t* val_off, const double* vals);
+                        const int64_t* val_off, const double* vals, const uint64_t* proc_seed = nullptr);
 Network* network_load_hugin(const char* path);
 
 // ---- Junction tree structure (Bayes/FactorElimination.hs:283-307, JTree.hs:89-105) -------------
@@ -83,6 +91,8 @@ struct Table {
   int64_t size = 1;              // physical entries
   int64_t off = 0;               // entry offset in its pool (potential pool / shared arena / row arena)
   int slice_slot = -1;           // T_POT mentioning observed variables: index into Program::slices
+  std::vector<int64_t> full_stride;  // T_POT: stride of each pscope variable in the reference layout of the whole CPT
+  int64_t full_base = 0;         // T_POT: offset of the fixed variables' states in the whole CPT
   int alias_of = -1;             // a final product of a single table is that table
   int def_step = -1, last_use = -1;
 };
@@ -143,18 +153,21 @@ struct Group {  // one reference-level `marginal` call: a message or a posterior
 
 struct Slice {  // per-row entry offset of a sliced potential: sum_j stride_j * state(var_j)
   int pot;
-  std::vector<int> vars;
-  std::vector<int64_t> strides;
+  std::vector<int> vars;              // observed (per-row) variables of the CPT
+  std::vector<int64_t> strides;       // their strides in the stored layout
+  std::vector<int64_t> full_strides;  // ... and in the reference layout of the whole CPT
+  int64_t stored_entries = 0;         // entries of the stored (restricted) table
 };
 
 struct Program {
   const Network* net = nullptr;
   std::vector<int> observed;     // in the caller's order (changeEvidence list order)
-  std::vector<char> is_observed; // per vertex
+  std::vector<char> is_observed; // per vertex (fixed variables included)
+  std::vector<int> fixed_state;  // per vertex: compile-time state or -1
   std::vector<Table> tables;
   std::vector<Step> steps;       // shared steps and per-row steps interleaved in dependency order
   std::vector<Group> groups;
-  std::vector<Slice> slices;
+  std::vector<Slice> slices;      // potentials that are sliced per row
   std::vector<int64_t> pot_off;  // vertex -> entry offset in the potential pool
   int64_t pot_entries = 0;
   int64_t shared_entries = 0;    // shared arena size
@@ -169,6 +182,9 @@ struct Query {
   std::vector<int> vars;
 };
 struct CompileOptions {
+  // variables with a state known at compile time (the slice of a split clique this GPU owns): treated like
+  // observed variables, and potentials mentioning them are stored restricted to that state
+  std::vector<std::pair<int, int>> fixed;
   bool fuse = true;    // chain a step into its only consumer (the intermediate table stays in registers)
   int max_levels = 4;  // levels per fused step
   int max_outer = 4;   // stored inputs of the outer levels of a fused step

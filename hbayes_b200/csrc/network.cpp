@@ -16,6 +16,7 @@
 #include <sstream>
 
 #include "model.hpp"
+#include "procedural.hpp"
 
 namespace hb {
 
@@ -37,18 +38,24 @@ static void check_network(const Network& net) {
       for (size_t j = 0; j < i; ++j)
         if (sc[i] == sc[j]) throw Error(HB_E_ARG, "CPT " + std::to_string(v) + ": repeated vertex in scope");
     }
-    if ((int64_t)net.values[v].size() != scope_entries(net, sc))
+    if (net.procedural(v) ? !net.values[v].empty() : (int64_t)net.values[v].size() != scope_entries(net, sc))
       throw Error(HB_E_ARG, "CPT " + std::to_string(v) + ": value count does not match its scope");
   }
 }
 
+double Network::cpt_value(int v, int64_t idx) const {
+  if (!procedural(v)) return values[v][(size_t)idx];
+  return proc_cpt_value(proc_seed[v], dims[v], (uint64_t)(cpt_entries(v) / dims[v]), (uint64_t)idx);
+}
+
 Network* network_create(int n_vars, const int32_t* dims, const int64_t* cpt_off, const int32_t* cpt_scope,
-                        const int64_t* val_off, const double* vals) {
+                        const int64_t* val_off, const double* vals, const uint64_t* proc_seed) {
   if (n_vars <= 0 || !dims || !cpt_off || !cpt_scope || !val_off || !vals) throw Error(HB_E_ARG, "hb_net_create: null or empty argument");
   auto net = std::make_unique<Network>();
   net->dims.assign(dims, dims + n_vars);
   net->scope.resize(n_vars);
   net->values.resize(n_vars);
+  if (proc_seed) net->proc_seed.assign(proc_seed, proc_seed + n_vars);
   for (int v = 0; v < n_vars; ++v) {
     if (cpt_off[v + 1] < cpt_off[v] || val_off[v + 1] < val_off[v]) throw Error(HB_E_ARG, "hb_net_create: offsets must be non-decreasing");
     net->scope[v].assign(cpt_scope + cpt_off[v], cpt_scope + cpt_off[v + 1]);
@@ -236,7 +243,7 @@ std::string describe_network(const Network& net) {
   o << "],\"values\":[";
   for (int v = 0; v < net.n(); ++v) {
     o << (v ? "," : "") << "[";
-    for (size_t i = 0; i < net.values[v].size(); ++i) o << (i ? "," : "") << net.values[v][i];
+    for (size_t i = 0; i < net.values[v].size(); ++i) o << (i ? "," : "") << net.values[v][i];  // procedural CPTs print as []
     o << "]";
   }
   o << "]}";

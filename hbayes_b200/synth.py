@@ -42,14 +42,52 @@ def splitmix64_array(seed, n):
         return z ^ (z >> np.uint64(31))
 
 
-class SynthNet:
-    """dims[v], parents[v] (CPT scope = [v] + parents[v]), values[v] in reference layout."""
+def proc_hash(seed, idx):
+    """stateless SplitMix64 of (seed, idx); idx: uint64 array.  Same bits as hbayes_b200/csrc/procedural.hpp."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & _M) + (np.asarray(idx, np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
 
-    def __init__(self, dims, parents, values, names=None):
+
+def proc_cpt_values(seed, d, npar, idx):
+    """entries `idx` of a procedural CPT (d child states, npar parent configurations), bit-identical to the C++/CUDA
+    proc_cpt_value: u = 0.05 + 0.95 * uniform(hash), value = u(idx) / (u(0, pa) + u(1, pa) + ...)."""
+    idx = np.asarray(idx, np.uint64)
+    pa = idx % np.uint64(npar)
+
+    def u(i):
+        unif = (proc_hash(seed, i) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+        return 0.05 + 0.95 * unif
+
+    total = np.zeros(idx.shape, np.float64)
+    for k in range(d):
+        total = total + u(np.uint64(k) * np.uint64(npar) + pa)
+    return u(idx) / total
+
+
+class SynthNet:
+    """dims[v], parents[v] (CPT scope = [v] + parents[v]), values[v] in reference layout.  proc_seed[v] != 0 marks a
+    procedural CPT (values[v] empty): see proc_cpt_values."""
+
+    def __init__(self, dims, parents, values, names=None, proc_seed=None):
         self.dims = [int(d) for d in dims]
         self.parents = [list(map(int, p)) for p in parents]
         self.values = [np.asarray(v, np.float64) for v in values]
         self.names = names or ["n%d" % i for i in range(len(dims))]
+        self.proc_seed = [int(x) for x in proc_seed] if proc_seed is not None else [0] * len(self.dims)
+
+    def materialise(self):
+        """explicit copy: procedural CPTs evaluated on the host (small twins only)"""
+        vals = []
+        for v in range(self.n):
+            if self.proc_seed[v]:
+                npar = int(np.prod([self.dims[p] for p in self.parents[v]])) if self.parents[v] else 1
+                vals.append(proc_cpt_values(self.proc_seed[v], self.dims[v], npar, np.arange(self.dims[v] * npar, dtype=np.uint64)))
+            else:
+                vals.append(self.values[v])
+        return SynthNet(self.dims, self.parents, vals, self.names)
 
     @property
     def n(self):
@@ -208,3 +246,17 @@ def config_c5_query(net, metric_order):
     p = [v for v in metric_order if v not in r]
     observed = choose_observed(net.n - 1, max(1, net.n // 10), 400002)
     return p, r, observed
+
+
+def config_c4(n_parents=29, seed=4300001):
+    """BASELINE config C4: one binary child with `n_parents` binary root parents -> a single cluster whose CPT has
+    2^(n_parents+1) entries (2^30 = 8 GiB at 29 parents).  The child's CPT is procedural (nobody materialises it on
+    the host); the parents' priors are small stored tables.  ids: parents 0..n_parents-1, child n_parents.
+    Split variables = the first three parents (outermost strides of the CPT after the child): 8 slices."""
+    rng = SplitMix64(seed)
+    n = n_parents + 1
+    dims = [2] * n
+    parents = [[] for _ in range(n_parents)] + [list(range(n_parents))]
+    values = [_random_cpt(rng, dims, v, []) for v in range(n_parents)] + [np.zeros(0)]
+    proc_seed = [0] * n_parents + [seed + 17]
+    return SynthNet(dims, parents, values, proc_seed=proc_seed), [0, 1, 2]

@@ -58,6 +58,14 @@ int hb_device_count(void);
  * (child first) and values cpt_vals[val_off[v]..val_off[v+1]). */
 int hb_net_create(int32_t n_vars, const int32_t* dims, const int64_t* cpt_off, const int32_t* cpt_scope,
                   const int64_t* val_off, const double* cpt_vals, hb_net** out);
+/* same, but CPT v with proc_seed[v] != 0 is PROCEDURAL: it has no stored values (val_off[v+1] == val_off[v]); entry
+ * idx is u(idx) / sum_k u(k * npar + idx % npar), u = 0.05 + 0.95 * uniform(splitmix64(seed, idx)) -- the synthetic
+ * generators' recipe made stateless (hbayes_b200/csrc/procedural.hpp), for tables too large to build on the host
+ * (BASELINE config C4).  Each GPU generates only the slice it owns. */
+int hb_net_create_procedural(int32_t n_vars, const int32_t* dims, const int64_t* cpt_off, const int32_t* cpt_scope,
+                             const int64_t* val_off, const double* cpt_vals, const uint64_t* proc_seed, hb_net** out);
+/* entries [offset, offset + count) of CPT v in reference layout, stored or procedural */
+int hb_net_cpt_values(const hb_net* net, int32_t v, int64_t offset, int64_t count, double* out);
 /* importBayesianGraph + runBN (Bayes/ImportExport/HuginNet.hs:160-195), dialect of SURVEY Appendix C */
 int hb_net_load_hugin(const char* path, hb_net** out);
 int hb_net_n_vars(const hb_net* net);
@@ -79,6 +87,10 @@ int hb_jt_compile(const hb_net* net, int32_t cmp, const int32_t* devices, int32_
  * is evaluated on the Haskell side: the metric is static) */
 int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const int32_t* devices, int32_t n_devices,
                              hb_jt** out);
+/* createJunctionTree for ONE slice of a split clique (see hb_jt_set_split): the tree is built, the split is set, and
+ * nothing is calibrated (the unsplit tables may not fit one GPU). */
+int hb_jt_compile_split(const hb_net* net, int32_t cmp, const int32_t* devices, int32_t n_devices, int32_t n_fixed,
+                        const int32_t* vars, const int32_t* states, hb_jt** out);
 /* parity hook: {"elim_order","clusters","root","parent_sep","sep_parent","sep_child","sep_vars","children","factors"} */
 int hb_jt_describe_json(const hb_jt* jt, char** out_json);
 /* parity hook: the operation trace (every message and every single-variable posterior, with product scopes)
@@ -94,6 +106,15 @@ int hb_jt_posterior(hb_jt* jt, int32_t n_q, const int32_t* q_vars, int32_t* out_
  * out: double [n_rows][sum_v dims[v]], variables in ascending id.  Rows of one call may have different
  * observed sets with HB_HOST_PTRS (grouped internally); with HB_DEVICE_PTRS all rows must share one. */
 int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags);
+/* Split clique (BASELINE config C4): fixes vars[i] to states[i] for every later batch call on this
+ * handle -- the slice of the oversized table this GPU owns.  Potentials mentioning the variables are stored
+ * restricted to those states (1/prod dims of the memory), evidence rows must carry the same states, and batch
+ * results are left UNNORMALISED: the caller sums the result matrices of all slices (ncclAllReduce(sum) over the
+ * ranks; the sum over the split variable is the exchange step) and calls hb_jt_normalise_batch.  Results agree
+ * with the unsplit engine to ~1e-15 relative, not bit for bit (the sum over the split variable is reassociated). */
+int hb_jt_set_split(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states);
+/* factorNorm + factorDivide of a summed, unnormalised result matrix [n_rows][sum dims] in place */
+int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags);
 /* CUDA stream (a cudaStream_t) the handle launches on; NULL = the default stream */
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream);
 /* bytes of device workspace the row arena may use (0 = default) */
