@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -581,6 +582,15 @@ struct Executor {
   std::vector<int64_t> in_base;         // first (step,input) index of each step
   std::vector<OutDesc> out_desc;
   std::vector<int> out_steps;
+  // The product/sum-out launches of one tile only depend on (RT, rows in the tile): they are captured once
+  // into a CUDA graph and replayed (programs with hundreds of small steps are launch-bound otherwise).
+  std::map<int, cudaGraphExec_t> graphs;  // rows in tile -> instantiated graph, valid for the current RT
+  cudaStream_t capture_stream = nullptr;
+  int n_row_steps = 0;
+  void drop_graphs() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+  }
   bool timing = false;
   std::vector<cudaEvent_t> events;  // 4 per tile of the last run when timing is on
   size_t events_used = 0;
@@ -594,6 +604,8 @@ struct Executor {
   }
   ~Executor() {
     cudaSetDevice(device);
+    drop_graphs();
+    if (capture_stream) cudaStreamDestroy(capture_stream);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
                     (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_out_chunks, (void*)d_norm_cols, (void*)d_gen_in,
@@ -844,6 +856,7 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
 static void set_row_stride(Executor& ex, int64_t RT) {
   if (RT == ex.RT) return;
   const Program& P = *ex.P;
+  ex.drop_graphs();
   free_dev(ex.d_arena);
   free_dev(ex.d_rowoff);
   free_dev(ex.d_maps_rt);
@@ -973,6 +986,8 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     }
   }
   ex->d_maps = upload(maps);
+  for (const Step& st : P.steps)
+    if (st.kind == STEP_PRODSUM && !st.shared) ++ex->n_row_steps;
   // column chunks of the normalise/expand kernel
   {
     int max_w = 1;
@@ -1063,13 +1078,42 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     prep_rows_kernel<<<(((nr + 63) & ~63) + BLOCK - 1) / BLOCK, BLOCK, 0, stream>>>(pa);
     ++launches;
     mark();
-    int64_t gi = 0, gs = 0;
-    for (size_t si = 0; si < P.steps.size(); ++si) {
-      const Step& st = P.steps[si];
-      if (st.kind != STEP_PRODSUM) continue;
-      if (!st.shared) launch_prodsum(*ex, st, (int)si, stride, nr, stream, gi, gs), ++launches;
-      if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
+    auto launch_steps = [&](cudaStream_t on) {
+      int64_t gi = 0, gs = 0;
+      for (size_t si = 0; si < P.steps.size(); ++si) {
+        const Step& st = P.steps[si];
+        if (st.kind != STEP_PRODSUM) continue;
+        if (!st.shared) launch_prodsum(*ex, st, (int)si, stride, nr, on, gi, gs);
+        if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
+      }
+    };
+    static const bool graphs_on = !(getenv("HB_GRAPHS") && atoi(getenv("HB_GRAPHS")) == 0);
+    if (graphs_on && ex->n_row_steps >= 16) {
+      auto it = ex->graphs.find(nr);
+      if (it == ex->graphs.end()) {
+        if (!ex->capture_stream) HB_CUDA(cudaStreamCreateWithFlags(&ex->capture_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        HB_CUDA(cudaStreamBeginCapture(ex->capture_stream, cudaStreamCaptureModeThreadLocal));
+        try {
+          launch_steps(ex->capture_stream);
+        } catch (...) {
+          cudaStreamEndCapture(ex->capture_stream, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        HB_CUDA(cudaStreamEndCapture(ex->capture_stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) throw Error(HB_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        if (ex->graphs.size() >= 8) ex->drop_graphs();  // ragged tails: keep the cache small
+        it = ex->graphs.emplace(nr, exec).first;
+      }
+      HB_CUDA(cudaGraphLaunch(it->second, stream));
+    } else {
+      launch_steps(stream);
     }
+    launches += ex->n_row_steps;
     mark();
     if (!ex->out_desc.empty()) {
       OutArgs oa{ex->d_out_desc, ex->d_out_chunks, ex->d_maps, ex->d_rowoff, d_evidence + r0 * n_vars,
