@@ -20,6 +20,9 @@ from .api import (  # noqa: F401
     VariableElimination,
     changeEvidence,
     createJunctionTree,
+    factorProduct,
+    factorProjectOut,
+    marginalizeOneVariable,
     importBayesianGraph,
     minDegreeOrder,
     minFillOrder,

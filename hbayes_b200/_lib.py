@@ -49,6 +49,7 @@ SIGNATURES = {
     "hb_jt_set_timing": (C.c_int, [vp, i32]),
     "hb_jt_last_timing": (C.c_int, [vp, f64p]),
     "hb_jt_free": (None, [vp]),
+    "hb_factor_marginalize": (C.c_int, [i32, i32p, i32, i32p, i32p, i64p, f64p, i32, i32, i32p, i32p, f64p, i64, i64p]),
     "hb_ve_compile": (C.c_int, [vp, i32p, i32, i32p, i32, i32p, i32, vpp]),
     "hb_ve_result_scope": (C.c_int, [vp, i32, i32p, i32p, i32p]),
     "hb_ve_program_json": (C.c_int, [vp, i32, i32p, cpp]),

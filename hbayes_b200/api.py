@@ -337,3 +337,51 @@ def posteriorMarginal(net: BayesianNetwork, p, r, assignment, device=0) -> Facto
 
 def priorMarginal(net: BayesianNetwork, ea, eb, device=0) -> Factor:
     return VariableElimination(net, ea, eb, device=device).posterior([])
+
+
+# ---- class Factor's product / projectOut (Bayes/Factor.hs:113-188) on free-standing factors --------
+
+
+def _factor_marginalize(factors: Sequence[Factor], sum_var: int, device=0) -> Factor:
+    dims = {}
+    for f in factors:
+        for v, d in zip(f.variables, f.dims):
+            dims[v] = d
+    n_vars = (max(dims) + 1) if dims else 1
+    dim_arr = np.ones(n_vars, np.int32)
+    for v, d in dims.items():
+        dim_arr[v] = d
+    scope_off = np.zeros(len(factors) + 1, np.int32)
+    val_off = np.zeros(len(factors) + 1, np.int64)
+    for i, f in enumerate(factors):
+        scope_off[i + 1] = scope_off[i] + len(f.variables)
+        val_off[i + 1] = val_off[i] + len(f.values)
+    sa, sp = _i32(np.concatenate([np.asarray(f.variables, np.int32) for f in factors] + [np.zeros(0, np.int32)]))
+    vals = np.ascontiguousarray(np.concatenate([f.values for f in factors] + [np.zeros(1)]))
+    size = int(np.prod([d for v, d in dims.items() if v != sum_var])) if dims else 1
+    out = np.zeros(max(size, 1), np.float64)
+    scope = np.zeros(max(len(dims), 1), np.int32)
+    ns, nw = C.c_int32(), C.c_int64()
+    check(lib().hb_factor_marginalize(n_vars, dim_arr.ctypes.data_as(i32p), len(factors), scope_off.ctypes.data_as(i32p), sp,
+                                      val_off.ctypes.data_as(i64p), vals.ctypes.data_as(f64p), sum_var, device,
+                                      scope.ctypes.data_as(i32p), C.byref(ns), out.ctypes.data_as(f64p), len(out), C.byref(nw)))
+    sc = scope[: ns.value].tolist()
+    return Factor(sc, [dims[v] for v in sc], out[: nw.value].copy())
+
+
+def factorProduct(factors: Sequence[Factor], device=0) -> Factor:
+    """factorProduct (Bayes/Factor/CPT.hs:138): scope = foldr1 union, value = ps * (v1 * (v2 * ...))"""
+    return _factor_marginalize(factors, -1, device)
+
+
+def factorProjectOut(variables: Sequence[int], factor: Factor, device=0) -> Factor:
+    """factorProjectOut (CPT.hs:140-141).  One variable is the reference operation bit for bit (the only form the
+    hot path uses, Buckets.hs:109); several variables are summed one after the other, which reassociates the sum."""
+    for v in variables:
+        factor = _factor_marginalize([factor], v, device)
+    return factor
+
+
+def marginalizeOneVariable(factors: Sequence[Factor], variable: int, device=0) -> Factor:
+    """Buckets.hs:105-111: product of a bucket, then sum out `variable` -- one fused kernel launch"""
+    return _factor_marginalize(factors, variable, device)

@@ -515,6 +515,51 @@ int hb_jt_last_stats(const hb_jt* jt, int64_t* out8) {
 }
 void hb_jt_free(hb_jt* jt) { delete jt; }
 
+int hb_factor_marginalize(int32_t n_vars, const int32_t* dims, int32_t k, const int32_t* scope_off, const int32_t* scopes,
+                          const int64_t* val_off, const double* vals, int32_t sum_var, int32_t device, int32_t* out_scope,
+                          int32_t* n_scope, double* out, int64_t out_len, int64_t* n_written) {
+  return guarded([&] {
+    if (n_vars <= 0 || !dims || k < 0 || !scope_off || !val_off || !out || !n_written || (k > 0 && (!scopes || !vals)))
+      throw Error(HB_E_ARG, "null or empty argument");
+    std::vector<FreeFactor> fs((size_t)k);
+    bool mentions = sum_var < 0;
+    for (int i = 0; i < k; ++i) {
+      fs[i].scope.assign(scopes + scope_off[i], scopes + scope_off[i + 1]);
+      fs[i].values.assign(vals + val_off[i], vals + val_off[i + 1]);
+      for (int v : fs[i].scope) mentions = mentions || v == sum_var;
+    }
+    if (!mentions) throw Error(HB_E_ARG, "the variable to sum out occurs in no factor");
+    int32_t dev_list[1] = {device};
+    const int dev = pick_device(dev_list, 1);
+    std::unique_ptr<FactorOp> op(compile_factor_op(std::vector<int>(dims, dims + n_vars), fs, sum_var));
+    const Program& P = *op->prog;
+    if (out_len < P.out_width) throw Error(HB_E_ARG, "output buffer too small");
+    std::unique_ptr<Executor, void (*)(Executor*)> ex(executor_create(P, dev, 64 << 20), executor_destroy);
+    std::vector<int8_t> row((size_t)n_vars, -1);
+    int8_t* d_ev = nullptr;
+    double* d_out = nullptr;
+    cuda_ok(cudaMalloc(&d_ev, row.size()), "cudaMalloc");
+    cuda_ok(cudaMalloc(&d_out, (size_t)P.out_width * sizeof(double)), "cudaMalloc");
+    try {
+      cuda_ok(cudaMemcpy(d_ev, row.data(), row.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
+      executor_run(ex.get(), 1, d_ev, d_out, nullptr, nullptr, /*normalise=*/false);
+      executor_check(ex.get(), nullptr);
+      cuda_ok(cudaMemcpy(out, d_out, (size_t)P.out_width * sizeof(double), cudaMemcpyDeviceToHost), "cudaMemcpy");
+    } catch (...) {
+      cudaFree(d_ev);
+      cudaFree(d_out);
+      throw;
+    }
+    cudaFree(d_ev);
+    cudaFree(d_out);
+    const Group& g = P.groups.back();
+    if (out_scope)
+      for (size_t i = 0; i < g.out_scope.size(); ++i) out_scope[i] = g.out_scope[i];
+    if (n_scope) *n_scope = (int32_t)g.out_scope.size();
+    *n_written = P.out_width;
+  });
+}
+
 int hb_ve_compile(const hb_net* net, const int32_t* p, int32_t np, const int32_t* r, int32_t nr, const int32_t* devices,
                   int32_t n_devices, hb_ve** out) {
   return guarded([&] {

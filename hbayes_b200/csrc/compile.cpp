@@ -129,6 +129,21 @@ struct Compiler {
     return add(t);
   }
 
+  // a free-standing factor (hb_factor_*): values appended to the potential pool, reference layout
+  int free_factor(const std::vector<int>& scope, const std::vector<double>& values) {
+    Table t;
+    t.kind = T_POT;
+    t.scope = scope;
+    t.scalar = scope.empty();  // createCPTWithDims [] = Scalar
+    set_physical(t);
+    if ((int64_t)values.size() != t.size) throw Error(HB_E_ARG, "factor value count does not match its scope");
+    t.off = P.pot_entries;
+    if (P.extra_values.empty()) P.extra_off = P.pot_entries;
+    P.extra_values.insert(P.extra_values.end(), values.begin(), values.end());
+    P.pot_entries += t.size;
+    return add(t);
+  }
+
   // factorFromInstantiation (Bayes/Factor.hs:90-94) of an observed variable: 1.0 at the row's state.
   int indicator(int v) {
     Table t;
@@ -643,6 +658,41 @@ Program* compile_ve(const Network& net, const std::vector<int>& p, const std::ve
   prog->groups.push_back(std::move(g));
   C.finish(opt);
   return prog.release();
+}
+
+FactorOp* compile_factor_op(const std::vector<int>& dims, const std::vector<FreeFactor>& factors, int sum_var) {
+  auto op = std::make_unique<FactorOp>();
+  op->net = std::make_unique<Network>();
+  Network& net = *op->net;  // every vertex gets a trivial uniform prior: only the dimensions matter here
+  net.dims = dims;
+  for (int v = 0; v < (int)dims.size(); ++v) {
+    if (dims[v] < 1 || dims[v] > 127) throw Error(HB_E_ARG, "vertex dimension must be in 1..127");
+    net.scope.push_back({v});
+    net.values.push_back(std::vector<double>((size_t)dims[v], 1.0 / dims[v]));
+    net.names.push_back("n" + std::to_string(v));
+  }
+  if (sum_var >= (int)dims.size()) throw Error(HB_E_ARG, "unknown variable to sum out");
+  op->prog = std::make_unique<Program>();
+  CompileOptions opt;
+  opt.fuse = false;
+  Compiler C(net, *op->prog, {}, opt);
+  std::vector<int> ids;
+  for (const FreeFactor& f : factors) {
+    for (size_t i = 0; i < f.scope.size(); ++i) {
+      if (f.scope[i] < 0 || f.scope[i] >= (int)dims.size()) throw Error(HB_E_ARG, "factor mentions an unknown vertex");
+      for (size_t j = 0; j < i; ++j)
+        if (f.scope[i] == f.scope[j]) throw Error(HB_E_ARG, "factor repeats a vertex");
+    }
+    ids.push_back(C.free_factor(f.scope, f.values));
+  }
+  Group g;
+  g.kind = 3;
+  int res = C.product_sumout(ids, -1, g);                 // factorProduct
+  if (sum_var >= 0) res = C.product_sumout({res}, sum_var, g);  // factorProjectOut [sum_var] (1.0 * p, then the sum)
+  C.emit_output(res, g);
+  op->prog->groups.push_back(std::move(g));
+  C.finish(opt);
+  return op.release();
 }
 
 // Parity hook (hb_jt_describe_json / hb_ve_describe_json): the reference-level operation trace of every

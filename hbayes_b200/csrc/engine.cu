@@ -943,6 +943,8 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
         HB_CUDA(cudaMemcpy(ex->d_pots + P.pot_off[v], staged.data(), (size_t)entries * sizeof(double), cudaMemcpyHostToDevice));
       }
     }
+    if (!P.extra_values.empty())
+      HB_CUDA(cudaMemcpy(ex->d_pots + P.extra_off, P.extra_values.data(), P.extra_values.size() * sizeof(double), cudaMemcpyHostToDevice));
     HB_CUDA(cudaGetLastError());
   }
   HB_CUDA(cudaMalloc(&ex->d_shared, std::max<int64_t>(P.shared_entries, 1) * sizeof(double)));

@@ -6,6 +6,7 @@
 // tree, e.g. Bayes/FactorElimination.hs:130-143).
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -169,6 +170,8 @@ struct Program {
   std::vector<Group> groups;
   std::vector<Slice> slices;      // potentials that are sliced per row
   std::vector<int64_t> pot_off;  // vertex -> entry offset in the potential pool
+  std::vector<double> extra_values;  // free-standing factors (hb_factor_*), appended to the pool at extra_off
+  int64_t extra_off = 0;
   int64_t pot_entries = 0;
   int64_t shared_entries = 0;    // shared arena size
   int64_t row_entries = 0;       // per-row arena size (after liveness reuse)
@@ -194,6 +197,19 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
                     const std::vector<Query>& queries, const CompileOptions& opt = CompileOptions());
 Program* compile_ve(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
                     const std::vector<int>& observed, const CompileOptions& opt = CompileOptions());
+
+// One factor-algebra operation on free-standing factors: factorProduct of `factors` and, when sum_var >= 0,
+// factorProjectOut [sum_var] of the product (= marginalizeOneVariable, Buckets.hs:105-111).  `dims` gives the
+// dimension of every vertex id that occurs.  The program has a single group whose out_scope is the result scope.
+struct FreeFactor {
+  std::vector<int> scope;
+  std::vector<double> values;
+};
+struct FactorOp {
+  std::unique_ptr<Network> net;  // carrier of the vertex dimensions
+  std::unique_ptr<Program> prog;
+};
+FactorOp* compile_factor_op(const std::vector<int>& dims, const std::vector<FreeFactor>& factors, int sum_var);
 
 std::string describe_network(const Network& net);
 std::string describe_tree(const Tree& t);

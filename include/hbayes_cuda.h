@@ -130,6 +130,18 @@ int hb_jt_set_timing(hb_jt* jt, int32_t on);
 int hb_jt_last_timing(hb_jt* jt, double* out4);
 void hb_jt_free(hb_jt* jt);
 
+/* ---- factor algebra on free-standing factors ------------------------------------------------- */
+/* factorProduct (Bayes/Factor/CPT.hs:138 = _factorProduct, PrivateCPT.hs:215-238) of k factors and, when
+ * sum_var >= 0, factorProjectOut [sum_var] of the product (CPT.hs:140-141): together marginalizeOneVariable
+ * (Bayes/VariableElimination/Buckets.hs:105-111), the unit the GPU kernels fuse.  Factor i has scope
+ * scopes[scope_off[i]..scope_off[i+1]) (vertex ids, reference order; empty = Scalar) and values
+ * vals[val_off[i]..val_off[i+1]) with the first variable slowest; dims[v] is the dimension of vertex v.
+ * out_scope receives the result's variable order (foldr1 union of the scopes, minus sum_var), out its values.
+ * One call = one compile + one launch: meant for tests and for checking the algebra, not for throughput. */
+int hb_factor_marginalize(int32_t n_vars, const int32_t* dims, int32_t k, const int32_t* scope_off, const int32_t* scopes,
+                          const int64_t* val_off, const double* vals, int32_t sum_var, int32_t device, int32_t* out_scope,
+                          int32_t* n_scope, double* out, int64_t out_len, int64_t* n_written);
+
 /* ---- variable elimination ------------------------------------------------------------------ */
 /* posteriorMarginal g p r (Bayes/VariableElimination.hs:116-130): p = variables to eliminate, in order,
  * r = remaining (query) variables.  priorMarginal is the same with no evidence. */

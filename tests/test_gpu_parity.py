@@ -189,3 +189,33 @@ def test_properties_at_scale():
             assert (blk[np.arange(rows), ev[:, v]] > 0.999999).all()
     perm = np.random.RandomState(0).permutation(rows)
     assert same_bits(pjt.posteriors_batch(ev[perm]), out[perm])
+
+
+def test_asia_goldens_through_the_c_abi():
+    """Bayes/Test/ReferencePatterns.hs:119-131 (asia priors, state 0 = yes), abs 1e-4 as the reference asserts"""
+    gold = {"A": .01, "S": .5, "T": .0104, "L": .055, "B": .45, "E": .0648, "X": .1103, "D": .4360}
+    for fname in ("asia.net", "asia_rev.net"):
+        net = hb.importBayesianGraph(os.path.join(G, fname))
+        jt = hb.createJunctionTree(hb.nodeComparisonForTriangulation, net)
+        for name, want in gold.items():
+            got = hb.posterior(jt, [net.ids[name]]).values
+            assert abs(got[0] - want) < 1e-4 and abs(got[1] - (1 - want)) < 1e-4
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ve_equals_jt_on_synthetic_networks(seed):
+    """the reference's VE == JT cross-check (Test/CompareEliminations.hs:67-84, rel 2e-5) on random networks,
+    both engines on the GPU, at the north-star tolerance"""
+    net = random_net(40 + seed, n=8 + 2 * seed, states=(2, 4), max_parents=3)
+    pnet, _ = pair(net=net)
+    jt = hb.JunctionTree(pnet)
+    rng = np.random.RandomState(seed)
+    observed = sorted(rng.permutation(net.n)[:3].tolist())
+    ev = synth.evidence_matrix(net, 64, observed, 9 + seed)
+    post = jt.posteriors_batch(ev)
+    off = np.concatenate([[0], np.cumsum(net.dims)])
+    order = hb.minFillOrder(pnet)
+    for v in range(0, net.n, 3):
+        p = [x for x in order if x != v] + [x for x in range(net.n) if x not in order and x != v]
+        ve = hb.VariableElimination(pnet, p, [v]).posterior_batch(ev)
+        assert max_rel_err(ve, post[:, off[v]:off[v + 1]]) <= 1e-12

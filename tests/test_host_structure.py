@@ -125,3 +125,44 @@ def test_ve_orders_and_traces(shape):
         _, _, want = onet.posterior_marginal(p, r, ev, trace=True)
         got = ve.program([v for v, _ in ev])["groups"][0]["steps"]
         assert got == want
+
+
+def _tree_properties(d, n_vars):
+    """Bayes/FactorElimination.hs:341-378: every variable's clusters form a connected subtree (running
+    intersection), separators are the intersections of their end clusters, every CPT family sits in its cluster."""
+    clusters = [set(c) for c in d["clusters"]]
+    nc = len(clusters)
+    parent = [-1] * nc
+    for s, (p, c) in enumerate(zip(d["sep_parent"], d["sep_child"])):
+        parent[c] = p
+        assert set(d["sep_vars"][s]) == clusters[p] & clusters[c]
+    assert sum(1 for p in parent if p < 0) == 1 and parent[d["root"]] == -1
+    for v in range(n_vars):
+        holders = [c for c in range(nc) if v in clusters[c]]
+        assert holders, "variable in no cluster"
+        # connected subtree <=> exactly one holder whose parent is not a holder
+        tops = [c for c in holders if parent[c] < 0 or v not in clusters[parent[c]]]
+        assert len(tops) == 1, (v, holders)
+    for c in range(nc):  # maximal: no cluster contains another
+        assert not any(c != o and clusters[c] <= clusters[o] for o in range(nc))
+    return clusters
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_running_intersection_and_family_coverage(seed):
+    net = random_net(100 + seed, n=6 + 3 * seed, states=(2, 4), max_parents=3, shuffle=seed % 3 == 0)
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    for cmp in (hb.nodeComparisonForTriangulation, hb.numberOfAddedEdges):
+        d = hb.JunctionTree(pnet, cmp=cmp, device=None).describe()
+        clusters = _tree_properties(d, net.n)
+        placed = sorted(v for f in d["factors"] for v in f)
+        assert placed == list(range(net.n))  # every CPT assigned exactly once
+        for c, fs in enumerate(d["factors"]):
+            for v in fs:
+                assert set(net.scopes[v]) <= clusters[c]
+
+
+def test_c3_tree_properties():
+    net, _ = synth.config_c3()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    _tree_properties(hb.JunctionTree(pnet, device=None).describe(), net.n)
