@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhbayes_cuda.so")
+LIB_PATH = os.environ.get("HB_LIB") or os.path.join(HERE, "libhbayes_cuda.so")  # HB_LIB: A/B builds of the same library
 
 HB_OK, HB_E_ARG, HB_E_NO_CLUSTER, HB_E_CUDA, HB_E_OOM, HB_E_IO, HB_E_UNSUPPORTED, HB_E_NCCL = 0, -1, -2, -3, -4, -5, -6, -7
 HB_STRUCTURE_ONLY = -1

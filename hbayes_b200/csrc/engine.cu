@@ -50,7 +50,10 @@ constexpr int MAXK = 6;       // chain inputs handled by the templated kernel
 constexpr int MAXS = 4;       // structural scalars per step
 constexpr int MAXL = 4;       // levels of a fused chain
 constexpr int MAXOBS = 8;     // observed variables inside one query
-constexpr int BLOCK = 256;
+#ifndef HB_BLOCK
+#define HB_BLOCK 256
+#endif
+constexpr int BLOCK = HB_BLOCK;
 
 // A table as a kernel sees it: element (e, row) lives at base[e * mult + rowterm(row)].
 struct TabRef {
@@ -238,8 +241,11 @@ constexpr int FU = 2;  // output entries evaluated in lock-step by one thread of
 // sum (0: run-time count).  The innermost level is where the loads are: it is fully static, so all its
 // FU * DI * KI loads are issued back to back.  The outer levels are walked as an odometer (run-time
 // uniform control flow, executed once per finished inner sum).
+#ifndef HB_FUSED_MINB
+#define HB_FUSED_MINB 2
+#endif
 template <int KO, int KI, int V, int DI>
-__global__ void __launch_bounds__(BLOCK, 2) fused_kernel(const __grid_constant__ FusedArgs<KO + KI> a) {
+__global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __grid_constant__ FusedArgs<KO + KI> a) {
   constexpr int K = KO + KI;
   typedef Rows<V> R;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) * V;
