@@ -24,6 +24,7 @@ from .api import (  # noqa: F401
     factorProjectOut,
     marginalizeOneVariable,
     importBayesianGraph,
+    learnEM,
     minDegreeOrder,
     minFillOrder,
     nodeComparisonForTriangulation,

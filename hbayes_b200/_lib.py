@@ -41,6 +41,8 @@ SIGNATURES = {
     "hb_jt_set_evidence": (C.c_int, [vp, i32, i32p, i32p]),
     "hb_jt_posterior": (C.c_int, [vp, i32, i32p, i32p, f64p, i64, i64p]),
     "hb_jt_posteriors_batch": (C.c_int, [vp, i64, vp, vp, i32]),
+    "hb_jt_queries_batch": (C.c_int, [vp, i32, i32p, i32p, i64, vp, vp, i32, i32p]),
+    "hb_jt_queries_width": (C.c_int, [vp, i32, i32p, i32p, i64p]),
     "hb_jt_set_split": (C.c_int, [vp, i32, i32p, i32p]),
     "hb_jt_normalise_batch": (C.c_int, [vp, i64, vp, i32]),
     "hb_jt_set_stream": (C.c_int, [vp, vp]),

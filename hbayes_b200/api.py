@@ -251,6 +251,30 @@ class JunctionTree(_Batched):
         """One query per row: changeEvidence row; posterior [v] for all v.  Returns [n_rows][sum dims]."""
         return self._run_matrix(lib().hb_jt_posteriors_batch, evidence, out, self.net.width)
 
+    def queries_batch(self, queries: Sequence[Sequence[int]], evidence: np.ndarray):
+        """batched `posterior jt q` for a list of queries; returns [(Factor-like scope, dims, values [rows][size])]"""
+        flat, off = [], [0]
+        for q in queries:
+            flat += list(q)
+            off.append(len(flat))
+        fa, fp = _i32(flat)
+        oa, op = _i32(off)
+        width = C.c_int64()
+        check(lib().hb_jt_queries_width(self._h, len(queries), op, fp, C.byref(width)))
+        ev = np.ascontiguousarray(evidence, np.int8)
+        out = np.empty((ev.shape[0], width.value), np.float64)
+        scopes = np.zeros(len(flat), np.int32)
+        check(lib().hb_jt_queries_batch(self._h, len(queries), op, fp, ev.shape[0], ev.ctypes.data, out.ctypes.data, HB_HOST_PTRS,
+                                        scopes.ctypes.data_as(i32p)))
+        res, col = [], 0
+        for i, q in enumerate(queries):
+            sc = scopes[off[i]:off[i + 1]].tolist()
+            dims = [self.net.dims[v] for v in sc]
+            size = int(np.prod(dims))
+            res.append((sc, dims, out[:, col:col + size]))
+            col += size
+        return res
+
     def set_split(self, fixed: Sequence[tuple]):
         """split clique: this handle owns the slice `fixed` = [(vertex, state)]; batch results become unnormalised"""
         va, vp_ = _i32([e[0] for e in fixed])
@@ -385,3 +409,32 @@ def factorProjectOut(variables: Sequence[int], factor: Factor, device=0) -> Fact
 def marginalizeOneVariable(factors: Sequence[Factor], variable: int, device=0) -> Factor:
     """Buckets.hs:105-111: product of a bucket, then sum out `variable` -- one fused kernel launch"""
     return _factor_marginalize(factors, variable, device)
+
+
+def learnEM(samples: np.ndarray, net: BayesianNetwork, device=0):
+    """One expectation/maximisation step (Bayes/EM.hs:36-66): for every sample, `posterior` of each CPT family and of
+    its parents under that sample's evidence; the family posteriors are summed over the samples and divided by the
+    summed parent posteriors (`divide _ 0 = 0`).  `samples`: int8 [n_samples][n_vars] evidence matrix (-1 = missing)
+    with ONE observed set.  Returns the new CPT values per vertex in the CPT's own layout [child, parents...].
+    All samples go through the GPU in one batch; the sum over samples is a NumPy pairwise sum (the reference folds
+    left sample by sample), so results agree to ~1e-13 relative, not bit for bit."""
+    jt = JunctionTree(net, device=device)
+    queries = []
+    for v in range(net.n):
+        queries.append(net.scopes[v])
+        if len(net.scopes[v]) > 1:
+            queries.append(net.scopes[v][1:])
+    res = iter(jt.queries_batch(queries, samples))
+    new_values = []
+    for v in range(net.n):
+        sc, dims, vals = next(res)
+        fam = vals.sum(0).reshape(dims).transpose([sc.index(x) for x in net.scopes[v]])  # -> [child, parents...]
+        if len(net.scopes[v]) > 1:
+            psc, pdims, pvals = next(res)
+            par = pvals.sum(0).reshape(pdims).transpose([psc.index(x) for x in net.scopes[v][1:]])[None, ...]
+        else:
+            par = np.full([1] * 1, float(samples.shape[0]))  # posterior of nothing: Scalar 1.0 per sample
+        with np.errstate(divide="ignore", invalid="ignore"):
+            new = np.where(par == 0.0, 0.0, fam / par)
+        new_values.append(np.ascontiguousarray(new).reshape(-1))
+    return new_values

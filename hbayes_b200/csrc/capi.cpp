@@ -251,11 +251,18 @@ struct hb_jt {
     for (auto& f : s.fixed) key.push_back(f.first), key.push_back(f.second);
     auto it = s.cache.find(key);
     if (it != s.cache.end()) return *it->second;
-    std::vector<Query> qs;
+    std::vector<Query> qs;  // `query`: empty = posterior [v] for every v; else queries separated by -1
     if (query.empty())
       for (int v = 0; v < s.net.n(); ++v) qs.push_back(Query{{v}});
-    else
-      qs.push_back(Query{query});
+    else {
+      qs.push_back(Query{});
+      for (int v : query) {
+        if (v == -1)
+          qs.push_back(Query{});
+        else
+          qs.back().vars.push_back(v);
+      }
+    }
     auto c = std::make_unique<Compiled>();
     CompileOptions opt;
     opt.fixed = s.fixed;
@@ -456,6 +463,45 @@ int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, do
   return guarded([&] {
     if (!jt) throw Error(HB_E_ARG, "null handle");
     run_matrix(jt->s, [&](const std::vector<int>& obs) -> Compiled& { return jt->program(obs, {}); }, n_rows, evidence, out, flags);
+  });
+}
+int hb_jt_queries_batch(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t n_rows,
+                        const int8_t* evidence, double* out, int32_t flags, int32_t* out_scopes) {
+  return guarded([&] {
+    if (!jt || n_queries <= 0 || !query_off || !query_vars) throw Error(HB_E_ARG, "null or empty query list");
+    std::vector<int> flat;
+    for (int q = 0; q < n_queries; ++q) {
+      if (query_off[q + 1] <= query_off[q]) throw Error(HB_E_ARG, "empty query");
+      if (q) flat.push_back(-1);
+      flat.insert(flat.end(), query_vars + query_off[q], query_vars + query_off[q + 1]);
+    }
+    const Program* last = nullptr;
+    run_matrix(jt->s, [&](const std::vector<int>& obs) -> Compiled& {
+      Compiled& c = jt->program(obs, flat);
+      last = c.prog.get();
+      return c;
+    }, n_rows, evidence, out, flags);
+    if (out_scopes && last) {  // result variable order of every query (rule A.5 / A.10), concatenated like query_vars
+      int at = 0;
+      for (const Group& g : last->groups)
+        if (g.kind == 2)
+          for (int v : g.out_scope) out_scopes[at++] = v;
+    }
+  });
+}
+int hb_jt_queries_width(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t* width) {
+  return guarded([&] {
+    if (!jt || n_queries <= 0 || !query_off || !query_vars || !width) throw Error(HB_E_ARG, "null or empty query list");
+    int64_t w = 0;
+    for (int q = 0; q < n_queries; ++q) {
+      int64_t p = 1;
+      for (int i = query_off[q]; i < query_off[q + 1]; ++i) {
+        if (query_vars[i] < 0 || query_vars[i] >= jt->s.net.n()) throw Error(HB_E_ARG, "query on unknown vertex");
+        p *= jt->s.net.dims[query_vars[i]];
+      }
+      w += p;
+    }
+    *width = w;
   });
 }
 int hb_jt_set_split(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states) {

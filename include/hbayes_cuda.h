@@ -115,6 +115,14 @@ int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, do
 int hb_jt_set_split(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states);
 /* factorNorm + factorDivide of a summed, unnormalised result matrix [n_rows][sum dims] in place */
 int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags);
+/* Batched `posterior jt q` for a LIST of queries (each a set of variables inside one cluster, e.g. a CPT family and
+ * its parents: the E-step of Bayes/EM.hs:47-66 for all samples at once).  Query i = query_vars[query_off[i]..
+ * query_off[i+1]).  out: [n_rows][sum_i prod dims(query i)] (hb_jt_queries_width); each block is laid out in the
+ * result variable order of the reference, written to out_scopes (same shape as query_vars) when not NULL.
+ * Mixed observed sets need one call per observed set (the result order may depend on it). */
+int hb_jt_queries_batch(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t n_rows,
+                        const int8_t* evidence, double* out, int32_t flags, int32_t* out_scopes);
+int hb_jt_queries_width(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t* width);
 /* CUDA stream (a cudaStream_t) the handle launches on; NULL = the default stream */
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream);
 /* bytes of device workspace the row arena may use (0 = default) */
