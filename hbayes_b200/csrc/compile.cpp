@@ -477,7 +477,16 @@ struct Compiler {
     // shared arena: no reuse (computed once, read by every row)
     for (auto& t : P.tables)
       if (t.kind == T_SHARED && t.alias_of < 0 && t.def_step >= 0) t.off = P.shared_entries, P.shared_entries += t.size;
-    // row arena: first-fit over a free list, tables released after their last reader
+    // row arena.  When giving every per-row table its own place costs at most twice the memory of reusing freed
+    // space, do that: reuse orders otherwise independent steps (write-after-read) and the engine overlaps
+    // independent steps inside its CUDA graph.  Otherwise (long elimination chains over huge tables): first-fit
+    // over a free list, tables released after their last reader.
+    {
+      int64_t no_reuse = 0;
+      for (const Step& st : P.steps)
+        if (st.kind == STEP_PRODSUM && !st.shared) no_reuse += P.tables[st.out].size;
+      P.row_entries_no_reuse = no_reuse;
+    }
     std::vector<std::pair<int64_t, int64_t>> free_list;  // (offset, size), sorted by offset
     int64_t top = 0;
     std::vector<std::vector<int>> dies_at(P.steps.size());
@@ -509,6 +518,12 @@ struct Compiler {
         P.row_entries = std::max(P.row_entries, top);
       }
       for (int id : dies_at[s]) release(P.tables[id].off, P.tables[id].size);
+    }
+    if (P.row_entries_no_reuse <= 2 * P.row_entries) {
+      int64_t at = 0;
+      for (const Step& st : P.steps)
+        if (st.kind == STEP_PRODSUM && !st.shared) P.tables[st.out].off = at, at += P.tables[st.out].size;
+      P.row_entries = at;
     }
   }
 };

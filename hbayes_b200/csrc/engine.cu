@@ -593,6 +593,14 @@ struct Executor {
   std::map<int, cudaGraphExec_t> graphs;  // rows in tile -> instantiated graph, valid for the current RT
   cudaStream_t capture_stream = nullptr;
   int n_row_steps = 0;
+  // Inside the graph independent steps may overlap: during capture they are spread over several streams,
+  // ordered only by their true dependencies (computed once from the arena regions they read and write:
+  // read-after-write, and write-after-read/write because the arena reuses memory by liveness).
+  std::vector<cudaStream_t> side_streams;
+  std::vector<cudaEvent_t> step_events;
+  std::vector<std::vector<int>> step_deps;  // per row step (in launch order): earlier row steps it must follow
+  std::vector<int> step_lane;               // per row step: which stream it is captured on
+  int n_lanes = 8;
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     graphs.clear();
@@ -612,6 +620,8 @@ struct Executor {
     cudaSetDevice(device);
     drop_graphs();
     if (capture_stream) cudaStreamDestroy(capture_stream);
+    for (cudaStream_t st : side_streams) cudaStreamDestroy(st);
+    for (cudaEvent_t e : step_events) cudaEventDestroy(e);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
                     (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_out_chunks, (void*)d_norm_cols, (void*)d_gen_in,
@@ -994,8 +1004,49 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     }
   }
   ex->d_maps = upload(maps);
-  for (const Step& st : P.steps)
-    if (st.kind == STEP_PRODSUM && !st.shared) ++ex->n_row_steps;
+  {
+    const int LANES = std::max(1, std::min(64, getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 16));
+    ex->n_lanes = LANES;
+    struct Access {
+      std::vector<std::pair<int64_t, int64_t>> reads;
+      std::pair<int64_t, int64_t> write;
+    };
+    std::vector<Access> acc;
+    auto overlap = [](const std::pair<int64_t, int64_t>& a, const std::pair<int64_t, int64_t>& b) {
+      return a.first < b.first + b.second && b.first < a.first + a.second;
+    };
+    std::vector<int> lane_last(LANES, -1);
+    int rr = 0;
+    for (const Step& st : P.steps) {
+      if (st.kind != STEP_PRODSUM || st.shared) continue;
+      Access a;
+      a.write = {P.tables[st.out].off, P.tables[st.out].size};
+      for (int i = 0; i < st.n_inputs(); ++i) {
+        const Table& t = P.tables[flat_input(st, i).table];
+        if (t.kind == T_ROW) a.reads.push_back({t.off, t.size});
+      }
+      for (int id : st.scalars)
+        if (P.tables[id].kind == T_ROW) a.reads.push_back({P.tables[id].off, P.tables[id].size});
+      const int s = (int)acc.size();
+      std::vector<int> deps;
+      int producer = -1;
+      for (int t = s - 1; t >= 0; --t) {
+        bool raw = false, war = overlap(acc[t].write, a.write);
+        for (auto& r : a.reads) raw = raw || overlap(acc[t].write, r);
+        for (auto& r : acc[t].reads) war = war || overlap(r, a.write);
+        if (raw || war) deps.push_back(t);
+        if (raw && producer < 0) producer = t;
+      }
+      // the steps of one reference operation group (a message, a posterior) form a chain: same stream
+      (void)producer;
+      (void)rr;
+      const int lane = st.group >= 0 ? st.group % LANES : 0;
+      ex->step_deps.push_back(deps);
+      ex->step_lane.push_back(lane);
+      acc.push_back(std::move(a));
+      ++ex->n_row_steps;
+    }
+  }
   // column chunks of the normalise/expand kernel
   {
     int max_w = 1;
@@ -1101,9 +1152,48 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
       if (it == ex->graphs.end()) {
         if (!ex->capture_stream) HB_CUDA(cudaStreamCreateWithFlags(&ex->capture_stream, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
+        while ((int)ex->side_streams.size() < ex->n_lanes - 1) {
+          cudaStream_t st;
+          HB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+          ex->side_streams.push_back(st);
+        }
+        while ((int)ex->step_events.size() < ex->n_row_steps + ex->n_lanes) {
+          cudaEvent_t e;
+          HB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          ex->step_events.push_back(e);
+        }
+        static const bool overlap_on = !(getenv("HB_GRAPH_LANES") && atoi(getenv("HB_GRAPH_LANES")) == 0);
+        auto lane_stream = [&](int lane) { return lane == 0 || !overlap_on ? ex->capture_stream : ex->side_streams[lane - 1]; };
         HB_CUDA(cudaStreamBeginCapture(ex->capture_stream, cudaStreamCaptureModeThreadLocal));
         try {
-          launch_steps(ex->capture_stream);
+          // fork: every side stream joins the capture
+          cudaEvent_t fork = ex->step_events[ex->n_row_steps];
+          HB_CUDA(cudaEventRecord(fork, ex->capture_stream));
+          if (overlap_on)
+            for (cudaStream_t st : ex->side_streams) HB_CUDA(cudaStreamWaitEvent(st, fork, 0));
+          int64_t gi = 0, gs = 0;
+          int s = 0;
+          for (size_t si = 0; si < P.steps.size(); ++si) {
+            const Step& st = P.steps[si];
+            if (st.kind != STEP_PRODSUM) continue;
+            if (!st.shared) {
+              cudaStream_t on = lane_stream(ex->step_lane[s]);
+              if (overlap_on)
+                for (int dep : ex->step_deps[s])
+                  if (ex->step_lane[dep] != ex->step_lane[s]) HB_CUDA(cudaStreamWaitEvent(on, ex->step_events[dep], 0));
+              launch_prodsum(*ex, st, (int)si, stride, nr, on, gi, gs);
+              if (overlap_on) HB_CUDA(cudaEventRecord(ex->step_events[s], on));
+              ++s;
+            }
+            if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
+          }
+          // join
+          if (overlap_on)
+            for (size_t l = 0; l < ex->side_streams.size(); ++l) {
+              cudaEvent_t e = ex->step_events[ex->n_row_steps + 1 + l];
+              HB_CUDA(cudaEventRecord(e, ex->side_streams[l]));
+              HB_CUDA(cudaStreamWaitEvent(ex->capture_stream, e, 0));
+            }
         } catch (...) {
           cudaStreamEndCapture(ex->capture_stream, &graph);
           if (graph) cudaGraphDestroy(graph);

@@ -174,7 +174,8 @@ struct Program {
   int64_t extra_off = 0;
   int64_t pot_entries = 0;
   int64_t shared_entries = 0;    // shared arena size
-  int64_t row_entries = 0;       // per-row arena size (after liveness reuse)
+  int64_t row_entries = 0;       // per-row arena size
+  int64_t row_entries_no_reuse = 0;  // what it would be without reusing freed space
   int64_t out_width = 0;         // doubles written per row
   // statistics (per row, physical)
   int64_t stat_prod = 0, stat_reads = 0, stat_row_read = 0, stat_row_write = 0, stat_max_table = 0;
