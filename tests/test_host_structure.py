@@ -166,3 +166,16 @@ def test_c3_tree_properties():
     net, _ = synth.config_c3()
     pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
     _tree_properties(hb.JunctionTree(pnet, device=None).describe(), net.n)
+
+
+def test_plain_c_program_uses_the_abi(tmp_path):
+    import subprocess
+
+    exe = str(tmp_path / "c_abi_smoke")
+    src = os.path.join(ROOT, "tests", "c_abi_smoke.c")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", src, "-o", exe, "-L" + libdir, "-lhbayes_cuda", "-Wl,-rpath," + libdir],
+                   check=True)
+    r = subprocess.run([exe, os.path.join(G, "cancer.net")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert '"clusters":[[2,3,4],[0,3,4],[1,3]]' in r.stdout
