@@ -55,7 +55,7 @@ def config_dict(n_gpus, rows_per_gpu):
         "n_vars": 37,
         "out_doubles_per_row": 107,
         "sharding": "rows x%d, no collective" % n_gpus,
-        "l2_policy": "working set per step >> L2 (row arena 13.9 GB, output 0.9 GB per GPU): no flush needed",
+        "l2_policy": "working set per step >> L2 (row arena 21 GB, output 0.9 GB per GPU): no flush needed",
     }
 
 
