@@ -219,3 +219,22 @@ def test_ve_equals_jt_on_synthetic_networks(seed):
         p = [x for x in order if x != v] + [x for x in range(net.n) if x not in order and x != v]
         ve = hb.VariableElimination(pnet, p, [v]).posterior_batch(ev)
         assert max_rel_err(ve, post[:, off[v]:off[v + 1]]) <= 1e-12
+
+
+def test_disconnected_and_single_variable_networks():
+    """empty separators make the messages structural Scalars (the `ps` path of _factorProduct), isolated
+    observed variables make whole results the constant 1.0"""
+    nets = [
+        synth.SynthNet([3], [[]], [[0.2, 0.5, 0.3]]),
+        synth.SynthNet([2, 3, 2, 2], [[], [], [1], []], [[0.3, 0.7], [0.2, 0.5, 0.3], [0.1, 0.4, 0.6, 0.9, 0.6, 0.4], [0.5, 0.5]]),
+    ]
+    for net in nets:
+        pnet, onet = pair(net=net)
+        pjt, ojt = hb.JunctionTree(pnet), OracleJT(onet)
+        assert pjt.describe() == ojt.describe()
+        rng = np.random.RandomState(4)
+        for observed in ([], [0], list(range(net.n))[-1:], list(range(net.n))):
+            ev = np.full((37, net.n), -1, np.int8)
+            for v in observed:
+                ev[:, v] = rng.randint(0, net.dims[v], 37)
+            assert_same(pjt.posteriors_batch(ev), ojt.posteriors_batch(ev), (net.n, observed))
