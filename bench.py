@@ -60,39 +60,70 @@ def config_dict(n_gpus, rows_per_gpu):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled every few
+    milliseconds (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints); falls back
+    to spawning nvidia-smi when the NVML binding is not importable."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+        self.index, self.mhz, self.max_mhz, self.reasons, self.stop_flag, self.thread = index, [], None, set(), False, None
+        self.nvml = None
+        try:
+            import pynvml
 
-    def _run(self):
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.mhz.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def _poll_smi(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 6:
+                    self.mhz.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for i, name in enumerate(self.NAMES):
+                        if f[2 + i].lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def start(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread = threading.Thread(target=self._poll_nvml if self.nvml else self._poll_smi, daemon=True)
         self.thread.start()
 
     def stop(self):
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=6)
-        mhz = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(self.mhz)) if self.mhz else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.mhz), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_port_rate(n_rows, threads):
