@@ -314,21 +314,8 @@ struct Compiler {
     std::vector<int64_t> fstride(nq, 1);
     st.n_full = 1;
     for (int i = nq - 1; i >= 0; --i) fstride[i] = st.n_full, st.n_full *= net.dims[t.scope[i]];
-    // physical strides of the stored table (an alias shares its target's layout)
+    st.full_scope = t.scope;  // full_map is built in finish(), once the stored layouts are final
     const Table& stored = T(rid);
-    st.full_map.assign((size_t)st.n_full, 0);
-    std::vector<int> digit(nq, 0);
-    for (int64_t e = 0; e < st.n_full; ++e) {
-      int64_t off = 0;
-      for (int i = 0; i < nq; ++i)
-        for (size_t j = 0; j < stored.pscope.size(); ++j)
-          if (stored.pscope[j] == t.scope[i]) off += stored.pstride[j] * digit[i];
-      st.full_map[e] = (int32_t)off;
-      for (int i = nq - 1; i >= 0; --i) {
-        if (++digit[i] < net.dims[t.scope[i]]) break;
-        digit[i] = 0;
-      }
-    }
     for (int i = 0; i < nq; ++i)
       if (P.is_observed[t.scope[i]]) {
         st.obs_var.push_back(t.scope[i]);
@@ -411,38 +398,88 @@ struct Compiler {
         if (!dead[s]) kept.push_back(std::move(P.steps[s]));
       P.steps.swap(kept);
     }
-    // ---- 3. index maps and statistics ----
+    // ---- 3. stored layouts, index maps and statistics ----
     for (Step& st : P.steps) {
-      if (st.kind != STEP_PRODSUM) continue;
-      const Table& out = P.tables[st.out];
+      if (st.kind == STEP_OUTPUT) {  // full entry -> stored entry of the result (layouts are final by now)
+        const Table& stored = P.tables[st.result];
+        const int nq = (int)st.full_scope.size();
+        st.full_map.assign((size_t)st.n_full, 0);
+        std::vector<int> digit(nq, 0);
+        for (int64_t e = 0; e < st.n_full; ++e) {
+          int64_t off = 0;
+          for (int i = 0; i < nq; ++i)
+            for (size_t j = 0; j < stored.pscope.size(); ++j)
+              if (stored.pscope[j] == st.full_scope[i]) off += stored.pstride[j] * digit[i];
+          st.full_map[e] = (int32_t)off;
+          for (int i = nq - 1; i >= 0; --i) {
+            if (++digit[i] < net.dims[st.full_scope[i]]) break;
+            digit[i] = 0;
+          }
+        }
+        continue;
+      }
+      Table& out = P.tables[st.out];
       const int nk = (int)out.pscope.size();
-      // split the output index: trailing variables with product C go into `lo`, the rest into `hi`
-      int split = nk;
+      auto stride_in = [&](const Table& t, int v) -> int64_t {
+        for (size_t i = 0; i < t.pscope.size(); ++i)
+          if (t.pscope[i] == v) return t.pstride[i];
+        return 0;
+      };
+      // blocking variable: the output variable whose absence from the innermost-level inputs saves the most
+      // loads when a thread walks two of its states together; the output is stored with that variable fastest
+      int wpos = -1;
+      if (opt.block) {
+        const Level& inner = st.levels.back();
+        double terms = 1;
+        for (const Level& l : st.levels) terms *= l.d;
+        double best = -1;
+        for (int j = 0; j < nk; ++j) {
+          const int U = net.dims[out.pscope[j]];
+          const double keep = (double)((U + 1) / 2) / U;  // loads left for an input that does not depend on it
+          double saved = 0;
+          if ((int)inner.in.size() <= 3)
+            for (const StepInput& in : inner.in)
+              if (stride_in(P.tables[in.table], out.pscope[j]) == 0) saved += terms * (1.0 - keep);
+          if (saved >= best) best = saved, wpos = j;  // ties: the last variable (the natural row-major layout)
+        }
+      } else if (nk > 0)
+        wpos = nk - 1;
+      st.w_var = wpos >= 0 ? out.pscope[wpos] : -1;
+      st.U = wpos >= 0 ? net.dims[st.w_var] : 1;
+      st.n_red = st.n_out / st.U;
+      std::vector<int> red;  // the other output variables, in scope order
+      for (int j = 0; j < nk; ++j)
+        if (j != wpos) red.push_back(out.pscope[j]);
+      {  // stored layout of the output: row-major over `red`, then w fastest
+        int64_t acc = st.U;
+        std::vector<int64_t> ps(nk, 1);
+        for (int j = nk - 1; j >= 0; --j)
+          if (j != wpos) ps[j] = acc, acc *= net.dims[out.pscope[j]];
+        out.pstride = ps;
+      }
+      const int nr = (int)red.size();
+      int split = nr;
       int64_t C = 1;
-      while (split > 0 && C * C < st.n_out && C * net.dims[out.pscope[split - 1]] <= 4096) C *= net.dims[out.pscope[--split]];
+      while (split > 0 && C * C < st.n_red && C * net.dims[red[split - 1]] <= 4096) C *= net.dims[red[--split]];
       st.C = C;
-      st.n_hi = st.n_out / C;
+      st.n_hi = st.n_red / C;
       int64_t terms = 1;
       for (size_t l = 0; l < st.levels.size(); ++l) {
         terms *= st.levels[l].d;
         for (StepInput& in : st.levels[l].in) {
           const Table& t = P.tables[in.table];
-          auto stride_of = [&](int v) -> int64_t {
-            for (size_t i = 0; i < t.pscope.size(); ++i)
-              if (t.pscope[i] == v) return t.pstride[i];
-            return 0;
-          };
           in.lstride.clear();
-          for (size_t m = 0; m <= l; ++m) in.lstride.push_back(st.levels[m].sum_var >= 0 ? stride_of(st.levels[m].sum_var) : 0);
+          for (size_t m = 0; m <= l; ++m) in.lstride.push_back(st.levels[m].sum_var >= 0 ? stride_in(t, st.levels[m].sum_var) : 0);
+          in.wstride = st.w_var >= 0 ? stride_in(t, st.w_var) : 0;
           auto fill = [&](std::vector<uint32_t>& dst, size_t count, int from, int to) {
             dst.assign(count, 0);
-            std::vector<int> digit(nk, 0);
+            std::vector<int> digit(nr, 0);
             int64_t off = 0;
             for (size_t e = 0; e < count; ++e) {
               dst[e] = (uint32_t)off;
               for (int j = to - 1; j >= from; --j) {
-                const int64_t sj = stride_of(out.pscope[j]);
-                if (++digit[j] < net.dims[out.pscope[j]]) {
+                const int64_t sj = stride_in(t, red[j]);
+                if (++digit[j] < net.dims[red[j]]) {
                   off += sj;
                   break;
                 }
@@ -452,7 +489,7 @@ struct Compiler {
             }
           };
           fill(in.hi, (size_t)st.n_hi, 0, split);
-          fill(in.lo, (size_t)C, split, nk);
+          fill(in.lo, (size_t)C, split, nr);
           if (!st.shared) {
             P.stat_reads += st.n_out * terms;
             if (t.kind == T_ROW) P.stat_row_read += std::min<int64_t>(t.size, st.n_out * terms);
@@ -747,7 +784,7 @@ std::string describe_program(const Program& P) {
   for (size_t i = 0; i < P.steps.size(); ++i) {
     const Step& s = P.steps[i];
     o << (i ? "," : "") << "{\"kind\":" << s.kind << ",\"shared\":" << (s.shared ? 1 : 0) << ",\"group\":" << s.group << ",\"n_out\":" << s.n_out
-      << ",\"C\":" << s.C << ",\"out\":" << s.out;
+      << ",\"C\":" << s.C << ",\"out\":" << s.out << ",\"w_var\":" << s.w_var << ",\"U\":" << s.U;
     if (s.kind == STEP_PRODSUM) {
       o << ",\"out_scope\":";
       js_list(o, P.tables[s.out].pscope);
@@ -762,6 +799,7 @@ std::string describe_program(const Program& P) {
           o << (k ? "," : "") << "{\"table\":" << lv.in[k].table << ",\"kind\":" << t.kind << ",\"pot\":" << t.pot << ",\"off\":" << t.off
             << ",\"size\":" << t.size << ",\"lstride\":";
           js_nums(o, lv.in[k].lstride);
+          o << ",\"wstride\":" << lv.in[k].wstride;
           o << ",\"scope\":";
           js_list(o, t.pscope);
           o << ",\"strides\":";

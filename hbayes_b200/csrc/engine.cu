@@ -70,6 +70,7 @@ struct InArg {
   const uint32_t* hi;
   const uint32_t* lo;
   unsigned sstride;       // stride of the summed variable, in elements (pre-multiplied like the maps)
+  unsigned wstride;       // stride of the step's blocking variable (pre-multiplied)
 };
 
 template <int K>
@@ -78,8 +79,10 @@ struct StepArgs {
   TabRef sc[MAXS];
   int n_sc;
   int d;                  // terms per output entry
-  unsigned C;             // o = hiI * C + loI
+  unsigned C;             // reduced output index o' = hiI * C + loI
   unsigned n_out;
+  unsigned U, n_red;      // blocking variable: U states, n_red = n_out / U reduced entries; output entry = o' * U + u
+  unsigned wst[K > 0 ? K : 1];  // stride of the blocking variable in each input (pre-multiplied; 0: independent of it)
   double* out;            // arena + off * RT (row) or shared + off
   int out_is_row;
   int nr;                 // rows in this tile
@@ -87,10 +90,10 @@ struct StepArgs {
 };
 
 struct GenericArgs {      // any number of inputs / scalars, descriptors in global memory
-  const InArg* in;
+  const InArg* in;        // InArg::wstride holds the blocking-variable stride
   const TabRef* sc;
   int k, n_sc, d;
-  unsigned C, n_out;
+  unsigned C, n_out, U;
   double* out;
   int out_is_row, nr;
   long long RT;
@@ -135,14 +138,42 @@ struct Rows<2> {
   __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
 };
 
+// Walks a strip of (reduced output entry o', pair of blocking-variable states) items.
+struct Strip {
+  unsigned it, it_end, op, ch, nch, hiI, loI;
+  __device__ __forceinline__ bool init(unsigned n_red, unsigned U, unsigned C) {
+    nch = (U + 1) >> 1;
+    const unsigned n_items = n_red * nch;
+    const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;
+    const unsigned per = (n_items + lanes - 1) / lanes;
+    it = lane * per;
+    it_end = min(n_items, it + per);
+    if (it >= it_end) return false;
+    op = it / nch;
+    ch = it - op * nch;
+    hiI = op / C;
+    loI = op - hiI * C;
+    return true;
+  }
+  __device__ __forceinline__ void next(unsigned C) {
+    ++it;
+    if (++ch == nch) {
+      ch = 0;
+      ++op;
+      if (++loI == C) loI = 0, ++hiI;
+    }
+  }
+};
+
 // The fused clique-message kernel: out[o] = 0 + sum_s ps * (in1[o,s] * (in2[o,s] * (... * inK[o,s]))).
 // One thread owns V adjacent evidence rows (threadIdx.x) and walks a contiguous strip of output entries
 // (threadIdx.y / blockIdx.y), U entries per iteration so that U*K*D independent loads are in flight.
 // All lanes of a warp share the output entry: index-map loads are broadcasts, and every row-table access
 // of the warp is one contiguous 256*V-byte segment.  D = terms per entry (0: run-time count).
-template <int K, int V, int D>
+// MASK: bit i set = input i depends on the blocking variable (two loads per item); clear = one load serves both
+// blocked states.  The mask is a template parameter so that the loads stay unconditional, back to back.
+template <int K, int V, int D, int MASK>
 __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ StepArgs<K> a) {
-  constexpr int U = 2;
   typedef Rows<V> R;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (row >= a.nr) return;  // V == 2: the pad row after an odd tile exists in the arena and in rowoff
@@ -163,57 +194,43 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
   double* outp = a.out + (a.out_is_row ? row : 0);
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
   const int d = D > 0 ? D : a.d;
-  // contiguous strip of output entries for this (blockIdx.y, threadIdx.y)
-  const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;
-  const unsigned per = (a.n_out + lanes - 1) / lanes;
-  unsigned o = lane * per;
-  const unsigned o_end = min(a.n_out, o + per);
-  if (o >= o_end) return;
-  unsigned hiI = o / a.C, loI = o - hiI * a.C;
-  while (o < o_end) {
-    unsigned off[U][K];
-    const int nu = (o + 1 < o_end) ? U : 1;
+  Strip sp;
+  if (!sp.init(a.n_red, a.U, a.C)) return;
+  for (; sp.it < sp.it_end; sp.next(a.C)) {
+    const unsigned u0 = 2 * sp.ch;
+    const bool has1 = u0 + 1 < a.U;
+    unsigned off0[K], off1[K];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (u < nu) {
-#pragma unroll
-        for (int i = 0; i < K; ++i) off[u][i] = __ldg(a.in[i].hi + hiI) + __ldg(a.in[i].lo + loI);
-        if (++loI == a.C) loI = 0, ++hiI;
-      } else {
-#pragma unroll
-        for (int i = 0; i < K; ++i) off[u][i] = off[0][i];  // tail: recompute entry 0, never stored
-      }
+    for (int i = 0; i < K; ++i) {
+      off0[i] = __ldg(a.in[i].hi + sp.hiI) + __ldg(a.in[i].lo + sp.loI) + u0 * a.wst[i];
+      off1[i] = off0[i] + (has1 ? a.wst[i] : 0);  // odd U: the last pair repeats its first state, not stored
     }
-    R acc[U];
+    R acc0 = R::splat(0.0, 0.0), acc1 = R::splat(0.0, 0.0);
+    auto term = [&](int s) {
+      R x0[K], x1[K];
 #pragma unroll
-    for (int u = 0; u < U; ++u) acc[u] = R::splat(0.0, 0.0);
+      for (int i = 0; i < K; ++i) {
+        x0[i] = R::load(p0[i], p1[i], isrow[i], off0[i] + s * ss[i]);
+        if ((MASK >> i) & 1)
+          x1[i] = R::load(p0[i], p1[i], isrow[i], off1[i] + s * ss[i]);
+        else
+          x1[i] = x0[i];
+      }
+      R c0 = x0[K - 1], c1 = x1[K - 1];
+#pragma unroll
+      for (int i = K - 2; i >= 0; --i) c0 = x0[i].mul(c0), c1 = x1[i].mul(c1);
+      if (has_ps) c0 = ps.mul(c0), c1 = ps.mul(c1);
+      acc0 = acc0.add(c0), acc1 = acc1.add(c1);
+    };
     if (D > 0) {
 #pragma unroll
-      for (int s = 0; s < (D > 0 ? D : 1); ++s) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], off[u][K - 1] + s * ss[K - 1]);
-#pragma unroll
-          for (int i = K - 2; i >= 0; --i) c = R::load(p0[i], p1[i], isrow[i], off[u][i] + s * ss[i]).mul(c);
-          if (has_ps) c = ps.mul(c);
-          acc[u] = acc[u].add(c);
-        }
-      }
+      for (int s = 0; s < (D > 0 ? D : 1); ++s) term(s);
     } else {
-      for (int s = 0; s < d; ++s) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], off[u][K - 1] + s * ss[K - 1]);
-#pragma unroll
-          for (int i = K - 2; i >= 0; --i) c = R::load(p0[i], p1[i], isrow[i], off[u][i] + s * ss[i]).mul(c);
-          if (has_ps) c = ps.mul(c);
-          acc[u] = acc[u].add(c);
-        }
-      }
+      for (int s = 0; s < d; ++s) term(s);
     }
-    acc[0].store(outp + (size_t)o * om);
-    if (nu > 1) acc[1].store(outp + (size_t)(o + 1) * om);
-    o += nu;
+    const size_t o = (size_t)sp.op * a.U + u0;
+    acc0.store(outp + o * om);
+    if (has1) acc1.store(outp + (o + 1) * om);
   }
 }
 
@@ -229,6 +246,8 @@ struct FusedArgs {
   int L;
   int d[MAXL];
   unsigned C, n_out;
+  unsigned U, n_red;      // blocking variable (see StepArgs)
+  unsigned wst[K];
   double* out;
   int out_is_row, nr;
   long long RT;
@@ -244,7 +263,7 @@ constexpr int FU = 2;  // output entries evaluated in lock-step by one thread of
 #ifndef HB_FUSED_MINB
 #define HB_FUSED_MINB 2
 #endif
-template <int KO, int KI, int V, int DI>
+template <int KO, int KI, int V, int DI, int MASK>
 __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __grid_constant__ FusedArgs<KO + KI> a) {
   constexpr int K = KO + KI;
   typedef Rows<V> R;
@@ -261,100 +280,80 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
   }
   double* outp = a.out + (a.out_is_row ? row : 0);
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
-  const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;
-  const unsigned per = (a.n_out + lanes - 1) / lanes;
-  unsigned o = lane * per;
-  const unsigned o_end = min(a.n_out, o + per);
-  if (o >= o_end) return;
-  unsigned hiI = o / a.C, loI = o - hiI * a.C;
   const int inner = a.L - 1;
   const int d_inner = DI > 0 ? DI : a.d[inner];
   unsigned sti[KI];  // stride of the innermost summed variable in the innermost inputs
 #pragma unroll
   for (int i = 0; i < KI; ++i) sti[i] = a.st[KO + i][inner];
-  while (o < o_end) {
-    unsigned cur[FU][K];
-    const int nu = min((unsigned)FU, o_end - o);
+  Strip sp;
+  if (!sp.init(a.n_red, a.U, a.C)) return;
+  for (; sp.it < sp.it_end; sp.next(a.C)) {
+    const unsigned u0 = 2 * sp.ch;
+    const bool has1 = u0 + 1 < a.U;
+    unsigned cur0[K], cur1[K];
 #pragma unroll
-    for (int u = 0; u < FU; ++u) {
-      if (u < nu) {
-#pragma unroll
-        for (int i = 0; i < K; ++i) cur[u][i] = __ldg(a.in[i].hi + hiI) + __ldg(a.in[i].lo + loI);
-        if (++loI == a.C) loI = 0, ++hiI;
-      } else {
-#pragma unroll
-        for (int i = 0; i < K; ++i) cur[u][i] = cur[0][i];  // tail: entry 0 again, never stored
-      }
+    for (int i = 0; i < K; ++i) {
+      cur0[i] = __ldg(a.in[i].hi + sp.hiI) + __ldg(a.in[i].lo + sp.loI) + u0 * a.wst[i];
+      cur1[i] = cur0[i] + (has1 ? a.wst[i] : 0);  // odd U: the last pair repeats its first state, not stored
     }
-    R acc[MAXL - 1][FU], v[FU];
+    R acc0[MAXL - 1], acc1[MAXL - 1], v0, v1;
     int digit[MAXL - 1];
 #pragma unroll
-    for (int l = 0; l < MAXL - 1; ++l) {
-      digit[l] = 0;
-#pragma unroll
-      for (int u = 0; u < FU; ++u) acc[l][u] = R::splat(0.0, 0.0);
-    }
+    for (int l = 0; l < MAXL - 1; ++l) digit[l] = 0, acc0[l] = R::splat(0.0, 0.0), acc1[l] = R::splat(0.0, 0.0);
     for (;;) {
-      // ---- innermost level: v = 0 + sum_s in_1 * (in_2 * ...), static shape ----
+      // ---- innermost level: v = 0 + sum_s in_1 * (in_2 * ...), static shape; an input whose MASK bit is clear
+      // does not depend on the blocking variable and is loaded once for both blocked states ----
+      v0 = R::splat(0.0, 0.0), v1 = R::splat(0.0, 0.0);
+      auto term = [&](int q) {
+        R x0[KI], x1[KI];
 #pragma unroll
-      for (int u = 0; u < FU; ++u) v[u] = R::splat(0.0, 0.0);
+        for (int i = 0; i < KI; ++i) {
+          x0[i] = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur0[KO + i] + q * sti[i]);
+          if ((MASK >> i) & 1)
+            x1[i] = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur1[KO + i] + q * sti[i]);
+          else
+            x1[i] = x0[i];
+        }
+        R c0 = x0[KI - 1], c1 = x1[KI - 1];
+#pragma unroll
+        for (int i = KI - 2; i >= 0; --i) c0 = x0[i].mul(c0), c1 = x1[i].mul(c1);
+        v0 = v0.add(c0), v1 = v1.add(c1);
+      };
       if (DI > 0) {
 #pragma unroll
-        for (int q = 0; q < (DI > 0 ? DI : 1); ++q) {
-#pragma unroll
-          for (int u = 0; u < FU; ++u) {
-            R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], cur[u][K - 1] + q * sti[KI - 1]);
-#pragma unroll
-            for (int i = KI - 2; i >= 0; --i) c = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur[u][KO + i] + q * sti[i]).mul(c);
-            v[u] = v[u].add(c);
-          }
-        }
+        for (int q = 0; q < (DI > 0 ? DI : 1); ++q) term(q);
       } else {
-        for (int q = 0; q < d_inner; ++q) {
-#pragma unroll
-          for (int u = 0; u < FU; ++u) {
-            R c = R::load(p0[K - 1], p1[K - 1], isrow[K - 1], cur[u][K - 1] + q * sti[KI - 1]);
-#pragma unroll
-            for (int i = KI - 2; i >= 0; --i) c = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur[u][KO + i] + q * sti[i]).mul(c);
-            v[u] = v[u].add(c);
-          }
-        }
+        for (int q = 0; q < d_inner; ++q) term(q);
       }
       // ---- carry the finished value up through the outer levels ----
       int l = inner - 1;
 #pragma unroll
       for (int ll = MAXL - 2; ll >= 0; --ll) {
         if (ll == l) {
-          R r[FU];
+          R r0, r1;
           bool have = false;
 #pragma unroll
           for (int i = KO - 1; i >= 0; --i) {
             if (a.lvl[i] == ll) {
-#pragma unroll
-              for (int u = 0; u < FU; ++u) {
-                const R x = R::load(p0[i], p1[i], isrow[i], cur[u][i]);
-                r[u] = have ? x.mul(r[u]) : x;
-              }
+              const R x0 = R::load(p0[i], p1[i], isrow[i], cur0[i]);
+              const R x1 = R::load(p0[i], p1[i], isrow[i], cur1[i]);
+              r0 = have ? x0.mul(r0) : x0;
+              r1 = have ? x1.mul(r1) : x1;
               have = true;
             }
           }
-#pragma unroll
-          for (int u = 0; u < FU; ++u) acc[ll][u] = acc[ll][u].add(have ? v[u].mul(r[u]) : v[u]);
+          acc0[ll] = acc0[ll].add(have ? v0.mul(r0) : v0);
+          acc1[ll] = acc1[ll].add(have ? v1.mul(r1) : v1);
           if (++digit[ll] < a.d[ll]) {
 #pragma unroll
-            for (int u = 0; u < FU; ++u)
-#pragma unroll
-              for (int i = 0; i < K; ++i) cur[u][i] += a.st[i][ll];
+            for (int i = 0; i < K; ++i) cur0[i] += a.st[i][ll], cur1[i] += a.st[i][ll];
             l = -2;  // next term of this level: back to the innermost sum
           } else {
             const unsigned back = (unsigned)(a.d[ll] - 1);
 #pragma unroll
-            for (int u = 0; u < FU; ++u) {
-#pragma unroll
-              for (int i = 0; i < K; ++i) cur[u][i] -= back * a.st[i][ll];
-              v[u] = acc[ll][u];
-              acc[ll][u] = R::splat(0.0, 0.0);
-            }
+            for (int i = 0; i < K; ++i) cur0[i] -= back * a.st[i][ll], cur1[i] -= back * a.st[i][ll];
+            v0 = acc0[ll], v1 = acc1[ll];
+            acc0[ll] = R::splat(0.0, 0.0), acc1[ll] = R::splat(0.0, 0.0);
             digit[ll] = 0;
             l = ll - 1;
           }
@@ -362,10 +361,9 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
       }
       if (l == -1) break;  // level 0 finished (or there is no outer level): v is the output entry
     }
-#pragma unroll
-    for (int u = 0; u < FU; ++u)
-      if (u < nu) v[u].store(outp + (size_t)(o + u) * om);
-    o += nu;
+    const size_t o = (size_t)sp.op * a.U + u0;
+    v0.store(outp + o * om);
+    if (has1) v1.store(outp + (o + 1) * om);
   }
 }
 
@@ -379,13 +377,14 @@ __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArg
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
   const unsigned step = gridDim.y * blockDim.y;
   for (unsigned o = blockIdx.y * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
-    const unsigned hiI = o / a.C, loI = o - hiI * a.C;
+    const unsigned op = o / a.U, u = o - op * a.U;
+    const unsigned hiI = op / a.C, loI = op - hiI * a.C;
     double acc = 0.0;
     for (int s = 0; s < a.d; ++s) {
       double c = ps;
       for (int i = a.k - 1; i >= 0; --i) {
         const InArg& in = a.in[i];
-        const unsigned off = __ldg(in.hi + hiI) + __ldg(in.lo + loI) + s * in.sstride;
+        const unsigned off = __ldg(in.hi + hiI) + __ldg(in.lo + loI) + u * in.wstride + s * in.sstride;
         const double v = row_ptr(in.t, row)[off];
         c = (i == a.k - 1) ? v : __dmul_rn(v, c);
       }
@@ -682,6 +681,7 @@ InArg in_arg(const Executor& ex, const Step& st, int si, int i, int64_t RT) {
   a.hi = pool + ex.hi_off[ex.in_base[si] + i];
   a.lo = pool + ex.lo_off[ex.in_base[si] + i];
   a.sstride = (unsigned)(in.lstride[level] * (t.kind == T_ROW ? RT : 1));
+  a.wstride = (unsigned)(in.wstride * (t.kind == T_ROW ? RT : 1));
   return a;
 }
 
@@ -738,14 +738,38 @@ Reuse reuse_of(const Program& P, const Step& st) {
   return r;
 }
 
+// picks the kernel instantiation whose MASK template argument equals the run-time mask
+template <int K, int V, int D, int M>
+struct ProdsumMask {
+  static void go(int mask, const StepArgs<K>& a, const LaunchShape& sh, cudaStream_t stream) {
+    if (mask == M)
+      prodsum_kernel<K, V, D, M><<<sh.grid, sh.block, 0, stream>>>(a);
+    else
+      ProdsumMask<K, V, D, M - 1>::go(mask, a, sh, stream);
+  }
+};
+template <int K, int V, int D>
+struct ProdsumMask<K, V, D, -1> {
+  static void go(int, const StepArgs<K>&, const LaunchShape&, cudaStream_t) { throw Error(HB_E_UNSUPPORTED, "bad blocking mask"); }
+};
+
+template <int K, int V, int D>
+void launch_kvd(const StepArgs<K>& a, int mask, const LaunchShape& sh, cudaStream_t stream) {
+  constexpr int FULL = (1 << K) - 1;
+  if constexpr (V == 2 && K <= 3)
+    ProdsumMask<K, V, D, FULL>::go(mask, a, sh, stream);
+  else
+    prodsum_kernel<K, V, D, FULL><<<sh.grid, sh.block, 0, stream>>>(a);  // every input loaded for both states
+}
+
 template <int K, int V>
-void launch_kv(const StepArgs<K>& a, int d, const LaunchShape& sh, cudaStream_t stream) {
+void launch_kv(const StepArgs<K>& a, int d, int mask, const LaunchShape& sh, cudaStream_t stream) {
   switch (d) {
-    case 1: prodsum_kernel<K, V, 1><<<sh.grid, sh.block, 0, stream>>>(a); break;
-    case 2: prodsum_kernel<K, V, 2><<<sh.grid, sh.block, 0, stream>>>(a); break;
-    case 3: prodsum_kernel<K, V, 3><<<sh.grid, sh.block, 0, stream>>>(a); break;
-    case 4: prodsum_kernel<K, V, 4><<<sh.grid, sh.block, 0, stream>>>(a); break;
-    default: prodsum_kernel<K, V, 0><<<sh.grid, sh.block, 0, stream>>>(a); break;
+    case 1: launch_kvd<K, V, 1>(a, mask, sh, stream); break;
+    case 2: launch_kvd<K, V, 2>(a, mask, sh, stream); break;
+    case 3: launch_kvd<K, V, 3>(a, mask, sh, stream); break;
+    case 4: launch_kvd<K, V, 4>(a, mask, sh, stream); break;
+    default: launch_kvd<K, V, 0>(a, mask, sh, stream); break;
   }
 }
 
@@ -754,7 +778,14 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   const Program& P = *ex.P;
   StepArgs<K> a;
   memset(&a, 0, sizeof a);
-  for (int i = 0; i < K; ++i) a.in[i] = in_arg(ex, st, si, i, RT);
+  int mask = 0;
+  for (int i = 0; i < K; ++i) {
+    a.in[i] = in_arg(ex, st, si, i, RT);
+    a.wst[i] = a.in[i].wstride;
+    if (a.wst[i] != 0 || K > 3) mask |= 1 << i;
+  }
+  a.U = (unsigned)st.U;
+  a.n_red = (unsigned)st.n_red;
   a.n_sc = (int)st.scalars.size();
   for (int i = 0; i < a.n_sc; ++i) a.sc[i] = tab_ref(ex, P.tables[st.scalars[i]], RT);
   a.d = st.levels[0].d;
@@ -765,22 +796,41 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
   a.nr = nr;
   a.RT = RT;
-  // two rows per thread (16-byte accesses) as soon as a tile has a full warp of row pairs
+  const int64_t items2 = st.n_red * ((st.U + 1) / 2) * 2;
   if (two_rows_per_thread(nr))
-    launch_kv<K, 2>(a, a.d, launch_shape((nr + 1) / 2, 2, st.n_out, reuse_of(P, st)), stream);
+    launch_kv<K, 2>(a, a.d, mask, launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st)), stream);
   else
-    launch_kv<K, 1>(a, a.d, launch_shape(nr, 1, st.n_out), stream);
+    launch_kv<K, 1>(a, a.d, (1 << K) - 1, launch_shape(nr, 1, items2), stream);
 }
 
 constexpr int MAX_KO = 4, MAX_KI = 3;  // the same limits the compiler's fusion pass uses (CompileOptions)
 
+template <int KO, int KI, int V, int DI, int M>
+struct FusedMask {
+  static void go(int mask, const FusedArgs<KO + KI>& a, const LaunchShape& sh, cudaStream_t stream) {
+    if (mask == M)
+      fused_kernel<KO, KI, V, DI, M><<<sh.grid, sh.block, 0, stream>>>(a);
+    else
+      FusedMask<KO, KI, V, DI, M - 1>::go(mask, a, sh, stream);
+  }
+};
+template <int KO, int KI, int V, int DI>
+struct FusedMask<KO, KI, V, DI, -1> {
+  static void go(int, const FusedArgs<KO + KI>&, const LaunchShape&, cudaStream_t) { throw Error(HB_E_UNSUPPORTED, "bad blocking mask"); }
+};
+
 template <int KO, int KI, int V>
-void launch_fused_d(const FusedArgs<KO + KI>& a, int di, const LaunchShape& sh, cudaStream_t stream) {
-  switch (di) {
-    case 2: fused_kernel<KO, KI, V, 2><<<sh.grid, sh.block, 0, stream>>>(a); break;
-    case 3: fused_kernel<KO, KI, V, 3><<<sh.grid, sh.block, 0, stream>>>(a); break;
-    case 4: fused_kernel<KO, KI, V, 4><<<sh.grid, sh.block, 0, stream>>>(a); break;
-    default: fused_kernel<KO, KI, V, 0><<<sh.grid, sh.block, 0, stream>>>(a); break;
+void launch_fused_d(const FusedArgs<KO + KI>& a, int di, int mask, const LaunchShape& sh, cudaStream_t stream) {
+  constexpr int FULL = (1 << KI) - 1;
+  if constexpr (V == 2) {
+    switch (di) {
+      case 2: FusedMask<KO, KI, V, 2, FULL>::go(mask, a, sh, stream); break;
+      case 3: FusedMask<KO, KI, V, 3, FULL>::go(mask, a, sh, stream); break;
+      case 4: FusedMask<KO, KI, V, 4, FULL>::go(mask, a, sh, stream); break;
+      default: FusedMask<KO, KI, V, 0, FULL>::go(mask, a, sh, stream); break;
+    }
+  } else {
+    fused_kernel<KO, KI, V, 0, FULL><<<sh.grid, sh.block, 0, stream>>>(a);  // tiny batches: run-time count, no reuse
   }
 }
 
@@ -792,26 +842,32 @@ void launch_fused(const Executor& ex, const Step& st, int si, int64_t RT, int nr
   memset(&a, 0, sizeof a);
   a.L = (int)st.levels.size();
   for (int l = 0; l < a.L; ++l) a.d[l] = st.levels[l].d;
+  int mask = 0;
   for (int i = 0; i < K; ++i) {
     int level = 0;
     const StepInput& in = flat_input(st, i, &level);
     a.in[i] = in_arg(ex, st, si, i, RT);
+    a.wst[i] = a.in[i].wstride;
+    if (i >= KO && a.wst[i] != 0) mask |= 1 << (i - KO);
     a.lvl[i] = level;
     const int64_t mult = P.tables[in.table].kind == T_ROW ? RT : 1;
     for (int m = 0; m <= level; ++m) a.st[i][m] = (unsigned)(in.lstride[m] * mult);
   }
   a.C = (unsigned)st.C;
   a.n_out = (unsigned)st.n_out;
+  a.U = (unsigned)st.U;
+  a.n_red = (unsigned)st.n_red;
   const Table& out = P.tables[st.out];
   a.out_is_row = out.kind == T_ROW;
   a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
   a.nr = nr;
   a.RT = RT;
   const int di = st.levels.back().d;
+  const int64_t items2 = st.n_red * ((st.U + 1) / 2) * 2;
   if (two_rows_per_thread(nr))
-    launch_fused_d<KO, KI, 2>(a, di, launch_shape((nr + 1) / 2, 2, st.n_out, reuse_of(P, st)), stream);
+    launch_fused_d<KO, KI, 2>(a, di, mask, launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st)), stream);
   else
-    launch_fused_d<KO, KI, 1>(a, 0, launch_shape(nr, 1, st.n_out), stream);  // tiny batches: the run-time-count form
+    launch_fused_d<KO, KI, 1>(a, 0, (1 << KI) - 1, launch_shape(nr, 1, items2), stream);
 }
 
 template <int KO>
@@ -865,6 +921,7 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
     a.d = st.levels[0].d;
     a.C = (unsigned)st.C;
     a.n_out = (unsigned)st.n_out;
+    a.U = (unsigned)st.U;
     const Table& out = P.tables[st.out];
     a.out_is_row = out.kind == T_ROW;
     a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;

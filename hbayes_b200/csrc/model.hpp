@@ -101,7 +101,8 @@ struct Table {
 struct StepInput {
   int table = -1;
   std::vector<int64_t> lstride;  // stride (entries) along the summed variable of level 0..own level (0 if absent)
-  std::vector<uint32_t> hi, lo;  // entry offset of output index o: hi[o / C] + lo[o % C]
+  int64_t wstride = 0;           // stride along the step's blocking variable (0: the input does not depend on it)
+  std::vector<uint32_t> hi, lo;  // entry offset of reduced output index o': hi[o' / C] + lo[o' % C]
 };
 
 // One reference operation (itemProduct of a bucket + itemProjectOut of one variable).  A step holds a
@@ -123,6 +124,13 @@ struct Step {
   std::vector<int> scalars;     // structural scalars of level 0, ps = s1 * (s2 * ...), applied as ps * chain (never fused)
   int out = -1;                 // output table
   int64_t n_out = 1, C = 1, n_hi = 1;
+  // Register blocking: one output variable w (the fastest one of the output's stored layout) is walked by
+  // the thread itself, two states at a time; an input of the innermost level that does not mention w is
+  // loaded once for both.  n_red = n_out / U entries of the other output variables go through hi/lo.
+  int w_var = -1;
+  int U = 1;
+  int64_t n_red = 1;
+  std::vector<int> full_scope;  // STEP_OUTPUT: the result's structural scope
   // STEP_OUTPUT: normalise table `result` and expand it to the full query scope
   int result = -1;
   int64_t out_col = 0, n_full = 1;
@@ -190,6 +198,7 @@ struct CompileOptions {
   // observed variables, and potentials mentioning them are stored restricted to that state
   std::vector<std::pair<int, int>> fixed;
   bool fuse = true;    // chain a step into its only consumer (the intermediate table stays in registers)
+  bool block = true;   // choose the blocking variable of each step by the loads it saves (false: the last variable)
   int max_levels = 4;  // levels per fused step
   int max_outer = 4;   // stored inputs of the outer levels of a fused step
   int max_inner = 3;   // stored inputs of its innermost level
