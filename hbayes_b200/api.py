@@ -219,6 +219,20 @@ class JunctionTree(_Batched):
         check(lib().hb_jt_describe_json(self._h, C.byref(p)))
         return _take_json(p)
 
+    def save(self, path):
+        """network + tree structure to a binary file (cf. Bayes/ImportExport.hs:36-46)"""
+        check(lib().hb_jt_save(self._h, str(path).encode()))
+
+    @staticmethod
+    def load(path, net: BayesianNetwork, device=0):
+        """`net` must be the network the tree was built from (it supplies names / dims to the Python side)"""
+        dp, nd, keep = _device_args(device)
+        h = C.c_void_p()
+        check(lib().hb_jt_load(str(path).encode(), dp, nd, C.byref(h)))
+        jt = JunctionTree.__new__(JunctionTree)
+        jt.net, jt._keep, jt._h = net, keep, h
+        return jt
+
     def program(self, observed: Iterable[int] = ()):
         """parity hook: operation trace + physical steps compiled for changeEvidence on `observed` (in that order)"""
         oa, op = _i32(list(observed))

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -411,6 +412,148 @@ int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const
   }
   return jt_compile(net, 0, elim_order, devices, n_devices, out);
 }
+// ---- persistence: network + junction-tree structure in one little-endian binary file -----------------------
+namespace {
+const char JT_MAGIC[8] = {'H', 'B', 'J', 'T', 'r', '0', '1', '\0'};
+
+struct Writer {
+  FILE* f;
+  void i64(int64_t v) {
+    if (fwrite(&v, sizeof v, 1, f) != 1) throw Error(HB_E_IO, "write failed");
+  }
+  void ints(const std::vector<int>& v) {
+    i64((int64_t)v.size());
+    for (int x : v) i64(x);
+  }
+  void lists(const std::vector<std::vector<int>>& v) {
+    i64((int64_t)v.size());
+    for (auto& x : v) ints(x);
+  }
+};
+struct Reader {
+  FILE* f;
+  int64_t i64() {
+    int64_t v;
+    if (fread(&v, sizeof v, 1, f) != 1) throw Error(HB_E_IO, "truncated file");
+    return v;
+  }
+  int64_t count(int64_t limit) {
+    const int64_t n = i64();
+    if (n < 0 || n > limit) throw Error(HB_E_IO, "corrupt file");
+    return n;
+  }
+  std::vector<int> ints() {
+    std::vector<int> v((size_t)count(1 << 28));
+    for (int& x : v) x = (int)i64();
+    return v;
+  }
+  std::vector<std::vector<int>> lists() {
+    std::vector<std::vector<int>> v((size_t)count(1 << 24));
+    for (auto& x : v) x = ints();
+    return v;
+  }
+};
+}  // namespace
+
+int hb_jt_save(const hb_jt* jt, const char* path) {
+  return guarded([&] {
+    if (!jt || !path) throw Error(HB_E_ARG, "null argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) throw Error(HB_E_IO, std::string("cannot create ") + path);
+    std::unique_ptr<FILE, int (*)(FILE*)> guard(f, fclose);
+    if (fwrite(JT_MAGIC, 1, 8, f) != 8) throw Error(HB_E_IO, "write failed");
+    Writer w{f};
+    const Network& net = jt->s.net;
+    const Tree& t = *jt->tree;
+    w.ints(net.dims);
+    w.lists(net.scope);
+    for (int v = 0; v < net.n(); ++v) {
+      w.i64(net.procedural(v) ? (int64_t)net.proc_seed[v] : 0);
+      w.i64((int64_t)net.values[v].size());
+      if (!net.values[v].empty() && fwrite(net.values[v].data(), sizeof(double), net.values[v].size(), f) != net.values[v].size())
+        throw Error(HB_E_IO, "write failed");
+      w.i64((int64_t)net.names[v].size());
+      if (fwrite(net.names[v].data(), 1, net.names[v].size(), f) != net.names[v].size()) throw Error(HB_E_IO, "write failed");
+    }
+    w.ints(t.elim_order);
+    w.lists(t.clusters);
+    w.i64(t.root);
+    w.ints(t.parent_sep);
+    w.ints(t.sep_parent);
+    w.ints(t.sep_child);
+    w.lists(t.sep_vars);
+    w.lists(t.children);
+    w.lists(t.factors);
+    w.ints(t.by_rank);
+  });
+}
+
+int hb_jt_load(const char* path, const int32_t* devices, int32_t n_devices, hb_jt** out) {
+  return guarded([&] {
+    if (!path || !out) throw Error(HB_E_ARG, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) throw Error(HB_E_IO, std::string("cannot open ") + path);
+    std::unique_ptr<FILE, int (*)(FILE*)> guard(f, fclose);
+    char magic[8];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, JT_MAGIC, 8) != 0) throw Error(HB_E_IO, "not a libhbayes_cuda junction-tree file");
+    Reader r{f};
+    auto jt = std::make_unique<hb_jt>();
+    Network& net = jt->s.net;
+    net.dims = r.ints();
+    net.scope = r.lists();
+    const int n = net.n();
+    if ((int)net.scope.size() != n) throw Error(HB_E_IO, "corrupt file");
+    net.values.resize(n);
+    net.proc_seed.assign(n, 0);
+    for (int v = 0; v < n; ++v) {
+      net.proc_seed[v] = (uint64_t)r.i64();
+      net.values[v].resize((size_t)r.count((int64_t)1 << 34));
+      if (!net.values[v].empty() && fread(net.values[v].data(), sizeof(double), net.values[v].size(), f) != net.values[v].size())
+        throw Error(HB_E_IO, "truncated file");
+      std::string name((size_t)r.count(1 << 16), ' ');
+      if (!name.empty() && fread(&name[0], 1, name.size(), f) != name.size()) throw Error(HB_E_IO, "truncated file");
+      net.names.push_back(name);
+    }
+    // the same consistency checks as hb_net_create
+    {
+      std::vector<int32_t> dims(net.dims.begin(), net.dims.end()), scopes;
+      std::vector<int64_t> coff(1, 0), voff(1, 0);
+      std::vector<double> vals(1, 0.0);
+      for (int v = 0; v < n; ++v) {
+        scopes.insert(scopes.end(), net.scope[v].begin(), net.scope[v].end());
+        coff.push_back((int64_t)scopes.size());
+        voff.push_back(voff.back() + (int64_t)net.values[v].size());
+      }
+      std::vector<double> flat;
+      for (int v = 0; v < n; ++v) flat.insert(flat.end(), net.values[v].begin(), net.values[v].end());
+      flat.push_back(0.0);
+      std::unique_ptr<Network> checked(network_create(n, dims.data(), coff.data(), scopes.data(), voff.data(), flat.data(), net.proc_seed.data()));
+    }
+    auto t = std::make_unique<Tree>();
+    t->elim_order = r.ints();
+    t->clusters = r.lists();
+    t->root = (int)r.i64();
+    t->parent_sep = r.ints();
+    t->sep_parent = r.ints();
+    t->sep_child = r.ints();
+    t->sep_vars = r.lists();
+    t->children = r.lists();
+    t->factors = r.lists();
+    t->by_rank = r.ints();
+    const size_t nc = t->clusters.size();
+    if (t->parent_sep.size() != nc || t->children.size() != nc || t->factors.size() != nc || t->by_rank.size() != nc ||
+        t->sep_child.size() != t->sep_parent.size() || t->sep_vars.size() != t->sep_parent.size() || t->root < 0 || (size_t)t->root >= nc)
+      throw Error(HB_E_IO, "corrupt file");
+    jt->tree = std::move(t);
+    jt->s.device = pick_device(devices, n_devices);
+    jt->post_off.assign(1, 0);
+    for (int d : net.dims) jt->post_off.push_back(jt->post_off.back() + d);
+    Compiled& prior = jt->program({}, {});
+    if (jt->s.device >= 0) jt->run_one(prior, jt->posts);
+    *out = jt.release();
+  });
+}
+
 int hb_jt_describe_json(const hb_jt* jt, char** out_json) {
   return guarded([&] {
     if (!jt || !out_json) throw Error(HB_E_ARG, "null argument");

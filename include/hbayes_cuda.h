@@ -91,6 +91,11 @@ int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const
  * nothing is calibrated (the unsplit tables may not fit one GPU). */
 int hb_jt_compile_split(const hb_net* net, int32_t cmp, const int32_t* devices, int32_t n_devices, int32_t n_fixed,
                         const int32_t* vars, const int32_t* states, hb_jt** out);
+/* Persistence (the counterpart of the Binary save/load of a junction tree, Bayes/ImportExport.hs:36-46): the network
+ * and the tree structure in one binary file.  Loading skips moralisation / triangulation / spanning tree; schedules
+ * are recompiled on demand (milliseconds) and the tree is re-calibrated on the GPU. */
+int hb_jt_save(const hb_jt* jt, const char* path);
+int hb_jt_load(const char* path, const int32_t* devices, int32_t n_devices, hb_jt** out);
 /* parity hook: {"elim_order","clusters","root","parent_sep","sep_parent","sep_child","sep_vars","children","factors"} */
 int hb_jt_describe_json(const hb_jt* jt, char** out_json);
 /* parity hook: the operation trace (every message and every single-variable posterior, with product scopes)

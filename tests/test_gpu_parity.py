@@ -238,3 +238,14 @@ def test_disconnected_and_single_variable_networks():
             for v in observed:
                 ev[:, v] = rng.randint(0, net.dims[v], 37)
             assert_same(pjt.posteriors_batch(ev), ojt.posteriors_batch(ev), (net.n, observed))
+
+
+def test_saved_tree_gives_the_same_posteriors(tmp_path):
+    pnet, onet = pair("asia.net")
+    jt = hb.JunctionTree(pnet)
+    jt.save(tmp_path / "asia.hbjt")
+    back = hb.JunctionTree.load(tmp_path / "asia.hbjt", pnet)
+    ev = np.full((50, pnet.n), -1, np.int8)
+    ev[:, 7] = np.arange(50) % 2
+    assert same_bits(back.posteriors_batch(ev), jt.posteriors_batch(ev))
+    assert same_bits(back.posterior([3]).values, OracleJT(onet).posterior([3])[1])

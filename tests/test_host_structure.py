@@ -179,3 +179,18 @@ def test_plain_c_program_uses_the_abi(tmp_path):
     r = subprocess.run([exe, os.path.join(G, "cancer.net")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert '"clusters":[[2,3,4],[0,3,4],[1,3]]' in r.stdout
+
+
+def test_save_and_load_round_trip(tmp_path):
+    net, observed = synth.config_c2()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    jt = hb.JunctionTree(pnet, device=None)
+    path = tmp_path / "c2.hbjt"
+    jt.save(path)
+    back = hb.JunctionTree.load(path, pnet, device=None)
+    assert back.describe() == jt.describe()
+    assert back.program(observed) == jt.program(observed)
+    (tmp_path / "junk").write_bytes(b"not a tree")
+    with pytest.raises(hb.HbError) as e:
+        hb.JunctionTree.load(tmp_path / "junk", pnet, device=None)
+    assert e.value.code == _lib.HB_E_IO
