@@ -487,10 +487,13 @@ struct OutArgs {
   int normalise;           // 0: leave the query results unnormalised (partial sums of a split clique)
 };
 
-constexpr int OUT_ROWS = 64;     // evidence rows per CTA
+#ifndef HB_OUT_ROWS
+#define HB_OUT_ROWS 32
+#endif
+constexpr int OUT_ROWS = HB_OUT_ROWS;  // evidence rows per CTA
 constexpr int OUT_COLS = 128;    // at most this many output columns per chunk (a single wider query gets its own chunk)
 
-// CTA = 64 rows x one column chunk.  Phase 1: thread = (row, query) -- norm = 0 + x0 + x1 + ... over the
+// CTA = OUT_ROWS (32) rows x one column chunk.  Phase 1: thread = (row, query) -- norm = 0 + x0 + x1 + ... over the
 // result's layout order, every entry of the full table is (1.0 / norm) * value, where an entry that
 // contradicts the evidence has the value 0.0 (zero-probability evidence gives NaN exactly as 0 * (1/0)
 // does in the reference); arena reads are coalesced along the rows, the tile goes to shared memory.
