@@ -249,3 +249,47 @@ def test_saved_tree_gives_the_same_posteriors(tmp_path):
     ev[:, 7] = np.arange(50) % 2
     assert same_bits(back.posteriors_batch(ev), jt.posteriors_batch(ev))
     assert same_bits(back.posterior([3]).values, OracleJT(onet).posterior([3])[1])
+
+
+def _star(n_children, root_dim, child_dim, seed):
+    """one root with many children: the root's bucket holds more tables than the templated kernels take (generic path)"""
+    rng = synth.SplitMix64(seed)
+    dims = [root_dim] + [child_dim] * n_children
+    parents = [[]] + [[0]] * n_children
+    values = [synth._random_cpt(rng, dims, v, parents[v]) for v in range(len(dims))]
+    return synth.SynthNet(dims, parents, values)
+
+
+@pytest.mark.parametrize("net", [_star(9, 3, 2, 1), _star(12, 5, 7, 2), synth.random_dag_net(14, 777, states=(5, 7), max_parents=2)],
+                         ids=["star9", "star12_dims5x7", "dag_dims5to7"])
+def test_many_factor_buckets_and_wide_variables(net):
+    """buckets with > 6 tables (prodsum_generic_kernel) and variables with 5-7 states (odd blocking pairs)"""
+    pnet, onet = pair(net=net)
+    pjt, ojt = hb.JunctionTree(pnet), OracleJT(onet)
+    assert pjt.describe() == ojt.describe()
+    rng = np.random.RandomState(6)
+    for observed in ([], [1, 3], [0], [2, 5, 6]):
+        ev = np.full((130, net.n), -1, np.int8)
+        for v in observed:
+            ev[:, v] = rng.randint(0, net.dims[v], 130)
+        assert_same(pjt.posteriors_batch(ev), ojt.posteriors_batch(ev), observed)
+    others = list(range(1, net.n))
+    ve = hb.VariableElimination(pnet, others, [0])
+    ev = np.full((33, net.n), -1, np.int8)
+    ev[:, 2] = rng.randint(0, net.dims[2], 33)
+    assert_same(ve.posterior_batch(ev), onet.posterior_marginal_batch(others, [0], ev), "ve star")
+
+
+@pytest.mark.parametrize("seed", range(20, 44))
+def test_random_stress(seed):
+    """more random networks, denser evidence, shuffled ids, ragged row counts"""
+    net = random_net(seed, n=5 + seed % 17, states=(2, 2 + seed % 4), max_parents=1 + seed % 4, shuffle=seed % 3 == 0)
+    pnet, onet = pair(net=net)
+    pjt, ojt = hb.JunctionTree(pnet, cmp=seed % 2), OracleJT(onet, cmp=["weighted", "added"][seed % 2])
+    rng = np.random.RandomState(seed)
+    observed = sorted(rng.permutation(net.n)[: rng.randint(0, net.n)].tolist())
+    rows = [1, 2, 3, 7, 63, 65, 200][seed % 7]
+    ev = np.full((rows, net.n), -1, np.int8)
+    for v in observed:
+        ev[:, v] = rng.randint(0, net.dims[v], rows)
+    assert_same(pjt.posteriors_batch(ev), ojt.posteriors_batch(ev), ("stress", seed, observed, rows))
