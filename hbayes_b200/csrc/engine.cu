@@ -120,7 +120,13 @@ struct Rows<1> {
   __device__ __forceinline__ static Rows splat(double a, double) { return {a}; }
   __device__ __forceinline__ Rows mul(const Rows& o) const { return {__dmul_rn(x, o.x)}; }
   __device__ __forceinline__ Rows add(const Rows& o) const { return {__dadd_rn(x, o.x)}; }
-  __device__ __forceinline__ void store(double* p) const { *p = x; }
+  __device__ __forceinline__ void store(double* p) const {
+#ifndef HB_PLAIN_STORES
+    __stcs(p, x);
+#else
+    *p = x;
+#endif
+  }
 };
 template <>
 struct Rows<2> {
@@ -135,7 +141,13 @@ struct Rows<2> {
   __device__ __forceinline__ static Rows splat(double a, double b) { return {a, b}; }
   __device__ __forceinline__ Rows mul(const Rows& o) const { return {__dmul_rn(x, o.x), __dmul_rn(y, o.y)}; }
   __device__ __forceinline__ Rows add(const Rows& o) const { return {__dadd_rn(x, o.x), __dadd_rn(y, o.y)}; }
-  __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+  __device__ __forceinline__ void store(double* p) const {
+#ifndef HB_PLAIN_STORES
+    __stcs(reinterpret_cast<double2*>(p), make_double2(x, y));  // evict-first: a derived table is read again only many launches later
+#else
+    *reinterpret_cast<double2*>(p) = make_double2(x, y);
+#endif
+  }
 };
 
 // Walks a strip of (reduced output entry o', pair of blocking-variable states) items.
