@@ -87,6 +87,7 @@ struct Session {
   // kernels of chunk i+1 (stream)
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_done;
+  cudaEvent_t rest_uploaded = nullptr;
   int64_t chunk_rows = 1 << 18;
   // split clique: variables fixed to this handle's slice; batch results are then left unnormalised
   std::vector<std::pair<int, int>> fixed;
@@ -97,6 +98,7 @@ struct Session {
     if (d_ev) cudaFree(d_ev);
     if (d_out) cudaFree(d_out);
     for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
+    if (rest_uploaded) cudaEventDestroy(rest_uploaded);
     if (copy_stream) cudaStreamDestroy(copy_stream);
   }
   // the device-resident form of a compiled program, created on first use
@@ -166,13 +168,13 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
   const int64_t width = c0.prog->out_width;
   s.reserve((size_t)n_rows * n_vars, (size_t)n_rows * width * sizeof(double));
   if (!s.copy_stream) cuda_ok(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)n_rows * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
   // Chunk schedule: the device->host copy of a chunk overlaps the kernels of the next one, so only the copy of
-  // the LAST chunk is exposed -- chunks therefore shrink towards the end (40/30/20/10 % of a large batch).
+  // the LAST chunk is exposed, and copying can only start after the FIRST chunk's kernels -- so both ends are
+  // small: 10/30/30/20/10 % of a large batch.
   if (const char* env = getenv("HB_CHUNK_ROWS")) s.chunk_rows = std::max<int64_t>(64, atoll(env));
   std::vector<int64_t> cuts;  // chunk end rows
   if (n_rows >= 4 * s.chunk_rows / 2 && !getenv("HB_CHUNK_ROWS")) {
-    for (double f : {0.4, 0.7, 0.9}) cuts.push_back((int64_t)(n_rows * f) / 64 * 64);
+    for (double f : {0.1, 0.4, 0.7, 0.9}) cuts.push_back((int64_t)(n_rows * f) / 64 * 64);
   } else {
     const int64_t n_chunks = std::max<int64_t>(1, (n_rows + s.chunk_rows - 1) / s.chunk_rows);
     const int64_t per = ((n_rows + n_chunks - 1) / n_chunks + 63) / 64 * 64;
@@ -180,11 +182,21 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
   }
   cuts.push_back(n_rows);
   Executor* ex0 = s.executor(c0);
+  // evidence: the first chunk's rows on the compute stream, the rest on the (still idle) copy stream meanwhile
+  const int64_t first_rows = cuts[0] > 0 ? cuts[0] : n_rows;
+  cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)first_rows * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+  if (first_rows < n_rows) {
+    if (!s.rest_uploaded) cuda_ok(cudaEventCreateWithFlags(&s.rest_uploaded, cudaEventDisableTiming), "cudaEventCreate");
+    cuda_ok(cudaMemcpyAsync(s.d_ev + first_rows * n_vars, evidence + first_rows * n_vars, (size_t)(n_rows - first_rows) * n_vars,
+                            cudaMemcpyHostToDevice, s.copy_stream), "cudaMemcpy(evidence)");
+    cuda_ok(cudaEventRecord(s.rest_uploaded, s.copy_stream), "cudaEventRecord");
+  }
   bool first_chunk = true;
   int64_t r0 = 0;
   for (size_t c = 0; c < cuts.size(); r0 = cuts[c], ++c) {
     const int64_t m = cuts[c] - r0;
     if (m <= 0) continue;
+    if (r0 == first_rows && first_rows < n_rows) cuda_ok(cudaStreamWaitEvent(s.stream, s.rest_uploaded, 0), "cudaStreamWaitEvent");
     executor_run(ex0, m, s.d_ev + r0 * n_vars, s.d_out + r0 * width, s.stream, &rs, s.fixed.empty());
     s.note(c0, rs, !first_chunk);
     first_chunk = false;
