@@ -101,8 +101,7 @@ struct Compiler {
     t.scope = net.scope[v];
     t.off = P.pot_off[v];
     const int ns = (int)t.scope.size();
-    std::vector<int64_t> full(ns, 1), stored(ns, 0);
-    for (int i = ns - 2; i >= 0; --i) full[i] = full[i + 1] * net.dims[t.scope[i + 1]];
+    std::vector<int64_t> stored(ns, 0);
     int64_t acc = 1;  // stored layout: the reference layout with the fixed variables removed
     for (int i = ns - 1; i >= 0; --i)
       if (P.fixed_state[t.scope[i]] < 0) stored[i] = acc, acc *= net.dims[t.scope[i]];
@@ -112,16 +111,12 @@ struct Compiler {
     for (int i = 0; i < ns; ++i) {
       const int x = t.scope[i];
       if (P.fixed_state[x] >= 0)
-        t.full_base += full[i] * P.fixed_state[x];
+        continue;  // restricted away when the pool is built (engine.cu)
       else if (P.is_observed[x])
         sl.vars.push_back(x), sl.strides.push_back(stored[i]);
       else
-        t.pscope.push_back(x), t.pstride.push_back(stored[i]), t.full_stride.push_back(full[i]), t.size *= net.dims[x];
+        t.pscope.push_back(x), t.pstride.push_back(stored[i]), t.size *= net.dims[x];
     }
-    // the observed (per-row) variables keep their place in the stored layout: remember their full strides too
-    for (int i = 0; i < ns; ++i)
-      if (P.fixed_state[t.scope[i]] < 0 && P.is_observed[t.scope[i]]) sl.full_strides.push_back(full[i]);
-    sl.stored_entries = acc;
     if (!sl.vars.empty()) {
       t.slice_slot = (int)P.slices.size();
       P.slices.push_back(sl);

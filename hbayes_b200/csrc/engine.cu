@@ -1,25 +1,33 @@
 // engine.cu -- sm_100a kernels and the row-tiled replay of a compiled Program.
 //
 // Data layout in HBM
-//   potential pool   double[pot_entries]            all CPTs, reference layout, batch-invariant
+//   potential pool   double[pot_entries]            all CPTs (restricted to the fixed states of a split clique),
+//                                                   reference layout, batch-invariant; procedural CPTs are
+//                                                   generated here on the device
 //   shared arena     double[shared_entries]         evidence-independent derived tables (computed once)
 //   row arena        double[row_entries][RT]        per-row derived tables, ROW-FASTEST: entry e of row r
 //                                                   of a tile sits at (off + e) * RT + r, so the 32 lanes
-//                                                   of a warp (32 consecutive rows, same entry) read and
-//                                                   write 256 contiguous bytes
+//                                                   of a warp (2 rows each, same entry) read and write 512
+//                                                   contiguous bytes
 //   slice offsets    int32[n_slices][RT]            entry offset of each sliced CPT for each row
 //   evidence         int8[n_rows][n_vars]           caller's matrix, -1 = unobserved
 //   output           double[n_rows][out_width]      caller's matrix
 //
 // Kernels
-//   prep_rows_kernel     evidence -> slice offsets + consistency check          (Bayes/Factor.hs:90-94)
-//   prodsum_kernel<K>    fused factor product + sum-out of one variable + evidence slicing
-//                        (marginalizeOneVariable = _factorProduct + cptFactorProjectOutWith,
-//                         Buckets.hs:105-111, PrivateCPT.hs:215-266)
-//   output_kernel        factorNorm + factorDivide + expansion to the query scope
-//                        (PrivateCPT.hs:167-187, Factor.hs:171-172)
+//   prep_rows_kernel            evidence -> slice offsets + consistency check        (Bayes/Factor.hs:90-94)
+//   prodsum_kernel<K,V,D,MASK>  fused factor product + sum-out of one variable + evidence slicing
+//                               (marginalizeOneVariable = _factorProduct + cptFactorProjectOutWith,
+//                                Buckets.hs:105-111, PrivateCPT.hs:215-266)
+//   fused_kernel<KO,KI,V,DI,MASK>  a chain of up to four such operations whose intermediate tables stay in
+//                               registers (Step::levels)
+//   prodsum_generic_kernel      the same for buckets with more tables than the templates take
+//   output_kernel               factorNorm + factorDivide + expansion to the query scope
+//                               (PrivateCPT.hs:167-187, Factor.hs:171-172)
+//   normalise_kernel            the same normalisation after the slices of a split clique have been summed
+//   proc_fill_kernel            procedural CPT values (procedural.hpp)
 // All arithmetic is binary64 with explicit round-to-nearest multiply/add (no FMA contraction), in the
 // reference's association order: ps * (v1 * (v2 * ...)) and 0 + t0 + t1 + ...
+// The per-row steps of a tile are captured into a CUDA graph in which independent steps overlap (executor_run).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -472,7 +480,6 @@ __global__ void __launch_bounds__(BLOCK) prep_rows_kernel(const PrepArgs a) {
 // ---- normalise + expand ------------------------------------------------------------------------
 struct OutDesc {
   TabRef t;                // rowoff is rebased per tile at launch
-  long long off_entries;   // (unused on device; kept for debugging)
   int slice;               // slice slot or -1
   int n_phys, n_full;
   long long out_col;
@@ -817,8 +824,6 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   else
     launch_kv<K, 1>(a, a.d, (1 << K) - 1, launch_shape(nr, 1, items2), stream);
 }
-
-constexpr int MAX_KO = 4, MAX_KI = 3;  // the same limits the compiler's fusion pass uses (CompileOptions)
 
 template <int KO, int KI, int V, int DI, int M>
 struct FusedMask {

@@ -92,8 +92,6 @@ struct Table {
   int64_t size = 1;              // physical entries
   int64_t off = 0;               // entry offset in its pool (potential pool / shared arena / row arena)
   int slice_slot = -1;           // T_POT mentioning observed variables: index into Program::slices
-  std::vector<int64_t> full_stride;  // T_POT: stride of each pscope variable in the reference layout of the whole CPT
-  int64_t full_base = 0;         // T_POT: offset of the fixed variables' states in the whole CPT
   int alias_of = -1;             // a final product of a single table is that table
   int def_step = -1, last_use = -1;
 };
@@ -164,8 +162,6 @@ struct Slice {  // per-row entry offset of a sliced potential: sum_j stride_j * 
   int pot;
   std::vector<int> vars;              // observed (per-row) variables of the CPT
   std::vector<int64_t> strides;       // their strides in the stored layout
-  std::vector<int64_t> full_strides;  // ... and in the reference layout of the whole CPT
-  int64_t stored_entries = 0;         // entries of the stored (restricted) table
 };
 
 struct Program {
