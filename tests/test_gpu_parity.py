@@ -293,3 +293,17 @@ def test_random_stress(seed):
     for v in observed:
         ev[:, v] = rng.randint(0, net.dims[v], rows)
     assert_same(pjt.posteriors_batch(ev), ojt.posteriors_batch(ev), ("stress", seed, observed, rows))
+
+
+def test_plain_c_example_runs(tmp_path):
+    import subprocess
+    from hbayes_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cancer_query")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", os.path.join(root, "examples", "cancer_query.c"), "-o", exe, "-L" + libdir, "-lhbayes_cuda",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe, os.path.join(G, "cancer.net")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "var 2: 0.425000 0.575000" in r.stdout  # P(A | D = Present), Bayes/Test/ReferencePatterns.hs:146
