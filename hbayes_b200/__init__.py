@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     VariableElimination,
     changeEvidence,
     createJunctionTree,
+    degreeOrder,
     factorProduct,
     factorProjectOut,
     marginalizeOneVariable,

@@ -33,6 +33,7 @@ SIGNATURES = {
     "hb_net_describe_json": (C.c_int, [vp, cpp]),
     "hb_net_free": (None, [vp]),
     "hb_ve_order": (C.c_int, [vp, i32, i32p, i32p]),
+    "hb_ve_degree_order": (C.c_int, [vp, i32p, i32, i32p]),
     "hb_jt_compile": (C.c_int, [vp, i32, i32p, i32, vpp]),
     "hb_jt_compile_with_order": (C.c_int, [vp, i32p, i32p, i32, vpp]),
     "hb_jt_compile_split": (C.c_int, [vp, i32, i32p, i32, i32, i32p, i32p, vpp]),

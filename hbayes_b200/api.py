@@ -124,6 +124,14 @@ def _order(net: BayesianNetwork, metric: int):
     return out[: k.value].tolist()
 
 
+def degreeOrder(net: BayesianNetwork, order) -> int:
+    """degreeOrder (Bayes/VariableElimination.hs:186-207)"""
+    oa, op = _i32(list(order))
+    w = C.c_int32()
+    check(lib().hb_ve_degree_order(net._h, op, len(oa), C.byref(w)))
+    return int(w.value)
+
+
 def minDegreeOrder(net):
     return _order(net, 0)
 

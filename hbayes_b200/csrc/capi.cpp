@@ -385,6 +385,13 @@ int hb_ve_order(const hb_net* net, int32_t metric, int32_t* order_out, int32_t* 
   });
 }
 
+int hb_ve_degree_order(const hb_net* net, const int32_t* order, int32_t n, int32_t* width) {
+  return guarded([&] {
+    if (!net || !width || n < 0 || (n > 0 && !order)) throw Error(HB_E_ARG, "null argument");
+    *width = ve_degree_order(net->net, std::vector<int>(order, order + n));
+  });
+}
+
 static int jt_compile(const hb_net* net, int32_t cmp, const int32_t* order, const int32_t* devices, int32_t n_devices, hb_jt** out) {
   return guarded([&] {
     if (!net || !out) throw Error(HB_E_ARG, "null argument");

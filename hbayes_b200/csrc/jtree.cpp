@@ -276,6 +276,30 @@ std::vector<int> ve_elimination_order(const Network& net, int metric) {
   return out;
 }
 
+// degreeOrder (VariableElimination.hs:186-207): the largest number of neighbours a variable has at the moment it is
+// eliminated, on the interaction graph WITH fill-in edges between its neighbours (the width the order induces).
+int ve_degree_order(const Network& net, const std::vector<int>& order) {
+  const int n = net.n();
+  BitMatrix adj(n);
+  for (int v = 0; v < n; ++v)
+    for (int x : net.scope[v])
+      for (int y : net.scope[v])
+        if (x != y) adj.set(x, y);
+  int width = 0;
+  for (int v : order) {
+    if (v < 0 || v >= n) throw Error(HB_E_ARG, "elimination order mentions an unknown vertex");
+    std::vector<int> nb = adj.members(v);
+    width = std::max(width, (int)nb.size());
+    for (int x : nb) {
+      for (int y : nb)
+        if (x != y) adj.set(x, y);
+      adj.clear(x, v);
+    }
+    std::fill(adj.row(v), adj.row(v) + adj.w, 0);
+  }
+  return width;
+}
+
 static void js_list(std::ostringstream& o, const std::vector<int>& v) {
   o << "[";
   for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << v[i];

@@ -67,6 +67,7 @@ int tree_covering_cluster(const Network& net, const Tree& t, const std::vector<i
 int tree_find_cluster(const Tree& t, const std::vector<int>& q);
 
 std::vector<int> ve_elimination_order(const Network& net, int metric /*0 minDegree, 1 minFill*/);
+int ve_degree_order(const Network& net, const std::vector<int>& order);
 
 // ---- Compiled program: flat step list replayed per evidence row --------------------------------
 //

@@ -77,6 +77,9 @@ void hb_net_free(hb_net* net);
 /* minDegreeOrder (metric 0) / minFillOrder (metric 1) (Bayes/VariableElimination.hs:210-236);
  * order_out has room for n_vars ids, *n_out receives how many were written */
 int hb_ve_order(const hb_net* net, int32_t metric, int32_t* order_out, int32_t* n_out);
+/* degreeOrder (Bayes/VariableElimination.hs:186-207): the width an elimination order induces (largest neighbour count
+ * at elimination time, with fill-in) */
+int hb_ve_degree_order(const hb_net* net, const int32_t* order, int32_t n, int32_t* width);
 
 /* ---- junction tree ------------------------------------------------------------------------- */
 /* createJunctionTree cmp g (Bayes/FactorElimination.hs:298-307).  cmp: 0 = nodeComparisonForTriangulation

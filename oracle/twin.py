@@ -710,6 +710,23 @@ def elimination_order_for_metric(net, metric):
     return out
 
 
+def degree_order(net, order):
+    """degreeOrder (VariableElimination.hs:186-207): max neighbour count at elimination time, fill-in edges added."""
+    adj = {v: set(n) for v, n in interaction_graph(net).items()}
+    w = 0
+    for dv in order:
+        v = dv[0] if isinstance(dv, tuple) else dv
+        r = list(adj.get(v, ()))
+        w = max(w, len(r))
+        for x in r:
+            for y in r:
+                if x != y:
+                    adj[x].add(y)
+            adj[x].discard(v)
+        adj.pop(v, None)
+    return w
+
+
 def min_degree_order(net):
     return elimination_order_for_metric(net, lambda adj, v: len(adj[v]))
 

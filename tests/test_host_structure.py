@@ -194,3 +194,15 @@ def test_save_and_load_round_trip(tmp_path):
     with pytest.raises(hb.HbError) as e:
         hb.JunctionTree.load(tmp_path / "junk", pnet, device=None)
     assert e.value.code == _lib.HB_E_IO
+
+
+def test_degree_order_matches_twin():
+    from oracle import twin
+
+    for shape in [(3, 3), (4, 6)]:
+        g = synth.grid_net(shape[0], shape[1], 3)
+        pnet = hb.BayesianNetwork.from_tables(g.dims, g.scopes, g.values)
+        tnet = twin.Network.from_tables(g.dims, g.parents, [v.tolist() for v in g.values])
+        for order in (hb.minFillOrder(pnet), hb.minDegreeOrder(pnet), list(range(g.n))):
+            assert hb.degreeOrder(pnet, order) == twin.degree_order(tnet, order)
+    assert hb.degreeOrder(pnet, list(range(g.n))) >= 2
