@@ -4,6 +4,8 @@
   C1  cancer.net, single evidence set through the stateful reference API (latency) and 2^16-row batches
   C3  500-node random DAG (max cluster 2^20.2), 4096 evidence rows per batch, 125 observed
   C5  20x20 grid via VariableElimination (reference min-fill order), rows per batch given by --c5-rows
+  EM  one learnEM step (Bayes/EM.hs:36-45) on the C2 network: 2^18 samples, 9 observed; then the learnt tables go
+      back into the same handle with changeFactor (no recompilation)
 
 Each line: config, rows, ms per pass (CUDA events around the C-ABI call, device-resident buffers), queries/s,
 algorithmic GB/s of the product/sum-out kernels, and the oracle port on the host cores for the same rows.
@@ -116,11 +118,57 @@ def c5(rows):
     return r
 
 
+def em(rows=1 << 18):
+    import oracle
+
+    net, observed = synth.config_c2()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    jt = hb.JunctionTree(pnet)
+    ev = synth.config_c2_evidence(net, observed, rows)
+    d_ev = torch.from_numpy(ev).cuda()
+    learnt = jt.em_step(d_ev)  # compiles the family-query program, sizes the arena
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        learnt = jt.em_step(d_ev)
+    ms = (time.perf_counter() - t) / reps * 1e3
+    st = jt.last_stats()
+    # where the time goes: one chunk, CUDA-event time of the junction-tree pass alone (the rest is the sample-order sum)
+    os.environ["HB_EM_CHUNK_ROWS"] = str(rows)
+    jt.set_timing(True)
+    jt.em_step(d_ev)
+    t = time.perf_counter()
+    jt.em_step(d_ev)
+    one_chunk_ms = (time.perf_counter() - t) * 1e3
+    pass_ms = jt.last_timing()["total_ms"]
+    del os.environ["HB_EM_CHUNK_ROWS"]
+    t = time.perf_counter()
+    for v, f in enumerate(learnt):
+        perm = [f.variables.index(x) for x in net.scopes[v]]
+        own = np.ascontiguousarray(f.values.reshape(f.dims).transpose(perm)).reshape(-1)
+        jt.change_factor(hb.Factor(net.scopes[v], [net.dims[x] for x in net.scopes[v]], own))
+    change_ms = (time.perf_counter() - t) * 1e3
+    k = 2048
+    t = time.perf_counter()
+    want = oracle.learn_em(net.dims, net.scopes, net.values, ev[:k])
+    cpu = k / (time.perf_counter() - t)
+    got = hb.JunctionTree(pnet).em_step(ev[:k])
+    same = all(g.variables == w[0] and g.values.tobytes() == w[1].tobytes() for g, w in zip(got, want))
+    width = sum(int(np.prod([net.dims[x] for x in sc])) + (int(np.prod([net.dims[x] for x in sc[1:]])) if len(sc) > 1 else 0)
+                for sc in net.scopes)
+    return {"config": "EM step on the C2 network (37 nodes, 9 observed)", "rows": rows, "ms_per_step": ms,
+            "samples_per_s": rows / ms * 1e3, "launches": st["launches"], "result_columns_per_sample": width,
+            "one_chunk_ms": one_chunk_ms, "one_chunk_tree_pass_ms": pass_ms,
+            "change_all_factors_ms": change_ms, "cpu_port_samples_per_s": cpu, "cpu_threads": 1,
+            "bit_identical_first_%d" % k: bool(same)}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="C1,C3,C5")
+    ap.add_argument("--only", default="C1,C3,C5,EM")
     ap.add_argument("--c5-rows", type=int, default=64)
     a = ap.parse_args()
     for name in a.only.split(","):
-        res = {"C1": c1, "C3": c3, "C5": lambda: c5(a.c5_rows)}[name]()
+        res = {"C1": c1, "C3": c3, "C5": lambda: c5(a.c5_rows), "EM": em}[name]()
         print(json.dumps(res), flush=True)

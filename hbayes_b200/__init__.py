@@ -9,6 +9,8 @@ The names follow the reference (alpheccar/hbayes) so that its examples and tests
     priorMarginal         Bayes/VariableElimination.hs:134-147
     posteriorMarginal     Bayes/VariableElimination.hs:116-130
     minDegreeOrder / minFillOrder   Bayes/VariableElimination.hs:225-236
+    changeFactor          Bayes/Factor.hs:66-81, Bayes/FactorElimination/JTree.hs:107-115
+    learnEM               Bayes/EM.hs:36-45
 
 plus the batched forms (one evidence row per query) that the GPU exists for.  All arithmetic happens in
 libhbayes_cuda.so; this package only marshals arrays.  It never imports `oracle/`.
@@ -19,6 +21,7 @@ from .api import (  # noqa: F401
     JunctionTree,
     VariableElimination,
     changeEvidence,
+    changeFactor,
     createJunctionTree,
     degreeOrder,
     factorProduct,

@@ -46,6 +46,8 @@ SIGNATURES = {
     "hb_jt_posteriors_batch": (C.c_int, [vp, i64, vp, vp, i32]),
     "hb_jt_queries_batch": (C.c_int, [vp, i32, i32p, i32p, i64, vp, vp, i32, i32p]),
     "hb_jt_queries_width": (C.c_int, [vp, i32, i32p, i32p, i64p]),
+    "hb_jt_change_factor": (C.c_int, [vp, i32, i32p, f64p, i32p]),
+    "hb_jt_em_step": (C.c_int, [vp, i64, vp, f64p, i32p, i32]),
     "hb_jt_set_split": (C.c_int, [vp, i32, i32p, i32p]),
     "hb_jt_normalise_batch": (C.c_int, [vp, i64, vp, i32]),
     "hb_jt_set_stream": (C.c_int, [vp, vp]),
@@ -60,6 +62,7 @@ SIGNATURES = {
     "hb_ve_program_json": (C.c_int, [vp, i32, i32p, cpp]),
     "hb_ve_posterior": (C.c_int, [vp, i32, i32p, i32p, i32p, f64p, i64, i64p]),
     "hb_ve_posterior_batch": (C.c_int, [vp, i64, vp, vp, i32]),
+    "hb_ve_change_factor": (C.c_int, [vp, i32, i32p, f64p, i32p]),
     "hb_ve_set_stream": (C.c_int, [vp, vp]),
     "hb_ve_set_workspace": (C.c_int, [vp, i64]),
     "hb_ve_last_stats": (C.c_int, [vp, i64p]),

@@ -93,6 +93,15 @@ class BayesianNetwork:
         check(lib().hb_net_cpt_values(self._h, v, offset, count, out.ctypes.data_as(f64p)))
         return out
 
+    def change_factor(self, factor: "Factor") -> "BayesianNetwork":
+        """changeFactor f g on a network (Bayes/Factor.hs:66-81): a NEW network in which the CPT whose variable list
+        equals the factor's (same variables, same order) carries the factor's values; no match -> an equal network."""
+        values = [np.asarray(v, np.float64) for v in self.values]
+        for v in range(self.n):
+            if list(self.scopes[v]) == list(factor.variables):
+                values[v] = np.asarray(factor.values, np.float64).reshape(-1)
+        return BayesianNetwork.from_tables(self.dims, self.scopes, values)
+
     @property
     def n(self):
         return len(self.dims)
@@ -297,6 +306,40 @@ class JunctionTree(_Batched):
             col += size
         return res
 
+    def change_factor(self, factor: "Factor") -> bool:
+        """changeFactor f jt (Bayes/FactorElimination/JTree.hs:107-115): new values for the CPT with the factor's variable
+        list, evidence kept, tree recalibrated; the compiled schedules stay (a potential upload).  True if a CPT matched."""
+        fa, fp = _i32(list(factor.variables))
+        vals = np.ascontiguousarray(factor.values, np.float64).reshape(-1)
+        hit = C.c_int32()
+        check(lib().hb_jt_change_factor(self._h, len(fa), fp, vals.ctypes.data_as(f64p), C.byref(hit)))
+        if hit.value:
+            self.net = self.net.change_factor(factor)
+        return bool(hit.value)
+
+    def em_step(self, samples):
+        """learnEM's expectation + maximisation on this tree's network (Bayes/EM.hs:36-66), samples = int8 evidence matrix
+        (-1 = missing; rows may have different observed sets) on the host or a CUDA tensor.  Returns, per vertex, the learnt
+        table as the reference lays it out: Factor over [parents in the order of their posterior..., child]."""
+        if isinstance(samples, np.ndarray):
+            ev = np.ascontiguousarray(samples, np.int8)
+            ptr, flags, rows = ev.ctypes.data, HB_HOST_PTRS, ev.shape[0]
+        else:
+            assert samples.is_cuda and samples.is_contiguous() and samples.element_size() == 1
+            ptr, flags, rows = samples.data_ptr(), HB_DEVICE_PTRS, samples.shape[0]
+        total = sum(int(np.prod([self.net.dims[x] for x in sc])) for sc in self.net.scopes)
+        out = np.zeros(total, np.float64)
+        scopes = np.zeros(sum(len(sc) for sc in self.net.scopes), np.int32)
+        check(lib().hb_jt_em_step(self._h, rows, ptr, out.ctypes.data_as(f64p), scopes.ctypes.data_as(i32p), flags))
+        res, at, sat = [], 0, 0
+        for sc0 in self.net.scopes:
+            sc = scopes[sat:sat + len(sc0)].tolist()
+            dims = [self.net.dims[x] for x in sc]
+            size = int(np.prod(dims))
+            res.append(Factor(sc, dims, out[at:at + size].copy()))
+            at, sat = at + size, sat + len(sc0)
+        return res
+
     def set_split(self, fixed: Sequence[tuple]):
         """split clique: this handle owns the slice `fixed` = [(vertex, state)]; batch results become unnormalised"""
         va, vp_ = _i32([e[0] for e in fixed])
@@ -354,6 +397,16 @@ class VariableElimination(_Batched):
 
     def posterior_batch(self, evidence, out=None):
         return self._run_matrix(lib().hb_ve_posterior_batch, evidence, out, self.width)
+
+    def change_factor(self, factor: "Factor") -> bool:
+        """changeFactor on the network behind this handle (Bayes/Factor.hs:66-81); True if a CPT matched"""
+        fa, fp = _i32(list(factor.variables))
+        vals = np.ascontiguousarray(factor.values, np.float64).reshape(-1)
+        hit = C.c_int32()
+        check(lib().hb_ve_change_factor(self._h, len(fa), fp, vals.ctypes.data_as(f64p), C.byref(hit)))
+        if hit.value:
+            self.net = self.net.change_factor(factor)
+        return bool(hit.value)
 
     def __del__(self):
         try:
@@ -433,30 +486,28 @@ def marginalizeOneVariable(factors: Sequence[Factor], variable: int, device=0) -
     return _factor_marginalize(factors, variable, device)
 
 
-def learnEM(samples: np.ndarray, net: BayesianNetwork, device=0):
-    """One expectation/maximisation step (Bayes/EM.hs:36-66): for every sample, `posterior` of each CPT family and of
-    its parents under that sample's evidence; the family posteriors are summed over the samples and divided by the
-    summed parent posteriors (`divide _ 0 = 0`).  `samples`: int8 [n_samples][n_vars] evidence matrix (-1 = missing)
-    with ONE observed set.  Returns the new CPT values per vertex in the CPT's own layout [child, parents...].
-    All samples go through the GPU in one batch; the sum over samples is a NumPy pairwise sum (the reference folds
-    left sample by sample), so results agree to ~1e-13 relative, not bit for bit."""
-    jt = JunctionTree(net, device=device)
-    queries = []
-    for v in range(net.n):
-        queries.append(net.scopes[v])
-        if len(net.scopes[v]) > 1:
-            queries.append(net.scopes[v][1:])
-    res = iter(jt.queries_batch(queries, samples))
-    new_values = []
-    for v in range(net.n):
-        sc, dims, vals = next(res)
-        fam = vals.sum(0).reshape(dims).transpose([sc.index(x) for x in net.scopes[v]])  # -> [child, parents...]
-        if len(net.scopes[v]) > 1:
-            psc, pdims, pvals = next(res)
-            par = pvals.sum(0).reshape(pdims).transpose([psc.index(x) for x in net.scopes[v][1:]])[None, ...]
-        else:
-            par = np.full([1] * 1, float(samples.shape[0]))  # posterior of nothing: Scalar 1.0 per sample
-        with np.errstate(divide="ignore", invalid="ignore"):
-            new = np.where(par == 0.0, 0.0, fam / par)
-        new_values.append(np.ascontiguousarray(new).reshape(-1))
-    return new_values
+def changeFactor(factor: Factor, container):
+    """`changeFactor f c` of the FactorContainer class (Bayes/Factor.hs:76-81): a network gives a NEW network; a
+    JunctionTree / VariableElimination handle is updated in place (and returned), its schedules untouched."""
+    if isinstance(container, BayesianNetwork):
+        return container.change_factor(factor)
+    container.change_factor(factor)
+    return container
+
+
+def learnEM(samples, net: BayesianNetwork, device=0, reference_layout=False):
+    """`learnEM samples g` (Bayes/EM.hs:36-45), one expectation/maximisation step, entirely on the GPU: per sample
+    changeEvidence + `posterior` of every CPT family and of its parents, summed sample after sample and divided with
+    `divide _ 0 = 0` -- bit-identical to the reference's fold.  `samples`: int8 [n_samples][n_vars] evidence matrix
+    (-1 = missing; the observed set may differ from row to row).
+    Returns the learnt CPT values per vertex in the CPT's own layout [child, parents...] (a pure re-layout of what the
+    reference returns), or with reference_layout=True the reference's own Factors, whose variable order is
+    [parents in the order of their posterior..., child] (cptDivide, Bayes/Factor/CPT.hs:159-160)."""
+    learnt = JunctionTree(net, device=device).em_step(samples)
+    if reference_layout:
+        return learnt
+    out = []
+    for v, f in enumerate(learnt):
+        perm = [f.variables.index(x) for x in net.scopes[v]]
+        out.append(np.ascontiguousarray(f.values.reshape(f.dims).transpose(perm)).reshape(-1))
+    return out

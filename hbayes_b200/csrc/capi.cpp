@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,6 +65,7 @@ int pick_device(const int32_t* devices, int32_t n_devices) {
 struct Compiled {
   std::unique_ptr<Program> prog;
   Executor* ex = nullptr;
+  bool stale = false;  // the network's CPT values changed after `ex` uploaded them (changeFactor)
   ~Compiled() {
     if (ex) executor_destroy(ex);
   }
@@ -91,6 +93,23 @@ struct Session {
   int64_t chunk_rows = 1 << 18;
   // split clique: variables fixed to this handle's slice; batch results are then left unnormalised
   std::vector<std::pair<int, int>> fixed;
+  // grow-only device scratch of hb_jt_em_step (result matrix of a chunk, group staging, evidence, row indices):
+  // freeing gigabytes per call costs more than the step itself
+  struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* ensure(size_t bytes) {
+      if (bytes > cap) {
+        if (p) cudaFree(p), p = nullptr, cap = 0;
+        cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc(EM scratch)");
+        cap = bytes;
+      }
+      return p;
+    }
+    ~Scratch() {
+      if (p) cudaFree(p);
+    }
+  } em_mat, em_tmp, em_ev, em_rows;
 
   ~Session() {
     if (device >= 0) cudaSetDevice(device);
@@ -104,7 +123,8 @@ struct Session {
   // the device-resident form of a compiled program, created on first use
   Executor* executor(Compiled& c) {
     if (device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
-    if (!c.ex) c.ex = executor_create(*c.prog, device, workspace);
+    if (!c.ex) c.ex = executor_create(*c.prog, device, workspace), c.stale = false;
+    if (c.stale) executor_refresh_potentials(c.ex), c.stale = false;
     executor_set_timing(c.ex, timing);
     last_ex = c.ex;
     return c.ex;
@@ -253,6 +273,7 @@ struct hb_jt {
   std::unique_ptr<Tree> tree;
   std::vector<int> ev_vars, ev_states;  // current changeEvidence list
   std::vector<double> posts;            // posterior [v] for every v under the current evidence
+  bool posts_stale = false;             // a changeFactor happened since `posts` was computed
   std::vector<int64_t> post_off;
 
   // program for changeEvidence `observed` (in that order) + the given queries (empty = posterior [v] for all v)
@@ -316,6 +337,35 @@ static void check_evidence_list(const Network& net, int32_t n, const int32_t* va
     if (vars[i] < 0 || vars[i] >= net.n()) throw Error(HB_E_ARG, "evidence on unknown vertex");
     if (states[i] < 0 || states[i] >= net.dims[vars[i]]) throw Error(HB_E_ARG, "evidence state out of range");
   }
+}
+
+namespace {
+struct DevBuf {  // a device allocation that lives for one call
+  void* p = nullptr;
+  explicit DevBuf(size_t bytes) { cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 8)), "cudaMalloc(EM buffers)"); }
+  ~DevBuf() { cudaFree(p); }
+  DevBuf(const DevBuf&) = delete;
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+}  // namespace
+
+// changeFactor on the handle's private copy of the network (Bayes/Factor.hs:66-71): the CPT whose variable list
+// equals `scope` gets the new values; every device-resident program of the handle re-uploads its potentials.
+static bool change_factor(Session& s, int32_t n_scope, const int32_t* scope, const double* values) {
+  if (n_scope <= 0 || !scope || !values) throw Error(HB_E_ARG, "null or empty factor");
+  Network& net = s.net;
+  const std::vector<int> sc(scope, scope + n_scope);
+  for (int x : sc)
+    if (x < 0 || x >= net.n()) throw Error(HB_E_ARG, "factor on unknown vertex");
+  int hit = -1;
+  for (int v = 0; v < net.n() && hit < 0; ++v)
+    if (net.scope[v] == sc) hit = v;
+  if (hit < 0) return false;
+  if (net.procedural(hit)) throw Error(HB_E_UNSUPPORTED, "changeFactor on a procedural CPT");
+  net.values[hit].assign(values, values + net.cpt_entries(hit));
+  for (auto& kv : s.cache) kv.second->stale = kv.second->ex != nullptr;  // re-uploaded on next use (Session::executor)
+  return true;
 }
 
 extern "C" {
@@ -594,6 +644,7 @@ int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t*
     jt->ev_vars = v;
     jt->ev_states = st;
     jt->run_one(c, jt->posts);
+    jt->posts_stale = false;
   });
 }
 int hb_jt_posterior(hb_jt* jt, int32_t n_q, const int32_t* q_vars, int32_t* out_scope, double* out, int64_t out_len,
@@ -604,6 +655,7 @@ int hb_jt_posterior(hb_jt* jt, int32_t n_q, const int32_t* q_vars, int32_t* out_
     if (n_q == 1) {
       const int v = q_vars[0];
       if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "query on unknown vertex");
+      if (jt->posts_stale) jt->run_one(jt->program(jt->ev_vars, {}), jt->posts), jt->posts_stale = false;
       if (out_len < net.dims[v]) throw Error(HB_E_ARG, "output buffer too small");
       for (int i = 0; i < net.dims[v]; ++i) out[i] = jt->posts[jt->post_off[v] + i];
       if (out_scope) out_scope[0] = v;
@@ -664,6 +716,230 @@ int hb_jt_queries_width(hb_jt* jt, int32_t n_queries, const int32_t* query_off, 
       w += p;
     }
     *width = w;
+  });
+}
+int hb_jt_change_factor(hb_jt* jt, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced) {
+  return guarded([&] {
+    if (!jt) throw Error(HB_E_ARG, "null handle");
+    const bool hit = change_factor(jt->s, n_scope, scope, values);
+    if (replaced) *replaced = hit ? 1 : 0;
+    if (hit) jt->posts_stale = true;  // recalibrated under the kept evidence when the next posterior is asked for
+  });
+}
+
+int hb_jt_em_step(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out_values, int32_t* out_scopes, int32_t flags) {
+  return guarded([&] {
+    if (!jt || !evidence || !out_values || n_rows <= 0) throw Error(HB_E_ARG, "null argument or no samples (foldl1 of an empty list)");
+    Session& s = jt->s;
+    const Network& net = s.net;
+    const int n_vars = net.n();
+    if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
+    if (!s.fixed.empty()) throw Error(HB_E_UNSUPPORTED, "hb_jt_em_step on a split handle");
+    cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+    const bool tracing = getenv("HB_EM_TRACE") != nullptr;  // host-side phase times on stderr (synchronises)
+    auto t_last = std::chrono::steady_clock::now();
+    auto trace = [&](const char* what) {
+      if (!tracing) return;
+      cudaStreamSynchronize(s.stream);
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[hb_jt_em_step] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    };
+    // the samples on the host (they decide the programs), grouped by observed set in order of first appearance
+    std::vector<int8_t> host_ev;
+    const int8_t* dev_evidence = (flags & HB_DEVICE_PTRS) ? evidence : nullptr;
+    if (flags & HB_DEVICE_PTRS) {
+      host_ev.resize((size_t)n_rows * n_vars);
+      cuda_ok(cudaMemcpyAsync(host_ev.data(), evidence, host_ev.size(), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(evidence)");
+      cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+      evidence = host_ev.data();
+    }
+    std::map<std::vector<int>, int> group_of;
+    std::vector<std::vector<int>> group_obs;
+    std::vector<int> row_group((size_t)n_rows);
+    const int8_t* rep = nullptr;  // a row of the previous row's group: most batches have one observed set
+    for (int64_t r = 0; r < n_rows; ++r) {
+      const int8_t* row = evidence + r * n_vars;
+      bool same = rep != nullptr;
+      int v = 0;
+      for (; same && v + 8 <= n_vars; v += 8) {  // observed <=> sign bit clear: compare the sign bits of 8 entries at once
+        uint64_t a, b;
+        memcpy(&a, row + v, 8), memcpy(&b, rep + v, 8);
+        same = ((a ^ b) & 0x8080808080808080ull) == 0;
+      }
+      for (; same && v < n_vars; ++v) same = (row[v] >= 0) == (rep[v] >= 0);
+      if (same) {
+        row_group[(size_t)r] = row_group[(size_t)r - 1];
+        continue;
+      }
+      std::vector<int> obs = observed_of_row(row, n_vars);
+      auto it = group_of.find(obs);
+      if (it == group_of.end()) it = group_of.emplace(obs, (int)group_obs.size()).first, group_obs.push_back(obs);
+      row_group[(size_t)r] = it->second;
+      rep = row;
+    }
+    trace("group rows");
+    // queries: posterior jt' (factorVariables cpt) and posterior jt' (tail ...) per vertex (EM.hs:60-66)
+    std::vector<int> flat, q_vertex, q_is_parents;
+    for (int v = 0; v < n_vars; ++v) {
+      if (!flat.empty()) flat.push_back(-1);
+      flat.insert(flat.end(), net.scope[v].begin(), net.scope[v].end());
+      q_vertex.push_back(v), q_is_parents.push_back(0);
+      if (net.scope[v].size() > 1) {
+        flat.push_back(-1);
+        flat.insert(flat.end(), net.scope[v].begin() + 1, net.scope[v].end());
+        q_vertex.push_back(v), q_is_parents.push_back(1);
+      }
+    }
+    const int n_q = (int)q_vertex.size();
+    // result layouts per group; the accumulators keep the layout of the first sample (cptSum: foldr1 union, acc first)
+    struct Layout {
+      std::vector<std::vector<int>> scope;  // per query
+      std::vector<int64_t> col;             // per query: first column
+    };
+    auto layout_of = [&](const Program& P) {
+      Layout L;
+      int64_t at = 0;
+      for (const Group& g : P.groups)
+        if (g.kind == 2) {
+          L.scope.push_back(g.out_scope);
+          L.col.push_back(at);
+          int64_t w = 1;
+          for (int x : g.out_scope) w *= net.dims[x];
+          at += w;
+        }
+      if ((int)L.scope.size() != n_q || at != P.out_width) throw Error(HB_E_ARG, "internal: EM query list does not match the program");
+      return L;
+    };
+    std::vector<Compiled*> progs;
+    std::vector<Layout> layouts;
+    for (const auto& obs : group_obs) {
+      progs.push_back(&jt->program(obs, flat));
+      layouts.push_back(layout_of(*progs.back()->prog));
+    }
+    const Layout& L0 = layouts[0];
+    const int64_t width = progs[0]->prog->out_width;
+    // column of group g's layout -> column of the first sample's layout
+    auto column_map = [&](const Layout& L) {
+      std::vector<uint32_t> m((size_t)width);
+      for (int q = 0; q < n_q; ++q) {
+        const std::vector<int>& from = L.scope[q];
+        const std::vector<int>& to = L0.scope[q];
+        std::vector<int64_t> tstride(from.size());
+        for (size_t i = 0; i < from.size(); ++i) {
+          int64_t st = 1;
+          size_t j = to.size();
+          while (j-- > 0 && to[j] != from[i]) st *= net.dims[to[j]];
+          tstride[i] = st;
+        }
+        int64_t n = 1;
+        for (int x : from) n *= net.dims[x];
+        for (int64_t e = 0; e < n; ++e) {
+          int64_t rem = e, dst = 0;
+          for (size_t i = from.size(); i-- > 0;) dst += (rem % net.dims[from[i]]) * tstride[i], rem /= net.dims[from[i]];
+          m[(size_t)(L.col[q] + e)] = (uint32_t)(L0.col[q] + dst);
+        }
+      }
+      return m;
+    };
+    // rows per chunk: the result matrix of a chunk stays below 1 GiB
+    int64_t chunk = std::max<int64_t>(64, (((int64_t)1 << 30) / (width * 8)) / 64 * 64);
+    if (const char* env = getenv("HB_EM_CHUNK_ROWS")) chunk = std::max<int64_t>(1, atoll(env));
+    chunk = std::min(chunk, n_rows);
+    const bool mixed = group_obs.size() > 1;
+    DevBuf d_acc((size_t)width * 8);
+    double* d_mat = (double*)s.em_mat.ensure((size_t)chunk * width * 8);
+    int8_t* d_ev = (int8_t*)s.em_ev.ensure((size_t)chunk * n_vars);
+    double* d_tmp = mixed ? (double*)s.em_tmp.ensure((size_t)chunk * width * 8) : nullptr;
+    int64_t* d_rows = mixed ? (int64_t*)s.em_rows.ensure((size_t)chunk * 8) : nullptr;
+    std::vector<uint32_t*> d_colmap(group_obs.size(), nullptr);
+    std::vector<std::unique_ptr<DevBuf>> colmap_bufs;
+    if (mixed)
+      for (size_t g = 0; g < group_obs.size(); ++g) {
+        std::vector<uint32_t> m = column_map(layouts[g]);
+        colmap_bufs.push_back(std::make_unique<DevBuf>(m.size() * 4));
+        d_colmap[g] = colmap_bufs.back()->as<uint32_t>();
+        cuda_ok(cudaMemcpyAsync(d_colmap[g], m.data(), m.size() * 4, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(column map)");
+        cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");  // m is a local
+      }
+    cuda_ok(cudaMemsetAsync(d_acc.p, 0, (size_t)width * 8, s.stream), "cudaMemset");
+    trace("programs + buffers");
+    RunStats rs;
+    bool first = true;
+    std::vector<int8_t> ev_rows;
+    std::vector<int64_t> idx;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+      const int64_t m = std::min(chunk, n_rows - r0);
+      if (!mixed) {
+        if (!dev_evidence)
+          cuda_ok(cudaMemcpyAsync(d_ev, evidence + r0 * n_vars, (size_t)m * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+        executor_run(s.executor(*progs[0]), m, dev_evidence ? dev_evidence + r0 * n_vars : d_ev, d_mat, s.stream, &rs);
+        s.note(*progs[0], rs, !first);
+        first = false;
+      } else {
+        for (size_t g = 0; g < group_obs.size(); ++g) {
+          ev_rows.clear();
+          idx.clear();
+          for (int64_t r = r0; r < r0 + m; ++r)
+            if (row_group[(size_t)r] == (int)g) {
+              ev_rows.insert(ev_rows.end(), evidence + r * n_vars, evidence + (r + 1) * n_vars);
+              idx.push_back(r - r0);
+            }
+          if (idx.empty()) continue;
+          const int64_t k = (int64_t)idx.size();
+          cuda_ok(cudaMemcpyAsync(d_ev, ev_rows.data(), ev_rows.size(), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+          cuda_ok(cudaMemcpyAsync(d_rows, idx.data(), idx.size() * 8, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(row index)");
+          executor_run(s.executor(*progs[g]), k, d_ev, d_tmp, s.stream, &rs);
+          s.note(*progs[g], rs, !first);
+          first = false;
+          em_scatter(d_mat, d_tmp, d_rows, d_colmap[g], k, width, s.stream);
+          cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");  // ev_rows / idx are reused
+        }
+      }
+      trace("tree pass (chunk)");
+      em_accumulate(d_acc.as<double>(), d_mat, m, width, s.stream);
+      s.stats[0] += mixed ? 1 + (int64_t)group_obs.size() : 1;
+      trace("sample-order sum");
+    }
+    for (Compiled* c : progs) executor_check(s.executor(*c), s.stream);
+    // cptDivide: learnt table of v over (parents in the order of their posterior) ++ [v]
+    std::vector<uint32_t> a_col;
+    std::vector<int32_t> b_col;
+    int scope_at = 0;
+    for (int q = 0; q < n_q; ++q) {
+      if (q_is_parents[q]) continue;
+      const int v = q_vertex[q];
+      const bool has_parents = q + 1 < n_q && q_is_parents[q + 1];
+      std::vector<int> ref_scope = has_parents ? L0.scope[q + 1] : std::vector<int>{};
+      ref_scope.push_back(v);
+      const std::vector<int>& asc = L0.scope[q];
+      std::vector<int64_t> astride(ref_scope.size());
+      for (size_t i = 0; i < ref_scope.size(); ++i) {
+        int64_t st = 1;
+        size_t j = asc.size();
+        while (j-- > 0 && asc[j] != ref_scope[i]) st *= net.dims[asc[j]];
+        astride[i] = st;
+      }
+      int64_t n = 1;
+      for (int x : ref_scope) n *= net.dims[x];
+      for (int64_t e = 0; e < n; ++e) {
+        int64_t rem = e, src = 0;
+        for (size_t i = ref_scope.size(); i-- > 0;) src += (rem % net.dims[ref_scope[i]]) * astride[i], rem /= net.dims[ref_scope[i]];
+        a_col.push_back((uint32_t)(L0.col[q] + src));
+        b_col.push_back(has_parents ? (int32_t)(L0.col[q + 1] + e / net.dims[v]) : -1);
+      }
+      if (out_scopes)
+        for (int x : ref_scope) out_scopes[scope_at++] = x;
+    }
+    const int64_t n_entries = (int64_t)a_col.size();
+    DevBuf d_a((size_t)n_entries * 4), d_b((size_t)n_entries * 4), d_new((size_t)n_entries * 8);
+    cuda_ok(cudaMemcpyAsync(d_a.p, a_col.data(), (size_t)n_entries * 4, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy");
+    cuda_ok(cudaMemcpyAsync(d_b.p, b_col.data(), (size_t)n_entries * 4, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy");
+    em_divide(d_new.as<double>(), d_acc.as<double>(), d_a.as<uint32_t>(), d_b.as<int32_t>(), n_entries, (double)n_rows, s.stream);
+    s.stats[0] += 1;
+    cuda_ok(cudaMemcpyAsync(out_values, d_new.p, (size_t)n_entries * 8, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    trace("divide + copy out");
   });
 }
 int hb_jt_set_split(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states) {
@@ -826,6 +1102,13 @@ int hb_ve_posterior_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, dou
   return guarded([&] {
     if (!ve) throw Error(HB_E_ARG, "null handle");
     run_matrix(ve->s, [&](const std::vector<int>& obs) -> Compiled& { return ve->program(obs); }, n_rows, evidence, out, flags);
+  });
+}
+int hb_ve_change_factor(hb_ve* ve, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced) {
+  return guarded([&] {
+    if (!ve) throw Error(HB_E_ARG, "null handle");
+    const bool hit = change_factor(ve->s, n_scope, scope, values);
+    if (replaced) *replaced = hit ? 1 : 0;
   });
 }
 int hb_ve_set_stream(hb_ve* ve, void* cuda_stream) {

@@ -989,16 +989,13 @@ static void set_row_stride(Executor& ex, int64_t RT) {
   ex.d_out_desc = upload(ex.out_desc);
 }
 
-Executor* executor_create(const Program& P, int device, int64_t workspace_bytes) {
-  HB_CUDA(cudaSetDevice(device));
-  auto ex = std::make_unique<Executor>();
-  ex->P = &P;
-  ex->device = device;
+// Fills the potential pool: every CPT restricted to the fixed (split) states; stored ones are gathered on the
+// host, procedural ones are generated on the device.  Also used by changeFactor (executor_refresh_potentials).
+static void upload_potentials(Executor& ex) {
+  const Program& P = *ex.P;
   const Network& net = *P.net;
-  // potential pool
   // potential pool: every CPT restricted to the fixed (split) states; stored ones are gathered on the host,
   // procedural ones are generated on the device
-  HB_CUDA(cudaMalloc(&ex->d_pots, std::max<int64_t>(P.pot_entries, 1) * sizeof(double)));
   {
     std::vector<double> staged;
     for (int v = 0; v < net.n(); ++v) {
@@ -1017,7 +1014,7 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
         if (dim.size() > 40) throw Error(HB_E_UNSUPPORTED, "procedural CPT with more than 40 free variables");
         ProcFillArgs a;
         memset(&a, 0, sizeof a);
-        a.dst = ex->d_pots + P.pot_off[v];
+        a.dst = ex.d_pots + P.pot_off[v];
         a.entries = entries;
         a.seed = net.proc_seed[v];
         a.npar = (unsigned long long)(net.cpt_entries(v) / net.dims[v]);
@@ -1041,13 +1038,26 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
             digit[j] = 0;
           }
         }
-        HB_CUDA(cudaMemcpy(ex->d_pots + P.pot_off[v], staged.data(), (size_t)entries * sizeof(double), cudaMemcpyHostToDevice));
+        HB_CUDA(cudaMemcpy(ex.d_pots + P.pot_off[v], staged.data(), (size_t)entries * sizeof(double), cudaMemcpyHostToDevice));
       }
     }
     if (!P.extra_values.empty())
-      HB_CUDA(cudaMemcpy(ex->d_pots + P.extra_off, P.extra_values.data(), P.extra_values.size() * sizeof(double), cudaMemcpyHostToDevice));
+      HB_CUDA(cudaMemcpy(ex.d_pots + P.extra_off, P.extra_values.data(), P.extra_values.size() * sizeof(double), cudaMemcpyHostToDevice));
     HB_CUDA(cudaGetLastError());
   }
+}
+
+// batch-invariant steps: evaluated once per set of potentials, with a single pseudo-row
+static void run_shared_steps(Executor& ex);
+
+Executor* executor_create(const Program& P, int device, int64_t workspace_bytes) {
+  HB_CUDA(cudaSetDevice(device));
+  auto ex = std::make_unique<Executor>();
+  ex->P = &P;
+  ex->device = device;
+  const Network& net = *P.net;
+  HB_CUDA(cudaMalloc(&ex->d_pots, std::max<int64_t>(P.pot_entries, 1) * sizeof(double)));
+  upload_potentials(*ex);
   HB_CUDA(cudaMalloc(&ex->d_shared, std::max<int64_t>(P.shared_entries, 1) * sizeof(double)));
   // index-map pool
   std::vector<uint32_t>& maps = ex->maps;
@@ -1171,18 +1181,29 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     workspace_bytes = std::min<int64_t>((int64_t)(free_b * 0.6), (int64_t)24 << 30);
   }
   ex->workspace = workspace_bytes;
-  // batch-invariant steps: evaluated once, here, with a single pseudo-row
-  set_row_stride(*ex, 64);
+  run_shared_steps(*ex);
+  return ex.release();
+}
+
+static void run_shared_steps(Executor& ex) {
+  const Program& P = *ex.P;
+  if (!ex.RT) set_row_stride(ex, 64);  // shared tables do not depend on the row stride; the descriptors need one
   int64_t gi = 0, gs = 0;
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
     if (st.kind != STEP_PRODSUM) continue;
-    if (st.shared) launch_prodsum(*ex, st, (int)si, 64, 1, 0, gi, gs);
+    if (st.shared) launch_prodsum(ex, st, (int)si, ex.RT, 1, 0, gi, gs);
     if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
   }
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaDeviceSynchronize());
-  return ex.release();
+}
+
+void executor_refresh_potentials(Executor* ex) {
+  HB_CUDA(cudaSetDevice(ex->device));
+  HB_CUDA(cudaDeviceSynchronize());
+  upload_potentials(*ex);  // same addresses: captured graphs stay valid
+  run_shared_steps(*ex);
 }
 
 void executor_destroy(Executor* ex) { delete ex; }

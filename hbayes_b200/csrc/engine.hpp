@@ -20,6 +20,11 @@ struct RunStats {          // filled by executor_run (host-side counts, no devic
 Executor* executor_create(const Program& P, int device, int64_t workspace_bytes);
 void executor_destroy(Executor* ex);
 
+// changeFactor (Bayes/FactorElimination/JTree.hs:107-115): the network's CPT values changed, the schedule did
+// not.  Re-uploads the potential pool from P.net and re-evaluates the batch-invariant steps; synchronises
+// the device.  Captured graphs stay valid (same addresses).
+void executor_refresh_potentials(Executor* ex);
+
 // One pass of the program over n_rows evidence rows.  d_evidence: int8 [n_rows][n_vars] (-1 = unobserved),
 // d_out: double [n_rows][out_width]; both DEVICE pointers.  Asynchronous on `stream` (a cudaStream_t).
 // A row whose observed set differs from the program's, or whose state is out of range, raises the
@@ -41,5 +46,16 @@ int executor_device(const Executor* ex);
 // [0] prep_rows_kernel, [1] all prodsum kernels, [2] output_kernel, [3] whole pass.
 void executor_set_timing(Executor* ex, bool on);
 void executor_last_timing(Executor* ex, void* stream, double out4[4]);
+
+// ---- learnEM accumulation (em.cu); plain device buffers, no Executor ----
+// d_acc[c] = (...((d_acc[c] + rows[0][c]) + rows[1][c]) + ...): the reference's sample-by-sample cptSum.
+void em_accumulate(double* d_acc, const double* d_rows, int64_t n_rows, int64_t width, void* stream);
+// d_dst[d_row_of[i]][d_col_of[c]] = d_src[i][c]
+void em_scatter(double* d_dst, const double* d_src, const int64_t* d_row_of, const uint32_t* d_col_of, int64_t n_rows, int64_t width,
+                void* stream);
+// cptDivide of the accumulated family / parent tables, entry e of the concatenated learnt tables reading
+// family column d_a_col[e] and parent column d_b_col[e] (-1: no parents, scale by 1/n_samples).
+void em_divide(double* d_out, const double* d_acc, const uint32_t* d_a_col, const int32_t* d_b_col, int64_t n_entries, double n_samples,
+               void* stream);
 
 }  // namespace hb

@@ -131,6 +131,20 @@ int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags)
 int hb_jt_queries_batch(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t n_rows,
                         const int8_t* evidence, double* out, int32_t flags, int32_t* out_scopes);
 int hb_jt_queries_width(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t* width);
+/* changeFactor f jt (Bayes/FactorElimination/JTree.hs:107-115, Bayes/Factor.hs:66-81): replaces the values of the
+ * CPT whose variable LIST equals scope (same variables in the same order: isUsingSameVariablesAs is list equality,
+ * Bayes/Factor/PrivateCPT.hs:135-136) and recalibrates under the current evidence.  values: prod dims(scope) doubles,
+ * first variable slowest.  *replaced = 1 if a CPT matched, 0 if none did (the reference then returns the tree
+ * unchanged; so does this call).  The compiled schedules are kept: on the device this is a potential upload. */
+int hb_jt_change_factor(hb_jt* jt, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced);
+/* learnEM samples g (Bayes/EM.hs:36-66), one expectation/maximisation step on the handle's network: per sample
+ * (row) changeEvidence + posterior of every CPT family and of its parents, summed sample after sample (cptSum) and
+ * divided (cptDivide, divide _ 0 = 0).  Rows may have different observed sets.  out_values: sum_v cpt entries
+ * doubles, vertex after vertex, each table laid out as the reference returns it -- variable order written to
+ * out_scopes (sum_v |scope v| ids): the parents in the order of their joint posterior, then the child, NOT the
+ * CPT's own [child, parents] order (cptDivide's union [b, a], Bayes/Factor/CPT.hs:159-160).  evidence is a host or
+ * device pointer according to flags; out_values and out_scopes are host pointers. */
+int hb_jt_em_step(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out_values, int32_t* out_scopes, int32_t flags);
 /* CUDA stream (a cudaStream_t) the handle launches on; NULL = the default stream */
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream);
 /* bytes of device workspace the row arena may use (0 = default) */
@@ -171,6 +185,8 @@ int hb_ve_posterior(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* st
                     int64_t out_len, int64_t* n_written);
 /* one posteriorMarginal per row (assignment = observed entries in ascending vertex id); out: [n_rows][prod_r dims[r]] */
 int hb_ve_posterior_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags);
+/* changeFactor f g on the network behind a variable-elimination handle (Bayes/Factor.hs:66-81); see hb_jt_change_factor */
+int hb_ve_change_factor(hb_ve* ve, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced);
 int hb_ve_set_stream(hb_ve* ve, void* cuda_stream);
 int hb_ve_set_workspace(hb_ve* ve, int64_t bytes);
 int hb_ve_last_stats(const hb_ve* ve, int64_t* out8);

@@ -194,6 +194,27 @@ class OracleJT:
             pass
 
 
+def learn_em(dims, scopes, values, samples):
+    """learnEM (Bayes/EM.hs:36-66) with the posteriors of the C++ oracle's junction tree and the twin's cptSum /
+    cptDivide.  samples: int8 matrix (-1 = missing).  Returns [(scope, values)] per vertex in the reference's layout."""
+    from . import twin
+
+    onet = OracleNet.from_arrays(dims, scopes, values)
+    ojt = OracleJT(onet)
+    tnet = twin.Network.from_tables(dims, [list(sc[1:]) for sc in scopes], [list(map(float, v)) for v in values])
+
+    def posterior_fn(evidence, vs, _state={"ev": None}):
+        if _state["ev"] is not evidence:
+            ojt.change_evidence(evidence)
+            _state["ev"] = evidence
+        sc, vals = ojt.posterior(vs)
+        return twin.Factor([(x, dims[x]) for x in sc], [float(x) for x in vals])
+
+    rows = [[(v, int(s)) for v, s in enumerate(row) if s >= 0] for row in np.asarray(samples)]
+    learnt = twin.learn_em(tnet, rows, posterior_fn)
+    return [([dv[0] for dv in f.vars], np.asarray(f.vals, np.float64)) for f in learnt]
+
+
 def factor_product(factors):
     """factors = [(scope [(var, dim)...], values)]; returns (scope vars, values)."""
     soff = [0]

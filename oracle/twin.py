@@ -669,6 +669,94 @@ def posterior(t, v, trace=None):
 
 
 # --------------------------------------------------------------------------
+# changeFactor (Factor.hs:66-81; JTree.hs:107-115) and learnEM (EM.hs:16-66; CPT.hs:144-163)
+# --------------------------------------------------------------------------
+
+
+def change_factor_in_list(f, l):
+    """changeFactorInFunctor (Factor.hs:66-71): isUsingSameVariablesAs is LIST equality (PrivateCPT.hs:135-136)."""
+    return [f if ((not cf.is_scalar()) and cf.vars == f.vars) else cf for cf in l]
+
+
+def change_factor_jt(f, t):
+    """instance FactorContainer (JTree Cluster) (JTree.hs:107-115): replace in every node, keep the evidence,
+    clear the separators, collect + distribute."""
+    for c in t.factors:
+        t.factors[c] = change_factor_in_list(f, t.factors[c])
+    for s in t.sep_value:
+        t.sep_value[s] = None
+    return distribute(collect(t))
+
+
+def _factor_op(unit, op, l):
+    """_factorProduct (Op _ unit op) (PrivateCPT.hs:215-238) for an arbitrary element operator."""
+    naked = foldr1(l_union, [f.vars for f in l])
+    scalars = [f for f in l if f.is_scalar()]
+    cpts = [f for f in l if not f.is_scalar()]
+    ps = foldr1(op, [f.vals[0] for f in scalars]) if scalars else unit
+    if not cpts:
+        return Factor.scalar_(ps)
+    strides = [index_strides_for(f.vars, naked) for f in cpts]
+    values = []
+    for x in indices_for_domain(naked):
+        values.append(op(ps, foldr1(op, [f.vals[index_position(st, x)] for st, f in zip(strides, cpts)])))
+    return create_cpt_with_dims(naked, values)
+
+
+def _divide(a, b):
+    """instance FactorElement Double (CPT.hs:113-114): divide _ 0 = 0; divide a b = a / b."""
+    if b == 0:
+        return 0.0
+    return a / b
+
+
+def cpt_sum(l):
+    """cptSum (CPT.hs:162-163)."""
+    return _factor_op(0.0, lambda a, b: a + b, l)
+
+
+def cpt_divide(a, b):
+    """cptDivide (CPT.hs:144-160)."""
+    if a.is_scalar() and b.is_scalar():
+        return Factor.scalar_(_divide(a.vals[0], b.vals[0]))
+    if a.is_scalar():
+        return factor_scale(a.vals[0], b)
+    if b.is_scalar():
+        vb = b.vals[0]
+        return Factor.scalar_(0.0) if vb == 0.0 else factor_scale(1.0 / vb, a)
+    return _factor_op(1.0, _divide, [b, a])
+
+
+def learn_em(net, samples, posterior_fn=None):
+    """learnEM (EM.hs:36-66).  samples: one evidence list [(vertex, state)] per sample.  posterior_fn(evidence, [vertex])
+    -> Factor gives `posterior (changeEvidence evidence jt) vars`; default: this twin's own junction tree.
+    Returns one Factor per vertex -- with the variable order cptDivide produces."""
+    if posterior_fn is None:
+        t = create_junction_tree(net)
+
+        def posterior_fn(evidence, vs, _state={"ev": None}):
+            if _state["ev"] is not evidence:
+                change_evidence(t, [(net.dv(v), s) for v, s in evidence])
+                _state["ev"] = evidence
+            return posterior(t, [net.dv(v) for v in vs])
+
+    def compute_sample(sample):  # computeSample / computeNode (EM.hs:47-66)
+        out = []
+        for v in range(net.n):
+            f = [dv[0] for dv in net.cpts[v].vars]
+            a = posterior_fn(sample, f)
+            b = Factor.scalar_(1.0) if len(f) == 1 else posterior_fn(sample, f[1:])
+            out.append((a, b))
+        return out
+
+    acc = None
+    for sample in samples:  # foldl1 sumG (EM.hs:18-27,44)
+        cur = compute_sample(sample)
+        acc = cur if acc is None else [(cpt_sum([xa, ya]), cpt_sum([xb, yb])) for (xa, xb), (ya, yb) in zip(acc, cur)]
+    return [cpt_divide(a, b) for a, b in acc]  # divideG (EM.hs:29-32,45)
+
+
+# --------------------------------------------------------------------------
 # Variable elimination entry points + orders (VariableElimination.hs:116-236)
 # --------------------------------------------------------------------------
 

@@ -225,3 +225,62 @@ def test_factor_algebra_properties():
         # project all = norm
         _, allout = oracle.factor_project_out(full, vals, sc)
         assert np.allclose(allout, vals.sum(), rtol=1e-12)
+
+
+# ---- `next` rows: changeFactor and learnEM restated (oracle/twin.py) ------------------------------
+
+
+def test_twin_change_factor_like_compare_eliminations():
+    """Bayes/Test/CompareEliminations.hs:30-62: a tree built on the network with a wrong `wet` table, corrected with
+    changeFactor, answers like the tree of the right network; a factor with another variable ORDER replaces nothing."""
+    right = twin.load_hugin(os.path.join(G, "sprinkler.net"))
+    wet = 2
+    cpts = list(right.cpts)
+    cpts[wet] = twin.Factor(right.cpts[wet].vars, [1.0] * 8)
+    wrong = twin.Network(right.dims, right.parents, cpts, right.names)
+    f = right.cpts[wet]
+    assert [dv[0] for dv in f.vars] == [2, 1, 3] and f.vals == [1, 0.2, 0.1, 0.05, 0, 0.8, 0.9, 0.95]
+    t = twin.create_junction_tree(wrong)
+    ref = twin.create_junction_tree(right)
+    swapped = twin.Factor([f.vars[0], f.vars[2], f.vars[1]], f.vals)
+    before = [twin.posterior(t, [right.dv(v)]).vals for v in range(6)]
+    twin.change_factor_jt(swapped, t)
+    assert [twin.posterior(t, [right.dv(v)]).vals for v in range(6)] == before
+    twin.change_factor_jt(f, t)
+    for ev in ([], [(2, 1)], [(2, 1), (1, 1)]):
+        twin.change_evidence(t, [(right.dv(v), s) for v, s in ev])
+        twin.change_evidence(ref, [(right.dv(v), s) for v, s in ev])
+        for v in range(6):
+            assert twin.posterior(t, [right.dv(v)]).vals == twin.posterior(ref, [right.dv(v)]).vals
+    assert twin.posterior(t, [right.dv(3)]).vals != before[3]
+
+
+def test_cpt_divide_and_sum_follow_the_reference_operators():
+    """Bayes/Factor/CPT.hs:113-114,144-163: divide _ 0 = 0; tables divide as 1.0 `divide` (b `divide` a) over the
+    variable order b ++ (a minus b); a scalar denominator scales by 1.0 / b"""
+    a = twin.Factor([(0, 2), (1, 2)], [0.3, 0.0, 0.1, 0.6])  # [child, parent]
+    b = twin.Factor([(1, 2)], [0.4, 0.6])
+    q = twin.cpt_divide(a, b)
+    assert q.vars == [(1, 2), (0, 2)]
+    assert q.vals == [1.0 / (0.4 / 0.3), 1.0 / (0.4 / 0.1), 0.0, 1.0 / (0.6 / 0.6)]
+    assert twin.cpt_divide(a, twin.Factor.scalar_(4.0)).vals == [(1.0 / 4.0) * x for x in a.vals]
+    assert twin.cpt_divide(a, twin.Factor.scalar_(0.0)).is_scalar()
+    s = twin.cpt_sum([a, twin.Factor([(1, 2), (0, 2)], [1.0, 2.0, 3.0, 4.0])])
+    assert s.vars == a.vars and s.vals == [0.0 + (0.3 + 1.0), 0.0 + (0.0 + 3.0), 0.0 + (0.1 + 2.0), 0.0 + (0.6 + 4.0)]
+    assert twin.cpt_sum([twin.Factor.scalar_(2.0), twin.Factor.scalar_(1.0)]).vals == [3.0]
+
+
+@pytest.mark.parametrize("seed", [3, 6])
+def test_learn_em_twin_equals_cpp_oracle_posteriors(seed):
+    """the EM fold driven by the pure-Python junction tree and by the C++ oracle's: same bits, same layouts"""
+    net = synth.random_dag_net(6, 9000 + seed, states=(2, 3), max_parents=2)
+    samples = synth.evidence_matrix(net, 10, [0, 2, 3], 5)
+    samples[4, 2] = -1  # one sample with another observed set
+    got = oracle.learn_em(net.dims, net.scopes, net.values, samples)
+    tnet = twin.Network.from_tables(net.dims, net.parents, [list(map(float, v)) for v in net.values])
+    want = twin.learn_em(tnet, [[(v, int(s)) for v, s in enumerate(r) if s >= 0] for r in samples])
+    for v, ((sc, vals), f) in enumerate(zip(got, want)):
+        assert sc == [dv[0] for dv in f.vars] and vals.tolist() == f.vals
+        assert sc[-1] == v and sorted(sc) == sorted(net.scopes[v])  # parents first, child last
+        col = vals.reshape(-1, net.dims[v]).sum(1)
+        assert np.all((np.abs(col - 1) < 1e-12) | (col == 0))
