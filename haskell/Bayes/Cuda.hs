@@ -11,6 +11,7 @@ It keeps the reference's names and argument shapes for the path it replaces:
   * 'changeEvidence'      (Bayes/FactorElimination/JTree.hs:454-466)
   * 'posterior'           (Bayes/FactorElimination.hs:314-327)
   * 'priorMarginal', 'posteriorMarginal' (Bayes/VariableElimination.hs:116-147)
+  * 'changeFactor' on a tree (Bayes/FactorElimination/JTree.hs:107-115), 'learnEM' (Bayes/EM.hs:36-45)
 
 Networks are still built with the reference's own model layer ('Bayes.BayesianNetwork', or
 'Bayes.ImportExport.HuginNet.importBayesianGraph' + 'runBN'); only inference moves to the GPU.
@@ -24,16 +25,19 @@ module Bayes.Cuda
   , createJunctionTree
   , changeEvidence
   , posterior
+  , changeFactor
+  , learnEM
   , posteriorsBatch
   , priorMarginal
   , posteriorMarginal
   ) where
 
-import           Bayes                         (SBN, allVertexValues)
+import           Bayes                         (SBN, allVertexValues, fmapWithVertex)
 import           Bayes.Factor                  (DV (..), DVI, Factor (..), Vertex (..), instantiationVariable)
 import           Bayes.Factor.CPT              (CPT)
 import           Bayes.PrivateTypes            (DVI (..))
 import           Control.Monad                 (forM, when)
+import           Data.Maybe                    (fromJust)
 import           Data.Int                      (Int32, Int64, Int8)
 import           Foreign
 import           Foreign.C.String
@@ -59,6 +63,10 @@ foreign import ccall safe "hb_jt_posterior"
   c_jt_posterior :: Ptr HbJt -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> Int64 -> Ptr Int64 -> IO CInt
 foreign import ccall safe "hb_jt_posteriors_batch"
   c_jt_posteriors_batch :: Ptr HbJt -> Int64 -> Ptr Int8 -> Ptr Double -> Int32 -> IO CInt
+foreign import ccall safe "hb_jt_change_factor"
+  c_jt_change_factor :: Ptr HbJt -> Int32 -> Ptr Int32 -> Ptr Double -> Ptr Int32 -> IO CInt
+foreign import ccall safe "hb_jt_em_step"
+  c_jt_em_step :: Ptr HbJt -> Int64 -> Ptr Int8 -> Ptr Double -> Ptr Int32 -> Int32 -> IO CInt
 foreign import ccall safe "hb_ve_compile"
   c_ve_compile :: Ptr HbNet -> Ptr Int32 -> Int32 -> Ptr Int32 -> Int32 -> Ptr Int32 -> Int32 -> Ptr (Ptr HbVe) -> IO CInt
 foreign import ccall safe "&hb_ve_free"    p_ve_free :: FunPtr (Ptr HbVe -> IO ())
@@ -147,6 +155,39 @@ posterior jt dvs = unsafePerformIO $ withForeignPtr (jtHandle jt) $ \h -> do
         vals  <- peekArray size pOut
         let dvOf i = DV (Vertex (fromIntegral i)) (jtDims jt !! fromIntegral i)
         return (factorWithVariables (map dvOf scope) vals)
+
+-- | 'changeFactor' of @instance FactorContainer (JTree Cluster)@: the CPT with the same variable LIST gets the new
+-- values, the evidence is kept, the tree recalibrated; on the GPU the compiled schedules stay (a potential upload).
+-- A factor that matches no CPT leaves the tree unchanged, as in the reference.
+changeFactor :: CPT -> GpuJunctionTree -> GpuJunctionTree
+changeFactor f jt = unsafePerformIO $ withForeignPtr (jtHandle jt) $ \h -> do
+  let scope = factorVariables f
+  withArrayLen [ vertexId v | DV v _ <- scope ] $ \n pS -> withArray (factorToList f) $ \pV ->
+    c_jt_change_factor h (fromIntegral n) pS pV nullPtr >>= check
+  return jt
+
+-- | 'learnEM samples g' (Bayes/EM.hs:36-45): one expectation/maximisation step, all samples in one GPU batch.
+-- The learnt tables come back with the variable order the reference's cptDivide gives them
+-- ([parents in the order of their posterior .., child]) and replace the vertex values of @g@.
+learnEM :: [[DVI]] -> SBN CPT -> SBN CPT
+learnEM samples g = unsafePerformIO $ do
+  let jt     = createJunctionTree WeightedEdges g
+      dims   = jtDims jt
+      nVars  = length dims
+      scopes = map factorVariables (allVertexValues g)
+      sizes  = [ product [ d | DV _ d <- sc ] | sc <- scopes ]
+      row s  = [ maybe (-1) fromIntegral (lookup v [ (fromIntegral a, b) | (a, b) <- map dviPair s ]) | v <- [0 .. nVars - 1] ] :: [Int8]
+  withForeignPtr (jtHandle jt) $ \h ->
+    withArray (concatMap row samples) $ \pEv ->
+    allocaArray (sum sizes) $ \pOut -> allocaArray (sum (map length scopes)) $ \pScopes -> do
+      c_jt_em_step h (fromIntegral (length samples)) pEv pOut pScopes 0 >>= check
+      vals <- peekArray (sum sizes) pOut
+      scs  <- peekArray (sum (map length scopes)) pScopes
+      let dvOf i = DV (Vertex (fromIntegral i)) (dims !! fromIntegral i)
+          cut ns xs = case ns of { [] -> []; (k : ks) -> let (a, b) = splitAt k xs in a : cut ks b }
+          tables = [ fromJust (factorWithVariables (map dvOf sc) vs)
+                   | (sc, vs) <- zip (cut (map length scopes) scs) (cut sizes vals) ] :: [CPT]
+      return (fmapWithVertex (\(Vertex v) _ -> tables !! v) g)
 
 -- | New, additive: one junction-tree query per evidence row (-1 = unobserved); the result holds, per
 -- row, the posterior of every variable in ascending vertex id.

@@ -139,7 +139,8 @@ int hb_jt_queries_width(hb_jt* jt, int32_t n_queries, const int32_t* query_off, 
 int hb_jt_change_factor(hb_jt* jt, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced);
 /* learnEM samples g (Bayes/EM.hs:36-66), one expectation/maximisation step on the handle's network: per sample
  * (row) changeEvidence + posterior of every CPT family and of its parents, summed sample after sample (cptSum) and
- * divided (cptDivide, divide _ 0 = 0).  Rows may have different observed sets.  out_values: sum_v cpt entries
+ * divided (cptDivide, divide _ 0 = 0).  A row means changeEvidence [v =: s | v ascending, observed], as in the other
+ * batch calls; rows may have different observed sets.  out_values: sum_v cpt entries
  * doubles, vertex after vertex, each table laid out as the reference returns it -- variable order written to
  * out_scopes (sum_v |scope v| ids): the parents in the order of their joint posterior, then the child, NOT the
  * CPT's own [child, parents] order (cptDivide's union [b, a], Bayes/Factor/CPT.hs:159-160).  evidence is a host or
