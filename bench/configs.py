@@ -4,6 +4,7 @@
   C1  cancer.net, single evidence set through the stateful reference API (latency) and 2^16-row batches
   C3  500-node random DAG (max cluster 2^20.2), 4096 evidence rows per batch, 125 observed
   C5  20x20 grid via VariableElimination (reference min-fill order), rows per batch given by --c5-rows
+  MPE most probable explanation (Bayes/VariableElimination.hs:101-114) of the 28 unobserved variables of the C2 network
   EM  one learnEM step (Bayes/EM.hs:36-45) on the C2 network: 2^18 samples, 9 observed; then the learnt tables go
       back into the same handle with changeFactor (no recompilation)
 
@@ -164,11 +165,86 @@ def em(rows=1 << 18):
             "bit_identical_first_%d" % k: bool(same)}
 
 
+def greedy_order(net, observed):
+    """elimination order of the unobserved variables: greedy smallest resulting table, WITH fill-in edges (the
+    reference's minFillOrder adds none and skips isolated vertices, so it is a poor order once p is forced first)"""
+    adj = {v: set() for v in range(net.n) if v not in observed}
+    for sc in net.scopes:
+        fam = [x for x in sc if x in adj]
+        for a in fam:
+            adj[a].update(b for b in fam if b != a)
+    order = []
+    while adj:
+        v = min(adj, key=lambda x: (np.prod([net.dims[y] for y in adj[x]] + [net.dims[x]]), x))
+        nb = adj.pop(v)
+        for a in nb:
+            adj[a].discard(v)
+            adj[a].update(b for b in nb if b != a)
+        order.append(v)
+    return order
+
+
+def mpe(rows=1 << 18):
+    """most probable explanation of all 28 unobserved variables of the C2 network per evidence row"""
+    from oracle import twin
+
+    net, _ = synth.config_c2()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    # evidence on the 9 non-isolated variables of lowest degree: the reference's algorithm sums the evidence variables out
+    # FIRST, i.e. multiplies every table that mentions one into a single product -- C2's own observed set holds hubs
+    # of degree 9 and that product alone would be a 5.3 M-entry table per row
+    deg = {v: set() for v in range(net.n)}
+    for sc in net.scopes:
+        for a in sc:
+            deg[a].update(b for b in sc if b != a)
+    observed = sorted(sorted([v for v in deg if deg[v]], key=lambda v: (len(deg[v]), -v))[:9])
+    p = list(observed)
+    r = greedy_order(net, observed)
+    h = hb.MostProbableExplanation(pnet, p, r)
+    ev = synth.evidence_matrix(net, rows, observed, 37004)
+    d_ev = torch.from_numpy(ev).cuda()
+    states, values = h.explain_batch(d_ev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        h.explain_batch(d_ev, states, values)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    st = h.last_stats()
+    # size-independent property on every row: the value IS the joint probability of (explanation, evidence)
+    full = ev.copy()
+    full[:, r] = states.cpu().numpy()
+    joint = np.ones(rows)
+    for v in range(net.n):
+        sc = net.scopes[v]
+        idx = np.ravel_multi_index([full[:, x].astype(np.int64) for x in sc], [net.dims[x] for x in sc])
+        joint *= np.asarray(net.values[v])[idx]
+    vals = values.cpu().numpy()
+    rel = float(np.max(np.abs(joint - vals) / vals))
+    # twin parity on a few rows (pure Python: seconds per row)
+    tnet = twin.Network.from_tables(net.dims, net.parents, [list(map(float, v)) for v in net.values])
+    same = True
+    k = 3
+    t = time.perf_counter()
+    for row in range(k):
+        tv, ti = twin.mpe(tnet, p, r, [(v, int(s)) for v, s in enumerate(ev[row]) if s >= 0])
+        want = dict(ti[0])
+        same = same and [want[v] for v in r] == full[row, r].tolist() and np.float64(tv).tobytes() == vals[row].tobytes()
+    cpu = k / (time.perf_counter() - t)
+    return {"config": "MPE of the 28 unobserved variables of the C2 network (9 low-degree variables observed, greedy min-size order)", "rows": rows,
+            "ms_per_pass": ms, "explanations_per_s": rows / ms * 1e3, "launches": st["launches"],
+            "value_equals_joint_max_rel_err": rel, "twin_rows_checked": k, "bit_identical_to_twin": bool(same),
+            "python_twin_explanations_per_s": cpu}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="C1,C3,C5,EM")
+    ap.add_argument("--only", default="C1,C3,C5,EM,MPE")
     ap.add_argument("--c5-rows", type=int, default=64)
     a = ap.parse_args()
     for name in a.only.split(","):
-        res = {"C1": c1, "C3": c3, "C5": lambda: c5(a.c5_rows), "EM": em}[name]()
+        res = {"C1": c1, "C3": c3, "C5": lambda: c5(a.c5_rows), "EM": em, "MPE": mpe}[name]()
         print(json.dumps(res), flush=True)

@@ -11,6 +11,7 @@ The names follow the reference (alpheccar/hbayes) so that its examples and tests
     minDegreeOrder / minFillOrder   Bayes/VariableElimination.hs:225-236
     changeFactor          Bayes/Factor.hs:66-81, Bayes/FactorElimination/JTree.hs:107-115
     learnEM               Bayes/EM.hs:36-45
+    mpe                   Bayes/VariableElimination.hs:101-114
 
 plus the batched forms (one evidence row per query) that the GPU exists for.  All arithmetic happens in
 libhbayes_cuda.so; this package only marshals arrays.  It never imports `oracle/`.
@@ -19,6 +20,7 @@ from .api import (  # noqa: F401
     BayesianNetwork,
     Factor,
     JunctionTree,
+    MostProbableExplanation,
     VariableElimination,
     changeEvidence,
     changeFactor,
@@ -31,6 +33,7 @@ from .api import (  # noqa: F401
     learnEM,
     minDegreeOrder,
     minFillOrder,
+    mpe,
     nodeComparisonForTriangulation,
     numberOfAddedEdges,
     posterior,

@@ -62,6 +62,10 @@ SIGNATURES = {
     "hb_ve_program_json": (C.c_int, [vp, i32, i32p, cpp]),
     "hb_ve_posterior": (C.c_int, [vp, i32, i32p, i32p, i32p, f64p, i64, i64p]),
     "hb_ve_posterior_batch": (C.c_int, [vp, i64, vp, vp, i32]),
+    "hb_ve_compile_mpe": (C.c_int, [vp, i32p, i32, i32p, i32, i32p, i32, vpp]),
+    "hb_ve_mpe": (C.c_int, [vp, i32, i32p, i32p, vp, f64p, i32p, i32p]),
+    "hb_ve_mpe_batch": (C.c_int, [vp, i64, vp, vp, vp, i32]),
+    "hb_ve_mpe_order": (C.c_int, [vp, i32, i32p, i32p, i32p]),
     "hb_ve_change_factor": (C.c_int, [vp, i32, i32p, f64p, i32p]),
     "hb_ve_set_stream": (C.c_int, [vp, vp]),
     "hb_ve_set_workspace": (C.c_int, [vp, i64]),

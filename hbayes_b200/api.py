@@ -415,6 +415,73 @@ class VariableElimination(_Batched):
             pass
 
 
+class MostProbableExplanation(_Batched):
+    """`mpe g p r` (Bayes/VariableElimination.hs:99-114) compiled for replay: p summed out, r maximised (MAXCPT)."""
+
+    _prefix = "hb_ve_"
+
+    def __init__(self, net: BayesianNetwork, p: Sequence[int], r: Sequence[int], device=0):
+        self.net, self.p, self.r = net, list(p), list(r)
+        dp, nd, self._keep = _device_args(device)
+        pa, pp = _i32(self.p)
+        ra, rp = _i32(self.r)
+        h = C.c_void_p()
+        check(lib().hb_ve_compile_mpe(net._h, pp, len(self.p), rp, len(self.r), dp, nd, C.byref(h)))
+        self._h = h
+
+    def program(self, observed: Iterable[int] = ()):
+        oa, op = _i32(list(observed))
+        p = C.c_void_p()
+        check(lib().hb_ve_program_json(self._h, len(oa), op, C.byref(p)))
+        return _take_json(p)
+
+    def order(self, observed: Iterable[int] = ()):
+        """variable order of the reference's instantiation list for this observed list"""
+        oa, op = _i32(list(observed))
+        out = np.zeros(len(self.r), np.int32)
+        n = C.c_int32()
+        check(lib().hb_ve_mpe_order(self._h, len(oa), op, out.ctypes.data_as(i32p), C.byref(n)))
+        return out[: n.value].tolist()
+
+    def explain(self, assignment: Sequence[tuple] = ()):
+        """-> (P(instantiation, evidence), [[(vertex, state)]]) with the instantiation list as `mpe` returns it"""
+        va, vp_ = _i32([e[0] for e in assignment])
+        sa, sp = _i32([e[1] for e in assignment])
+        states = np.zeros(len(self.r), np.int8)
+        value = C.c_double()
+        order = np.zeros(len(self.r), np.int32)
+        n = C.c_int32()
+        check(lib().hb_ve_mpe(self._h, len(assignment), vp_, sp, states.ctypes.data, C.byref(value), order.ctypes.data_as(i32p),
+                              C.byref(n)))
+        by_var = dict(zip(self.r, states.tolist()))
+        inst = [(v, by_var[v]) for v in order[: n.value].tolist()]
+        return value.value, ([inst] if inst else [])
+
+    def explain_batch(self, evidence, states=None, values=None):
+        """one mpe per evidence row: (int8 [rows][len(r)] states in the order of r, float64 [rows] values).
+        NumPy arrays, or CUDA tensors (all rows then share one observed set; results stay on the device)."""
+        if isinstance(evidence, np.ndarray):
+            ev = np.ascontiguousarray(evidence, np.int8)
+            states = np.empty((ev.shape[0], len(self.r)), np.int8) if states is None else states
+            values = np.empty(ev.shape[0], np.float64) if values is None else values
+            check(lib().hb_ve_mpe_batch(self._h, ev.shape[0], ev.ctypes.data, states.ctypes.data, values.ctypes.data, HB_HOST_PTRS))
+            return states, values
+        import torch
+
+        assert evidence.is_cuda and evidence.is_contiguous() and evidence.element_size() == 1
+        rows = evidence.shape[0]
+        states = torch.empty((rows, len(self.r)), dtype=torch.int8, device=evidence.device) if states is None else states
+        values = torch.empty(rows, dtype=torch.float64, device=evidence.device) if values is None else values
+        check(lib().hb_ve_mpe_batch(self._h, rows, evidence.data_ptr(), states.data_ptr(), values.data_ptr(), HB_DEVICE_PTRS))
+        return states, values
+
+    def __del__(self):
+        try:
+            lib().hb_ve_free(self._h)
+        except Exception:
+            pass
+
+
 # ---- the reference's function names -----------------------------------------------------------
 
 
@@ -432,6 +499,12 @@ def posterior(jt: JunctionTree, variables):
 
 def posteriorMarginal(net: BayesianNetwork, p, r, assignment, device=0) -> Factor:
     return VariableElimination(net, p, r, device=device).posterior(assignment)
+
+
+def mpe(net: BayesianNetwork, p, r, assignment, device=0):
+    """`mpe g someP someR assignment` (Bayes/VariableElimination.hs:101-114): Most Probable Explanation, or MAP when r is a
+    subset.  Returns the reference's [DVISet]: a list with one instantiation [(vertex, state), ...] in its order."""
+    return MostProbableExplanation(net, p, r, device=device).explain(assignment)[1]
 
 
 def priorMarginal(net: BayesianNetwork, ea, eb, device=0) -> Factor:

@@ -322,11 +322,12 @@ struct hb_jt {
 struct hb_ve {
   Session s;
   std::vector<int> p, r;
+  bool mpe = false;  // compiled with hb_ve_compile_mpe: r is maximised instead of kept
   Compiled& program(const std::vector<int>& observed) {
     auto it = s.cache.find(observed);
     if (it != s.cache.end()) return *it->second;
     auto c = std::make_unique<Compiled>();
-    c->prog.reset(compile_ve(s.net, p, r, observed));
+    c->prog.reset(mpe ? compile_mpe(s.net, p, r, observed) : compile_ve(s.net, p, r, observed));
     return *(s.cache[observed] = std::move(c));
   }
 };
@@ -1060,6 +1061,117 @@ int hb_ve_compile(const hb_net* net, const int32_t* p, int32_t np, const int32_t
     *out = ve.release();
   });
 }
+int hb_ve_compile_mpe(const hb_net* net, const int32_t* p, int32_t np, const int32_t* r, int32_t nr, const int32_t* devices,
+                      int32_t n_devices, hb_ve** out) {
+  const int rc = hb_ve_compile(net, p, np, r, nr, devices, n_devices, out);
+  if (rc == HB_OK) (*out)->mpe = true;
+  return rc;
+}
+int hb_ve_mpe_order(hb_ve* ve, int32_t n_obs, const int32_t* observed, int32_t* order_out, int32_t* n_out) {
+  return guarded([&] {
+    if (!ve || !order_out || !n_out || n_obs < 0 || (n_obs > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
+    if (!ve->mpe) throw Error(HB_E_ARG, "not an mpe handle (hb_ve_compile_mpe)");
+    const Program& P = *ve->program(std::vector<int>(observed, observed + n_obs)).prog;
+    for (size_t i = 0; i < P.mpe_order.size(); ++i) order_out[i] = P.mpe_order[i];
+    *n_out = (int32_t)P.mpe_order.size();
+  });
+}
+// one pass of an mpe program over rows that share one observed set; device buffers
+static void mpe_rows(hb_ve* ve, Compiled& c, int64_t n_rows, const int8_t* d_ev, int8_t* d_states, double* d_value, bool accumulate) {
+  Session& s = ve->s;
+  RunStats rs;
+  executor_run(s.executor(c), n_rows, d_ev, d_value, s.stream, &rs, /*normalise=*/false, d_states);
+  s.note(c, rs, accumulate);
+}
+int hb_ve_mpe_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, int8_t* out_states, double* out_value, int32_t flags) {
+  return guarded([&] {
+    if (!ve || n_rows < 0 || (n_rows > 0 && (!evidence || !out_states))) throw Error(HB_E_ARG, "null argument");
+    if (!ve->mpe) throw Error(HB_E_ARG, "not an mpe handle (hb_ve_compile_mpe)");
+    if (n_rows == 0) return;
+    Session& s = ve->s;
+    const int n_vars = s.net.n();
+    const int64_t nr = (int64_t)ve->r.size();
+    if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
+    cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+    if (flags & HB_DEVICE_PTRS) {
+      std::vector<int8_t> first(n_vars);
+      cuda_ok(cudaMemcpyAsync(first.data(), evidence, n_vars, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(first row)");
+      cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+      Compiled& c = ve->program(observed_of_row(first.data(), n_vars));
+      double* d_value = out_value ? out_value : (double*)s.em_mat.ensure((size_t)n_rows * 8);
+      mpe_rows(ve, c, n_rows, evidence, out_states, d_value, false);
+      executor_check(s.executor(c), s.stream);
+      return;
+    }
+    // host buffers: rows grouped by observed set (one program each), in order of first appearance
+    std::map<std::vector<int>, std::vector<int64_t>> groups;
+    for (int64_t r = 0; r < n_rows; ++r) groups[observed_of_row(evidence + r * n_vars, n_vars)].push_back(r);
+    int8_t* d_ev = (int8_t*)s.em_ev.ensure((size_t)n_rows * n_vars);
+    int8_t* d_states = (int8_t*)s.em_rows.ensure((size_t)n_rows * nr);
+    double* d_value = (double*)s.em_mat.ensure((size_t)n_rows * 8);
+    std::vector<int8_t> ev, st;
+    std::vector<double> val;
+    bool first = true;
+    for (auto& kv : groups) {
+      Compiled& c = ve->program(kv.first);
+      const int64_t m = (int64_t)kv.second.size();
+      const bool whole = m == n_rows;
+      const int8_t* src = evidence;
+      if (!whole) {
+        ev.resize((size_t)m * n_vars);
+        for (int64_t i = 0; i < m; ++i) memcpy(ev.data() + i * n_vars, evidence + kv.second[i] * n_vars, n_vars);
+        src = ev.data();
+      }
+      cuda_ok(cudaMemcpyAsync(d_ev, src, (size_t)m * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+      mpe_rows(ve, c, m, d_ev, d_states, d_value, !first);
+      first = false;
+      executor_check(s.executor(c), s.stream);
+      if (whole) {
+        cuda_ok(cudaMemcpyAsync(out_states, d_states, (size_t)m * nr, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(states)");
+        if (out_value) cuda_ok(cudaMemcpyAsync(out_value, d_value, (size_t)m * 8, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(value)");
+        cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+      } else {
+        st.resize((size_t)m * nr), val.resize((size_t)m);
+        cuda_ok(cudaMemcpyAsync(st.data(), d_states, st.size(), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(states)");
+        cuda_ok(cudaMemcpyAsync(val.data(), d_value, val.size() * 8, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(value)");
+        cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+        for (int64_t i = 0; i < m; ++i) {
+          memcpy(out_states + kv.second[i] * nr, st.data() + i * nr, (size_t)nr);
+          if (out_value) out_value[kv.second[i]] = val[(size_t)i];
+        }
+      }
+    }
+  });
+}
+int hb_ve_mpe(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* states, int8_t* out_states, double* out_value,
+              int32_t* out_order, int32_t* n_order) {
+  return guarded([&] {
+    if (!ve || !out_states) throw Error(HB_E_ARG, "null argument");
+    if (!ve->mpe) throw Error(HB_E_ARG, "not an mpe handle (hb_ve_compile_mpe)");
+    check_evidence_list(ve->s.net, n, vars, states);
+    Session& s = ve->s;
+    if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
+    cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+    Compiled& c = ve->program(std::vector<int>(vars, vars + n));  // the assignment in the caller's order
+    std::vector<int8_t> row(s.net.n(), -1);
+    for (int i = 0; i < n; ++i) row[vars[i]] = (int8_t)states[i];
+    const size_t nr = ve->r.size();
+    int8_t* d_ev = (int8_t*)s.em_ev.ensure(row.size());
+    int8_t* d_states = (int8_t*)s.em_rows.ensure(nr);
+    double* d_value = (double*)s.em_mat.ensure(8);
+    cuda_ok(cudaMemcpyAsync(d_ev, row.data(), row.size(), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+    mpe_rows(ve, c, 1, d_ev, d_states, d_value, false);
+    executor_check(s.executor(c), s.stream);
+    cuda_ok(cudaMemcpyAsync(out_states, d_states, nr, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(states)");
+    double value = 0.0;
+    cuda_ok(cudaMemcpyAsync(&value, d_value, 8, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(value)");
+    cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    if (out_value) *out_value = value;
+    if (out_order)
+      for (size_t i = 0; i < c.prog->mpe_order.size(); ++i) out_order[i] = c.prog->mpe_order[i];
+    if (n_order) *n_order = (int32_t)c.prog->mpe_order.size();
+  });
+}
 int hb_ve_result_scope(hb_ve* ve, int32_t n_obs, const int32_t* observed, int32_t* scope_out, int32_t* n_out) {
   return guarded([&] {
     if (!ve || !scope_out || !n_out || n_obs < 0 || (n_obs > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
@@ -1078,6 +1190,7 @@ int hb_ve_posterior(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* st
                     int64_t out_len, int64_t* n_written) {
   return guarded([&] {
     if (!ve || !out) throw Error(HB_E_ARG, "null argument");
+    if (ve->mpe) throw Error(HB_E_ARG, "an mpe handle answers hb_ve_mpe / hb_ve_mpe_batch only");
     check_evidence_list(ve->s.net, n, vars, states);
     Compiled& c = ve->program(std::vector<int>(vars, vars + n));
     if (out_len < c.prog->out_width) throw Error(HB_E_ARG, "output buffer too small");
@@ -1101,6 +1214,7 @@ int hb_ve_posterior(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* st
 int hb_ve_posterior_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags) {
   return guarded([&] {
     if (!ve) throw Error(HB_E_ARG, "null handle");
+    if (ve->mpe) throw Error(HB_E_ARG, "an mpe handle answers hb_ve_mpe / hb_ve_mpe_batch only");
     run_matrix(ve->s, [&](const std::vector<int>& obs) -> Compiled& { return ve->program(obs); }, n_rows, evidence, out, flags);
   });
 }

@@ -153,7 +153,33 @@ struct Compiler {
   }
 
   // One reference operation: itemProduct of `inputs` followed (sum_var >= 0) by itemProjectOut sum_var.
-  int product_sumout(const std::vector<int>& inputs, int sum_var, Group& g) {
+  // MAXCPT bookkeeping: table id -> variables of the instantiation every entry carries, in list order.  The order
+  // is structural (multiply concatenates, maximization prepends: MaxCPT.hs:29-47), so it is known at compile time.
+  std::map<int, std::vector<int>> inst;
+  const std::vector<int>& inst_of(int id) {
+    static const std::vector<int> none;
+    auto it = inst.find(id);
+    return it == inst.end() ? none : it->second;
+  }
+
+  int product_sumout(const std::vector<int>& inputs, int sum_var, Group& g, bool is_max = false) {
+    const int result = product_sumout_traced(inputs, sum_var, g, is_max);
+    if (is_max || !inst.empty()) {  // op ps (v1 `op` (v2 ...)): the scalars' instantiations first, then the tables'
+      std::vector<int> vars;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int id : inputs)
+          if ((T(id).scalar ? 0 : 1) == pass)
+            for (int v : inst_of(id)) vars.push_back(v);
+      bool any_table = false, mentions = false;
+      for (int id : inputs)
+        if (!T(id).scalar) any_table = true, mentions = mentions || contains(T(id).scope, sum_var);
+      if (is_max && any_table && mentions && sum_var >= 0) vars.insert(vars.begin(), sum_var);  // addTo newInst possible
+      if (!vars.empty() && result != one) inst[result] = vars;
+    }
+    return result;
+  }
+
+  int product_sumout_traced(const std::vector<int>& inputs, int sum_var, Group& g, bool is_max) {
     Group::TraceStep tr;
     tr.var = sum_var;
     for (int id : inputs) tr.inputs.push_back(T(id).scope);
@@ -169,6 +195,7 @@ struct Compiler {
       key.push_back(T(id).scope == T(r).scope ? r : id);
     }
     key.push_back(-2 - sum_var);
+    if (is_max) key.push_back(-1);
     auto memo = cse.find(key);
     if (memo != cse.end()) {
       tr.prod = memo->second.prod;
@@ -176,7 +203,7 @@ struct Compiler {
       g.trace.push_back(tr);
       return memo->second.table;
     }
-    const int result = product_sumout_new(inputs, sum_var, tr);
+    const int result = product_sumout_new(inputs, sum_var, tr, is_max);
     g.trace.push_back(tr);
     cse[key] = Memo{result, tr.prod};
     return result;
@@ -188,7 +215,7 @@ struct Compiler {
   };
   std::map<std::vector<int>, Memo> cse;
 
-  int product_sumout_new(const std::vector<int>& inputs, int sum_var, Group::TraceStep& tr) {
+  int product_sumout_new(const std::vector<int>& inputs, int sum_var, Group::TraceStep& tr, bool is_max = false) {
     std::vector<int> naked = T(inputs.back()).scope;
     for (int i = (int)inputs.size() - 2; i >= 0; --i) naked = list_union(T(inputs[i]).scope, naked);
     std::vector<int> chain, scalars;  // structural partition isScalarFactor (PrivateCPT.hs:223)
@@ -228,12 +255,14 @@ struct Compiler {
       out.kind = T(st.scalars[0]).kind;
       return add(out);
     }
+    if (is_max && sums) shared = false;  // the argmax tables are per row
     out.kind = shared ? T_SHARED : T_ROW;
     set_physical(out);
     st.shared = shared;
     Level lv;
     lv.sum_var = sums ? sum_var : -1;
     lv.d = sums ? net.dims[sum_var] : 1;
+    lv.is_max = is_max && sums;
     for (int id : real) {
       StepInput in;
       in.table = id;
@@ -248,8 +277,10 @@ struct Compiler {
   }
 
   // marginal (VariableElimination.hs:56-73) over symbolic factors; `assignment` = indicator tables.
+  // mpe = true: mpemarginal (VariableElimination.hs:79-97) -- after the sums over p the buckets become MAXCPTs and
+  // the variables of r are maximised out in turn; the final product is then a scalar.
   int marginal(const std::vector<int>& lf, const std::vector<int>& p, const std::vector<int>& r,
-               const std::vector<int>& assignment, Group& g) {
+               const std::vector<int>& assignment, Group& g, bool mpe = false) {
     std::vector<int> order = p;
     order.insert(order.end(), r.begin(), r.end());
     std::map<int, std::vector<int>> buckets;  // Data.Map DV [f]; DV order = vertex id
@@ -281,9 +312,21 @@ struct Compiler {
         add_bucket(f2);
       }
     }
+    if (mpe)
+      for (int dv : r) {
+        std::vector<int> fk = buckets.at(dv);
+        int f2 = product_sumout(fk, dv, g, true);
+        if (head < order.size()) ++head;
+        if (T(f2).scalar)
+          buckets[dv] = {f2};
+        else {
+          buckets.erase(dv);
+          add_bucket(f2);
+        }
+      }
     std::vector<int> fin;
     for (auto& kv : buckets) fin.insert(fin.end(), kv.second.begin(), kv.second.end());
-    return product_sumout(fin, -1, g);
+    return product_sumout(fin, -1, g, mpe);
   }
 
   std::vector<int> first_appearance(const std::vector<int>& factors) const {  // nub . concatMap factorVariables
@@ -367,12 +410,12 @@ struct Compiler {
       std::vector<char> dead(P.steps.size(), 0);
       for (int s = 0; s < (int)P.steps.size(); ++s) {
         Step& S = P.steps[s];
-        if (S.kind != STEP_PRODSUM || !S.scalars.empty() || S.levels[0].in.empty()) continue;
+        if (S.kind != STEP_PRODSUM || !S.scalars.empty() || S.levels[0].in.empty() || S.levels[0].is_max) continue;
         const int tid = S.levels[0].in[0].table;
         const int q = producer[tid];
         if (q < 0 || uses[tid] != 1) continue;
         const Step& Q = P.steps[q];
-        if (Q.shared != S.shared || !Q.scalars.empty()) continue;
+        if (Q.shared != S.shared || !Q.scalars.empty() || Q.levels[0].is_max) continue;
         const int q_inner = (int)Q.levels.back().in.size();
         if ((int)(S.levels.size() + Q.levels.size()) > opt.max_levels || q_inner < 1 || q_inner > opt.max_inner ||
             S.n_inputs() - 1 + Q.n_inputs() - q_inner > opt.max_outer)
@@ -496,6 +539,17 @@ struct Compiler {
         P.stat_row_write += st.n_out;
         P.stat_max_table = std::max(P.stat_max_table, st.n_out * terms);
       }
+    }
+    // ---- 3b. argmax tables of the maximisation steps (mpe): one int8 per output entry, never reused ----
+    for (Step& st : P.steps) {
+      if (st.kind != STEP_PRODSUM || !st.levels[0].is_max) continue;
+      const Table& out = P.tables[st.out];
+      Program::MaxStep ms;
+      ms.var = st.levels[0].sum_var;
+      ms.arg_off = st.arg_off = P.arg_entries;
+      P.arg_entries += out.size;
+      for (size_t j = 0; j < out.pscope.size(); ++j) ms.dep_slot.push_back(out.pscope[j]), ms.dep_stride.push_back(out.pstride[j]);  // vertex ids; compile_mpe turns them into slots
+      P.max_steps.push_back(std::move(ms));
     }
     // ---- 4. liveness and arena placement ----
     for (auto& t : P.tables) t.def_step = t.last_use = -1;
@@ -707,6 +761,47 @@ Program* compile_ve(const Network& net, const std::vector<int>& p, const std::ve
   return prog.release();
 }
 
+// mpe g p r assignment (VariableElimination.hs:101-114) -> mpemarginal (:79-97).
+Program* compile_mpe(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
+                     const std::vector<int>& observed, const CompileOptions& opt) {
+  auto prog = std::make_unique<Program>();
+  Compiler C(net, *prog, observed, opt);
+  for (int v : p)
+    if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "elimination order mentions an unknown vertex");
+  for (size_t i = 0; i < r.size(); ++i) {
+    const int v = r[i];
+    if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "maximisation order mentions an unknown vertex");
+    if (contains(p, v) || std::find(r.begin(), r.begin() + i, v) != r.begin() + i) throw Error(HB_E_ARG, "a variable occurs twice in the elimination orders");
+    // the reference multiplies by the indicator and then maximises (a tie among zeros picks the last state); the
+    // engine never enumerates an observed variable, so evidence belongs to the summed list, as the reference's
+    // documentation asks ("should contain evidence variables", VariableElimination.hs:104)
+    if (prog->is_observed[v]) throw Error(HB_E_UNSUPPORTED, "mpe: an observed variable must be in the summed list p, not in r");
+  }
+  std::vector<int> lf, asg;
+  for (int v = 0; v < net.n(); ++v) lf.push_back(C.potential(v));
+  for (int v : observed) asg.push_back(C.indicator(v));
+  Group g;
+  g.kind = 3;
+  g.query = r;
+  int res = C.marginal(lf, p, r, asg, g, true);
+  if (!C.T(res).scalar) throw Error(HB_E_ARG, "mpe: p and r must cover every variable (the final MAXCPT factor should be a scalar one)");
+  prog->mpe_r = r;
+  prog->mpe_order = C.inst_of(res);
+  C.emit_output(res, g);
+  prog->groups.push_back(std::move(g));
+  C.finish(opt);
+  for (Program::MaxStep& ms : prog->max_steps) {
+    auto slot_of = [&](int v) {
+      auto it = std::find(r.begin(), r.end(), v);
+      if (it == r.end()) throw Error(HB_E_ARG, "internal: a maximised table depends on a variable outside r");
+      return (int)(it - r.begin());
+    };
+    ms.slot = slot_of(ms.var);
+    for (int& d : ms.dep_slot) d = slot_of(d);
+  }
+  return prog.release();
+}
+
 FactorOp* compile_factor_op(const std::vector<int>& dims, const std::vector<FreeFactor>& factors, int sum_var) {
   auto op = std::make_unique<FactorOp>();
   op->net = std::make_unique<Network>();
@@ -788,7 +883,7 @@ std::string describe_program(const Program& P) {
       o << ",\"levels\":[";
       for (size_t l = 0; l < s.levels.size(); ++l) {
         const Level& lv = s.levels[l];
-        o << (l ? "," : "") << "{\"sum_var\":" << lv.sum_var << ",\"d\":" << lv.d << ",\"in\":[";
+        o << (l ? "," : "") << "{\"sum_var\":" << lv.sum_var << ",\"d\":" << lv.d << ",\"is_max\":" << (lv.is_max ? 1 : 0) << ",\"in\":[";
         for (size_t k = 0; k < lv.in.size(); ++k) {
           const Table& t = P.tables[lv.in[k].table];
           o << (k ? "," : "") << "{\"table\":" << lv.in[k].table << ",\"kind\":" << t.kind << ",\"pot\":" << t.pot << ",\"off\":" << t.off
@@ -806,6 +901,17 @@ std::string describe_program(const Program& P) {
       o << "]";
     } else
       o << ",\"result\":" << s.result << ",\"out_col\":" << s.out_col << ",\"n_full\":" << s.n_full;
+    o << "}";
+  }
+  o << "],\"mpe_order\":";
+  js_list(o, P.mpe_order);
+  o << ",\"arg_entries\":" << P.arg_entries << ",\"max_steps\":[";
+  for (size_t i = 0; i < P.max_steps.size(); ++i) {
+    const Program::MaxStep& ms = P.max_steps[i];
+    o << (i ? "," : "") << "{\"var\":" << ms.var << ",\"slot\":" << ms.slot << ",\"arg_off\":" << ms.arg_off << ",\"dep_slot\":";
+    js_list(o, ms.dep_slot);
+    o << ",\"dep_stride\":";
+    js_nums(o, ms.dep_stride);
     o << "}";
   }
   o << "]}";

@@ -105,6 +105,7 @@ struct GenericArgs {      // any number of inputs / scalars, descriptors in glob
   double* out;
   int out_is_row, nr;
   long long RT;
+  signed char* arg;       // max step (MAXCPT): argmax table, [entry][RT] like the arena; nullptr for a sum step
 };
 
 __device__ __forceinline__ const double* row_ptr(const TabRef& t, int row) {
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArg
     const unsigned op = o / a.U, u = o - op * a.U;
     const unsigned hiI = op / a.C, loI = op - hiI * a.C;
     double acc = 0.0;
+    int arg = 0;
     for (int s = 0; s < a.d; ++s) {
       double c = ps;
       for (int i = a.k - 1; i >= 0; --i) {
@@ -409,9 +411,13 @@ __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArg
         c = (i == a.k - 1) ? v : __dmul_rn(v, c);
       }
       if (a.k > 0 && a.n_sc > 0) c = __dmul_rn(ps, c);
-      acc = __dadd_rn(acc, c);
+      if (a.arg) {  // maximumBy (compare `on` fst): the later term wins unless the kept one compares GT (MaxCPT.hs:41)
+        if (s == 0 || acc <= c) acc = c, arg = s;
+      } else
+        acc = __dadd_rn(acc, c);
     }
     outp[(size_t)o * om] = acc;
+    if (a.arg) a.arg[(size_t)o * a.RT + row] = (signed char)arg;
   }
 }
 
@@ -581,6 +587,32 @@ __global__ void __launch_bounds__(BLOCK) normalise_kernel(const NormArgs a) {
   for (int c = a.col_begin[b]; c < a.col_begin[b + 1]; ++c) p[c] = __dmul_rn(inv, p[c]);
 }
 
+// mpe traceback (mpeInstantiations, Bayes/Factor/MaxCPT.hs:73-75): the reference carries the maximising
+// instantiation inside every MAXCPT entry; here each maximisation step left an argmax table, and the states are read
+// back from the last eliminated variable to the first -- a step's table is indexed by variables maximised after it.
+// desc, per step in REVERSE elimination order: slot, n_dep, arg_off lo, arg_off hi, then n_dep x (slot, stride).
+struct TraceArgs {
+  const int32_t* desc;
+  int n_steps, n_r, nr;
+  const signed char* args;
+  long long RT;
+  signed char* states;  // [nr][n_r] of this tile; -1 = the variable got no instantiation
+};
+__global__ void __launch_bounds__(BLOCK) mpe_trace_kernel(const TraceArgs a) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.nr) return;
+  signed char* st = a.states + (size_t)row * a.n_r;
+  for (int i = 0; i < a.n_r; ++i) st[i] = -1;
+  const int32_t* d = a.desc;
+  for (int j = 0; j < a.n_steps; ++j) {
+    const int slot = d[0], n = d[1];
+    long long idx = (long long)(unsigned)d[2] | ((long long)d[3] << 32);
+    for (int k = 0; k < n; ++k) idx += (long long)d[4 + 2 * k + 1] * st[d[4 + 2 * k]];
+    st[slot] = a.args[(size_t)idx * a.RT + row];
+    d += 4 + 2 * n;
+  }
+}
+
 }  // namespace
 
 // ================================ host side =====================================================
@@ -589,6 +621,9 @@ struct Executor {
   int device = 0;
   int64_t workspace = 0;
   double *d_pots = nullptr, *d_shared = nullptr, *d_arena = nullptr;
+  signed char* d_args = nullptr;  // argmax arena of the maximisation steps: int8 [arg_entries][RT]
+  int32_t* d_trace = nullptr;     // traceback descriptors (mpe), see mpe_trace_kernel
+  int n_trace = 0;
   uint32_t *d_maps = nullptr;     // index maps, element stride 1 (potentials, shared tables, output maps)
   uint32_t *d_maps_rt = nullptr;  // the same maps multiplied by RT (row tables)
   int32_t* d_rowoff = nullptr;
@@ -644,7 +679,7 @@ struct Executor {
     for (cudaStream_t st : side_streams) cudaStreamDestroy(st);
     for (cudaEvent_t e : step_events) cudaEventDestroy(e);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
-    for (void* p : {(void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
+    for (void* p : {(void*)d_args, (void*)d_trace, (void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
                     (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_out_chunks, (void*)d_norm_cols, (void*)d_gen_in,
                     (void*)d_gen_sc, (void*)d_flag})
       if (p) cudaFree(p);
@@ -904,6 +939,7 @@ void launch_fused_ki(const Executor& ex, const Step& st, int si, int64_t RT, int
 
 static bool is_generic(const Step& st) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
+  if (st.levels[0].is_max) return true;  // maximisation steps (mpe) run on the descriptor-driven kernel
   if (st.levels.size() > 1) return false;  // the compiler only fuses within MAXL levels / MAXK inputs, without scalars
   return !(k >= 1 && k <= MAXK && s <= MAXS);
 }
@@ -947,6 +983,7 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
     a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
     a.nr = nr;
     a.RT = RT;
+    a.arg = st.levels[0].is_max ? ex.d_args + st.arg_off * RT : nullptr;
     LaunchShape sh = launch_shape(nr, 1, st.n_out);
     prodsum_generic_kernel<<<sh.grid, sh.block, 0, stream>>>(a);
   }
@@ -961,6 +998,8 @@ static void set_row_stride(Executor& ex, int64_t RT) {
   free_dev(ex.d_arena);
   free_dev(ex.d_rowoff);
   free_dev(ex.d_maps_rt);
+  free_dev(ex.d_args);
+  if (P.arg_entries > 0) HB_CUDA(cudaMalloc(&ex.d_args, (size_t)(P.arg_entries * RT)));
   HB_CUDA(cudaMalloc(&ex.d_arena, std::max<int64_t>(P.row_entries, 1) * RT * sizeof(double)));
   HB_CUDA(cudaMalloc(&ex.d_rowoff, std::max<int64_t>((int64_t)P.slices.size(), 1) * RT * sizeof(int32_t)));
   ex.RT = RT;
@@ -1099,6 +1138,19 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     }
   }
   ex->d_maps = upload(maps);
+  if (!P.max_steps.empty()) {  // traceback descriptors, last maximised variable first
+    std::vector<int32_t> desc;
+    for (size_t j = P.max_steps.size(); j-- > 0;) {
+      const Program::MaxStep& ms = P.max_steps[j];
+      desc.push_back(ms.slot);
+      desc.push_back((int32_t)ms.dep_slot.size());
+      desc.push_back((int32_t)(uint32_t)(ms.arg_off & 0xffffffffll));
+      desc.push_back((int32_t)(ms.arg_off >> 32));
+      for (size_t k = 0; k < ms.dep_slot.size(); ++k) desc.push_back(ms.dep_slot[k]), desc.push_back((int32_t)ms.dep_stride[k]);
+    }
+    ex->d_trace = upload(desc);
+    ex->n_trace = (int)P.max_steps.size();
+  }
   {
     const int LANES = std::max(1, std::min(64, getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 16));
     ex->n_lanes = LANES;
@@ -1209,7 +1261,9 @@ void executor_refresh_potentials(Executor* ex) {
 void executor_destroy(Executor* ex) { delete ex; }
 int executor_device(const Executor* ex) { return ex->device; }
 
-void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream_, RunStats* stats, bool normalise) {
+void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream_, RunStats* stats, bool normalise,
+                  int8_t* d_mpe_states_) {
+  signed char* d_mpe_states = (signed char*)d_mpe_states_;
   if (n_rows <= 0) return;
   cudaStream_t stream = (cudaStream_t)stream_;
   const Program& P = *ex->P;
@@ -1217,7 +1271,7 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
   const int n_vars = P.net->n();
   // rows per tile: as many as the workspace allows, in multiples of 32 (one warp of rows), and few enough
   // that every row-table offset (entry * RT + row) fits 32 bits
-  const int64_t per_row = std::max<int64_t>(P.row_entries, 1) * 8 + (int64_t)P.slices.size() * 4;
+  const int64_t per_row = std::max<int64_t>(P.row_entries, 1) * 8 + (int64_t)P.slices.size() * 4 + P.arg_entries;
   // tiles are multiples of 64 rows; a batch smaller than that (huge per-row tables, few rows) gets an even stride
   auto round_rows = [](int64_t r) { return r >= 64 ? r / 64 * 64 : r / 2 * 2; };
   int64_t cap = round_rows(ex->workspace / per_row);
@@ -1324,6 +1378,11 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
                  d_out + r0 * P.out_width, nr, n_vars, stride, P.out_width, normalise ? 1 : 0};
       dim3 grid((nr + OUT_ROWS - 1) / OUT_ROWS, (unsigned)ex->out_chunks.size());
       output_kernel<<<grid, BLOCK, ex->out_tile_bytes, stream>>>(oa);
+      ++launches;
+    }
+    if (d_mpe_states && ex->n_trace > 0) {
+      TraceArgs ta{ex->d_trace, ex->n_trace, (int)P.mpe_r.size(), nr, ex->d_args, stride, d_mpe_states + r0 * (int64_t)P.mpe_r.size()};
+      mpe_trace_kernel<<<(nr + BLOCK - 1) / BLOCK, BLOCK, 0, stream>>>(ta);
       ++launches;
     }
     mark();

@@ -29,8 +29,9 @@ void executor_refresh_potentials(Executor* ex);
 // d_out: double [n_rows][out_width]; both DEVICE pointers.  Asynchronous on `stream` (a cudaStream_t).
 // A row whose observed set differs from the program's, or whose state is out of range, raises the
 // executor's error flag (see executor_check).
+// d_mpe_states (mpe programs only, else nullptr): int8 [n_rows][|r|], the maximising state of every variable of r.
 void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream, RunStats* stats,
-                  bool normalise = true);
+                  bool normalise = true, int8_t* d_mpe_states = nullptr);
 
 // factorNorm + factorDivide of an expanded, UNNORMALISED result matrix (device pointer), per row and per
 // query: the last step of a split-clique query after the partial results of the slices have been summed.

@@ -111,6 +111,7 @@ struct StepInput {
 struct Level {
   int sum_var = -1;  // eliminated vertex, -1 for a final product
   int d = 1;         // physical terms (1 when nothing is summed or the variable is observed)
+  bool is_max = false;  // MAXCPT (Bayes/Factor/MaxCPT.hs:38-47): keep the LAST maximal term and record its state
   std::vector<StepInput> in;  // stored inputs in reference chain order (after the fused inner value)
 };
 
@@ -137,6 +138,7 @@ struct Step {
   std::vector<int> obs_var;                    // observed query variables ...
   std::vector<int64_t> obs_stride, obs_dim;    // ... their stride and dimension in the full layout
   int group = -1;                              // provenance: index into Program::groups (first emitter)
+  int64_t arg_off = -1;                        // max step: entry offset of its argmax table in the argmax arena
   int n_inputs() const {
     int n = 0;
     for (const Level& l : levels) n += (int)l.in.size();
@@ -185,6 +187,18 @@ struct Program {
   // statistics (per row, physical)
   int64_t stat_prod = 0, stat_reads = 0, stat_row_read = 0, stat_row_write = 0, stat_max_table = 0;
   int64_t stat_ops = 0;          // reference-level product/sum-out operations behind the per-row steps
+  // ---- mpe (Bayes/VariableElimination.hs:79-114): maximisation steps in elimination order ----
+  struct MaxStep {
+    int var = -1;               // maximised vertex
+    int slot = -1;              // its position in mpe_r
+    int64_t arg_off = 0;        // argmax table: int8 state per entry of the step's output, same stored layout
+    std::vector<int> dep_slot;  // the output's variables (all maximised later) as positions in mpe_r ...
+    std::vector<int64_t> dep_stride;  // ... and their strides in the stored layout
+  };
+  std::vector<MaxStep> max_steps;
+  std::vector<int> mpe_r;        // variables to maximise, caller's order
+  std::vector<int> mpe_order;    // variable order of the reference's instantiation list (structural)
+  int64_t arg_entries = 0;       // per-row argmax arena size (int8 entries)
 };
 
 struct Query {
@@ -204,6 +218,10 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
                     const std::vector<Query>& queries, const CompileOptions& opt = CompileOptions());
 Program* compile_ve(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
                     const std::vector<int>& observed, const CompileOptions& opt = CompileOptions());
+// mpe g p r assignment (VariableElimination.hs:79-114): sum out p, maximise over r.  The program's single output is
+// the UNNORMALISED scalar P(mpe, e); the maximising states come from the argmax tables (Program::max_steps).
+Program* compile_mpe(const Network& net, const std::vector<int>& p, const std::vector<int>& r,
+                     const std::vector<int>& observed, const CompileOptions& opt = CompileOptions());
 
 // One factor-algebra operation on free-standing factors: factorProduct of `factors` and, when sum_var >= 0,
 // factorProjectOut [sum_var] of the product (= marginalizeOneVariable, Buckets.hs:105-111).  `dims` gives the

@@ -186,6 +186,22 @@ int hb_ve_posterior(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* st
                     int64_t out_len, int64_t* n_written);
 /* one posteriorMarginal per row (assignment = observed entries in ascending vertex id); out: [n_rows][prod_r dims[r]] */
 int hb_ve_posterior_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags);
+/* mpe g p r assignment (Bayes/VariableElimination.hs:79-114): the variables of p are summed out (the observed
+ * ones belong there), those of r maximised in turn with MAXCPT semantics (Bayes/Factor/MaxCPT.hs:25-71: the LAST
+ * maximal state wins a tie).  p and r must cover every variable.  The handle answers only the hb_ve_mpe* calls. */
+int hb_ve_compile_mpe(const hb_net* net, const int32_t* p, int32_t np, const int32_t* r, int32_t nr, const int32_t* devices,
+                      int32_t n_devices, hb_ve** out);
+/* One query, assignment in the caller's order.  out_states: nr int8, the maximising state of r[i] (-1: the variable
+ * got no instantiation); *out_value = P(that instantiation, evidence), unnormalised, bit-identical to the
+ * reference's MAXCPT scalar; out_order / *n_order (optional): the variables in the order of the reference's
+ * instantiation list [DVI] (mpeInstantiations, MaxCPT.hs:73-75). */
+int hb_ve_mpe(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* states, int8_t* out_states, double* out_value,
+              int32_t* out_order, int32_t* n_order);
+/* one mpe per evidence row (assignment = observed entries in ascending vertex id).  out_states: int8 [n_rows][nr];
+ * out_value: double [n_rows] or NULL.  Mixed observed sets are grouped with HB_HOST_PTRS. */
+int hb_ve_mpe_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, int8_t* out_states, double* out_value, int32_t flags);
+/* the instantiation-list variable order for a given observed list (structural) */
+int hb_ve_mpe_order(hb_ve* ve, int32_t n_obs, const int32_t* observed, int32_t* order_out, int32_t* n_out);
 /* changeFactor f g on the network behind a variable-elimination handle (Bayes/Factor.hs:66-81); see hb_jt_change_factor */
 int hb_ve_change_factor(hb_ve* ve, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced);
 int hb_ve_set_stream(hb_ve* ve, void* cuda_stream);

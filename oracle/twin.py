@@ -308,6 +308,94 @@ def marginal(lf, p, r, assignment, trace=None):
 
 
 # --------------------------------------------------------------------------
+# Max-product: MAXCPT and mpe (MaxCPT.hs:25-70; VariableElimination.hs:79-114).
+# An element is (value, possible instantiations); an instantiation is a list of (dv, state).
+# --------------------------------------------------------------------------
+
+
+def max_multiply(a, b):
+    """instance FactorElement (Double,PossibleInstantiations): multiply (MaxCPT.hs:29-31)."""
+    (da, la), (db, lb) = a, b
+    if not la:
+        return (da * db, lb)
+    if not lb:
+        return (da * db, la)
+    return (da * db, [xa + xb for xa in la for xb in lb])
+
+
+def convert_to_max_factor(f):
+    """convertToMaxFactor (PrivateCPT.hs:89-94)."""
+    return Factor(f.vars, [(v, []) for v in f.vals], f.scalar)
+
+
+def max_factor_product(l):
+    """factorProduct of MAXCPT = _factorProduct (Op (Scalar 1.0) (1.0,[]) multiply) (MaxCPT.hs:68)."""
+    if not l:
+        return Factor.scalar_((1.0, []))
+    return _factor_op((1.0, []), max_multiply, l)
+
+
+def maximization(l):
+    """maximization (MaxCPT.hs:38-47); l = [((value, possible), newInst)].  maximumBy keeps the LAST maximal element
+    (foldl1: the left one survives only when compare says GT)."""
+    if not l:
+        return (1.0, [])
+    best = l[0]
+    for y in l[1:]:
+        x = best
+        gt = not (x[0][0] < y[0][0]) and not (x[0][0] == y[0][0])  # compare on Double
+        best = x if gt else y
+    (d, possible), new_inst = best
+    if not new_inst:
+        return (d, possible)
+    if not possible:
+        return (d, [new_inst])
+    return (d, [new_inst + i for i in possible])
+
+
+def max_project_out(s, f):
+    """factorProjectOut of MAXCPT (MaxCPT.hs:70-71) = cptFactorProjectOutWith maximization (PrivateCPT.hs:243-266)."""
+    if f.is_scalar():
+        return f
+    d = f.vars
+    keep = l_diff(d, s)
+    strides = index_strides_for(d, keep + list(s))
+    values = []
+    for ki in indices_for_domain(keep):
+        l = []
+        for si in indices_for_domain(s):
+            l.append((f.vals[index_position(strides, ki + si)], list(zip(s, si))))
+        values.append(maximization(l))
+    return create_cpt_with_dims(keep, values)
+
+
+def mpe_marginal(lf, p, r, assignment):
+    """mpemarginal (VariableElimination.hs:79-97): sum over p, then maximise over r."""
+    b = create_buckets(lf, p, r)
+    for dv, a in assignment:
+        b = add_bucket(b, factor_from_instantiation(dv, a))
+    for dv in p:
+        b = marginalize_one_variable(b, dv)
+    b = Buckets(b.e, {k: [convert_to_max_factor(f) for f in v] for k, v in b.m.items()})
+    for dv in r:  # marginalizeOneVariable on MAXCPT items (Buckets.hs:105-111)
+        f2 = max_project_out([dv], max_factor_product(b.m[dv]))
+        b = update_bucket(dv, f2, b)
+    rest = []
+    for k in sorted(b.m.keys()):
+        rest.extend(b.m[k])
+    return max_factor_product(rest)
+
+
+def mpe(net, p, r, assignment):
+    """mpe (VariableElimination.hs:101-114).  p, r = vertex lists, assignment = [(vertex, state)].
+    Returns (value P(mpe, e), instantiations [[(vertex, state)]]) -- the reference returns the instantiations."""
+    res = mpe_marginal(list(net.cpts), [net.dv(v) for v in p], [net.dv(v) for v in r], [(net.dv(v), s) for v, s in assignment])
+    assert res.is_scalar(), "The final MAXCPT factor should be a scalar one"
+    value, insts = res.vals[0]
+    return value, [[(dv[0], st) for dv, st in inst] for inst in insts]
+
+
+# --------------------------------------------------------------------------
 # Bayesian network container (what runBN returns: DirectedSG () CPT)
 # --------------------------------------------------------------------------
 

@@ -206,3 +206,28 @@ def test_degree_order_matches_twin():
         for order in (hb.minFillOrder(pnet), hb.minDegreeOrder(pnet), list(range(g.n))):
             assert hb.degreeOrder(pnet, order) == twin.degree_order(tnet, order)
     assert hb.degreeOrder(pnet, list(range(g.n))) >= 2
+
+
+def test_mpe_instantiation_order_is_structural_and_matches_the_twin():
+    """the variable order of the reference's instantiation list (ReferencePatterns.hs:79-84 compares it literally) is
+    known at compile time: hb_ve_mpe_order on a structure-only handle == the twin's evaluated list"""
+    from oracle import twin
+
+    path = os.path.join(G, "asia.net")
+    pnet = hb.importBayesianGraph(path)
+    tnet = twin.load_hugin(path)
+    i = pnet.ids
+    x, b, d, a, s, l, t, e = [i[c] for c in "XBDASLTE"]
+    for p, r in (([x, d], [b, a, s, l, t, e]), ([x, d, b, l, t, e], [a, s]), ([d, x], [e, t, l, s, b, a])):
+        h = hb.MostProbableExplanation(pnet, p, r, device=None)
+        _, m = twin.mpe(tnet, p, r, [(x, 0), (d, 1)])
+        assert h.order([x, d]) == [v for v, _ in m[0]]
+    h = hb.MostProbableExplanation(pnet, [x, d], [b, a, s, l, t, e], device=None)
+    assert [pnet.names[v] for v in h.order([x, d])] == ["E", "T", "L", "S", "B", "A"]
+    with pytest.raises(hb.HbError):  # evidence on a maximised variable: not supported (see compile_mpe)
+        h.order([x, b])
+    # a variable in neither list: its last table is dropped by addBucket (Buckets.hs:92-98), in the twin and here alike
+    # (the dropped table carries every instantiation with it: the reference answers [] here)
+    value, m = twin.mpe(tnet, [x], [b, a, s, l, t, e], [(x, 0)])
+    assert m == [] and value == 1.0
+    assert hb.MostProbableExplanation(pnet, [x], [b, a, s, l, t, e], device=None).order([x]) == []

@@ -284,3 +284,37 @@ def test_learn_em_twin_equals_cpp_oracle_posteriors(seed):
         assert sc[-1] == v and sorted(sc) == sorted(net.scopes[v])  # parents first, child last
         col = vals.reshape(-1, net.dims[v]).sum(1)
         assert np.all((np.abs(col - 1) < 1e-12) | (col == 0))
+
+
+# ---- `next` row f4: max-product (oracle/twin.py: mpe) -----------------------------------------------
+
+YES, NO = 0, 1
+
+
+def test_twin_mpe_reproduces_the_reference_goldens_on_asia():
+    """Bayes/Test/ReferencePatterns.hs:75-84 (compareMpeAsia): the MPE and a MAP on asia.net under X = Yes, D = No,
+    including the ORDER of the instantiation list the reference compares against."""
+    net = twin.load_hugin(os.path.join(G, "asia.net"))
+    i = {n: k for k, n in enumerate(net.names)}
+    x, b, d, a, s, l, t, e = [i[c] for c in "XBDASLTE"]
+    named = lambda m: [[(net.names[v], st) for v, st in inst] for inst in m]
+    value, m = twin.mpe(net, [x, d], [b, a, s, l, t, e], [(x, YES), (d, NO)])
+    assert named(m) == [[("E", NO), ("T", NO), ("L", NO), ("S", NO), ("B", NO), ("A", NO)]]
+    value2, m2 = twin.mpe(net, [x, d, b, l, t, e], [a, s], [(x, YES), (d, NO)])
+    assert named(m2) == [[("S", YES), ("A", NO)]]  # "a MAP is not always the projection of a MPE"
+    # brute force: the MPE value is the largest joint entry consistent with the evidence
+    import itertools
+
+    def joint(st):
+        return float(np.prod([twin.factor_value(net.cpts[v], [(dv, st[dv[0]]) for dv in net.cpts[v].vars]) for v in range(net.n)]))
+
+    consistent = [st for st in itertools.product(range(2), repeat=net.n) if st[x] == YES and st[d] == NO]
+    best = max((joint(st), st) for st in consistent)
+    assert abs(best[0] - value) < 1e-15 and all(best[1][v] == stt for v, stt in m[0])
+
+
+def test_twin_mpe_ties_go_to_the_last_maximal_state():
+    """maximumBy keeps the last maximal element (MaxCPT.hs:41): a uniform variable is explained by its LAST state"""
+    net = twin.Network.from_tables([3, 2], [[], [0]], [[1 / 3, 1 / 3, 1 / 3], [0.5, 0.5, 0.5, 0.5, 0.5, 0.5]])
+    value, m = twin.mpe(net, [], [0, 1], [])
+    assert m == [[(1, 1), (0, 2)]] and value == (1 / 3) * 0.5
