@@ -12,6 +12,7 @@ It keeps the reference's names and argument shapes for the path it replaces:
   * 'posterior'           (Bayes/FactorElimination.hs:314-327)
   * 'priorMarginal', 'posteriorMarginal' (Bayes/VariableElimination.hs:116-147)
   * 'changeFactor' on a tree (Bayes/FactorElimination/JTree.hs:107-115), 'learnEM' (Bayes/EM.hs:36-45)
+  * 'mpe' (Bayes/VariableElimination.hs:101-114)
 
 Networks are still built with the reference's own model layer ('Bayes.BayesianNetwork', or
 'Bayes.ImportExport.HuginNet.importBayesianGraph' + 'runBN'); only inference moves to the GPU.
@@ -27,6 +28,7 @@ module Bayes.Cuda
   , posterior
   , changeFactor
   , learnEM
+  , mpe
   , posteriorsBatch
   , priorMarginal
   , posteriorMarginal
@@ -69,6 +71,10 @@ foreign import ccall safe "hb_jt_em_step"
   c_jt_em_step :: Ptr HbJt -> Int64 -> Ptr Int8 -> Ptr Double -> Ptr Int32 -> Int32 -> IO CInt
 foreign import ccall safe "hb_ve_compile"
   c_ve_compile :: Ptr HbNet -> Ptr Int32 -> Int32 -> Ptr Int32 -> Int32 -> Ptr Int32 -> Int32 -> Ptr (Ptr HbVe) -> IO CInt
+foreign import ccall safe "hb_ve_compile_mpe"
+  c_ve_compile_mpe :: Ptr HbNet -> Ptr Int32 -> Int32 -> Ptr Int32 -> Int32 -> Ptr Int32 -> Int32 -> Ptr (Ptr HbVe) -> IO CInt
+foreign import ccall safe "hb_ve_mpe"
+  c_ve_mpe :: Ptr HbVe -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int8 -> Ptr Double -> Ptr Int32 -> Ptr Int32 -> IO CInt
 foreign import ccall safe "&hb_ve_free"    p_ve_free :: FunPtr (Ptr HbVe -> IO ())
 foreign import ccall safe "hb_ve_posterior"
   c_ve_posterior :: Ptr HbVe -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> Int64 -> Ptr Int64 -> IO CInt
@@ -220,6 +226,27 @@ posteriorMarginal g p r assignment = unsafePerformIO $ withNet g $ \net dims ->
         vals  <- peekArray size pVals
         let dvOf i = DV (Vertex (fromIntegral i)) (dims !! fromIntegral i)
         maybe (ioError (userError "factorWithVariables")) return (factorWithVariables (map dvOf scope) vals)
+
+-- | 'mpe g someP someR assignment': the variables of @someP@ are summed out (the evidence variables belong there),
+-- those of @someR@ maximised.  The result is the reference's @[DVISet]@: one instantiation, in the reference's order
+-- (the library reports that order; ties go to the last maximal state as with 'maximumBy').
+mpe :: SBN CPT -> [DV] -> [DV] -> [DVI] -> [[DVI]]
+mpe g p r assignment = unsafePerformIO $ withNet g $ \net dims ->
+  withArrayLen [ vertexId v | DV v _ <- p ] $ \np pP ->
+  withArrayLen [ vertexId v | DV v _ <- r ] $ \nr pR ->
+  with (0 :: Int32) $ \pDev -> alloca $ \pOut -> do
+    c_ve_compile_mpe net pP (fromIntegral np) pR (fromIntegral nr) pDev 1 pOut >>= check
+    ve <- peek pOut >>= newForeignPtr p_ve_free
+    let (vs, ss) = unzip (map dviPair assignment)
+    withForeignPtr ve $ \h -> withArrayLen vs $ \n pV -> withArray ss $ \pS ->
+      allocaArray nr $ \pStates -> alloca $ \pValue -> allocaArray nr $ \pOrder -> alloca $ \pN -> do
+        c_ve_mpe h (fromIntegral n) pV pS pStates pValue pOrder pN >>= check
+        states <- peekArray nr pStates
+        k      <- peek pN
+        order  <- peekArray (fromIntegral k) pOrder
+        let byVar = zip [ vertexId v | DV v _ <- r ] states
+            dvi i = DVI (DV (Vertex (fromIntegral i)) (dims !! fromIntegral i)) (maybe 0 fromIntegral (lookup i byVar))
+        return (if null order then [] else [map dvi order])
 
 -- | 'priorMarginal g ea eb' = 'posteriorMarginal' without evidence (Bayes/VariableElimination.hs:134-147).
 priorMarginal :: SBN CPT -> [DV] -> [DV] -> CPT
