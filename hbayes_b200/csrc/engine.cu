@@ -95,6 +95,7 @@ struct StepArgs {
   int out_is_row;
   int nr;                 // rows in this tile
   long long RT;           // row stride of the arena
+  signed char* arg;       // maximisation step: argmax table [entry][RT]; nullptr otherwise
 };
 
 struct GenericArgs {      // any number of inputs / scalars, descriptors in global memory
@@ -129,6 +130,11 @@ struct Rows<1> {
   __device__ __forceinline__ static Rows splat(double a, double) { return {a}; }
   __device__ __forceinline__ Rows mul(const Rows& o) const { return {__dmul_rn(x, o.x)}; }
   __device__ __forceinline__ Rows add(const Rows& o) const { return {__dadd_rn(x, o.x)}; }
+  // maximumBy (compare `on` fst) (MaxCPT.hs:41): the later term replaces the kept one unless the kept one is GT
+  __device__ __forceinline__ void take_max(const Rows& c, int s, int* arg) {
+    if (s == 0 || x <= c.x) x = c.x, arg[0] = s;
+  }
+  __device__ __forceinline__ static void store_arg(signed char* p, const int* arg) { *p = (signed char)arg[0]; }
   __device__ __forceinline__ void store(double* p) const {
 #ifndef HB_PLAIN_STORES
     __stcs(p, x);
@@ -150,6 +156,13 @@ struct Rows<2> {
   __device__ __forceinline__ static Rows splat(double a, double b) { return {a, b}; }
   __device__ __forceinline__ Rows mul(const Rows& o) const { return {__dmul_rn(x, o.x), __dmul_rn(y, o.y)}; }
   __device__ __forceinline__ Rows add(const Rows& o) const { return {__dadd_rn(x, o.x), __dadd_rn(y, o.y)}; }
+  __device__ __forceinline__ void take_max(const Rows& c, int s, int* arg) {
+    if (s == 0 || x <= c.x) x = c.x, arg[0] = s;
+    if (s == 0 || y <= c.y) y = c.y, arg[1] = s;
+  }
+  __device__ __forceinline__ static void store_arg(signed char* p, const int* arg) {  // rows (2t, 2t+1): one aligned 2-byte store
+    *reinterpret_cast<char2*>(p) = make_char2((signed char)arg[0], (signed char)arg[1]);
+  }
   __device__ __forceinline__ void store(double* p) const {
 #ifndef HB_PLAIN_STORES
     __stcs(reinterpret_cast<double2*>(p), make_double2(x, y));  // evict-first: a derived table is read again only many launches later
@@ -193,7 +206,7 @@ struct Strip {
 // of the warp is one contiguous 256*V-byte segment.  D = terms per entry (0: run-time count).
 // MASK: bit i set = input i depends on the blocking variable (two loads per item); clear = one load serves both
 // blocked states.  The mask is a template parameter so that the loads stay unconditional, back to back.
-template <int K, int V, int D, int MASK>
+template <int K, int V, int D, int MASK, bool MAXM = false>
 __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ StepArgs<K> a) {
   typedef Rows<V> R;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) * V;
@@ -227,6 +240,7 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
       off1[i] = off0[i] + (has1 ? a.wst[i] : 0);  // odd U: the last pair repeats its first state, not stored
     }
     R acc0 = R::splat(0.0, 0.0), acc1 = R::splat(0.0, 0.0);
+    int arg0[V], arg1[V];  // MAXM: state of the kept term per row
     auto term = [&](int s) {
       R x0[K], x1[K];
 #pragma unroll
@@ -241,7 +255,10 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
 #pragma unroll
       for (int i = K - 2; i >= 0; --i) c0 = x0[i].mul(c0), c1 = x1[i].mul(c1);
       if (has_ps) c0 = ps.mul(c0), c1 = ps.mul(c1);
-      acc0 = acc0.add(c0), acc1 = acc1.add(c1);
+      if constexpr (MAXM)
+        acc0.take_max(c0, s, arg0), acc1.take_max(c1, s, arg1);
+      else
+        acc0 = acc0.add(c0), acc1 = acc1.add(c1);
     };
     if (D > 0) {
 #pragma unroll
@@ -252,6 +269,10 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
     const size_t o = (size_t)sp.op * a.U + u0;
     acc0.store(outp + o * om);
     if (has1) acc1.store(outp + (o + 1) * om);
+    if constexpr (MAXM) {
+      R::store_arg(a.arg + o * (size_t)a.RT + row, arg0);
+      if (has1) R::store_arg(a.arg + (o + 1) * (size_t)a.RT + row, arg1);
+    }
   }
 }
 
@@ -854,6 +875,18 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   a.nr = nr;
   a.RT = RT;
   const int64_t items2 = st.n_red * ((st.U + 1) / 2) * 2;
+  if (st.levels[0].is_max) {  // maximisation step (mpe): run-time term count, every input loaded for both blocked states
+    constexpr int FULL = (1 << K) - 1;
+    a.arg = ex.d_args + st.arg_off * RT;
+    if (two_rows_per_thread(nr)) {
+      const LaunchShape sh = launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st));
+      prodsum_kernel<K, 2, 0, FULL, true><<<sh.grid, sh.block, 0, stream>>>(a);
+    } else {
+      const LaunchShape sh = launch_shape(nr, 1, items2);
+      prodsum_kernel<K, 1, 0, FULL, true><<<sh.grid, sh.block, 0, stream>>>(a);
+    }
+    return;
+  }
   if (two_rows_per_thread(nr))
     launch_kv<K, 2>(a, a.d, mask, launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st)), stream);
   else
@@ -939,7 +972,6 @@ void launch_fused_ki(const Executor& ex, const Step& st, int si, int64_t RT, int
 
 static bool is_generic(const Step& st) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
-  if (st.levels[0].is_max) return true;  // maximisation steps (mpe) run on the descriptor-driven kernel
   if (st.levels.size() > 1) return false;  // the compiler only fuses within MAXL levels / MAXK inputs, without scalars
   return !(k >= 1 && k <= MAXK && s <= MAXS);
 }

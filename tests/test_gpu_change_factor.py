@@ -104,3 +104,18 @@ def test_random_network_every_table_replaced(seed):
     ojt = OracleJT(OracleNet.from_arrays(a.dims, a.scopes, new_values))
     assert same_bits(jt.posteriors_batch(ev), ojt.posteriors_batch(ev))
     assert same_bits(jt.posteriors_batch(np.full((3, a.n), -1, np.int8)), ojt.posteriors_batch(np.full((3, a.n), -1, np.int8)))
+
+
+def test_soft_evidence_tutorial():
+    """Bayes/Examples/Tutorial.hs:319-331 (inferencesWithSoftEvidence): a sensor node (softEvidence, BayesianNetwork.hs:86-96)
+    observed True, its table swapped with changeFactor for 90 / 50 / 10 % sensors on one tree"""
+    a, sensor = 0, 1
+    pnet = hb.BayesianNetwork.from_tables([2, 2], [[a], [sensor, a]], [[0.5, 0.5], [1.0, 0.0, 1.0, 0.0]])
+    jt = hb.changeEvidence([(sensor, 1)], hb.createJunctionTree(hb.nodeComparisonForTriangulation, pnet))
+    for p in (0.9, 0.5, 0.1):
+        se = hb.Factor([sensor, a], [2, 2], np.array([p, 1 - p, 1 - p, p]))  # `se` (BayesianNetwork.hs:99-104)
+        got = hb.posterior(hb.changeFactor(se, jt), [a]).values
+        ojt = OracleJT(OracleNet.from_arrays([2, 2], [[a], [sensor, a]], [[0.5, 0.5], se.values.tolist()]))
+        ojt.change_evidence([(sensor, 1)])
+        assert same_bits(got, ojt.posterior([a])[1])
+        assert np.allclose(got, [1 - p, p], rtol=0, atol=1e-15)
