@@ -1103,7 +1103,7 @@ int hb_ve_mpe_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, int8_t* o
       executor_check(s.executor(c), s.stream);
       return;
     }
-    // host buffers: rows grouped by observed set (one program each), in order of first appearance
+    // host buffers: rows grouped by observed set (one program each)
     std::map<std::vector<int>, std::vector<int64_t>> groups;
     for (int64_t r = 0; r < n_rows; ++r) groups[observed_of_row(evidence + r * n_vars, n_vars)].push_back(r);
     int8_t* d_ev = (int8_t*)s.em_ev.ensure((size_t)n_rows * n_vars);
