@@ -28,6 +28,7 @@ from .api import (  # noqa: F401
     degreeOrder,
     factorProduct,
     factorProjectOut,
+    factorProjectTo,
     marginalizeOneVariable,
     importBayesianGraph,
     learnEM,

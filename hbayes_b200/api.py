@@ -554,6 +554,11 @@ def factorProjectOut(variables: Sequence[int], factor: Factor, device=0) -> Fact
     return factor
 
 
+def factorProjectTo(variables: Sequence[int], factor: Factor, device=0) -> Factor:
+    """factorProjectTo s f = factorProjectOut (factorVariables f `difference` s) f  (Bayes/Factor.hs:183-188)"""
+    return factorProjectOut([v for v in factor.variables if v not in set(variables)], factor, device)
+
+
 def marginalizeOneVariable(factors: Sequence[Factor], variable: int, device=0) -> Factor:
     """Buckets.hs:105-111: product of a bucket, then sum out `variable` -- one fused kernel launch"""
     return _factor_marginalize(factors, variable, device)

@@ -677,6 +677,15 @@ struct Executor {
   std::vector<cudaEvent_t> step_events;
   std::vector<std::vector<int>> step_deps;  // per row step (in launch order): earlier row steps it must follow
   std::vector<int> step_lane;               // per row step: which stream it is captured on
+  // Launch nodes: the row steps ordered by dependency level (a topological order of step_deps): the steps that
+  // only depend on finished work are issued first, whatever their position in the reference's elimination order.
+  struct Node {
+    int si = -1;            // program step index
+    std::vector<int> deps;  // earlier nodes
+    int lane = 0;
+  };
+  std::vector<Node> nodes;
+  std::vector<int64_t> gen_in_at, gen_sc_at;  // per program step: descriptor offsets in d_gen_in / d_gen_sc, -1 = none
   int n_lanes = 8;
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
@@ -976,8 +985,28 @@ static bool is_generic(const Step& st) {
   return !(k >= 1 && k <= MAXK && s <= MAXS);
 }
 
-static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream, int64_t gen_in_at,
-                           int64_t gen_sc_at) {
+// the descriptor-driven form of a single-level step (prodsum_generic_kernel)
+static GenericArgs generic_args(const Executor& ex, const Step& st, int si, int64_t RT, int nr) {
+  const Program& P = *ex.P;
+  GenericArgs a;
+  a.in = ex.d_gen_in + ex.gen_in_at[si];
+  a.sc = ex.d_gen_sc + ex.gen_sc_at[si];
+  a.k = st.n_inputs();
+  a.n_sc = (int)st.scalars.size();
+  a.d = st.levels[0].d;
+  a.C = (unsigned)st.C;
+  a.n_out = (unsigned)st.n_out;
+  a.U = (unsigned)st.U;
+  const Table& out = P.tables[st.out];
+  a.out_is_row = out.kind == T_ROW;
+  a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
+  a.nr = nr;
+  a.RT = RT;
+  a.arg = st.levels[0].is_max ? ex.d_args + st.arg_off * RT : nullptr;
+  return a;
+}
+
+static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
   if (st.levels.size() > 1) {
     const int ki = (int)st.levels.back().in.size();
@@ -1000,22 +1029,7 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
       default: launch_k<6>(ex, st, si, RT, nr, stream); break;
     }
   } else {
-    const Program& P = *ex.P;
-    GenericArgs a;
-    a.in = ex.d_gen_in + gen_in_at;
-    a.sc = ex.d_gen_sc + gen_sc_at;
-    a.k = k;
-    a.n_sc = s;
-    a.d = st.levels[0].d;
-    a.C = (unsigned)st.C;
-    a.n_out = (unsigned)st.n_out;
-    a.U = (unsigned)st.U;
-    const Table& out = P.tables[st.out];
-    a.out_is_row = out.kind == T_ROW;
-    a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
-    a.nr = nr;
-    a.RT = RT;
-    a.arg = st.levels[0].is_max ? ex.d_args + st.arg_off * RT : nullptr;
+    const GenericArgs a = generic_args(ex, st, si, RT, nr);
     LaunchShape sh = launch_shape(nr, 1, st.n_out);
     prodsum_generic_kernel<<<sh.grid, sh.block, 0, stream>>>(a);
   }
@@ -1042,7 +1056,8 @@ static void set_row_stride(Executor& ex, int64_t RT) {
   std::vector<TabRef> gsc;
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
-    if (st.kind != STEP_PRODSUM || !is_generic(st)) continue;
+    if (st.kind != STEP_PRODSUM || ex.gen_in_at[si] < 0) continue;  // descriptor-driven steps
+    if (ex.gen_in_at[si] != (int64_t)gin.size() || ex.gen_sc_at[si] != (int64_t)gsc.size()) throw Error(HB_E_ARG, "internal: descriptor offsets");
     for (int i = 0; i < st.n_inputs(); ++i) gin.push_back(in_arg(ex, st, (int)si, i, RT));
     for (int id : st.scalars) gsc.push_back(tab_ref(ex, P.tables[id], RT));
   }
@@ -1226,6 +1241,42 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
       ++ex->n_row_steps;
     }
   }
+  {  // launch nodes
+    const int n = ex->n_row_steps;
+    std::vector<int> row_si;
+    for (size_t si = 0; si < P.steps.size(); ++si)
+      if (P.steps[si].kind == STEP_PRODSUM && !P.steps[si].shared) row_si.push_back((int)si);
+    std::vector<int> level(n, 0);
+    int n_levels = 0;
+    for (int s = 0; s < n; ++s) {
+      for (int dep : ex->step_deps[s]) level[s] = std::max(level[s], level[dep] + 1);
+      n_levels = std::max(n_levels, level[s] + 1);
+    }
+    std::vector<int> node_of(n, -1);
+    for (int l = 0; l < n_levels; ++l)
+      for (int s = 0; s < n; ++s) {
+        if (level[s] != l) continue;
+        Executor::Node one;
+        one.si = row_si[s];
+        one.lane = ex->step_lane[s];
+        node_of[s] = (int)ex->nodes.size();
+        ex->nodes.push_back(std::move(one));
+      }
+    for (int s = 0; s < n; ++s) {
+      std::vector<int>& deps = ex->nodes[node_of[s]].deps;
+      for (int dep : ex->step_deps[s]) deps.push_back(node_of[dep]);
+      std::sort(deps.begin(), deps.end());
+    }
+    ex->gen_in_at.assign(P.steps.size(), -1);
+    ex->gen_sc_at.assign(P.steps.size(), -1);
+    int64_t gi = 0, gs = 0;
+    for (size_t si = 0; si < P.steps.size(); ++si) {
+      const Step& st = P.steps[si];
+      if (st.kind != STEP_PRODSUM || !is_generic(st)) continue;
+      ex->gen_in_at[si] = gi, ex->gen_sc_at[si] = gs;
+      gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
+    }
+  }
   // column chunks of the normalise/expand kernel
   {
     int max_w = 1;
@@ -1272,12 +1323,9 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
 static void run_shared_steps(Executor& ex) {
   const Program& P = *ex.P;
   if (!ex.RT) set_row_stride(ex, 64);  // shared tables do not depend on the row stride; the descriptors need one
-  int64_t gi = 0, gs = 0;
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
-    if (st.kind != STEP_PRODSUM) continue;
-    if (st.shared) launch_prodsum(ex, st, (int)si, ex.RT, 1, 0, gi, gs);
-    if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
+    if (st.kind == STEP_PRODSUM && st.shared) launch_prodsum(ex, st, (int)si, ex.RT, 1, 0);
   }
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaDeviceSynchronize());
@@ -1329,17 +1377,12 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     prep_rows_kernel<<<(((nr + 63) & ~63) + BLOCK - 1) / BLOCK, BLOCK, 0, stream>>>(pa);
     ++launches;
     mark();
+    const std::vector<Executor::Node>& nodes = ex->nodes;
     auto launch_steps = [&](cudaStream_t on) {
-      int64_t gi = 0, gs = 0;
-      for (size_t si = 0; si < P.steps.size(); ++si) {
-        const Step& st = P.steps[si];
-        if (st.kind != STEP_PRODSUM) continue;
-        if (!st.shared) launch_prodsum(*ex, st, (int)si, stride, nr, on, gi, gs);
-        if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
-      }
+      for (const Executor::Node& n : nodes) launch_prodsum(*ex, P.steps[n.si], n.si, stride, nr, on);
     };
     static const bool graphs_on = !(getenv("HB_GRAPHS") && atoi(getenv("HB_GRAPHS")) == 0);
-    if (graphs_on && ex->n_row_steps >= 16) {
+    if (graphs_on && nodes.size() >= 16) {
       auto it = ex->graphs.find(nr);
       if (it == ex->graphs.end()) {
         if (!ex->capture_stream) HB_CUDA(cudaStreamCreateWithFlags(&ex->capture_stream, cudaStreamNonBlocking));
@@ -1363,21 +1406,14 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
           HB_CUDA(cudaEventRecord(fork, ex->capture_stream));
           if (overlap_on)
             for (cudaStream_t st : ex->side_streams) HB_CUDA(cudaStreamWaitEvent(st, fork, 0));
-          int64_t gi = 0, gs = 0;
-          int s = 0;
-          for (size_t si = 0; si < P.steps.size(); ++si) {
-            const Step& st = P.steps[si];
-            if (st.kind != STEP_PRODSUM) continue;
-            if (!st.shared) {
-              cudaStream_t on = lane_stream(ex->step_lane[s]);
-              if (overlap_on)
-                for (int dep : ex->step_deps[s])
-                  if (ex->step_lane[dep] != ex->step_lane[s]) HB_CUDA(cudaStreamWaitEvent(on, ex->step_events[dep], 0));
-              launch_prodsum(*ex, st, (int)si, stride, nr, on, gi, gs);
-              if (overlap_on) HB_CUDA(cudaEventRecord(ex->step_events[s], on));
-              ++s;
-            }
-            if (is_generic(st)) gi += (int64_t)st.n_inputs(), gs += (int64_t)st.scalars.size();
+          for (size_t ni = 0; ni < nodes.size(); ++ni) {
+            const Executor::Node& n = nodes[ni];
+            cudaStream_t on = lane_stream(n.lane);
+            if (overlap_on)
+              for (int dep : n.deps)
+                if (nodes[dep].lane != n.lane) HB_CUDA(cudaStreamWaitEvent(on, ex->step_events[dep], 0));
+            launch_prodsum(*ex, P.steps[n.si], n.si, stride, nr, on);
+            if (overlap_on) HB_CUDA(cudaEventRecord(ex->step_events[ni], on));
           }
           // join
           if (overlap_on)
@@ -1403,7 +1439,7 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     } else {
       launch_steps(stream);
     }
-    launches += ex->n_row_steps;
+    launches += (int64_t)nodes.size();
     mark();
     if (!ex->out_desc.empty()) {
       OutArgs oa{ex->d_out_desc, ex->d_out_chunks, ex->d_maps, ex->d_rowoff, d_evidence + r0 * n_vars,

@@ -105,3 +105,13 @@ def test_scalars_only_and_bad_arguments():
     assert s.variables == [] and s.values[0] == 0.125
     with pytest.raises(hb.HbError):
         hb.marginalizeOneVariable([hb.Factor([1], [2], np.array([0.5, 0.5]))], 3)  # variable in no factor
+
+
+@SETTINGS
+@given(factors(0, 12, max_vars=4), st.data())
+def test_project_to_keeps_the_listed_variables(f, data):  # Factor.hs:183-188
+    keep = data.draw(st.lists(st.sampled_from(f.variables), unique=True, max_size=len(f.variables))) if f.variables else []
+    got = hb.factorProjectTo(keep, f)
+    want = hb.factorProjectOut([v for v in f.variables if v not in keep], f)
+    assert got.variables == want.variables == [v for v in f.variables if v in keep]
+    assert same_bits(got.values, want.values)
