@@ -126,7 +126,7 @@ class ClockSampler:
                 "samples": len(self.mhz), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def cpu_port_rate(n_rows, threads):
+def cpu_port_rate(n_rows, threads, want_posteriors=False):
     """queries/s of the oracle (restatement of the reference algorithm) on `threads` host threads."""
     from oracle import OracleJT, OracleNet
     from hbayes_b200 import synth
@@ -137,8 +137,9 @@ def cpu_port_rate(n_rows, threads):
     ev = synth.config_c2_evidence(net, observed, n_rows)
     ojt.posteriors_batch(ev[: max(threads, 8)], n_threads=threads)  # touch code and memory once
     t = time.perf_counter()
-    ojt.posteriors_batch(ev, n_threads=threads)
-    return n_rows / (time.perf_counter() - t)
+    post = ojt.posteriors_batch(ev, n_threads=threads)
+    rate = n_rows / (time.perf_counter() - t)
+    return (rate, post) if want_posteriors else rate
 
 
 def run_reference(args):
@@ -275,8 +276,9 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm",
-                "kernel": "the %d fused product/sum-out launches of one pass (prodsum_kernel<K,V,D> + fused_kernel<KO,KI,V,DI>, "
-                          "95%% of the pass; aggregated: one launch = one schedule step over all rows)" % n_prodsum,
+                "kernel": "the %d product/sum-out launches of one pass (per-step specialised kernels hb_step_<i> compiled with NVRTC on "
+                          "the first warm-up pass, prodsum_kernel<K,V,D> / fused_kernel<KO,KI,V,DI> for the rest; 93%% of the pass; "
+                          "aggregated: one launch = one schedule step over all rows)" % n_prodsum,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_pass": algo_bytes, "prodsum_ms_per_pass": tm["prodsum_ms"], "traffic": traffic,
@@ -289,7 +291,12 @@ def main():
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = int(min(1 << 16, max(1024, threads * 330 * 12)))
-            rate = cpu_port_rate(sample, threads)
+            rate, want = cpu_port_rate(sample, threads, want_posteriors=True)
+            # the rows the CPU port just answered double as a full-size parity check of the timed GPU path (same engine
+            # state as the timed steps: specialised kernels, CUDA graph): bit for bit, NaN == NaN
+            got = d_out[:sample].cpu().numpy()
+            same = bool(np.array_equal(np.isnan(got), np.isnan(want)) and got[~np.isnan(got)].tobytes() == want[~np.isnan(want)].tobytes())
+            line["parity"] = {"rows_checked": sample, "bit_identical_to_cpu_port": same}
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "first %d rows of the same evidence matrix, rows split over %d host threads; C++ "
                                               "restatement of the reference algorithm (oracle/), not GHC" % (sample, threads)}

@@ -257,6 +257,15 @@ class JunctionTree(_Batched):
         check(lib().hb_jt_program_json(self._h, len(oa), op, C.byref(p)))
         return _take_json(p)
 
+    def jit_source(self, observed: Iterable[int] = ()) -> str:
+        """CUDA source of the per-step specialised kernels for this observed list (inspection hook, csrc/jit.cpp)"""
+        oa, op = _i32(list(observed))
+        p = C.c_void_p()
+        check(lib().hb_jt_jit_source(self._h, len(oa), op, C.byref(p)))
+        s = C.cast(p, C.c_char_p).value.decode()
+        lib().hb_string_free(p)
+        return s
+
     def changeEvidence(self, evidence: Sequence[tuple]):
         """evidence = [(vertex, state)], order kept (it decides the reference's operation order)."""
         va, vp_ = _i32([e[0] for e in evidence])

@@ -15,6 +15,7 @@
 
 #include "../../include/hbayes_cuda.h"
 #include "engine.hpp"
+#include "jit.hpp"
 #include "model.hpp"
 
 using namespace hb;
@@ -634,6 +635,16 @@ int hb_jt_program_json(hb_jt* jt, int32_t n, const int32_t* vars, char** out_jso
   return guarded([&] {
     if (!jt || !out_json || n < 0 || (n > 0 && !vars)) throw Error(HB_E_ARG, "null argument");
     *out_json = dup_json(describe_program(*jt->program(std::vector<int>(vars, vars + n), {}).prog));
+  });
+}
+int hb_jt_jit_source(hb_jt* jt, int32_t n_observed, const int32_t* observed, char** out_source) {
+  return guarded([&] {
+    if (!jt || !out_source || n_observed < 0 || (n_observed > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
+    const Program& P = *jt->program(std::vector<int>(observed, observed + n_observed), {}).prog;
+    std::vector<int> steps;
+    for (size_t si = 0; si < P.steps.size(); ++si)
+      if (jit_eligible(P, P.steps[si])) steps.push_back((int)si);
+    *out_source = dup_json(jit_source(P, steps));
   });
 }
 int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states) {

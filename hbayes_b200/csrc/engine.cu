@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "jit.hpp"
 #include "procedural.hpp"
 
 namespace hb {
@@ -686,6 +687,11 @@ struct Executor {
   };
   std::vector<Node> nodes;
   std::vector<int64_t> gen_in_at, gen_sc_at;  // per program step: descriptor offsets in d_gen_in / d_gen_sc, -1 = none
+  // Kernels specialised per step (jit.cpp), built on the first pass over a large batch; jit_fn[si] = nullptr: templated kernel
+  JitModule* jit = nullptr;
+  std::vector<void*> jit_fn;
+  bool jit_tried = false;
+  double work_seen = 0;  // joint entries evaluated so far (rows x product entries per row)
   int n_lanes = 8;
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
@@ -705,6 +711,7 @@ struct Executor {
   ~Executor() {
     cudaSetDevice(device);
     drop_graphs();
+    jit_destroy(jit);
     if (capture_stream) cudaStreamDestroy(capture_stream);
     for (cudaStream_t st : side_streams) cudaStreamDestroy(st);
     for (cudaEvent_t e : step_events) cudaEventDestroy(e);
@@ -1008,6 +1015,22 @@ static GenericArgs generic_args(const Executor& ex, const Step& st, int si, int6
 
 static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
+  if (!ex.jit_fn.empty() && ex.jit_fn[si] && two_rows_per_thread(nr)) {  // the step has a specialised kernel
+    // rows along x (two per thread), strips of groups along y: enough of both to fill 148 SMs twice
+    const unsigned row_threads = (unsigned)((nr + 1) / 2);
+    unsigned bx = 128;
+    while (bx > 1 && bx / 2 >= row_threads) bx /= 2;
+    const unsigned by = (unsigned)std::max<int64_t>(1, std::min<int64_t>(256 / bx, st.n_red));
+    const unsigned gx = (row_threads + bx - 1) / bx;
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>((296 + gx - 1) / gx, (st.n_red + by - 1) / by));
+    const double *arena = ex.d_arena, *pots = ex.d_pots, *shared = ex.d_shared;
+    double* arena_out = ex.d_arena;
+    const int32_t* rowoff = ex.d_rowoff;
+    long long rt = RT;
+    void* params[] = {&arena, &arena_out, &pots, &shared, &rowoff, &nr, &rt};
+    if (!jit_launch(ex.jit_fn[si], gx, gy, bx, by, params, stream)) throw Error(HB_E_CUDA, "launch of a specialised step kernel failed");
+    return;
+  }
   if (st.levels.size() > 1) {
     const int ki = (int)st.levels.back().in.size();
     if ((int)st.levels.size() > MAXL || s) throw Error(HB_E_UNSUPPORTED, "fused step exceeds the kernel limits");
@@ -1362,6 +1385,33 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
   if (RT > ex->RT || ex->RT > 4 * RT) {
     HB_CUDA(cudaStreamSynchronize(stream));
     set_row_stride(*ex, RT);
+  }
+  {  // Specialised kernels (jit.cpp) for the steps that issue far more loads than they have distinct addresses.  The
+     // compilation takes seconds, so it waits for a call of >= 2^31 joint entries (C2: 140 K rows) or 2^35 accumulated.
+    static const bool jit_on = !(getenv("HB_JIT") && atoi(getenv("HB_JIT")) == 0);
+    static const double jit_min_work = getenv("HB_JIT_MIN_WORK") ? atof(getenv("HB_JIT_MIN_WORK")) : 2147483648.0;
+    const double work = (double)n_rows * (double)std::max<int64_t>(P.stat_prod, 1);
+    ex->work_seen += work;
+    if (jit_on && !ex->jit_tried && (work >= jit_min_work || ex->work_seen >= 16.0 * jit_min_work)) {
+      ex->jit_tried = true;
+      std::vector<std::pair<int64_t, int>> cand;  // (loads saved per row, step)
+      for (size_t si = 0; si < P.steps.size(); ++si) {
+        const Step& st = P.steps[si];
+        if (!jit_eligible(P, st)) continue;
+        int64_t spec = 0, templ = 0;
+        jit_load_counts(P, st, &spec, &templ);
+        if (templ >= 32 && templ * 20 >= spec * 21) cand.push_back({templ - spec, (int)si});  // at least 5 % fewer loads
+      }
+      std::sort(cand.rbegin(), cand.rend());
+      if (cand.size() > 64) cand.resize(64);
+      std::vector<int> steps;
+      for (auto& c : cand) steps.push_back(c.second);
+      std::sort(steps.begin(), steps.end());
+      std::string why;
+      ex->jit = jit_build(P, steps, ex->jit_fn, &why);
+      if (!ex->jit) ex->jit_fn.clear();
+      ex->drop_graphs();
+    }
   }
   const int64_t stride = ex->RT;
   int64_t launches = 0, tiles = 0;

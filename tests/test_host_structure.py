@@ -231,3 +231,29 @@ def test_mpe_instantiation_order_is_structural_and_matches_the_twin():
     value, m = twin.mpe(tnet, [x], [b, a, s, l, t, e], [(x, 0)])
     assert m == [] and value == 1.0
     assert hb.MostProbableExplanation(pnet, [x], [b, a, s, l, t, e], device=None).order([x]) == []
+
+
+def test_specialised_step_kernels_source_compiles_for_sm_100a(tmp_path):
+    """csrc/jit.cpp: the per-step CUDA source the library hands to NVRTC on the first large batch -- one kernel per
+    eligible step, deterministic, and it compiles for sm_100a (nvcc here; numerics are checked on the GPU)"""
+    import shutil
+    import subprocess
+
+    net = random_net(11, n=10, states=(2, 3), max_parents=3)
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    jt = hb.JunctionTree(pnet, device=None)
+    src = jt.jit_source([1, 4])
+    assert src == hb.JunctionTree(pnet, device=None).jit_source([1, 4])
+    prog = jt.program([1, 4])
+    eligible = [i for i, s in enumerate(prog["physical"])
+                if s["kind"] == 0 and not s["shared"] and not s["scalars"] and sum(len(l["in"]) for l in s["levels"]) >= 1]
+    assert [int(x.split("(")[0]) for x in src.split("hb_step_")[1:]] == eligible
+    assert "__dmul_rn" in src and "__dadd_rn" in src and "fma" not in src
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    cu = tmp_path / "steps.cu"
+    cu.write_text(src)
+    r = subprocess.run([nvcc, "--fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-cubin", str(cu), "-o", str(tmp_path / "steps.cubin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
