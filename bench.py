@@ -273,6 +273,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ev_host.nbytes), "d2h_bytes_per_step": int(out_pinned.nbytes),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(stats["launches"]) * args.steps,
+            "specialised_kernels": jt.specialised_kernels(),
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm",

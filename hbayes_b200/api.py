@@ -257,6 +257,12 @@ class JunctionTree(_Batched):
         check(lib().hb_jt_program_json(self._h, len(oa), op, C.byref(p)))
         return _take_json(p)
 
+    def specialised_kernels(self) -> int:
+        """steps of the last batch call's program that run on a kernel specialised for them (csrc/jit.cpp)"""
+        n = C.c_int32()
+        check(lib().hb_jt_specialised_kernels(self._h, C.byref(n)))
+        return n.value
+
     def jit_source(self, observed: Iterable[int] = ()) -> str:
         """CUDA source of the per-step specialised kernels for this observed list (inspection hook, csrc/jit.cpp)"""
         oa, op = _i32(list(observed))

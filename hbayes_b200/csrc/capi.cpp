@@ -981,6 +981,11 @@ int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags)
     cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
   });
 }
+int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n) {
+  if (!jt || !n) return HB_E_ARG;
+  *n = jt->s.last_ex ? executor_specialised_kernels(jt->s.last_ex) : 0;
+  return HB_OK;
+}
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream) {
   if (!jt) return HB_E_ARG;
   jt->s.stream = (cudaStream_t)cuda_stream;

@@ -41,6 +41,8 @@ void executor_normalise(Executor* ex, int64_t n_rows, double* d_out, void* strea
 void executor_check(Executor* ex, void* stream);
 
 int executor_device(const Executor* ex);
+// how many steps of the program currently run on a kernel specialised for them (jit.cpp); 0 = templated kernels only
+int executor_specialised_kernels(const Executor* ex);
 
 // CUDA-event timing of the kernel groups on the launching stream (off by default).  After a run,
 // executor_last_timing synchronises the stream and returns milliseconds summed over the row tiles:

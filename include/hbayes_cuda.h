@@ -107,6 +107,9 @@ int hb_jt_program_json(hb_jt* jt, int32_t n, const int32_t* vars, char** out_jso
 /* Inspection hook: the CUDA source of the kernels specialised per schedule step for this observed list (what the
  * library hands to NVRTC on the first large batch; csrc/jit.cpp).  Free with hb_string_free. */
 int hb_jt_jit_source(hb_jt* jt, int32_t n_observed, const int32_t* observed, char** out_source);
+/* how many schedule steps of the last batch call's program run on a kernel specialised for them (0: none yet, NVRTC
+ * unavailable, or HB_JIT=0) */
+int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n);
 /* changeEvidence (Bayes/FactorElimination/JTree.hs:454-466); list order is preserved */
 int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states);
 /* posterior jt q_vars (Bayes/FactorElimination.hs:314-327).  out_scope receives the variable order of the
