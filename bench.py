@@ -31,6 +31,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout at some debug levels) and
+# anything else it logs go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
