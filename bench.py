@@ -31,8 +31,10 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout at some debug levels) and
-# anything else it logs go to stderr
+# stdout carries exactly one JSON line.  NCCL prints its banner ("NCCL version ...") to stdout at NCCL_DEBUG=VERSION, and
+# only honours NCCL_DEBUG_FILE above that level: raise VERSION to WARN (same banner, no more) and send it to stderr.
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
