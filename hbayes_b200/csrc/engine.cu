@@ -1404,9 +1404,14 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
         if (templ >= 32) cand.push_back({templ, (int)si});
       }
       std::sort(cand.rbegin(), cand.rend());
-      if (cand.size() > 96) cand.resize(96);  // bounds the compilation time (about 0.1 s per kernel)
       std::vector<int> steps;
-      for (auto& c : cand) steps.push_back(c.second);
+      int64_t budget = 8000;  // bounds the compilation time: C2 needs 4.6 K (49 kernels, 5.5 s)
+      for (auto& c : cand) {
+        const int64_t ops = jit_unrolled_ops(P.steps[c.second]);
+        if (ops > budget || steps.size() >= 96) continue;
+        budget -= ops;
+        steps.push_back(c.second);
+      }
       std::sort(steps.begin(), steps.end());
       std::string why;
       ex->jit = jit_build(P, steps, ex->jit_fn, &why);

@@ -229,8 +229,10 @@ struct Gen {
   }
 };
 
-// multiplications + additions of one unrolled group: the size of the generated body
-int64_t unrolled_ops(const Step& st) {
+}  // namespace
+
+// chain evaluations of one unrolled group: the size of the generated body (about 150 bytes of source each)
+int64_t jit_unrolled_ops(const Step& st) {
   int64_t ops = 0, terms = 1;
   for (const Level& l : st.levels) {
     terms *= l.d;
@@ -239,8 +241,6 @@ int64_t unrolled_ops(const Step& st) {
   return ops * st.U;
 }
 
-}  // namespace
-
 bool jit_eligible(const Program& P, const Step& st) {
   if (st.kind != STEP_PRODSUM || st.shared || !st.scalars.empty() || st.levels.empty() || st.levels[0].is_max) return false;
   if (P.tables[st.out].kind != T_ROW || st.U > 8 || st.n_inputs() < 1) return false;
@@ -248,7 +248,7 @@ bool jit_eligible(const Program& P, const Step& st) {
   for (const Level& l : st.levels)
     for (const StepInput& in : l.in)
       if (P.tables[in.table].kind == T_ONE) return false;
-  return unrolled_ops(st) <= 6000;
+  return jit_unrolled_ops(st) <= 600;  // compile time grows faster than linearly with the size of a straight-line kernel
 }
 
 // loads per row (8-byte slots, one row) the specialised kernel issues for the step / the templated kernels issue
