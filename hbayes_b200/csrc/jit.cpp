@@ -117,20 +117,26 @@ struct Gen {
   std::map<std::pair<int, int64_t>, std::string> loaded;
   int tmp = 0;
   int U = 1;
+  // The n_loop outermost levels stay run-time loops (a step whose fully unrolled body would be too large); the levels
+  // below them are unrolled.  ptr[i] = name of input i's pointer in the current scope (it absorbs the loop variables).
+  int n_loop = 0;
+  int scope = 0;
+  std::vector<std::string> ptr;
   Gen(const Program& p, const Step& s) : P(p), st(s) {}
 
   std::string load(const In& x, int64_t off) {
     auto key = std::make_pair(x.id, off);
     auto it = loaded.find(key);
     if (it != loaded.end()) return it->second;
-    std::string name = "x" + std::to_string(x.id) + "_" + std::to_string(off);
+    std::string name = "x" + std::to_string(x.id) + "_" + std::to_string(off) + (scope ? "_" + std::to_string(scope) : "");
     const Table& t = *x.t;
+    const std::string& q = ptr[x.id];
     if (t.kind == T_ROW)
-      o << "    const double2 " << name << " = *reinterpret_cast<const double2*>(p" << x.id << " + (size_t)" << off << " * RT);\n";
+      o << "    const double2 " << name << " = *reinterpret_cast<const double2*>(" << q << " + (size_t)" << off << " * RT);\n";
     else if (t.kind == T_POT && t.slice_slot >= 0)
-      o << "    const double2 " << name << " = make_double2(p" << x.id << "a[" << off << "], p" << x.id << "b[" << off << "]);\n";
+      o << "    const double2 " << name << " = make_double2(" << q << "a[" << off << "], " << q << "b[" << off << "]);\n";
     else
-      o << "    const double " << name << "s = __ldg(p" << x.id << " + " << off << "); const double2 " << name << " = make_double2(" << name << "s, "
+      o << "    const double " << name << "s = __ldg(" << q << " + " << off << "); const double2 " << name << " = make_double2(" << name << "s, "
         << name << "s);\n";
     loaded[key] = name;
     return name;
@@ -145,25 +151,66 @@ struct Gen {
     o << "    const double2 " << n << " = make_double2(__dadd_rn(" << a << ".x, " << b << ".x), __dadd_rn(" << a << ".y, " << b << ".y));\n";
     return n;
   }
+  // chain of the inputs of level li for entry u (offsets of the unrolled levels from `bound`), times the inner value
+  std::string term(size_t li, int u, const std::vector<int>& bound, const std::vector<std::string>& inner) {
+    std::string chain;
+    for (size_t k = ins.size(); k-- > 0;) {
+      const In& x = ins[k];
+      if (x.level != (int)li) continue;
+      int64_t off = (int64_t)u * x.in->wstride;
+      for (size_t m = (size_t)n_loop; m <= li; ++m) off += (int64_t)bound[m] * x.in->lstride[m];  // looped levels live in the pointer
+      const std::string v = load(x, off);
+      chain = chain.empty() ? v : mul(v, chain);
+    }
+    if (!inner.empty()) chain = chain.empty() ? inner[u] : mul(inner[u], chain);
+    return chain;
+  }
   // value_l of the U lock-step entries, with the summed states of the outer levels bound
   std::vector<std::string> level(size_t li, std::vector<int>& bound) {
     const Level& lv = st.levels[li];
     std::vector<std::string> acc(U);
+    if ((int)li < n_loop) {  // run-time loop over the states of this level's summed variable
+      for (int u = 0; u < U; ++u) {
+        acc[u] = "a" + std::to_string(li) + "_" + std::to_string(u);
+        o << "    double2 " << acc[u] << " = zero;\n";
+      }
+      o << "    for (unsigned k" << li << " = 0; k" << li << " < " << lv.d << "u; ++k" << li << ") {\n";
+      const auto saved_loaded = loaded;
+      const auto saved_ptr = ptr;
+      const int saved_scope = scope;
+      scope = (int)li + 1;
+      for (const In& x : ins) {  // inputs of this level and of the levels below move with the loop variable
+        if (x.level < (int)li || x.in->lstride[li] == 0) continue;
+        const Table& t = *x.t;
+        const std::string q = "q" + std::to_string(x.id) + "_" + std::to_string(li);
+        const std::string step = "k" + std::to_string(li) + " * " + std::to_string(x.in->lstride[li]) + "u";
+        if (t.kind == T_ROW)
+          o << "    const double* const " << q << " = " << ptr[x.id] << " + (size_t)(" << step << ") * RT;\n";
+        else if (t.kind == T_POT && t.slice_slot >= 0)
+          o << "    const double* const " << q << "a = " << ptr[x.id] << "a + (" << step << ");\n"
+            << "    const double* const " << q << "b = " << ptr[x.id] << "b + (" << step << ");\n";
+        else
+          o << "    const double* const " << q << " = " << ptr[x.id] << " + (" << step << ");\n";
+        ptr[x.id] = q;
+      }
+      std::vector<std::string> inner;
+      if (li + 1 < st.levels.size()) inner = level(li + 1, bound);
+      for (int u = 0; u < U; ++u) {
+        const std::string c = term(li, u, bound, inner);
+        o << "    " << acc[u] << " = make_double2(__dadd_rn(" << acc[u] << ".x, " << c << ".x), __dadd_rn(" << acc[u] << ".y, " << c << ".y));\n";
+      }
+      o << "    }\n";
+      loaded = saved_loaded;
+      ptr = saved_ptr;
+      scope = saved_scope;
+      return acc;
+    }
     for (int s = 0; s < lv.d; ++s) {
       bound[li] = s;
       std::vector<std::string> inner;
       if (li + 1 < st.levels.size()) inner = level(li + 1, bound);
       for (int u = 0; u < U; ++u) {
-        std::string chain;
-        for (size_t k = ins.size(); k-- > 0;) {
-          const In& x = ins[k];
-          if (x.level != (int)li) continue;
-          int64_t off = (int64_t)u * x.in->wstride;
-          for (size_t m = 0; m <= li; ++m) off += (int64_t)bound[m] * x.in->lstride[m];
-          const std::string v = load(x, off);
-          chain = chain.empty() ? v : mul(v, chain);
-        }
-        if (!inner.empty()) chain = chain.empty() ? inner[u] : mul(inner[u], chain);
+        const std::string chain = term(li, u, bound, inner);
         acc[u] = acc[u].empty() ? add("zero", chain) : add(acc[u], chain);
       }
     }
@@ -177,6 +224,9 @@ struct Gen {
     int id = 0;
     for (size_t l = 0; l < st.levels.size(); ++l)
       for (const StepInput& in : st.levels[l].in) ins.push_back(In{id++, (int)l, &P.tables[in.table], &in});
+    n_loop = jit_loop_levels(st);
+    ptr.clear();
+    for (const In& x : ins) ptr.push_back("p" + std::to_string(x.id));
     std::vector<int> red;  // output variables other than the blocking one, stored row-major (last fastest), then w
     for (int v : out.pscope)
       if (v != st.w_var) red.push_back(v);
@@ -232,14 +282,28 @@ struct Gen {
 
 }  // namespace
 
-// chain evaluations of one unrolled group: the size of the generated body (about 150 bytes of source each)
-int64_t jit_unrolled_ops(const Step& st) {
+// chain evaluations in the generated body of a group when the `n_loop` outermost levels stay run-time loops
+// (about 150 bytes of source each)
+static int64_t body_ops(const Step& st, int n_loop) {
   int64_t ops = 0, terms = 1;
-  for (const Level& l : st.levels) {
-    terms *= l.d;
-    ops += terms * (int64_t)std::max<size_t>(1, l.in.size());
+  for (size_t l = 0; l < st.levels.size(); ++l) {
+    if ((int)l >= n_loop) terms *= st.levels[l].d;
+    ops += terms * (int64_t)std::max<size_t>(1, st.levels[l].in.size());
   }
   return ops * st.U;
+}
+constexpr int64_t MAX_BODY_OPS = 600;  // compile time grows faster than linearly with the size of a straight-line kernel
+
+// how many outermost levels stay run-time loops so that the unrolled rest fits MAX_BODY_OPS (-1: not even the
+// innermost level alone fits)
+int jit_loop_levels(const Step& st) {
+  for (int n = 0; n < (int)st.levels.size(); ++n)
+    if (body_ops(st, n) <= MAX_BODY_OPS) return n;
+  return -1;
+}
+int64_t jit_unrolled_ops(const Step& st) {
+  const int n = jit_loop_levels(st);
+  return n < 0 ? -1 : body_ops(st, n);
 }
 
 bool jit_eligible(const Program& P, const Step& st) {
@@ -249,7 +313,12 @@ bool jit_eligible(const Program& P, const Step& st) {
   for (const Level& l : st.levels)
     for (const StepInput& in : l.in)
       if (P.tables[in.table].kind == T_ONE) return false;
-  return jit_unrolled_ops(st) <= 600;  // compile time grows faster than linearly with the size of a straight-line kernel
+  // Steps whose body only fits with run-time loops around it can be generated too (HB_JIT_LOOPS=1; parity-checked on
+  // C3), but at two CTAs per SM they spill and measured no faster than the templated kernels (C3: 6.6 vs 6.2 ms), so
+  // by default only fully unrolled steps are specialised.
+  static const bool loops_on = getenv("HB_JIT_LOOPS") && atoi(getenv("HB_JIT_LOOPS")) != 0;
+  const int n_loop = jit_loop_levels(st);
+  return n_loop == 0 || (loops_on && n_loop > 0);
 }
 
 // loads per row (8-byte slots, one row) the specialised kernel issues for the step / the templated kernels issue

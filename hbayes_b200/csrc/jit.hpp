@@ -11,7 +11,9 @@ struct JitModule;
 
 // May this step be turned into a specialised kernel?  (a per-row sum step without scalars, small enough to unroll)
 bool jit_eligible(const Program& P, const Step& st);
-// Size of the generated body of a step (chain evaluations of one unrolled group).
+// Size of the generated body of a step (chain evaluations of one group; the outermost jit_loop_levels(st) levels stay
+// run-time loops so that the unrolled rest stays small).
+int jit_loop_levels(const Step& st);
 int64_t jit_unrolled_ops(const Step& st);
 // Loads per row the specialised kernel of the step would issue, and what the templated kernels issue: a step is only
 // worth a specialised kernel when the first is clearly smaller.
