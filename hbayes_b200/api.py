@@ -257,6 +257,13 @@ class JunctionTree(_Batched):
         check(lib().hb_jt_program_json(self._h, len(oa), op, C.byref(p)))
         return _take_json(p)
 
+    def specialise(self, observed: Iterable[int] = ()) -> int:
+        """build the specialised kernels for this observed list now (seconds) rather than inside the first large batch"""
+        oa, op = _i32(list(observed))
+        n = C.c_int32()
+        check(lib().hb_jt_specialise(self._h, len(oa), op, C.byref(n)))
+        return n.value
+
     def specialised_kernels(self) -> int:
         """steps of the last batch call's program that run on a kernel specialised for them (csrc/jit.cpp)"""
         n = C.c_int32()

@@ -981,6 +981,14 @@ int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags)
     cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
   });
 }
+int hb_jt_specialise(hb_jt* jt, int32_t n_observed, const int32_t* observed, int32_t* n_kernels) {
+  return guarded([&] {
+    if (!jt || n_observed < 0 || (n_observed > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
+    Compiled& c = jt->program(std::vector<int>(observed, observed + n_observed), {});
+    const int n = executor_specialise(jt->s.executor(c));
+    if (n_kernels) *n_kernels = n;
+  });
+}
 int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n) {
   if (!jt || !n) return HB_E_ARG;
   *n = jt->s.last_ex ? executor_specialised_kernels(jt->s.last_ex) : 0;

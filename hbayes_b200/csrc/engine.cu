@@ -1364,6 +1364,39 @@ void executor_refresh_potentials(Executor* ex) {
 void executor_destroy(Executor* ex) { delete ex; }
 int executor_device(const Executor* ex) { return ex->device; }
 
+int executor_specialise(Executor* ex) {
+  static const bool jit_on = !(getenv("HB_JIT") && atoi(getenv("HB_JIT")) == 0);
+  if (!jit_on || ex->jit_tried) return executor_specialised_kernels(ex);
+  ex->jit_tried = true;
+  const Program& P = *ex->P;
+  HB_CUDA(cudaSetDevice(ex->device));
+  std::vector<std::pair<int64_t, int>> cand;  // (loads per row on the templated kernels, step)
+  for (size_t si = 0; si < P.steps.size(); ++si) {
+    const Step& st = P.steps[si];
+    if (!jit_eligible(P, st)) continue;
+    int64_t spec = 0, templ = 0;
+    jit_load_counts(P, st, &spec, &templ);
+    // measured on C2: also steps without fewer loads gain (no index maps, immediate strides); tiny steps do not matter
+    if (templ >= 32) cand.push_back({templ, (int)si});
+  }
+  std::sort(cand.rbegin(), cand.rend());
+  std::vector<int> steps;
+  int64_t budget = 8000;  // bounds the compilation time: C2 needs 4.6 K (49 kernels, 5.5 s)
+  for (auto& c : cand) {
+    const int64_t ops = jit_unrolled_ops(P.steps[c.second]);
+    if (ops > budget || steps.size() >= 96) continue;
+    budget -= ops;
+    steps.push_back(c.second);
+  }
+  std::sort(steps.begin(), steps.end());
+  std::string why;
+  HB_CUDA(cudaDeviceSynchronize());  // no launch of this executor is in flight while its kernels are swapped
+  ex->jit = jit_build(P, steps, ex->jit_fn, &why);
+  if (!ex->jit) ex->jit_fn.clear();
+  ex->drop_graphs();
+  return executor_specialised_kernels(ex);
+}
+
 void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double* d_out, void* stream_, RunStats* stats, bool normalise,
                   int8_t* d_mpe_states_) {
   signed char* d_mpe_states = (signed char*)d_mpe_states_;
@@ -1386,38 +1419,12 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     HB_CUDA(cudaStreamSynchronize(stream));
     set_row_stride(*ex, RT);
   }
-  {  // Specialised kernels (jit.cpp) for the heaviest steps of the program.  The
-     // compilation takes seconds, so it waits for a call of >= 2^31 joint entries (C2: 140 K rows) or 2^35 accumulated.
-    static const bool jit_on = !(getenv("HB_JIT") && atoi(getenv("HB_JIT")) == 0);
+  {  // Specialised kernels (jit.cpp) for the heaviest steps of the program.  The compilation takes seconds, so it waits
+     // for a call of >= 2^31 joint entries (C2: 140 K rows) or 2^35 accumulated -- or for executor_specialise().
     static const double jit_min_work = getenv("HB_JIT_MIN_WORK") ? atof(getenv("HB_JIT_MIN_WORK")) : 2147483648.0;
     const double work = (double)n_rows * (double)std::max<int64_t>(P.stat_prod, 1);
     ex->work_seen += work;
-    if (jit_on && !ex->jit_tried && (work >= jit_min_work || ex->work_seen >= 16.0 * jit_min_work)) {
-      ex->jit_tried = true;
-      std::vector<std::pair<int64_t, int>> cand;  // (loads per row on the templated kernels, step)
-      for (size_t si = 0; si < P.steps.size(); ++si) {
-        const Step& st = P.steps[si];
-        if (!jit_eligible(P, st)) continue;
-        int64_t spec = 0, templ = 0;
-        jit_load_counts(P, st, &spec, &templ);
-        // measured on C2: also steps without fewer loads gain (no index maps, immediate strides); tiny steps do not matter
-        if (templ >= 32) cand.push_back({templ, (int)si});
-      }
-      std::sort(cand.rbegin(), cand.rend());
-      std::vector<int> steps;
-      int64_t budget = 8000;  // bounds the compilation time: C2 needs 4.6 K (49 kernels, 5.5 s)
-      for (auto& c : cand) {
-        const int64_t ops = jit_unrolled_ops(P.steps[c.second]);
-        if (ops > budget || steps.size() >= 96) continue;
-        budget -= ops;
-        steps.push_back(c.second);
-      }
-      std::sort(steps.begin(), steps.end());
-      std::string why;
-      ex->jit = jit_build(P, steps, ex->jit_fn, &why);
-      if (!ex->jit) ex->jit_fn.clear();
-      ex->drop_graphs();
-    }
+    if (work >= jit_min_work || ex->work_seen >= 16.0 * jit_min_work) executor_specialise(ex);
   }
   const int64_t stride = ex->RT;
   int64_t launches = 0, tiles = 0;

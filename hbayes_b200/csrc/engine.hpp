@@ -41,6 +41,9 @@ void executor_normalise(Executor* ex, int64_t n_rows, double* d_out, void* strea
 void executor_check(Executor* ex, void* stream);
 
 int executor_device(const Executor* ex);
+// Generates, compiles (NVRTC) and loads the kernels specialised for the heaviest steps of the program now, instead of
+// at the first large batch; returns how many steps they cover (0: disabled or unavailable).  Idempotent.
+int executor_specialise(Executor* ex);
 // how many steps of the program currently run on a kernel specialised for them (jit.cpp); 0 = templated kernels only
 int executor_specialised_kernels(const Executor* ex);
 

@@ -107,6 +107,10 @@ int hb_jt_program_json(hb_jt* jt, int32_t n, const int32_t* vars, char** out_jso
 /* Inspection hook: the CUDA source of the kernels specialised per schedule step for this observed list (what the
  * library hands to NVRTC on the first large batch; csrc/jit.cpp).  Free with hb_string_free. */
 int hb_jt_jit_source(hb_jt* jt, int32_t n_observed, const int32_t* observed, char** out_source);
+/* Builds the specialised kernels of the program for this observed list NOW (upload + NVRTC compilation, seconds) instead
+ * of inside the first large batch call, e.g. right after hb_jt_compile in a service.  *n_kernels (optional) = steps
+ * covered; 0 when NVRTC is unavailable or HB_JIT=0 -- not an error, the precompiled kernels are used. */
+int hb_jt_specialise(hb_jt* jt, int32_t n_observed, const int32_t* observed, int32_t* n_kernels);
 /* how many schedule steps of the last batch call's program run on a kernel specialised for them (0: none yet, NVRTC
  * unavailable, or HB_JIT=0) */
 int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n);

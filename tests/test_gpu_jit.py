@@ -43,8 +43,14 @@ for seed, rows in ((5, 257), (9, 64), (12, 1000)):
         ve = hb.VariableElimination(pnet, p, r).posterior_batch(ev)
         out["ve%%d" %% seed] = ve
         assert same_bits(ve, onet.posterior_marginal_batch(p, r, ev)), ("ve", seed)
+# the explicit form: kernels built right after the compilation, before any batch (hb_jt_specialise)
+jt2 = hb.JunctionTree(pnet)
+n = jt2.specialise(observed)
+out["explicit"] = jt2.posteriors_batch(ev)
+assert jt2.specialised_kernels() == n
+assert same_bits(out["explicit"], got)
+print("specialise ->", n)
 np.savez(sys.argv[1], **out)
-print("launch stats", jt.last_stats()["launches"])
 '''
 
 
@@ -53,7 +59,7 @@ def run(tmp_path, name, env):
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}, path], capture_output=True, text=True, env=e, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    return path, r.stderr
+    return path, r.stderr + r.stdout
 
 
 def test_specialised_kernels_bit_identical_to_oracle_and_to_the_templated_kernels(tmp_path):
@@ -61,7 +67,9 @@ def test_specialised_kernels_bit_identical_to_oracle_and_to_the_templated_kernel
 
     jit, log = run(tmp_path, "jit", {"HB_JIT": "1", "HB_JIT_MIN_WORK": "1", "HB_JIT_VERBOSE": "1"})
     assert "specialised kernels" in log, log[-2000:]  # they were really built and used
-    plain, _ = run(tmp_path, "plain", {"HB_JIT": "0"})
+    assert int(log.rsplit("specialise ->", 1)[1].split()[0]) > 0
+    plain, plain_log = run(tmp_path, "plain", {"HB_JIT": "0"})
+    assert int(plain_log.rsplit("specialise ->", 1)[1].split()[0]) == 0
     a, b = np.load(jit), np.load(plain)
     assert sorted(a.files) == sorted(b.files) and len(a.files) >= 6
     for k in a.files:
