@@ -1015,7 +1015,7 @@ static GenericArgs generic_args(const Executor& ex, const Step& st, int si, int6
 
 static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
-  if (!ex.jit_fn.empty() && ex.jit_fn[si] && two_rows_per_thread(nr)) {  // the step has a specialised kernel
+  if (!ex.jit_fn.empty() && ex.jit_fn[si] && nr >= 64) {  // the step has a specialised kernel (rows along x: not for few-row tiles)
     // rows along x (two per thread), strips of groups along y: enough of both to fill 148 SMs twice
     const unsigned row_threads = (unsigned)((nr + 1) / 2);
     unsigned bx = 128;

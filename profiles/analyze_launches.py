@@ -21,8 +21,15 @@ net, observed = synth.config_c2()
 pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
 p = hb.JunctionTree(pnet, device=None).program(observed)
 steps = [x for x in p["physical"] if x["kind"] == 0 and not x["shared"]]
-L = [i for i in range(s + 1, e) if "prodsum" in names[i] or "fused" in names[i] or "staged" in names[i]]
+L = [i for i in range(s + 1, e) if "prodsum" in names[i] or "fused" in names[i] or "staged" in names[i] or "hb_step_" in names[i]]
 assert len(L) == len(steps), (len(L), len(steps))
+if any("hb_step_" in n for n in names):
+    # final engine: launches are issued by dependency level and the heavy steps run on kernels named after their step
+    # (hb_step_<index into the program's step list>); only those can be matched to a step by name
+    by_si = {si: x for si, x in enumerate(p["physical"])}
+    pairs = [(i, by_si[int(names[i].split("hb_step_")[1].split("(")[0])]) for i in L if "hb_step_" in names[i]]
+    L, steps = [a for a, _ in pairs], [b for _, b in pairs]
+    print("matched %d specialised launches by name; the templated launches of this pass are not attributed" % len(L))
 tot = totb = 0
 recs = []
 for li, st in zip(L, steps):
