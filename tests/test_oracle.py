@@ -318,3 +318,46 @@ def test_twin_mpe_ties_go_to_the_last_maximal_state():
     net = twin.Network.from_tables([3, 2], [[], [0]], [[1 / 3, 1 / 3, 1 / 3], [0.5, 0.5, 0.5, 0.5, 0.5, 0.5]])
     value, m = twin.mpe(net, [], [0, 1], [])
     assert m == [[(1, 1), (0, 2)]] and value == (1 / 3) * 0.5
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_twin_mpe_and_map_against_brute_force(seed):
+    """max-product restatement vs exhaustive enumeration on random networks: the MPE value is the largest joint entry
+    consistent with the evidence and the returned instantiation attains it; a MAP (some variables summed out) maximises
+    the summed joint"""
+    import itertools
+
+    rng = np.random.RandomState(seed)
+    net = synth.random_dag_net(4 + seed % 4, 9100 + seed, states=(2, 3), max_parents=2)
+    tnet = twin.Network.from_tables(net.dims, net.parents, [list(map(float, v)) for v in net.values])
+
+    def joint(st):
+        p = 1.0
+        for v in range(net.n):
+            sc = net.scopes[v]
+            p *= float(np.asarray(net.values[v]).reshape([net.dims[x] for x in sc])[tuple(st[x] for x in sc)])
+        return p
+
+    k = int(rng.randint(0, 2))
+    observed = [int(v) for v in rng.permutation(net.n)[:k]]
+    ev = [(v, int(rng.randint(net.dims[v]))) for v in observed]
+    others = [int(v) for v in rng.permutation(net.n) if v not in observed]
+    n_sum = int(rng.randint(0, len(others)))
+    p, r = observed + others[:n_sum], others[n_sum:]
+    value, inst = twin.mpe(tnet, p, r, ev)
+    got = dict(inst[0])
+    assert sorted(got) == sorted(r)
+    best = -1.0
+    for states in itertools.product(*[range(net.dims[v]) for v in r]):
+        fixed = dict(ev)
+        fixed.update(zip(r, states))
+        total = 0.0
+        free = [v for v in p if v not in observed]
+        for rest in itertools.product(*[range(net.dims[v]) for v in free]):
+            st = dict(fixed)
+            st.update(zip(free, rest))
+            total += joint(st)
+        if dict(zip(r, states)) == got:
+            mine = total
+        best = max(best, total)
+    assert abs(value - best) <= 1e-12 * best and abs(mine - best) <= 1e-12 * best
