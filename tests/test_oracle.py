@@ -361,3 +361,20 @@ def test_twin_mpe_and_map_against_brute_force(seed):
             mine = total
         best = max(best, total)
     assert abs(value - best) <= 1e-12 * best and abs(mine - best) <= 1e-12 * best
+
+
+def test_learn_em_on_complete_data_is_counting():
+    """with every variable observed the family posteriors are indicators, so learnEM (Bayes/EM.hs:36-45) must return the
+    empirical conditional frequencies -- in the reference's [parents..., child] layout, zero where a parent
+    configuration never occurs (divide _ 0 = 0)"""
+    net = synth.random_dag_net(5, 9300, states=(2, 3), max_parents=2)
+    samples = synth.evidence_matrix(net, 40, list(range(net.n)), 77)
+    learnt = oracle.learn_em(net.dims, net.scopes, net.values, samples)
+    for v, (sc, vals) in enumerate(learnt):
+        assert sc[-1] == v and sorted(sc[:-1]) == sorted(net.scopes[v][1:])
+        table = vals.reshape([net.dims[x] for x in sc])
+        for idx in np.ndindex(*table.shape):
+            par = np.all([samples[:, x] == s for x, s in zip(sc[:-1], idx[:-1])], axis=0) if len(sc) > 1 else np.ones(len(samples), bool)
+            both = par & (samples[:, v] == idx[-1])
+            want = 0.0 if both.sum() == 0 else both.sum() / par.sum()
+            assert abs(table[idx] - want) <= 4e-16 * max(want, 1.0), (v, idx, table[idx], want)
