@@ -279,6 +279,23 @@ class JunctionTree(_Batched):
         lib().hb_string_free(p)
         return s
 
+    def kernel_info(self):
+        """what the program of the last batch / specialise call runs on (hb_jt_kernel_info)"""
+        out = np.zeros(10, np.int64)
+        check(lib().hb_jt_kernel_info(self._h, out.ctypes.data_as(i64p)))
+        keys = ["on_chip_eligible", "rows_per_cta", "threads_per_cta", "levels", "smem_entries_per_row", "smem_bytes",
+                "fp64_mul_per_row", "fp64_add_per_row", "on_chip", "origin"]
+        return dict(zip(keys, out.tolist()))
+
+    def tree_source(self, observed: Iterable[int] = ()) -> str:
+        """CUDA source of the whole-schedule on-chip kernel for this observed list (raises HbError when there is none)"""
+        oa, op = _i32(list(observed))
+        p = C.c_void_p()
+        check(lib().hb_jt_tree_source(self._h, len(oa), op, C.byref(p)))
+        s = C.cast(p, C.c_char_p).value.decode()
+        lib().hb_string_free(p)
+        return s
+
     def changeEvidence(self, evidence: Sequence[tuple]):
         """evidence = [(vertex, state)], order kept (it decides the reference's operation order)."""
         va, vp_ = _i32([e[0] for e in evidence])

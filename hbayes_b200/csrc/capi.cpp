@@ -647,6 +647,16 @@ int hb_jt_jit_source(hb_jt* jt, int32_t n_observed, const int32_t* observed, cha
     *out_source = dup_json(jit_source(P, steps));
   });
 }
+int hb_jt_tree_source(hb_jt* jt, int32_t n_observed, const int32_t* observed, char** out_source) {
+  return guarded([&] {
+    if (!jt || !out_source || n_observed < 0 || (n_observed > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
+    const Program& P = *jt->program(std::vector<int>(observed, observed + n_observed), {}).prog;
+    TreePlan plan;
+    std::string why;
+    if (!tree_plan(P, plan, &why)) throw Error(HB_E_UNSUPPORTED, "no on-chip kernel for this program: " + why);
+    *out_source = dup_json(tree_source(P, plan));
+  });
+}
 int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states) {
   return guarded([&] {
     if (!jt) throw Error(HB_E_ARG, "null handle");
@@ -992,6 +1002,16 @@ int hb_jt_specialise(hb_jt* jt, int32_t n_observed, const int32_t* observed, int
 int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n) {
   if (!jt || !n) return HB_E_ARG;
   *n = jt->s.last_ex ? executor_specialised_kernels(jt->s.last_ex) : 0;
+  return HB_OK;
+}
+int hb_jt_kernel_info(const hb_jt* jt, int64_t* out10) {
+  if (!jt || !out10) return HB_E_ARG;
+  for (int i = 0; i < 10; ++i) out10[i] = 0;
+  out10[9] = -1;
+  if (!jt->s.last_ex) return HB_OK;
+  executor_tree_info(jt->s.last_ex, out10);
+  out10[8] = executor_on_chip(jt->s.last_ex) ? 1 : 0;
+  out10[9] = executor_jit_origin(jt->s.last_ex);
   return HB_OK;
 }
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream) {

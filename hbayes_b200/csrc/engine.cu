@@ -33,7 +33,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <future>
 #include <map>
 #include <memory>
 #include <string>
@@ -692,6 +694,24 @@ struct Executor {
   std::vector<void*> jit_fn;
   bool jit_tried = false;
   double work_seen = 0;  // joint entries evaluated so far (rows x product entries per row)
+  // Whole-schedule on-chip kernel (jit.cpp, hb_tree): when the per-row tables of a tile fit shared memory the whole pass
+  // is ONE launch and the HBM row arena is not used at all.
+  TreePlan tree;
+  bool tree_eligible = false;
+  void* tree_fn = nullptr;
+  int tree_grid = 0;
+  bool fma = false;  // 1e-12 mode: generated kernels are compiled with multiply-add contraction (never bit-exact)
+  // NVRTC runs on a background thread (host-only work); the cubin is installed by the next call that finds it ready,
+  // so a stream of batches never stalls on a compilation.
+  struct Pending {
+    std::future<std::shared_ptr<const std::string>> cubin;
+    std::shared_ptr<std::string> key = std::make_shared<std::string>();
+    std::shared_ptr<std::string> why = std::make_shared<std::string>();
+    bool is_tree = false;
+    std::vector<int> steps;
+  };
+  std::unique_ptr<Pending> pending;
+  int jit_origin = -1;  // where the installed cubin came from: 0 this process, 1 disk cache, 2 compiled now
   int n_lanes = 8;
   void drop_graphs() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
@@ -709,6 +729,7 @@ struct Executor {
     return events[events_used++];
   }
   ~Executor() {
+    if (pending && pending->cubin.valid()) pending->cubin.wait();
     cudaSetDevice(device);
     drop_graphs();
     jit_destroy(jit);
@@ -1340,12 +1361,17 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
   }
   ex->workspace = workspace_bytes;
   run_shared_steps(*ex);
+  {
+    std::string why;
+    ex->tree_eligible = tree_plan(P, ex->tree, &why);
+    if (!ex->tree_eligible && getenv("HB_JIT_VERBOSE") && atoi(getenv("HB_JIT_VERBOSE"))) fprintf(stderr, "[hbayes jit] no on-chip kernel: %s\n", why.c_str());
+  }
   return ex.release();
 }
 
 static void run_shared_steps(Executor& ex) {
   const Program& P = *ex.P;
-  if (!ex.RT) set_row_stride(ex, 64);  // shared tables do not depend on the row stride; the descriptors need one
+  if (!ex.RT) set_row_stride(ex, 2);  // shared tables do not depend on the row stride; the descriptors need one (two rows: always fits)
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
     if (st.kind == STEP_PRODSUM && st.shared) launch_prodsum(ex, st, (int)si, ex.RT, 1, 0);
@@ -1364,12 +1390,11 @@ void executor_refresh_potentials(Executor* ex) {
 void executor_destroy(Executor* ex) { delete ex; }
 int executor_device(const Executor* ex) { return ex->device; }
 
-int executor_specialise(Executor* ex) {
-  static const bool jit_on = !(getenv("HB_JIT") && atoi(getenv("HB_JIT")) == 0);
-  if (!jit_on || ex->jit_tried) return executor_specialised_kernels(ex);
-  ex->jit_tried = true;
-  const Program& P = *ex->P;
-  HB_CUDA(cudaSetDevice(ex->device));
+static bool jit_enabled() { return !(getenv("HB_JIT") && atoi(getenv("HB_JIT")) == 0); }
+static bool tree_enabled() { return jit_enabled() && !(getenv("HB_TREE") && atoi(getenv("HB_TREE")) == 0); }
+
+// the steps worth a specialised kernel of their own (when the program has no on-chip kernel)
+static std::vector<int> steps_to_specialise(const Program& P) {
   std::vector<std::pair<int64_t, int>> cand;  // (loads per row on the templated kernels, step)
   for (size_t si = 0; si < P.steps.size(); ++si) {
     const Step& st = P.steps[si];
@@ -1389,11 +1414,86 @@ int executor_specialise(Executor* ex) {
     steps.push_back(c.second);
   }
   std::sort(steps.begin(), steps.end());
-  std::string why;
+  return steps;
+}
+
+// starts the compilation of the program's kernels on a background thread (registry / disk cache hits return at once)
+static void start_specialise(Executor* ex) {
+  if (ex->jit_tried || !jit_enabled()) return;
+  ex->jit_tried = true;
+  const Program& P = *ex->P;
+  auto pend = std::make_unique<Executor::Pending>();
+  std::string src;
+  if (ex->tree_eligible && tree_enabled()) {
+    pend->is_tree = true;
+    src = tree_source(P, ex->tree);
+  } else {
+    pend->steps = steps_to_specialise(P);
+    if (pend->steps.empty()) return;
+    src = jit_source(P, pend->steps);
+  }
+  auto key = pend->key;
+  auto why = pend->why;
+  const bool fma = ex->fma;
+  pend->cubin = std::async(std::launch::async, [src = std::move(src), key, why, fma]() {
+    int origin = -1;
+    auto cubin = jit_compile(src, fma, why.get(), key.get(), &origin);
+    if (cubin) *why = std::to_string(origin);
+    return cubin;
+  });
+  ex->pending = std::move(pend);
+}
+
+// installs a finished compilation (wait = false: only if it is ready)
+static void finish_specialise(Executor* ex, bool wait) {
+  if (!ex->pending) return;
+  if (!wait && ex->pending->cubin.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return;
+  std::unique_ptr<Executor::Pending> pend = std::move(ex->pending);
+  std::shared_ptr<const std::string> cubin = pend->cubin.get();
+  if (!cubin) return;  // NVRTC unavailable or the compilation failed: the precompiled kernels stay in charge
+  const Program& P = *ex->P;
+  HB_CUDA(cudaSetDevice(ex->device));
   HB_CUDA(cudaDeviceSynchronize());  // no launch of this executor is in flight while its kernels are swapped
-  ex->jit = jit_build(P, steps, ex->jit_fn, &why);
-  if (!ex->jit) ex->jit_fn.clear();
+  std::string why;
+  JitModule* mod = jit_load(*cubin, *pend->key, &why);
+  if (!mod) return;
+  ex->jit_origin = atoi(pend->why->c_str());
+  if (pend->is_tree) {
+    void* fn = jit_function(mod, "hb_tree");
+    if (!fn || !jit_set_dynamic_smem(fn, (int)ex->tree.smem_bytes)) {
+      jit_destroy(mod);
+      return;
+    }
+    int per_sm = jit_occupancy(fn, ex->tree.T, ex->tree.smem_bytes);
+    if (per_sm <= 0) per_sm = 1;
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, ex->device));
+    ex->tree_grid = per_sm * prop.multiProcessorCount;
+    ex->tree_fn = fn;
+    if (getenv("HB_JIT_VERBOSE") && atoi(getenv("HB_JIT_VERBOSE")))
+      fprintf(stderr, "[hbayes jit] on-chip kernel hb_tree: %d rows x %d threads per CTA, %d CTAs per SM, %d levels, %lld arena entries per row, %zu bytes of shared memory\n",
+              ex->tree.R, ex->tree.T, per_sm, ex->tree.n_levels, (long long)ex->tree.arena_entries, ex->tree.smem_bytes);
+  } else {
+    ex->jit_fn.assign(P.steps.size(), nullptr);
+    for (int si : pend->steps) {
+      void* fn = jit_function(mod, "hb_step_" + std::to_string(si));
+      if (!fn) {
+        ex->jit_fn.clear();
+        jit_destroy(mod);
+        return;
+      }
+      ex->jit_fn[si] = fn;
+    }
+    if (getenv("HB_JIT_VERBOSE") && atoi(getenv("HB_JIT_VERBOSE"))) fprintf(stderr, "[hbayes jit] %zu specialised kernels\n", pend->steps.size());
+  }
+  jit_destroy(ex->jit);
+  ex->jit = mod;
   ex->drop_graphs();
+}
+
+int executor_specialise(Executor* ex) {
+  start_specialise(ex);
+  finish_specialise(ex, true);
   return executor_specialised_kernels(ex);
 }
 
@@ -1405,6 +1505,40 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
   const Program& P = *ex->P;
   HB_CUDA(cudaSetDevice(ex->device));
   const int n_vars = P.net->n();
+  {  // Kernels generated for this program (jit.cpp): the on-chip kernel, or per-step kernels for its heaviest steps.  NVRTC
+     // takes seconds, so the compilation starts in the background once the program has seen >= 2^31 joint entries in one
+     // call (C2: 140 K rows) or 2^35 in all, and is installed by the first later call that finds it finished; cached
+     // cubins (this process, disk) are found at once.  executor_specialise() does the same synchronously.
+    static const double jit_min_work = getenv("HB_JIT_MIN_WORK") ? atof(getenv("HB_JIT_MIN_WORK")) : 2147483648.0;
+    static const bool jit_sync = getenv("HB_JIT_SYNC") && atoi(getenv("HB_JIT_SYNC")) != 0;
+    const double work = (double)n_rows * (double)std::max<int64_t>(P.stat_prod, 1);
+    ex->work_seen += work;
+    if (work >= jit_min_work || ex->work_seen >= 16.0 * jit_min_work) start_specialise(ex);
+    finish_specialise(ex, jit_sync);
+  }
+  if (ex->tree_fn) {  // the whole pass in one launch: no row arena, no tiles
+    ex->events_used = 0;
+    if (ex->timing)
+      for (int i = 0; i < 2; ++i) HB_CUDA(cudaEventRecord(ex->next_event(), stream));
+    const double *pots = ex->d_pots, *shared = ex->d_shared;
+    long long nrows = n_rows;
+    int norm = normalise ? 1 : 0;
+    int* flag = ex->d_flag;
+    void* params[] = {&pots, &shared, &d_evidence, &d_out, &nrows, &flag, &norm};
+    const int64_t n_tiles = (n_rows + ex->tree.R - 1) / ex->tree.R;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, ex->tree_grid);
+    if (!jit_launch_smem(ex->tree_fn, grid, (unsigned)ex->tree.T, (unsigned)ex->tree.smem_bytes, params, stream))
+      throw Error(HB_E_CUDA, "launch of the on-chip kernel failed");
+    if (ex->timing)
+      for (int i = 0; i < 2; ++i) HB_CUDA(cudaEventRecord(ex->next_event(), stream));
+    if (stats) {
+      stats->launches = 1;
+      stats->tiles = n_tiles;
+      stats->rows_per_tile = ex->tree.R;
+      stats->arena_bytes = 0;
+    }
+    return;
+  }
   // rows per tile: as many as the workspace allows, in multiples of 32 (one warp of rows), and few enough
   // that every row-table offset (entry * RT + row) fits 32 bits
   const int64_t per_row = std::max<int64_t>(P.row_entries, 1) * 8 + (int64_t)P.slices.size() * 4 + P.arg_entries;
@@ -1415,16 +1549,9 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
   cap = std::min<int64_t>(cap, (int64_t)1 << 22);
   if (cap < 2) throw Error(HB_E_OOM, "the row arena of two rows (" + std::to_string(per_row * 2) + " bytes) exceeds the workspace or 32-bit offsets");
   const int64_t RT = std::min<int64_t>(cap, n_rows >= 64 ? (n_rows + 63) / 64 * 64 : (n_rows + 1) / 2 * 2);
-  if (RT > ex->RT || ex->RT > 4 * RT) {
+  if (RT > ex->RT || ex->RT > 4 * RT || ex->RT > cap) {
     HB_CUDA(cudaStreamSynchronize(stream));
     set_row_stride(*ex, RT);
-  }
-  {  // Specialised kernels (jit.cpp) for the heaviest steps of the program.  The compilation takes seconds, so it waits
-     // for a call of >= 2^31 joint entries (C2: 140 K rows) or 2^35 accumulated -- or for executor_specialise().
-    static const double jit_min_work = getenv("HB_JIT_MIN_WORK") ? atof(getenv("HB_JIT_MIN_WORK")) : 2147483648.0;
-    const double work = (double)n_rows * (double)std::max<int64_t>(P.stat_prod, 1);
-    ex->work_seen += work;
-    if (work >= jit_min_work || ex->work_seen >= 16.0 * jit_min_work) executor_specialise(ex);
   }
   const int64_t stride = ex->RT;
   int64_t launches = 0, tiles = 0;
@@ -1546,9 +1673,23 @@ void executor_normalise(Executor* ex, int64_t n_rows, double* d_out, void* strea
 void executor_set_timing(Executor* ex, bool on) { ex->timing = on; }
 
 int executor_specialised_kernels(const Executor* ex) {
+  if (ex->tree_fn) {  // the on-chip kernel covers every per-row step
+    int n = 0;
+    for (int lv : ex->tree.level) n += lv >= 0;
+    return n;
+  }
   int n = 0;
   for (void* f : ex->jit_fn) n += f != nullptr;
   return n;
+}
+bool executor_on_chip(const Executor* ex) { return ex->tree_fn != nullptr; }
+int executor_jit_origin(const Executor* ex) { return ex->jit_origin; }
+const char* executor_jit_key(const Executor* ex) { return ex->jit ? jit_module_key(ex->jit).c_str() : ""; }
+void executor_set_fma(Executor* ex, bool on) { ex->fma = on; }
+void executor_tree_info(const Executor* ex, int64_t out8[8]) {
+  const TreePlan& t = ex->tree;
+  const int64_t v[8] = {ex->tree_eligible ? 1 : 0, t.R, t.T, t.n_levels, t.arena_entries, (int64_t)t.smem_bytes, t.ops_mul, t.ops_add};
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
 }
 
 void executor_last_timing(Executor* ex, void* stream, double out4[4]) {

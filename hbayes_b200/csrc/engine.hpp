@@ -46,6 +46,16 @@ int executor_device(const Executor* ex);
 int executor_specialise(Executor* ex);
 // how many steps of the program currently run on a kernel specialised for them (jit.cpp); 0 = templated kernels only
 int executor_specialised_kernels(const Executor* ex);
+// true when the program runs on the whole-schedule on-chip kernel (one launch per batch, per-row tables in shared memory)
+bool executor_on_chip(const Executor* ex);
+// where the installed generated kernels came from: -1 none, 0 this process' registry, 1 disk cache, 2 compiled now
+int executor_jit_origin(const Executor* ex);
+const char* executor_jit_key(const Executor* ex);  // cache key of the installed cubin ("" when none)
+// 1e-12 mode: kernels generated AFTER this call are compiled with multiply-add contraction (not bit-exact)
+void executor_set_fma(Executor* ex, bool on);
+// on-chip plan: [0] eligible, [1] rows per tile, [2] threads per CTA, [3] dependency levels, [4] arena entries per row,
+// [5] shared-memory bytes per CTA, [6] fp64 multiplies per row, [7] fp64 adds per row
+void executor_tree_info(const Executor* ex, int64_t out8[8]);
 
 // CUDA-event timing of the kernel groups on the launching stream (off by default).  After a run,
 // executor_last_timing synchronises the stream and returns milliseconds summed over the row tiles:

@@ -15,13 +15,17 @@
 #include "jit.hpp"
 
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <initializer_list>
 #include <map>
+#include <cstring>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -52,6 +56,8 @@ struct Driver {
   int (*ModuleGetFunction)(void**, void*, const char*) = nullptr;
   int (*ModuleUnload)(void*) = nullptr;
   int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**) = nullptr;
+  int (*FuncSetAttribute)(void*, int, int) = nullptr;
+  int (*Occupancy)(int*, void*, int, size_t) = nullptr;
   bool ok = false;
 };
 
@@ -90,6 +96,8 @@ const Driver& driver() {
     *(void**)(&r.ModuleGetFunction) = dlsym(h, "cuModuleGetFunction");
     *(void**)(&r.ModuleUnload) = dlsym(h, "cuModuleUnload");
     *(void**)(&r.LaunchKernel) = dlsym(h, "cuLaunchKernel");
+    *(void**)(&r.FuncSetAttribute) = dlsym(h, "cuFuncSetAttribute");
+    *(void**)(&r.Occupancy) = dlsym(h, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     r.ok = r.ModuleLoadData && r.ModuleGetFunction && r.ModuleUnload && r.LaunchKernel;
     return r;
   }();
@@ -163,6 +171,7 @@ struct Gen {
       chain = chain.empty() ? v : mul(v, chain);
     }
     if (!inner.empty()) chain = chain.empty() ? inner[u] : mul(inner[u], chain);
+    if (li == 0 && !scalar_product.empty()) chain = chain.empty() ? scalar_product : mul(scalar_product, chain);  // ps * chain
     return chain;
   }
   // value_l of the U lock-step entries, with the summed states of the outer levels bound
@@ -217,40 +226,71 @@ struct Gen {
     return acc;
   }
 
-  std::string kernel(const std::string& name) {
-    const Network& net = *P.net;
+  // ---- pieces shared by the per-step kernels (hb_step_<i>) and the whole-schedule on-chip kernel (hb_tree) ----
+  // In the on-chip kernel the row arena is shared memory: `tree_off` gives every per-row table its place there and the
+  // row stride RT is the compile-time tile height, so every address below folds into an immediate.
+  const std::vector<int64_t>* tree_off = nullptr;
+  std::vector<int> red;  // output variables other than the blocking one, stored row-major (last fastest), then w
+  int64_t row_off(const Table& t) const { return tree_off ? (*tree_off)[(size_t)(&t - &P.tables[0])] : t.off; }
+
+  void prepare() {
     const Table& out = P.tables[st.out];
     U = st.U;
     int id = 0;
+    ins.clear();
     for (size_t l = 0; l < st.levels.size(); ++l)
       for (const StepInput& in : st.levels[l].in) ins.push_back(In{id++, (int)l, &P.tables[in.table], &in});
-    n_loop = jit_loop_levels(st);
+    n_loop = std::max(0, jit_loop_levels(st));
     ptr.clear();
     for (const In& x : ins) ptr.push_back("p" + std::to_string(x.id));
-    std::vector<int> red;  // output variables other than the blocking one, stored row-major (last fastest), then w
+    red.clear();
     for (int v : out.pscope)
       if (v != st.w_var) red.push_back(v);
-    // two CTAs per SM (<= 128 registers): measured on C2, 1 -> 86.2, 2 -> 89.7, 3 -> 75.9 M queries/s
-    o << "extern \"C\" __global__ void __launch_bounds__(256, " << (getenv("HB_JIT_MINBLOCKS") ? atoi(getenv("HB_JIT_MINBLOCKS")) : 2) << ") " << name
-      << "(const double* __restrict__ arena, double* __restrict__ arena_out, const double* __restrict__ pots,\n"
-         "    const double* __restrict__ shared, const int* __restrict__ rowoff, int nr, long long RT) {\n";
-    o << "  const int row = (blockIdx.x * blockDim.x + threadIdx.x) * 2;\n  if (row >= nr) return;\n";
-    o << "  const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;\n";
-    o << "  const unsigned per = (" << st.n_red << "u + lanes - 1) / lanes;\n";
-    o << "  const unsigned g_end = min(" << st.n_red << "u, lane * per + per);\n";
-    o << "  const double2 zero = make_double2(0.0, 0.0);\n";
-    for (const In& x : ins) {  // row pointers that do not depend on the group
+  }
+
+  // row pointers that do not depend on the group (needs `row`, `arena`, `arena_out`, `pots`, `shared`, `rowoff`, `RT` in scope)
+  void emit_bases(const char* ind) {
+    const Table& out = P.tables[st.out];
+    for (const In& x : ins) {
       const Table& t = *x.t;
       if (t.kind == T_ROW)
-        o << "  const double* const b" << x.id << " = arena + (size_t)" << t.off << " * RT + row;\n";
+        o << ind << "const double* const b" << x.id << " = arena + (size_t)" << row_off(t) << " * RT + row;\n";
       else if (t.kind == T_POT && t.slice_slot >= 0)
-        o << "  const double* const b" << x.id << "a = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row];\n"
-          << "  const double* const b" << x.id << "b = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row + 1];\n";
+        o << ind << "const double* const b" << x.id << "a = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row];\n"
+          << ind << "const double* const b" << x.id << "b = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row + 1];\n";
       else
-        o << "  const double* const b" << x.id << " = " << (t.kind == T_POT ? "pots" : "shared") << " + " << t.off << ";\n";
+        o << ind << "const double* const b" << x.id << " = " << (t.kind == T_POT ? "pots" : "shared") << " + " << t.off << ";\n";
     }
-    o << "  double* const outp = arena_out + (size_t)" << out.off << " * RT + row;\n";  // same arena: the output region is never read here
-    o << "  for (unsigned g = lane * per; g < g_end; ++g) {\n";
+    // structural scalars of level 0: ps = s1 * (s2 * ...), applied as ps * chain (PrivateCPT.hs:225-227)
+    std::string ps;
+    for (size_t k = st.scalars.size(); k-- > 0;) {
+      const Table& t = P.tables[st.scalars[k]];
+      const std::string n = "sc" + std::to_string(k);
+      if (t.kind == T_ROW)
+        o << ind << "const double2 " << n << " = *reinterpret_cast<const double2*>(arena + (size_t)" << row_off(t) << " * RT + row);\n";
+      else if (t.kind == T_POT && t.slice_slot >= 0)
+        o << ind << "const double2 " << n << " = make_double2(pots[" << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row]], pots[" << t.off
+          << " + rowoff[(size_t)" << t.slice_slot << " * RT + row + 1]]);\n";
+      else
+        o << ind << "const double2 " << n << " = make_double2(" << (t.kind == T_POT ? "pots" : "shared") << "[" << t.off << "], "
+          << (t.kind == T_POT ? "pots" : "shared") << "[" << t.off << "]);\n";
+      if (ps.empty())
+        ps = n;
+      else {
+        const std::string m = "scp" + std::to_string(k);
+        o << ind << "const double2 " << m << " = make_double2(__dmul_rn(" << n << ".x, " << ps << ".x), __dmul_rn(" << n << ".y, " << ps << ".y));\n";
+        ps = m;
+      }
+    }
+    scalar_product = ps;
+    o << ind << "double* const outp = arena_out + (size_t)" << row_off(out) << " * RT + row;\n";  // same arena: the output region is never read here
+  }
+  std::string scalar_product;  // name of ps, empty when the step has no structural scalars
+
+  // the body of one group `g` of output entries: digits, per-input pointers, the unrolled nest, the stores
+  void emit_group(bool streaming_store) {
+    const Network& net = *P.net;
+    loaded.clear();
     if (!red.empty()) o << "    unsigned rem = g;\n";
     for (size_t j = red.size(); j-- > 0;)
       o << "    const unsigned d" << red[j] << " = rem % " << net.dims[red[j]] << "u;" << (j ? " rem /= " + std::to_string(net.dims[red[j]]) + "u;" : "")
@@ -273,10 +313,43 @@ struct Gen {
     }
     std::vector<int> bound(st.levels.size(), 0);
     const std::vector<std::string> res = level(0, bound);
-    for (int u = 0; u < U; ++u)
-      o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT), " << res[u] << ");\n";
+    for (int u = 0; u < U; ++u) {
+      if (streaming_store)
+        o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT), " << res[u] << ");\n";
+      else
+        o << "    *reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT) = " << res[u] << ";\n";
+    }
+  }
+
+  std::string kernel(const std::string& name) {
+    prepare();
+    // two CTAs per SM (<= 128 registers): measured on C2, 1 -> 86.2, 2 -> 89.7, 3 -> 75.9 M queries/s
+    o << "extern \"C\" __global__ void __launch_bounds__(256, " << (getenv("HB_JIT_MINBLOCKS") ? atoi(getenv("HB_JIT_MINBLOCKS")) : 2) << ") " << name
+      << "(const double* __restrict__ arena, double* __restrict__ arena_out, const double* __restrict__ pots,\n"
+         "    const double* __restrict__ shared, const int* __restrict__ rowoff, int nr, long long RT) {\n";
+    o << "  const int row = (blockIdx.x * blockDim.x + threadIdx.x) * 2;\n  if (row >= nr) return;\n";
+    o << "  const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;\n";
+    o << "  const unsigned per = (" << st.n_red << "u + lanes - 1) / lanes;\n";
+    o << "  const unsigned g_end = min(" << st.n_red << "u, lane * per + per);\n";
+    o << "  const double2 zero = make_double2(0.0, 0.0);\n";
+    emit_bases("  ");
+    o << "  for (unsigned g = lane * per; g < g_end; ++g) {\n";
+    emit_group(true);
     o << "  }\n}\n\n";
     return o.str();
+  }
+
+  // The same step inside the on-chip kernel: its (group, row pair) items are dealt to the threads of the CTA, thread
+  // `rot` first, so that the small steps of one dependency level land on different warps.
+  void tree_step(int si, int R, int T, int rot) {
+    prepare();
+    const int64_t rp = R / 2, items = st.n_red * rp;
+    o << "    {  // step " << si << ": " << st.n_red << " groups of " << U << " x " << rp << " row pairs\n";
+    o << "    for (unsigned it = (tid + " << (T - rot % T) % T << "u) % " << T << "u; it < " << items << "u; it += " << T << "u) {\n";
+    o << "    const unsigned g = it / " << rp << "u, row = (it % " << rp << "u) * 2u;\n";
+    emit_bases("    ");
+    emit_group(false);
+    o << "    }\n    }\n";
   }
 };
 
@@ -337,6 +410,7 @@ void jit_load_counts(const Program& P, const Step& st, int64_t* specialised, int
 
 struct JitModule {
   void* module = nullptr;
+  std::string key;  // cache key of the cubin it was loaded from
   ~JitModule() {
     if (module && driver().ok) driver().ModuleUnload(module);
   }
@@ -351,22 +425,111 @@ std::string jit_source(const Program& P, const std::vector<int>& steps) {
   return src;
 }
 
-JitModule* jit_build(const Program& P, const std::vector<int>& steps, std::vector<void*>& fn_per_step, std::string* why) {
-  auto fail = [&](const std::string& m) -> JitModule* {
+// ---- cubin cache --------------------------------------------------------------------------------------
+// NVRTC takes seconds for the kernels of one program; the cubin only depends on the generated source and the compiler.
+// Three layers: this process (also filled by hb_jt_load from a saved handle), a directory on disk
+// (HB_CACHE_DIR, else $XDG_CACHE_HOME/hbayes_b200, else ~/.cache/hbayes_b200; HB_JIT_CACHE=0 turns it off), NVRTC.
+namespace {
+
+const char* const kNvrtcOptions[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-default-device", "--std=c++17", "--generate-line-info"};
+const char* const kNvrtcOptionsFma[] = {"--gpu-architecture=sm_100a", "--fmad=true", "-default-device", "--std=c++17", "--generate-line-info"};
+
+std::mutex g_cubin_mutex;
+std::map<std::string, std::shared_ptr<const std::string>>& cubin_registry() {
+  static std::map<std::string, std::shared_ptr<const std::string>> r;
+  return r;
+}
+
+std::string cache_dir() {
+  if (const char* off = getenv("HB_JIT_CACHE"))
+    if (atoi(off) == 0) return "";
+  if (const char* d = getenv("HB_CACHE_DIR")) return d;
+  if (const char* x = getenv("XDG_CACHE_HOME")) return std::string(x) + "/hbayes_b200";
+  if (const char* h = getenv("HOME")) return std::string(h) + "/.cache/hbayes_b200";
+  return "";
+}
+
+void make_dirs(const std::string& path) {
+  for (size_t i = 1; i <= path.size(); ++i)
+    if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0755);
+}
+
+std::string hex64(uint64_t v) {
+  char buf[17];
+  snprintf(buf, sizeof buf, "%016llx", (unsigned long long)v);
+  return buf;
+}
+
+}  // namespace
+
+std::string jit_cache_key(const std::string& src, bool fma) {
+  uint64_t a = 1469598103934665603ull, b = 0x9E3779B97F4A7C15ull;  // two independent 64-bit FNV-style hashes
+  auto feed = [&](const char* p, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+      a = (a ^ (unsigned char)p[i]) * 1099511628211ull;
+      b = (b + (unsigned char)p[i]) * 0xD6E8FEB86659FD93ull;
+      b ^= b >> 29;
+    }
+  };
+  feed(src.data(), src.size());
+  for (const char* o : (fma ? kNvrtcOptionsFma : kNvrtcOptions)) feed(o, strlen(o) + 1);
+  static const std::string ver = [] {
+    int major = 0, minor = 0;
+    void* h = open_first({"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"});
+    if (h)
+      if (auto f = (int (*)(int*, int*))dlsym(h, "nvrtcVersion")) f(&major, &minor);
+    return "nvrtc " + std::to_string(major) + "." + std::to_string(minor) + " hbjit 2";
+  }();
+  feed(ver.data(), ver.size());
+  return hex64(a) + hex64(b);
+}
+
+void jit_registry_put(const std::string& key, const std::string& cubin) {
+  std::lock_guard<std::mutex> lock(g_cubin_mutex);
+  cubin_registry()[key] = std::make_shared<const std::string>(cubin);
+}
+
+std::shared_ptr<const std::string> jit_registry_get(const std::string& key) {
+  std::lock_guard<std::mutex> lock(g_cubin_mutex);
+  auto it = cubin_registry().find(key);
+  return it == cubin_registry().end() ? nullptr : it->second;
+}
+
+// source -> cubin: registry, then disk, then NVRTC (host-only work: may run on any thread, no CUDA context needed)
+std::shared_ptr<const std::string> jit_compile(const std::string& src, bool fma, std::string* why, std::string* key_out, int* origin) {
+  auto fail = [&](const std::string& m) -> std::shared_ptr<const std::string> {
     if (why) *why = m;
     if (verbose()) fprintf(stderr, "[hbayes jit] %s\n", m.c_str());
     return nullptr;
   };
-  if (steps.empty()) return fail("no eligible step");
+  const std::string key = jit_cache_key(src, fma);
+  if (key_out) *key_out = key;
+  if (auto hit = jit_registry_get(key)) {
+    if (origin) *origin = 0;
+    return hit;
+  }
+  const std::string dir = cache_dir();
+  const std::string path = dir.empty() ? "" : dir + "/" + key + ".cubin";
+  if (!path.empty()) {
+    if (FILE* f = fopen(path.c_str(), "rb")) {
+      std::string bytes;
+      char buf[1 << 16];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof buf, f)) > 0) bytes.append(buf, n);
+      fclose(f);
+      if (bytes.size() > 64 && bytes.compare(0, 4, "\x7f" "ELF") == 0) {
+        jit_registry_put(key, bytes);
+        if (origin) *origin = 1;
+        if (verbose()) fprintf(stderr, "[hbayes jit] cubin %s from the disk cache\n", key.c_str());
+        return jit_registry_get(key);
+      }
+    }
+  }
   const Nvrtc& rt = nvrtc();
-  const Driver& drv = driver();
   if (!rt.ok) return fail("libnvrtc not available");
-  if (!drv.ok) return fail("libcuda not available");
-  const std::string src = jit_source(P, steps);
   nvrtcProgram prog = nullptr;
   if (rt.CreateProgram(&prog, src.c_str(), "hbayes_steps.cu", 0, nullptr, nullptr) != 0) return fail("nvrtcCreateProgram failed");
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-default-device", "--std=c++17", "--generate-line-info"};
-  const int rc = rt.CompileProgram(prog, 5, opts);
+  const int rc = rt.CompileProgram(prog, 5, fma ? kNvrtcOptionsFma : kNvrtcOptions);
   if (rc != 0) {
     size_t n = 0;
     rt.GetProgramLogSize(prog, &n);
@@ -383,23 +546,360 @@ JitModule* jit_build(const Program& P, const std::vector<int>& steps, std::vecto
   std::string cubin(size, '\0');
   rt.GetCUBIN(prog, &cubin[0]);
   rt.DestroyProgram(&prog);
-  auto mod = std::make_unique<JitModule>();
-  if (drv.ModuleLoadData(&mod->module, cubin.data()) != 0) return fail("cuModuleLoadData failed");
-  fn_per_step.assign(P.steps.size(), nullptr);
-  for (int si : steps) {
-    void* fn = nullptr;
-    const std::string name = "hb_step_" + std::to_string(si);
-    if (drv.ModuleGetFunction(&fn, mod->module, name.c_str()) != 0) return fail("cuModuleGetFunction(" + name + ") failed");
-    fn_per_step[si] = fn;
+  jit_registry_put(key, cubin);
+  if (!path.empty()) {  // atomically: another process may be writing the same key
+    make_dirs(dir);
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+      fclose(f);
+      if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+    }
   }
-  if (verbose()) fprintf(stderr, "[hbayes jit] %zu specialised kernels, %zu bytes of source, %zu bytes of cubin\n", steps.size(), src.size(), size);
+  if (origin) *origin = 2;
+  if (verbose()) fprintf(stderr, "[hbayes jit] compiled %zu bytes of source into %zu bytes of cubin (%s)\n", src.size(), size, key.c_str());
+  return jit_registry_get(key);
+}
+
+// loads a cubin on the current device
+JitModule* jit_load(const std::string& cubin, const std::string& key, std::string* why) {
+  const Driver& drv = driver();
+  if (!drv.ok) {
+    if (why) *why = "libcuda not available";
+    return nullptr;
+  }
+  auto mod = std::make_unique<JitModule>();
+  mod->key = key;
+  if (drv.ModuleLoadData(&mod->module, cubin.data()) != 0) {
+    if (why) *why = "cuModuleLoadData failed";
+    mod->module = nullptr;
+    return nullptr;
+  }
   return mod.release();
+}
+
+void* jit_function(JitModule* m, const std::string& name) {
+  void* fn = nullptr;
+  if (!m || driver().ModuleGetFunction(&fn, m->module, name.c_str()) != 0) return nullptr;
+  return fn;
+}
+
+const std::string& jit_module_key(const JitModule* m) { return m->key; }
+
+// ================= whole-schedule on-chip kernel ========================================
+// changeEvidence -> collect -> distribute -> posterior for every query, for a tile of R evidence rows, in ONE launch:
+// the per-row tables live in shared memory ([entry][R], row-fastest like the HBM arena), the steps of one dependency
+// level run back to back and levels are separated by __syncthreads; potentials come through L1/L2; only the evidence
+// rows and the posteriors touch HBM.  Every step body is the one the per-step kernels use (same Gen), so the
+// floating-point sequence of every entry is unchanged.
+namespace {
+constexpr int64_t TREE_SMEM_MAX = 227 * 1024;
+constexpr int64_t TREE_STAGE_MAX = 32 * 1024;  // output staging tile; wider results are written straight to HBM
+constexpr int64_t TREE_MAX_BODY = 60000;       // chain evaluations in the whole kernel (bounds the compilation time)
+
+int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
+}  // namespace
+
+bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
+  auto fail = [&](const std::string& m) {
+    if (why) *why = m;
+    return false;
+  };
+  plan = TreePlan();
+  if (!P.max_steps.empty() || !P.mpe_r.empty()) return fail("maximisation steps");
+  const size_t ns = P.steps.size();
+  plan.level.assign(ns, -1);
+  plan.off.assign(P.tables.size(), -1);
+  std::vector<int> producer(P.tables.size(), -1), last(P.tables.size(), -1);
+  int64_t body = 0;
+  int n_out_steps = 0;
+  for (size_t si = 0; si < ns; ++si) {
+    const Step& st = P.steps[si];
+    if (st.kind == STEP_OUTPUT) {
+      ++n_out_steps;
+      if ((int)st.obs_var.size() > 8) return fail("more than 8 observed variables in one query");
+      continue;
+    }
+    if (st.shared) continue;
+    if (st.levels.empty() || st.levels[0].is_max || P.tables[st.out].kind != T_ROW) return fail("unsupported step");
+    if (st.U > 32 || st.n_red >= ((int64_t)1 << 24)) return fail("step too large");
+    const int64_t ops = jit_unrolled_ops(st);
+    if (ops < 0) return fail("step body too large to unroll");
+    body += ops;
+    int lv = 0;
+    auto reads = [&](int id) {
+      const Table& t = P.tables[id];
+      if (t.kind == T_ONE) return false;
+      if (t.kind == T_ROW) {
+        if (producer[id] < 0) return false;
+        lv = std::max(lv, plan.level[producer[id]] + 1);
+      }
+      return true;
+    };
+    for (const Level& l : st.levels)
+      for (const StepInput& in : l.in)
+        if (!reads(in.table)) return fail("unsupported input table");
+    for (int id : st.scalars)
+      if (!reads(id)) return fail("unsupported scalar table");
+    plan.level[si] = lv;
+    producer[st.out] = (int)si;
+    plan.n_levels = std::max(plan.n_levels, lv + 1);
+  }
+  if (n_out_steps == 0) return fail("no query");
+  if (body > TREE_MAX_BODY) return fail("program too large for one kernel");
+  // liveness at level granularity: a table may be overwritten from the level AFTER its last reader's
+  for (size_t si = 0; si < ns; ++si) {
+    const Step& st = P.steps[si];
+    if (st.kind == STEP_OUTPUT) {
+      if (P.tables[st.result].kind == T_ROW) last[st.result] = plan.n_levels;  // read by the output phase
+      continue;
+    }
+    if (plan.level[si] < 0) continue;
+    for (const Level& l : st.levels)
+      for (const StepInput& in : l.in) last[in.table] = std::max(last[in.table], plan.level[si]);
+    for (int id : st.scalars) last[id] = std::max(last[id], plan.level[si]);
+  }
+  {
+    std::vector<std::pair<int64_t, int64_t>> free_list;  // (offset, size) sorted by offset
+    int64_t top = 0;
+    auto release = [&](int64_t off, int64_t size) {
+      auto it = std::lower_bound(free_list.begin(), free_list.end(), std::make_pair(off, (int64_t)0));
+      it = free_list.insert(it, {off, size});
+      if (it + 1 != free_list.end() && it->first + it->second == (it + 1)->first) it->second += (it + 1)->second, free_list.erase(it + 1);
+      if (it != free_list.begin() && (it - 1)->first + (it - 1)->second == it->first) (it - 1)->second += it->second, it = free_list.erase(it), --it;
+      if (it->first + it->second == top) top = it->first, free_list.erase(it);
+    };
+    std::vector<int> live;
+    for (int lv = 0; lv < plan.n_levels; ++lv) {
+      for (size_t i = 0; i < live.size();) {
+        if (last[live[i]] < lv) {
+          release(plan.off[live[i]], P.tables[live[i]].size);
+          live[i] = live.back(), live.pop_back();
+        } else
+          ++i;
+      }
+      std::vector<int> born;
+      for (size_t si = 0; si < ns; ++si)
+        if (plan.level[si] == lv) born.push_back(P.steps[si].out);
+      std::stable_sort(born.begin(), born.end(), [&](int a, int b) { return P.tables[a].size > P.tables[b].size; });
+      for (int id : born) {
+        const int64_t size = P.tables[id].size;
+        size_t best = free_list.size();  // best fit
+        for (size_t i = 0; i < free_list.size(); ++i)
+          if (free_list[i].second >= size && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+        if (best < free_list.size()) {
+          plan.off[id] = free_list[best].first;
+          free_list[best].first += size, free_list[best].second -= size;
+          if (free_list[best].second == 0) free_list.erase(free_list.begin() + best);
+        } else
+          plan.off[id] = top, top += size;
+        plan.arena_entries = std::max(plan.arena_entries, top);
+        live.push_back(id);
+      }
+    }
+    plan.arena_entries = std::max<int64_t>(plan.arena_entries, 1);
+  }
+  const int64_t NV = P.net->n(), NS = (int64_t)P.slices.size(), W = P.out_width;
+  auto bytes = [&](int64_t R, bool staged) {
+    return plan.arena_entries * R * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV);
+  };
+  int R = 0;
+  if (const char* env = getenv("HB_TREE_ROWS")) R = std::max(2, atoi(env) / 2 * 2);
+  bool staged = true;
+  if (!R)
+    for (int cand : {32, 16, 8, 4, 2}) {
+      staged = cand * (W | 1) * 8 <= TREE_STAGE_MAX;
+      if (bytes(cand, staged) <= TREE_SMEM_MAX) {
+        R = cand;
+        break;
+      }
+    }
+  if (!R) return fail("the per-row tables of two rows do not fit shared memory");
+  staged = R * (W | 1) * 8 <= TREE_STAGE_MAX;
+  if (bytes(R, staged) > TREE_SMEM_MAX) return fail("HB_TREE_ROWS does not fit shared memory");
+  plan.R = R;
+  plan.stage_pitch = staged ? (W | 1) : 0;
+  plan.smem_bytes = (size_t)bytes(R, staged);
+  // threads: enough for the widest level, between 64 and 256
+  int64_t widest = 1;
+  {
+    std::vector<int64_t> items(plan.n_levels, 0);
+    for (size_t si = 0; si < ns; ++si)
+      if (plan.level[si] >= 0) items[plan.level[si]] += P.steps[si].n_red * (R / 2);
+    for (int64_t x : items) widest = std::max(widest, x);
+  }
+  int T = 64;
+  while (T < 256 && T < widest) T *= 2;
+  if (const char* env = getenv("HB_TREE_THREADS")) T = std::max(32, std::min(1024, atoi(env) / 32 * 32));
+  plan.T = T;
+  int minb = (int)std::min<int64_t>(TREE_SMEM_MAX / (int64_t)plan.smem_bytes, 2048 / T);
+  minb = std::max(1, std::min(minb, 65536 / (T * 128)));  // leave at least 128 registers per thread
+  if (const char* env = getenv("HB_TREE_MINBLOCKS")) minb = std::max(1, atoi(env));
+  plan.min_blocks = minb;
+  for (size_t si = 0; si < ns; ++si) {
+    const Step& st = P.steps[si];
+    if (plan.level[si] < 0) continue;
+    int64_t terms = st.n_out;
+    for (size_t l = 0; l < st.levels.size(); ++l) {
+      terms *= st.levels[l].d;
+      const int64_t k = (int64_t)st.levels[l].in.size() + (l + 1 < st.levels.size() ? 1 : 0) + (l == 0 && !st.scalars.empty() ? 1 : 0);
+      plan.ops_mul += terms * std::max<int64_t>(0, k - 1);
+      plan.ops_add += terms;
+    }
+    if (st.scalars.size() > 1) plan.ops_mul += (int64_t)st.scalars.size() - 1;
+  }
+  return true;
+}
+
+std::string tree_source(const Program& P, const TreePlan& plan) {
+  const Network& net = *P.net;
+  const int R = plan.R, T = plan.T;
+  const int64_t NV = net.n(), NS = (int64_t)P.slices.size(), W = P.out_width, WP = plan.stage_pitch;
+  std::ostringstream o;
+  auto table = [&](const char* type, const char* name, const std::vector<int64_t>& v) {
+    o << "__constant__ " << type << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
+    for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << v[i];
+    if (v.empty()) o << "0";
+    o << "};\n";
+  };
+  std::vector<int64_t> obs, dims, sl_begin = {0}, sl_var, sl_stride;
+  for (int v = 0; v < NV; ++v) obs.push_back(P.fixed_state[v] >= 0 ? 2 + P.fixed_state[v] : (P.is_observed[v] ? 1 : 0)), dims.push_back(net.dims[v]);
+  for (const Slice& sl : P.slices) {
+    for (size_t j = 0; j < sl.vars.size(); ++j) sl_var.push_back(sl.vars[j]), sl_stride.push_back(sl.strides[j]);
+    sl_begin.push_back((int64_t)sl_var.size());
+  }
+  table("signed char", "OBS", obs);
+  table("signed char", "DIMS", dims);
+  table("int", "SL_BEGIN", sl_begin);
+  table("short", "SL_VAR", sl_var);
+  table("int", "SL_STRIDE", sl_stride);
+  // queries: Q = {kind (0 one, 1 potential pool, 2 shared arena, 3 per-row table), base, slice, n_phys, n_full, column,
+  // map offset, order offset, n_obs}, then per observed query variable (var, stride, dim)
+  std::vector<int64_t> q, qobs, qmap;
+  int nq = 0;
+  for (const Step& st : P.steps) {
+    if (st.kind != STEP_OUTPUT) continue;
+    const Table& t = P.tables[st.result];
+    const int64_t kind = t.kind == T_ONE ? 0 : t.kind == T_POT ? 1 : t.kind == T_SHARED ? 2 : 3;
+    const int64_t map_off = (int64_t)qmap.size();
+    for (int64_t f = 0; f < st.n_full; ++f) qmap.push_back(st.full_map[(size_t)f]);
+    const int64_t order_off = (int64_t)qmap.size();
+    int64_t n_phys = 0;  // the stored entries in the order the full layout visits them (norm is a left fold over that order)
+    for (int64_t f = 0; f < st.n_full; ++f) {
+      bool first_state = true;
+      for (size_t j = 0; j < st.obs_var.size(); ++j) first_state &= ((f / st.obs_stride[j]) % st.obs_dim[j]) == 0;
+      if (first_state) qmap.push_back(st.full_map[(size_t)f]), ++n_phys;
+    }
+    for (int64_t x : {kind, kind == 3 ? plan.off[st.result] : t.off, (int64_t)(t.kind == T_POT ? t.slice_slot : -1), n_phys, st.n_full, st.out_col, map_off,
+                      order_off, (int64_t)st.obs_var.size()})
+      q.push_back(x);
+    for (int j = 0; j < 8; ++j) {
+      const bool has = j < (int)st.obs_var.size();
+      qobs.push_back(has ? st.obs_var[j] : 0), qobs.push_back(has ? st.obs_stride[j] : 1), qobs.push_back(has ? st.obs_dim[j] : 1);
+    }
+    ++nq;
+  }
+  table("int", "Q", q);
+  table("int", "QOBS", qobs);
+  table("unsigned", "QMAP", qmap);
+  const int64_t rowoff_at = plan.arena_entries * R * 8, stage_at = rowoff_at + round8(NS * R * 4), ev_at = stage_at + (WP ? R * WP * 8 : 0);
+  o << "extern \"C\" __global__ void __launch_bounds__(" << T << ", " << plan.min_blocks << ") hb_tree(const double* __restrict__ pots,\n"
+       "    const double* __restrict__ shared, const signed char* __restrict__ ev, double* __restrict__ out, long long n_rows,\n"
+       "    int* __restrict__ flag, int normalise) {\n";
+  o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
+  o << "  double* const sm = reinterpret_cast<double*>(smem_raw);\n";
+  o << "  const double* const arena = sm;\n  double* const arena_out = sm;\n";
+  o << "  int* const rowoff = reinterpret_cast<int*>(smem_raw + " << rowoff_at << ");\n";
+  if (WP) o << "  double* const stage = reinterpret_cast<double*>(smem_raw + " << stage_at << ");\n";
+  o << "  signed char* const evs = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n";
+  o << "  constexpr unsigned RT = " << R << "u;\n";
+  o << "  const unsigned tid = threadIdx.x;\n";
+  o << "  const double2 zero = make_double2(0.0, 0.0);\n";
+  o << "  for (long long tile = blockIdx.x; tile * " << R << " < n_rows; tile += gridDim.x) {\n";
+  o << "    const long long row0 = tile * " << R << ";\n";
+  o << "    const int nr = (int)(n_rows - row0 < " << R << " ? n_rows - row0 : " << R << ");\n";
+  // evidence tile -> shared memory (pad rows of the last tile: unobserved everywhere, slice 0, results never written)
+  o << "    for (unsigned i = tid; i < " << R * NV << "u; i += " << T << "u) evs[i] = i < (unsigned)nr * " << NV << "u ? ev[row0 * " << NV << " + i] : (signed char)-1;\n";
+  o << "    __syncthreads();\n";
+  o << "    for (unsigned i = tid; i < (unsigned)nr * " << NV << "u; i += " << T << "u) {\n"
+       "      const int s = evs[i], ob = OBS[i % " << NV << "u];\n"
+       "      const bool bad = ob == 0 ? (s >= 0) : (ob == 1 ? (s < 0 || s >= DIMS[i % " << NV << "u]) : (s != ob - 2));\n"
+       "      if (bad) atomicOr(flag, 1);\n    }\n";
+  if (NS > 0)
+    o << "    for (unsigned i = tid; i < " << NS * R << "u; i += " << T << "u) {\n"
+         "      const unsigned j = i / " << R << "u, r = i % " << R << "u;\n"
+         "      int off = 0;\n"
+         "      for (int t = SL_BEGIN[j]; t < SL_BEGIN[j + 1]; ++t) {\n"
+         "        int s = evs[r * " << NV << "u + SL_VAR[t]];\n"
+         "        s = s < 0 ? 0 : (s >= DIMS[SL_VAR[t]] ? 0 : s);\n"
+         "        off += SL_STRIDE[t] * s;\n      }\n"
+         "      rowoff[i] = off;\n    }\n";
+  o << "    __syncthreads();\n";
+  for (int lv = 0; lv < plan.n_levels; ++lv) {
+    o << "    // ---- dependency level " << lv << " ----\n";
+    int64_t rot = 0;
+    for (size_t si = 0; si < P.steps.size(); ++si) {
+      if (plan.level[si] != lv) continue;
+      Gen g(P, P.steps[si]);
+      g.tree_off = &plan.off;
+      g.tree_step((int)si, R, T, (int)(rot % T));
+      o << g.o.str();
+      rot += P.steps[si].n_red * (R / 2);
+    }
+    o << "    __syncthreads();\n";
+  }
+  // factorNorm + factorDivide + expansion to the query scope (the output_kernel of engine.cu, reading shared memory)
+  o << "    for (unsigned i = tid; i < " << (int64_t)nq * R << "u; i += " << T << "u) {\n"
+       "      const unsigned r = i % " << R << "u, qi = i / " << R << "u;\n"
+       "      const int* const d = Q + qi * 9;\n"
+       "      const int kind = d[0], n_phys = d[3], n_full = d[4], n_obs = d[8];\n"
+       "      const double* gp = nullptr;\n"
+       "      if (kind == 1) gp = pots + d[1] + (d[2] >= 0 ? rowoff[d[2] * " << R << " + r] : 0);\n"
+       "      else if (kind == 2) gp = shared + d[1];\n"
+       "      const double* const sp = sm + (size_t)d[1] * RT + r;\n"
+       "      const unsigned* const order = QMAP + d[7];\n"
+       "      const unsigned* const fmap = QMAP + d[6];\n"
+       "      double norm = 0.0;\n"
+       "      for (int j = 0; j < n_phys; ++j) norm = __dadd_rn(norm, kind == 3 ? sp[(size_t)order[j] * RT] : (kind == 0 ? 1.0 : gp[order[j]]));\n"
+       "      const double inv = normalise ? __ddiv_rn(1.0, norm) : 1.0;\n"
+       "      int st[8];\n"
+       "      for (int j = 0; j < n_obs; ++j) st[j] = evs[r * " << NV << "u + QOBS[qi * 24 + j * 3]];\n";
+  if (WP)
+    o << "      double* const op = stage + r * " << WP << "u + d[5];\n";
+  else
+    o << "      double* const op = out + (row0 + r) * " << W << "ll + d[5];\n      if ((int)r >= nr) continue;\n";
+  o << "      for (int f = 0; f < n_full; ++f) {\n"
+       "        bool match = true;\n"
+       "        for (int j = 0; j < n_obs; ++j) match &= ((f / QOBS[qi * 24 + j * 3 + 1]) % QOBS[qi * 24 + j * 3 + 2]) == st[j];\n"
+       "        const double v = match ? (kind == 3 ? sp[(size_t)fmap[f] * RT] : (kind == 0 ? 1.0 : gp[fmap[f]])) : 0.0;\n"
+       "        op[f] = __dmul_rn(inv, v);\n      }\n    }\n";
+  if (WP) {
+    o << "    __syncthreads();\n";
+    o << "    for (unsigned i = tid; i < (unsigned)nr * " << W << "u; i += " << T << "u) out[row0 * " << W << "ll + i] = stage[(i / " << W << "u) * " << WP << "u + i % " << W
+      << "u];\n";
+  }
+  o << "  }\n}\n";
+  return o.str();
 }
 
 void jit_destroy(JitModule* m) { delete m; }
 
 bool jit_launch(void* fn, unsigned gx, unsigned gy, unsigned bx, unsigned by, void** params, void* stream) {
   return driver().LaunchKernel(fn, gx, gy, 1, bx, by, 1, 0, stream, params, nullptr) == 0;
+}
+
+bool jit_launch_smem(void* fn, unsigned grid, unsigned block, unsigned smem_bytes, void** params, void* stream) {
+  return driver().LaunchKernel(fn, grid, 1, 1, block, 1, 1, smem_bytes, stream, params, nullptr) == 0;
+}
+
+bool jit_set_dynamic_smem(void* fn, int bytes) {
+  return driver().FuncSetAttribute && driver().FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, bytes) == 0;
+}
+
+int jit_occupancy(void* fn, int block, size_t smem_bytes) {
+  int n = 0;
+  if (!driver().Occupancy || driver().Occupancy(&n, fn, block, smem_bytes) != 0) return 0;
+  return n;
 }
 
 }  // namespace hb

@@ -1,5 +1,6 @@
 // jit.hpp -- per-step kernel specialisation (NVRTC), see jit.cpp.
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -20,12 +21,43 @@ int64_t jit_unrolled_ops(const Step& st);
 void jit_load_counts(const Program& P, const Step& st, int64_t* specialised, int64_t* templated);
 // The CUDA source of the specialised kernels `hb_step_<si>` of the given steps (for tests and inspection).
 std::string jit_source(const Program& P, const std::vector<int>& steps);
-// Compiles and loads the kernels on the current device.  fn_per_step[si] = function handle or nullptr.  Returns nullptr
-// (with a reason in *why) when NVRTC / the driver API are not available or the compilation fails: not an error.
-JitModule* jit_build(const Program& P, const std::vector<int>& steps, std::vector<void*>& fn_per_step, std::string* why);
 void jit_destroy(JitModule* m);
 // kernel parameters: (const double* arena, double* arena_out (the same arena), const double* pots, const double* shared,
 //                     const int* rowoff, int nr, long long RT)
 bool jit_launch(void* fn, unsigned gx, unsigned gy, unsigned bx, unsigned by, void** params, void* stream);
+
+// ---- cubin cache: this process (jit_registry_*; hb_jt_save / hb_jt_load carry it across processes), a directory on disk
+// (HB_CACHE_DIR, default ~/.cache/hbayes_b200; HB_JIT_CACHE=0 disables it), then NVRTC ----
+std::string jit_cache_key(const std::string& src, bool fma);
+void jit_registry_put(const std::string& key, const std::string& cubin);
+std::shared_ptr<const std::string> jit_registry_get(const std::string& key);
+// Source -> cubin.  Host-only work (no CUDA context): safe on a background thread.  *origin: 0 = this process' registry,
+// 1 = disk cache, 2 = compiled now.  fma = true compiles with --fmad=true (the 1e-12 mode; never bit-exact).
+std::shared_ptr<const std::string> jit_compile(const std::string& src, bool fma, std::string* why, std::string* key_out, int* origin);
+JitModule* jit_load(const std::string& cubin, const std::string& key, std::string* why);  // on the current device
+void* jit_function(JitModule* m, const std::string& name);
+const std::string& jit_module_key(const JitModule* m);
+
+// ---- whole-schedule on-chip kernel `hb_tree`: one launch per batch, per-row tables in shared memory ----
+struct TreePlan {
+  int R = 0;                   // evidence rows per CTA tile (even: a thread works on two adjacent rows)
+  int T = 256;                 // threads per CTA
+  int min_blocks = 1;          // CTAs per SM the kernel is bounded for
+  int n_levels = 0;            // dependency levels (one __syncthreads each)
+  std::vector<int> level;      // per program step: level of a per-row product step, -1 otherwise
+  std::vector<int64_t> off;    // per table: entry offset of a per-row table in the shared-memory arena, -1 otherwise
+  int64_t arena_entries = 0;   // per row, with reuse of dead tables from one level to the next
+  int64_t stage_pitch = 0;     // doubles per row of the output staging tile (0: results are written straight to HBM)
+  size_t smem_bytes = 0;
+  int64_t ops_mul = 0, ops_add = 0;  // fp64 multiplies / adds per row (what the reference does, no more)
+};
+// false (reason in *why) when the program does not qualify: maximisation steps, tables too large for shared memory, ...
+bool tree_plan(const Program& P, TreePlan& plan, std::string* why);
+std::string tree_source(const Program& P, const TreePlan& plan);
+// kernel parameters of hb_tree: (const double* pots, const double* shared, const int8* evidence, double* out,
+//                                long long n_rows, int* flag, int normalise)
+bool jit_launch_smem(void* fn, unsigned grid, unsigned block, unsigned smem_bytes, void** params, void* stream);
+bool jit_set_dynamic_smem(void* fn, int bytes);
+int jit_occupancy(void* fn, int block, size_t smem_bytes);  // resident CTAs per SM, 0 = unknown
 
 }  // namespace hb

@@ -107,6 +107,10 @@ int hb_jt_program_json(hb_jt* jt, int32_t n, const int32_t* vars, char** out_jso
 /* Inspection hook: the CUDA source of the kernels specialised per schedule step for this observed list (what the
  * library hands to NVRTC on the first large batch; csrc/jit.cpp).  Free with hb_string_free. */
 int hb_jt_jit_source(hb_jt* jt, int32_t n_observed, const int32_t* observed, char** out_source);
+/* Inspection hook: the CUDA source of the whole-schedule on-chip kernel `hb_tree` for this observed list (csrc/jit.cpp,
+ * SURVEY 2.2 K4): changeEvidence + collect + distribute + every posterior for a tile of rows in one launch, per-row
+ * tables in shared memory.  HB_E_UNSUPPORTED when the program does not qualify (tables too large for shared memory). */
+int hb_jt_tree_source(hb_jt* jt, int32_t n_observed, const int32_t* observed, char** out_source);
 /* Builds the specialised kernels of the program for this observed list NOW (upload + NVRTC compilation, seconds) instead
  * of inside the first large batch call, e.g. right after hb_jt_compile in a service.  *n_kernels (optional) = steps
  * covered; 0 when NVRTC is unavailable or HB_JIT=0 -- not an error, the precompiled kernels are used. */
@@ -114,6 +118,12 @@ int hb_jt_specialise(hb_jt* jt, int32_t n_observed, const int32_t* observed, int
 /* how many schedule steps of the last batch call's program run on a kernel specialised for them (0: none yet, NVRTC
  * unavailable, or HB_JIT=0) */
 int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n);
+/* What the last batch call's (or hb_jt_specialise's) program runs on: [0] 1 if the program qualifies for the on-chip kernel,
+ * [1] evidence rows per CTA tile, [2] threads per CTA, [3] dependency levels, [4] shared-memory arena entries per row,
+ * [5] shared-memory bytes per CTA, [6] fp64 multiplies per row, [7] fp64 adds per row, [8] 1 if the on-chip kernel is
+ * installed and used, [9] origin of the installed generated kernels: -1 none, 0 this process (incl. hb_jt_load),
+ * 1 the disk cache, 2 compiled by NVRTC now. */
+int hb_jt_kernel_info(const hb_jt* jt, int64_t* out10);
 /* changeEvidence (Bayes/FactorElimination/JTree.hs:454-466); list order is preserved */
 int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states);
 /* posterior jt q_vars (Bayes/FactorElimination.hs:314-327).  out_scope receives the variable order of the
