@@ -130,7 +130,13 @@ struct Gen {
   int n_loop = 0;
   int scope = 0;
   std::vector<std::string> ptr;
+  // V = evidence rows per thread: 2 (adjacent rows, one 16-byte access per row table) or 1.  no_block: one output entry
+  // per item instead of a group of all states of the blocking variable (finer items for the narrow steps of hb_tree).
+  int V = 2;
+  bool no_block = false;
   Gen(const Program& p, const Step& s) : P(p), st(s) {}
+  const char* DV() const { return V == 2 ? "double2" : "double"; }
+  const char* zero() const { return V == 2 ? "zero" : "0.0"; }
 
   std::string load(const In& x, int64_t off) {
     auto key = std::make_pair(x.id, off);
@@ -139,24 +145,32 @@ struct Gen {
     std::string name = "x" + std::to_string(x.id) + "_" + std::to_string(off) + (scope ? "_" + std::to_string(scope) : "");
     const Table& t = *x.t;
     const std::string& q = ptr[x.id];
-    if (t.kind == T_ROW)
+    const char* ld = tree_off ? "*(" : "__ldg(";  // in hb_tree the potentials are staged in shared memory
+    if (V == 1) {
+      if (t.kind == T_ROW)
+        o << "    const double " << name << " = " << q << "[(size_t)" << off << " * RT];\n";
+      else if (t.kind == T_POT && t.slice_slot >= 0)
+        o << "    const double " << name << " = " << q << "a[" << off << "];\n";
+      else
+        o << "    const double " << name << " = " << ld << q << " + " << off << ");\n";
+    } else if (t.kind == T_ROW)
       o << "    const double2 " << name << " = *reinterpret_cast<const double2*>(" << q << " + (size_t)" << off << " * RT);\n";
     else if (t.kind == T_POT && t.slice_slot >= 0)
       o << "    const double2 " << name << " = make_double2(" << q << "a[" << off << "], " << q << "b[" << off << "]);\n";
     else
-      o << "    const double " << name << "s = __ldg(" << q << " + " << off << "); const double2 " << name << " = make_double2(" << name << "s, "
+      o << "    const double " << name << "s = " << ld << q << " + " << off << "); const double2 " << name << " = make_double2(" << name << "s, "
         << name << "s);\n";
     loaded[key] = name;
     return name;
   }
   std::string mul(const std::string& a, const std::string& b) {
     std::string n = "m" + std::to_string(++tmp);
-    o << "    const double2 " << n << " = make_double2(__dmul_rn(" << a << ".x, " << b << ".x), __dmul_rn(" << a << ".y, " << b << ".y));\n";
+    o << "    const " << DV() << " " << n << " = hb_mul(" << a << ", " << b << ");\n";
     return n;
   }
   std::string add(const std::string& a, const std::string& b) {
     std::string n = "s" + std::to_string(++tmp);
-    o << "    const double2 " << n << " = make_double2(__dadd_rn(" << a << ".x, " << b << ".x), __dadd_rn(" << a << ".y, " << b << ".y));\n";
+    o << "    const " << DV() << " " << n << " = hb_add(" << a << ", " << b << ");\n";
     return n;
   }
   // chain of the inputs of level li for entry u (offsets of the unrolled levels from `bound`), times the inner value
@@ -165,7 +179,7 @@ struct Gen {
     for (size_t k = ins.size(); k-- > 0;) {
       const In& x = ins[k];
       if (x.level != (int)li) continue;
-      int64_t off = (int64_t)u * x.in->wstride;
+      int64_t off = no_block ? 0 : (int64_t)u * x.in->wstride;
       for (size_t m = (size_t)n_loop; m <= li; ++m) off += (int64_t)bound[m] * x.in->lstride[m];  // looped levels live in the pointer
       const std::string v = load(x, off);
       chain = chain.empty() ? v : mul(v, chain);
@@ -181,7 +195,7 @@ struct Gen {
     if ((int)li < n_loop) {  // run-time loop over the states of this level's summed variable
       for (int u = 0; u < U; ++u) {
         acc[u] = "a" + std::to_string(li) + "_" + std::to_string(u);
-        o << "    double2 " << acc[u] << " = zero;\n";
+        o << "    " << DV() << " " << acc[u] << " = " << zero() << ";\n";
       }
       o << "    for (unsigned k" << li << " = 0; k" << li << " < " << lv.d << "u; ++k" << li << ") {\n";
       const auto saved_loaded = loaded;
@@ -195,10 +209,10 @@ struct Gen {
         const std::string step = "k" + std::to_string(li) + " * " + std::to_string(x.in->lstride[li]) + "u";
         if (t.kind == T_ROW)
           o << "    const double* const " << q << " = " << ptr[x.id] << " + (size_t)(" << step << ") * RT;\n";
-        else if (t.kind == T_POT && t.slice_slot >= 0)
-          o << "    const double* const " << q << "a = " << ptr[x.id] << "a + (" << step << ");\n"
-            << "    const double* const " << q << "b = " << ptr[x.id] << "b + (" << step << ");\n";
-        else
+        else if (t.kind == T_POT && t.slice_slot >= 0) {
+          o << "    const double* const " << q << "a = " << ptr[x.id] << "a + (" << step << ");\n";
+          if (V == 2) o << "    const double* const " << q << "b = " << ptr[x.id] << "b + (" << step << ");\n";
+        } else
           o << "    const double* const " << q << " = " << ptr[x.id] << " + (" << step << ");\n";
         ptr[x.id] = q;
       }
@@ -206,7 +220,7 @@ struct Gen {
       if (li + 1 < st.levels.size()) inner = level(li + 1, bound);
       for (int u = 0; u < U; ++u) {
         const std::string c = term(li, u, bound, inner);
-        o << "    " << acc[u] << " = make_double2(__dadd_rn(" << acc[u] << ".x, " << c << ".x), __dadd_rn(" << acc[u] << ".y, " << c << ".y));\n";
+        o << "    " << acc[u] << " = hb_add(" << acc[u] << ", " << c << ");\n";
       }
       o << "    }\n";
       loaded = saved_loaded;
@@ -220,7 +234,7 @@ struct Gen {
       if (li + 1 < st.levels.size()) inner = level(li + 1, bound);
       for (int u = 0; u < U; ++u) {
         const std::string chain = term(li, u, bound, inner);
-        acc[u] = acc[u].empty() ? add("zero", chain) : add(acc[u], chain);
+        acc[u] = acc[u].empty() ? add(zero(), chain) : add(acc[u], chain);
       }
     }
     return acc;
@@ -246,6 +260,10 @@ struct Gen {
     red.clear();
     for (int v : out.pscope)
       if (v != st.w_var) red.push_back(v);
+    if (no_block) {  // the stored layout is row-major over `red`, then w fastest: entry index = digits over red ++ [w]
+      if (st.w_var >= 0) red.push_back(st.w_var);
+      U = 1;
+    }
   }
 
   // row pointers that do not depend on the group (needs `row`, `arena`, `arena_out`, `pots`, `shared`, `rowoff`, `RT` in scope)
@@ -255,10 +273,10 @@ struct Gen {
       const Table& t = *x.t;
       if (t.kind == T_ROW)
         o << ind << "const double* const b" << x.id << " = arena + (size_t)" << row_off(t) << " * RT + row;\n";
-      else if (t.kind == T_POT && t.slice_slot >= 0)
-        o << ind << "const double* const b" << x.id << "a = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row];\n"
-          << ind << "const double* const b" << x.id << "b = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row + 1];\n";
-      else
+      else if (t.kind == T_POT && t.slice_slot >= 0) {
+        o << ind << "const double* const b" << x.id << "a = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row];\n";
+        if (V == 2) o << ind << "const double* const b" << x.id << "b = pots + " << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row + 1];\n";
+      } else
         o << ind << "const double* const b" << x.id << " = " << (t.kind == T_POT ? "pots" : "shared") << " + " << t.off << ";\n";
     }
     // structural scalars of level 0: ps = s1 * (s2 * ...), applied as ps * chain (PrivateCPT.hs:225-227)
@@ -266,19 +284,26 @@ struct Gen {
     for (size_t k = st.scalars.size(); k-- > 0;) {
       const Table& t = P.tables[st.scalars[k]];
       const std::string n = "sc" + std::to_string(k);
-      if (t.kind == T_ROW)
+      const char* pool = t.kind == T_POT ? "pots" : "shared";
+      if (V == 1) {
+        if (t.kind == T_ROW)
+          o << ind << "const double " << n << " = arena[(size_t)" << row_off(t) << " * RT + row];\n";
+        else if (t.kind == T_POT && t.slice_slot >= 0)
+          o << ind << "const double " << n << " = pots[" << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row]];\n";
+        else
+          o << ind << "const double " << n << " = " << pool << "[" << t.off << "];\n";
+      } else if (t.kind == T_ROW)
         o << ind << "const double2 " << n << " = *reinterpret_cast<const double2*>(arena + (size_t)" << row_off(t) << " * RT + row);\n";
       else if (t.kind == T_POT && t.slice_slot >= 0)
         o << ind << "const double2 " << n << " = make_double2(pots[" << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row]], pots[" << t.off
           << " + rowoff[(size_t)" << t.slice_slot << " * RT + row + 1]]);\n";
       else
-        o << ind << "const double2 " << n << " = make_double2(" << (t.kind == T_POT ? "pots" : "shared") << "[" << t.off << "], "
-          << (t.kind == T_POT ? "pots" : "shared") << "[" << t.off << "]);\n";
+        o << ind << "const double2 " << n << " = make_double2(" << pool << "[" << t.off << "], " << pool << "[" << t.off << "]);\n";
       if (ps.empty())
         ps = n;
       else {
         const std::string m = "scp" + std::to_string(k);
-        o << ind << "const double2 " << m << " = make_double2(__dmul_rn(" << n << ".x, " << ps << ".x), __dmul_rn(" << n << ".y, " << ps << ".y));\n";
+        o << ind << "const " << DV() << " " << m << " = hb_mul(" << n << ", " << ps << ");\n";
         ps = m;
       }
     }
@@ -305,10 +330,10 @@ struct Gen {
       const Table& t = *x.t;
       if (t.kind == T_ROW)
         o << "    const double* const p" << x.id << " = b" << x.id << " + (size_t)(" << base << ") * RT;\n";
-      else if (t.kind == T_POT && t.slice_slot >= 0)
-        o << "    const double* const p" << x.id << "a = b" << x.id << "a + (" << base << ");\n"
-          << "    const double* const p" << x.id << "b = b" << x.id << "b + (" << base << ");\n";
-      else
+      else if (t.kind == T_POT && t.slice_slot >= 0) {
+        o << "    const double* const p" << x.id << "a = b" << x.id << "a + (" << base << ");\n";
+        if (V == 2) o << "    const double* const p" << x.id << "b = b" << x.id << "b + (" << base << ");\n";
+      } else
         o << "    const double* const p" << x.id << " = b" << x.id << " + (" << base << ");\n";
     }
     std::vector<int> bound(st.levels.size(), 0);
@@ -316,8 +341,10 @@ struct Gen {
     for (int u = 0; u < U; ++u) {
       if (streaming_store)
         o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT), " << res[u] << ");\n";
-      else
+      else if (V == 2)
         o << "    *reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT) = " << res[u] << ";\n";
+      else
+        o << "    outp[(size_t)(g * " << U << "u + " << u << "u) * RT] = " << res[u] << ";\n";
     }
   }
 
@@ -341,12 +368,24 @@ struct Gen {
 
   // The same step inside the on-chip kernel: its (group, row pair) items are dealt to the threads of the CTA, thread
   // `rot` first, so that the small steps of one dependency level land on different warps.
+  // items the step is cut into for a tile of R rows and T threads: groups of all states of the blocking variable x row
+  // pairs when that already feeds every thread, else single output entries, else single entries x single rows
+  static void tree_mode(const Step& st, int R, int T, int* V, bool* no_block, int64_t* items) {
+    *V = 2, *no_block = false, *items = st.n_red * (R / 2);
+    if (*items >= T) return;
+    *no_block = true, *items = st.n_out * (R / 2);
+    if (*items >= T) return;
+    *V = 1, *items = st.n_out * R;
+  }
   void tree_step(int si, int R, int T, int rot) {
+    int64_t items = 0;
+    tree_mode(st, R, T, &V, &no_block, &items);
     prepare();
-    const int64_t rp = R / 2, items = st.n_red * rp;
-    o << "    {  // step " << si << ": " << st.n_red << " groups of " << U << " x " << rp << " row pairs\n";
+    const int64_t rows = V == 2 ? R / 2 : R;
+    o << "    {  // step " << si << ": " << items / rows << (no_block ? " entries" : " groups of " + std::to_string(U)) << " x " << rows
+      << (V == 2 ? " row pairs\n" : " rows\n");
     o << "    for (unsigned it = (tid + " << (T - rot % T) % T << "u) % " << T << "u; it < " << items << "u; it += " << T << "u) {\n";
-    o << "    const unsigned g = it / " << rp << "u, row = (it % " << rp << "u) * 2u;\n";
+    o << "    const unsigned g = it / " << rows << "u, row = (it % " << rows << "u)" << (V == 2 ? " * 2u" : "") << ";\n";
     emit_bases("    ");
     emit_group(false);
     o << "    }\n    }\n";
@@ -416,8 +455,21 @@ struct JitModule {
   }
 };
 
+// arithmetic of the generated kernels: explicit round-to-nearest multiply / add, never contracted (the 1e-12 mode
+// compiles the same source with --fmad=true and HB_FMA defined: plain operators, contraction allowed)
+static const char* const kPreamble =
+    "#ifdef HB_FMA\n"
+    "__device__ __forceinline__ double hb_mul(double a, double b) { return a * b; }\n"
+    "__device__ __forceinline__ double hb_add(double a, double b) { return a + b; }\n"
+    "#else\n"
+    "__device__ __forceinline__ double hb_mul(double a, double b) { return __dmul_rn(a, b); }\n"
+    "__device__ __forceinline__ double hb_add(double a, double b) { return __dadd_rn(a, b); }\n"
+    "#endif\n"
+    "__device__ __forceinline__ double2 hb_mul(double2 a, double2 b) { return make_double2(hb_mul(a.x, b.x), hb_mul(a.y, b.y)); }\n"
+    "__device__ __forceinline__ double2 hb_add(double2 a, double2 b) { return make_double2(hb_add(a.x, b.x), hb_add(a.y, b.y)); }\n\n";
+
 std::string jit_source(const Program& P, const std::vector<int>& steps) {
-  std::string src;
+  std::string src = kPreamble;
   for (int si : steps) {
     Gen g(P, P.steps[si]);
     src += g.kernel("hb_step_" + std::to_string(si));
@@ -432,7 +484,7 @@ std::string jit_source(const Program& P, const std::vector<int>& steps) {
 namespace {
 
 const char* const kNvrtcOptions[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-default-device", "--std=c++17", "--generate-line-info"};
-const char* const kNvrtcOptionsFma[] = {"--gpu-architecture=sm_100a", "--fmad=true", "-default-device", "--std=c++17", "--generate-line-info"};
+const char* const kNvrtcOptionsFma[] = {"--gpu-architecture=sm_100a", "--fmad=true", "-default-device", "--std=c++17", "--generate-line-info", "-DHB_FMA"};
 
 std::mutex g_cubin_mutex;
 std::map<std::string, std::shared_ptr<const std::string>>& cubin_registry() {
@@ -472,7 +524,10 @@ std::string jit_cache_key(const std::string& src, bool fma) {
     }
   };
   feed(src.data(), src.size());
-  for (const char* o : (fma ? kNvrtcOptionsFma : kNvrtcOptions)) feed(o, strlen(o) + 1);
+  if (fma)
+    for (const char* o : kNvrtcOptionsFma) feed(o, strlen(o) + 1);
+  else
+    for (const char* o : kNvrtcOptions) feed(o, strlen(o) + 1);
   static const std::string ver = [] {
     int major = 0, minor = 0;
     void* h = open_first({"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"});
@@ -529,7 +584,7 @@ std::shared_ptr<const std::string> jit_compile(const std::string& src, bool fma,
   if (!rt.ok) return fail("libnvrtc not available");
   nvrtcProgram prog = nullptr;
   if (rt.CreateProgram(&prog, src.c_str(), "hbayes_steps.cu", 0, nullptr, nullptr) != 0) return fail("nvrtcCreateProgram failed");
-  const int rc = rt.CompileProgram(prog, 5, fma ? kNvrtcOptionsFma : kNvrtcOptions);
+  const int rc = fma ? rt.CompileProgram(prog, 6, kNvrtcOptionsFma) : rt.CompileProgram(prog, 5, kNvrtcOptions);
   if (rc != 0) {
     size_t n = 0;
     rt.GetProgramLogSize(prog, &n);
@@ -594,6 +649,7 @@ const std::string& jit_module_key(const JitModule* m) { return m->key; }
 // floating-point sequence of every entry is unchanged.
 namespace {
 constexpr int64_t TREE_SMEM_MAX = 227 * 1024;
+constexpr int64_t TREE_INVARIANT_MAX = 40 * 1024;  // potentials + shared tables staged in shared memory up to this size
 constexpr int64_t TREE_STAGE_MAX = 32 * 1024;  // output staging tile; wider results are written straight to HBM
 constexpr int64_t TREE_MAX_BODY = 60000;       // chain evaluations in the whole kernel (bounds the compilation time)
 
@@ -700,8 +756,11 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
     plan.arena_entries = std::max<int64_t>(plan.arena_entries, 1);
   }
   const int64_t NV = P.net->n(), NS = (int64_t)P.slices.size(), W = P.out_width;
+  // the batch-invariant tables (potential pool, shared arena) are copied to shared memory once per CTA when they are small
+  const int64_t inv_entries = P.pot_entries + P.shared_entries;
+  plan.invariant_entries = inv_entries * 8 <= TREE_INVARIANT_MAX ? inv_entries : 0;
   auto bytes = [&](int64_t R, bool staged) {
-    return plan.arena_entries * R * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV);
+    return plan.arena_entries * R * 8 + plan.invariant_entries * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV);
   };
   int R = 0;
   if (const char* env = getenv("HB_TREE_ROWS")) R = std::max(2, atoi(env) / 2 * 2);
@@ -720,12 +779,12 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   plan.R = R;
   plan.stage_pitch = staged ? (W | 1) : 0;
   plan.smem_bytes = (size_t)bytes(R, staged);
-  // threads: enough for the widest level, between 64 and 256
+  // threads: enough for the widest level (output entries x row pairs), between 64 and 256
   int64_t widest = 1;
   {
     std::vector<int64_t> items(plan.n_levels, 0);
     for (size_t si = 0; si < ns; ++si)
-      if (plan.level[si] >= 0) items[plan.level[si]] += P.steps[si].n_red * (R / 2);
+      if (plan.level[si] >= 0) items[plan.level[si]] += P.steps[si].n_out * (R / 2);
     for (int64_t x : items) widest = std::max(widest, x);
   }
   int T = 64;
@@ -756,6 +815,7 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   const int R = plan.R, T = plan.T;
   const int64_t NV = net.n(), NS = (int64_t)P.slices.size(), W = P.out_width, WP = plan.stage_pitch;
   std::ostringstream o;
+  o << kPreamble;
   auto table = [&](const char* type, const char* name, const std::vector<int64_t>& v) {
     o << "__constant__ " << type << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
     for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << v[i];
@@ -802,13 +862,21 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   table("int", "Q", q);
   table("int", "QOBS", qobs);
   table("unsigned", "QMAP", qmap);
-  const int64_t rowoff_at = plan.arena_entries * R * 8, stage_at = rowoff_at + round8(NS * R * 4), ev_at = stage_at + (WP ? R * WP * 8 : 0);
-  o << "extern \"C\" __global__ void __launch_bounds__(" << T << ", " << plan.min_blocks << ") hb_tree(const double* __restrict__ pots,\n"
-       "    const double* __restrict__ shared, const signed char* __restrict__ ev, double* __restrict__ out, long long n_rows,\n"
+  const int64_t inv_at = plan.arena_entries * R * 8, rowoff_at = inv_at + plan.invariant_entries * 8, stage_at = rowoff_at + round8(NS * R * 4),
+                ev_at = stage_at + (WP ? R * WP * 8 : 0);
+  o << "extern \"C\" __global__ void __launch_bounds__(" << T << ", " << plan.min_blocks << ") hb_tree(const double* __restrict__ g_pots,\n"
+       "    const double* __restrict__ g_shared, const signed char* __restrict__ ev, double* __restrict__ out, long long n_rows,\n"
        "    int* __restrict__ flag, int normalise) {\n";
   o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
   o << "  double* const sm = reinterpret_cast<double*>(smem_raw);\n";
   o << "  const double* const arena = sm;\n  double* const arena_out = sm;\n";
+  if (plan.invariant_entries > 0) {  // potentials and shared tables: HBM -> shared memory once per CTA (the CTA is persistent)
+    o << "  double* const inv = reinterpret_cast<double*>(smem_raw + " << inv_at << ");\n";
+    o << "  for (unsigned i = threadIdx.x; i < " << P.pot_entries << "u; i += " << T << "u) inv[i] = g_pots[i];\n";
+    o << "  for (unsigned i = threadIdx.x; i < " << P.shared_entries << "u; i += " << T << "u) inv[" << P.pot_entries << "u + i] = g_shared[i];\n";
+    o << "  const double* const pots = inv;\n  const double* const shared = inv + " << P.pot_entries << ";\n";
+  } else
+    o << "  const double* const pots = g_pots;\n  const double* const shared = g_shared;\n";
   o << "  int* const rowoff = reinterpret_cast<int*>(smem_raw + " << rowoff_at << ");\n";
   if (WP) o << "  double* const stage = reinterpret_cast<double*>(smem_raw + " << stage_at << ");\n";
   o << "  signed char* const evs = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n";
@@ -844,7 +912,11 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
       g.tree_off = &plan.off;
       g.tree_step((int)si, R, T, (int)(rot % T));
       o << g.o.str();
-      rot += P.steps[si].n_red * (R / 2);
+      int v = 2;
+      bool nb = false;
+      int64_t items = 0;
+      Gen::tree_mode(P.steps[si], R, T, &v, &nb, &items);
+      rot += items;
     }
     o << "    __syncthreads();\n";
   }
