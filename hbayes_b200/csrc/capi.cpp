@@ -67,6 +67,7 @@ struct Compiled {
   std::unique_ptr<Program> prog;
   Executor* ex = nullptr;
   bool stale = false;  // the network's CPT values changed after `ex` uploaded them (changeFactor)
+  uint64_t last_used = 0;  // Session::tick of the last call that ran it (executors are evicted least recently used first)
   ~Compiled() {
     if (ex) executor_destroy(ex);
   }
@@ -86,6 +87,13 @@ struct Session {
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool timing = false;
   Executor* last_ex = nullptr;  // executor of the last batch call (for hb_*_last_timing)
+  Executor* last_post_ex = nullptr;  // executor of the last hb_jt_posteriors_batch call (for hb_jt_normalise_batch)
+  uint64_t tick = 0, call_start = 0;  // executors used since call_start belong to the running API call: never evicted
+  bool fma = false;  // 1e-12 mode for the kernels generated from now on (hb_jt_set_precision)
+  // Device-resident programs kept alive per handle (each owns a row arena, index maps, graphs and generated kernels).
+  // Mixed observed sets (grouped batches, EM with missing data, mpe) create one per set: beyond this many, the least
+  // recently used executors are destroyed (their Programs stay compiled on the host).  HB_MAX_EXECUTORS overrides.
+  int max_executors = 16;
   // host-buffer batches are cut into chunks: the device->host copy of chunk i (copy_stream) overlaps the
   // kernels of chunk i+1 (stream)
   cudaStream_t copy_stream = nullptr;
@@ -122,9 +130,43 @@ struct Session {
     if (copy_stream) cudaStreamDestroy(copy_stream);
   }
   // the device-resident form of a compiled program, created on first use
+  void evict(Compiled* keep, size_t leave) {  // destroys least recently used executors until at most `leave` others remain
+    for (;;) {
+      size_t live = 0;
+      Compiled* lru = nullptr;
+      for (auto& kv : cache) {
+        Compiled* x = kv.second.get();
+        if (!x->ex || x == keep) continue;
+        ++live;
+        if (x->last_used > call_start) continue;  // in use by the running call
+        if (!lru || x->last_used < lru->last_used) lru = x;
+      }
+      if (live <= leave || !lru) return;
+      if (last_ex == lru->ex) last_ex = nullptr;
+      if (last_post_ex == lru->ex) last_post_ex = nullptr;
+      cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+      cudaDeviceSynchronize();
+      executor_destroy(lru->ex);
+      lru->ex = nullptr;
+    }
+  }
   Executor* executor(Compiled& c) {
     if (device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
-    if (!c.ex) c.ex = executor_create(*c.prog, device, workspace), c.stale = false;
+    c.last_used = ++tick;
+    if (!c.ex) {
+      if (const char* env = getenv("HB_MAX_EXECUTORS")) max_executors = std::max(1, atoi(env));
+      evict(&c, (size_t)max_executors - 1);
+      try {
+        c.ex = executor_create(*c.prog, device, workspace);
+      } catch (const Error& e) {
+        if (e.code != HB_E_OOM) throw;
+        cudaGetLastError();
+        evict(&c, 0);  // out of device memory: drop every other device-resident program of this handle and retry once
+        c.ex = executor_create(*c.prog, device, workspace);
+      }
+      executor_set_fma(c.ex, fma);
+      c.stale = false;
+    }
     if (c.stale) executor_refresh_potentials(c.ex), c.stale = false;
     executor_set_timing(c.ex, timing);
     last_ex = c.ex;
@@ -174,6 +216,7 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
   const int n_vars = s.net.n();
   if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
   cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+  s.call_start = s.tick;
   RunStats rs;
   if (flags & HB_DEVICE_PTRS) {
     std::vector<int8_t> first(n_vars);
@@ -306,6 +349,7 @@ struct hb_jt {
   }
   void run_one(Compiled& c, std::vector<double>& out) {
     if (!s.fixed.empty()) throw Error(HB_E_UNSUPPORTED, "the single-row calls are not available on a split handle: use the batch call");
+    s.call_start = s.tick;
     std::vector<int8_t> row(s.net.n(), -1);
     for (size_t i = 0; i < ev_vars.size(); ++i) row[ev_vars[i]] = (int8_t)ev_states[i];
     out.assign((size_t)c.prog->out_width, 0.0);
@@ -503,6 +547,13 @@ struct Writer {
 };
 struct Reader {
   FILE* f;
+  int64_t size = 0;  // of the file: no count may promise more data than the file still holds
+  explicit Reader(FILE* file) : f(file) {
+    const long at = ftell(f);
+    fseek(f, 0, SEEK_END);
+    size = ftell(f);
+    fseek(f, at, SEEK_SET);
+  }
   int64_t i64() {
     int64_t v;
     if (fread(&v, sizeof v, 1, f) != 1) throw Error(HB_E_IO, "truncated file");
@@ -510,7 +561,7 @@ struct Reader {
   }
   int64_t count(int64_t limit) {
     const int64_t n = i64();
-    if (n < 0 || n > limit) throw Error(HB_E_IO, "corrupt file");
+    if (n < 0 || n > limit || n > size - (int64_t)ftell(f)) throw Error(HB_E_IO, "corrupt file");
     return n;
   }
   std::vector<int> ints() {
@@ -525,6 +576,78 @@ struct Reader {
   }
 };
 }  // namespace
+
+// A loaded tree is used as raw indices by the schedule compiler: every id is range-checked and the structure must be the
+// one createJunctionTree would hand over (clusters sorted, factors covering every vertex once inside their cluster,
+// separators joining a parent and a child whose intersection they are, one root, no cycle).
+static void validate_tree(const Network& net, const Tree& t) {
+  auto bad = [](const char* what) { throw Error(HB_E_IO, std::string("corrupt file: ") + what); };
+  const int n = net.n(), nc = (int)t.clusters.size(), nsep = t.n_seps();
+  if (nc < 1 || nsep != nc - 1) bad("cluster / separator count");
+  if ((int)t.parent_sep.size() != nc || (int)t.children.size() != nc || (int)t.factors.size() != nc || (int)t.by_rank.size() != nc ||
+      (int)t.sep_child.size() != nsep || (int)t.sep_vars.size() != nsep || t.root < 0 || t.root >= nc)
+    bad("table sizes");
+  auto sorted_ids = [&](const std::vector<int>& v) {
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i] < 0 || v[i] >= n || (i && v[i] <= v[i - 1])) return false;
+    return true;
+  };
+  if ((int)t.elim_order.size() != n) bad("elimination order");
+  {
+    std::vector<char> seen(n, 0);
+    for (int v : t.elim_order) {
+      if (v < 0 || v >= n || seen[v]) bad("elimination order");
+      seen[v] = 1;
+    }
+  }
+  for (const auto& c : t.clusters)
+    if (c.empty() || !sorted_ids(c)) bad("cluster");
+  {
+    std::vector<char> seen(nc, 0);
+    for (int c : t.by_rank) {
+      if (c < 0 || c >= nc || seen[c]) bad("cluster rank");
+      seen[c] = 1;
+    }
+    for (int i = 1; i < nc; ++i)
+      if (!(t.clusters[t.by_rank[i - 1]] < t.clusters[t.by_rank[i]])) bad("cluster rank order");
+  }
+  auto subset = [](const std::vector<int>& a, const std::vector<int>& b) { return std::includes(b.begin(), b.end(), a.begin(), a.end()); };
+  std::vector<char> has_factor(n, 0);
+  for (int c = 0; c < nc; ++c)
+    for (int v : t.factors[c]) {
+      if (v < 0 || v >= n || has_factor[v]) bad("factor assignment");
+      has_factor[v] = 1;
+      std::vector<int> fam = net.scope[v];
+      std::sort(fam.begin(), fam.end());
+      if (!subset(fam, t.clusters[c])) bad("factor outside its cluster");
+    }
+  for (int v = 0; v < n; ++v)
+    if (!has_factor[v]) bad("vertex without a cluster");
+  if (t.parent_sep[t.root] != -1) bad("root");
+  std::vector<int> child_of(nsep, -1);
+  for (int c = 0; c < nc; ++c) {
+    const int ps = t.parent_sep[c];
+    if (c != t.root) {
+      if (ps < 1 || ps > nsep || t.sep_child[ps - 1] != c) bad("parent separator");
+    }
+    for (int sp : t.children[c]) {
+      if (sp < 1 || sp > nsep || t.sep_parent[sp - 1] != c || child_of[sp - 1] >= 0) bad("children list");
+      child_of[sp - 1] = c;
+    }
+  }
+  for (int sp = 0; sp < nsep; ++sp) {
+    const int a = t.sep_parent[sp], b = t.sep_child[sp];
+    if (a < 0 || a >= nc || b < 0 || b >= nc || a == b || child_of[sp] != a || t.parent_sep[b] != sp + 1) bad("separator ends");
+    if (!sorted_ids(t.sep_vars[sp]) || !subset(t.sep_vars[sp], t.clusters[a]) || !subset(t.sep_vars[sp], t.clusters[b])) bad("separator variables");
+  }
+  for (int c = 0; c < nc; ++c) {  // every cluster reaches the root: no cycle
+    int at = c, hops = 0;
+    while (at != t.root) {
+      at = t.sep_parent[t.parent_sep[at] - 1];
+      if (++hops > nc) bad("cycle in the tree");
+    }
+  }
+}
 
 int hb_jt_save(const hb_jt* jt, const char* path) {
   return guarded([&] {
@@ -567,7 +690,7 @@ int hb_jt_load(const char* path, const int32_t* devices, int32_t n_devices, hb_j
     std::unique_ptr<FILE, int (*)(FILE*)> guard(f, fclose);
     char magic[8];
     if (fread(magic, 1, 8, f) != 8 || memcmp(magic, JT_MAGIC, 8) != 0) throw Error(HB_E_IO, "not a libhbayes_cuda junction-tree file");
-    Reader r{f};
+    Reader r(f);
     auto jt = std::make_unique<hb_jt>();
     Network& net = jt->s.net;
     net.dims = r.ints();
@@ -578,7 +701,7 @@ int hb_jt_load(const char* path, const int32_t* devices, int32_t n_devices, hb_j
     net.proc_seed.assign(n, 0);
     for (int v = 0; v < n; ++v) {
       net.proc_seed[v] = (uint64_t)r.i64();
-      net.values[v].resize((size_t)r.count((int64_t)1 << 34));
+      net.values[v].resize((size_t)r.count(((int64_t)1 << 34) / 8));
       if (!net.values[v].empty() && fread(net.values[v].data(), sizeof(double), net.values[v].size(), f) != net.values[v].size())
         throw Error(HB_E_IO, "truncated file");
       std::string name((size_t)r.count(1 << 16), ' ');
@@ -615,6 +738,7 @@ int hb_jt_load(const char* path, const int32_t* devices, int32_t n_devices, hb_j
     if (t->parent_sep.size() != nc || t->children.size() != nc || t->factors.size() != nc || t->by_rank.size() != nc ||
         t->sep_child.size() != t->sep_parent.size() || t->sep_vars.size() != t->sep_parent.size() || t->root < 0 || (size_t)t->root >= nc)
       throw Error(HB_E_IO, "corrupt file");
+    validate_tree(net, *t);
     jt->tree = std::move(t);
     jt->s.device = pick_device(devices, n_devices);
     jt->post_off.assign(1, 0);
@@ -677,7 +801,10 @@ int hb_jt_posterior(hb_jt* jt, int32_t n_q, const int32_t* q_vars, int32_t* out_
     if (n_q == 1) {
       const int v = q_vars[0];
       if (v < 0 || v >= net.n()) throw Error(HB_E_ARG, "query on unknown vertex");
-      if (jt->posts_stale) jt->run_one(jt->program(jt->ev_vars, {}), jt->posts), jt->posts_stale = false;
+      if (jt->s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
+      if (!jt->s.fixed.empty()) throw Error(HB_E_UNSUPPORTED, "the single-row calls are not available on a split handle: use the batch call");
+      // a handle that was never calibrated (or whose CPTs changed) answers after a calibration under the current evidence
+      if (jt->posts_stale || (int64_t)jt->posts.size() != jt->post_off.back()) jt->run_one(jt->program(jt->ev_vars, {}), jt->posts), jt->posts_stale = false;
       if (out_len < net.dims[v]) throw Error(HB_E_ARG, "output buffer too small");
       for (int i = 0; i < net.dims[v]; ++i) out[i] = jt->posts[jt->post_off[v] + i];
       if (out_scope) out_scope[0] = v;
@@ -699,6 +826,7 @@ int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, do
   return guarded([&] {
     if (!jt) throw Error(HB_E_ARG, "null handle");
     run_matrix(jt->s, [&](const std::vector<int>& obs) -> Compiled& { return jt->program(obs, {}); }, n_rows, evidence, out, flags);
+    jt->s.last_post_ex = jt->s.last_ex;  // every program of this call has the all-posteriors layout
   });
 }
 int hb_jt_queries_batch(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t n_rows,
@@ -758,6 +886,7 @@ int hb_jt_em_step(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out
     if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
     if (!s.fixed.empty()) throw Error(HB_E_UNSUPPORTED, "hb_jt_em_step on a split handle");
     cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+    s.call_start = s.tick;
     const bool tracing = getenv("HB_EM_TRACE") != nullptr;  // host-side phase times on stderr (synchronises)
     auto t_last = std::chrono::steady_clock::now();
     auto trace = [&](const char* what) {
@@ -971,22 +1100,22 @@ int hb_jt_set_split(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* st
     jt->s.fixed.clear();
     for (int i = 0; i < n; ++i) jt->s.fixed.push_back({vars[i], states[i]});
     jt->s.cache.clear();
-    jt->s.last_ex = nullptr;
+    jt->s.last_ex = jt->s.last_post_ex = nullptr;
   });
 }
 int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags) {
   return guarded([&] {
     if (!jt || !out || n_rows < 0) throw Error(HB_E_ARG, "null argument");
     Session& s = jt->s;
-    if (!s.last_ex) throw Error(HB_E_ARG, "no batch has run on this handle yet");
+    if (!s.last_post_ex) throw Error(HB_E_ARG, "hb_jt_posteriors_batch has not run on this handle yet");
     const int64_t width = s.net.width();
     if (flags & HB_DEVICE_PTRS) {
-      executor_normalise(s.last_ex, n_rows, out, s.stream);
+      executor_normalise(s.last_post_ex, n_rows, out, s.stream);
       return;
     }
     s.reserve(0, (size_t)n_rows * width * sizeof(double));
     cuda_ok(cudaMemcpyAsync(s.d_out, out, (size_t)n_rows * width * sizeof(double), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy");
-    executor_normalise(s.last_ex, n_rows, s.d_out, s.stream);
+    executor_normalise(s.last_post_ex, n_rows, s.d_out, s.stream);
     cuda_ok(cudaMemcpyAsync(out, s.d_out, (size_t)n_rows * width * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy");
     cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
   });
@@ -1023,7 +1152,7 @@ int hb_jt_set_workspace(hb_jt* jt, int64_t bytes) {
   if (!jt || bytes < 0) return HB_E_ARG;
   jt->s.workspace = bytes;
   jt->s.cache.clear();
-  jt->s.last_ex = nullptr;
+  jt->s.last_ex = jt->s.last_post_ex = nullptr;
   return HB_OK;
 }
 int hb_jt_set_timing(hb_jt* jt, int32_t on) {
@@ -1137,6 +1266,7 @@ int hb_ve_mpe_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, int8_t* o
     const int64_t nr = (int64_t)ve->r.size();
     if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
     cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+    s.call_start = s.tick;
     if (flags & HB_DEVICE_PTRS) {
       std::vector<int8_t> first(n_vars);
       cuda_ok(cudaMemcpyAsync(first.data(), evidence, n_vars, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(first row)");
@@ -1196,6 +1326,7 @@ int hb_ve_mpe(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* states, 
     Session& s = ve->s;
     if (s.device < 0) throw Error(HB_E_CUDA, "handle was compiled with HB_STRUCTURE_ONLY: no device, and there is no CPU fallback");
     cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+    s.call_start = s.tick;
     Compiled& c = ve->program(std::vector<int>(vars, vars + n));  // the assignment in the caller's order
     std::vector<int8_t> row(s.net.n(), -1);
     for (int i = 0; i < n; ++i) row[vars[i]] = (int8_t)states[i];
@@ -1239,6 +1370,7 @@ int hb_ve_posterior(hb_ve* ve, int32_t n, const int32_t* vars, const int32_t* st
     Compiled& c = ve->program(std::vector<int>(vars, vars + n));
     if (out_len < c.prog->out_width) throw Error(HB_E_ARG, "output buffer too small");
     Session& s = ve->s;
+    s.call_start = s.tick;
     std::vector<int8_t> row(s.net.n(), -1);
     for (int i = 0; i < n; ++i) row[vars[i]] = (int8_t)states[i];
     s.reserve(row.size(), (size_t)c.prog->out_width * sizeof(double));
@@ -1278,7 +1410,7 @@ int hb_ve_set_workspace(hb_ve* ve, int64_t bytes) {
   if (!ve || bytes < 0) return HB_E_ARG;
   ve->s.workspace = bytes;
   ve->s.cache.clear();
-  ve->s.last_ex = nullptr;
+  ve->s.last_ex = ve->s.last_post_ex = nullptr;
   return HB_OK;
 }
 int hb_ve_set_timing(hb_ve* ve, int32_t on) {

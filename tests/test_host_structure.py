@@ -257,3 +257,91 @@ def test_specialised_step_kernels_source_compiles_for_sm_100a(tmp_path):
     r = subprocess.run([nvcc, "--fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-cubin", str(cu), "-o", str(tmp_path / "steps.cubin")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_uncalibrated_handles_fail_loudly():
+    """posterior [v] on a handle that was never calibrated (structure only) is an error, not a read out of bounds"""
+    net = hb.importBayesianGraph(os.path.join(G, "cancer.net"))
+    jt = hb.JunctionTree(net, device=None)
+    with pytest.raises(hb.HbError) as e:
+        jt.posterior([0])
+    assert e.value.code == _lib.HB_E_CUDA
+    with pytest.raises(hb.HbError) as e:
+        jt.posterior([0, 3])
+    assert e.value.code == _lib.HB_E_CUDA
+
+
+def test_corrupt_tree_files_are_rejected(tmp_path):
+    """every index of a loaded tree is range-checked -- a damaged file gives HB_E_IO, never a crash"""
+    import struct
+
+    net = hb.importBayesianGraph(os.path.join(G, "asia.net"))
+    jt = hb.JunctionTree(net, device=None)
+    good = tmp_path / "asia.hbjt"
+    jt.save(good)
+    data = good.read_bytes()
+    assert hb.JunctionTree.load(good, net, device=None).describe() == jt.describe()
+    # the tree section is the tail of the file: damage every 8-byte word of the last 1.5 KB in turn
+    start = max(8, len(data) - 1536) // 8 * 8
+    rejected = 0
+    for at in range(start, len(data) - 7, 8):
+        for value in (1 << 30, -7, 3):
+            if struct.unpack_from("<q", data, at)[0] == value:
+                continue
+            bad = bytearray(data)
+            struct.pack_into("<q", bad, at, value)
+            p = tmp_path / "bad.hbjt"
+            p.write_bytes(bytes(bad))
+            try:
+                t = hb.JunctionTree.load(p, net, device=None)
+                t.program([0])  # whatever still loads must be a usable tree
+            except hb.HbError as e:
+                assert e.code in (_lib.HB_E_IO, _lib.HB_E_ARG), e
+                rejected += 1
+    assert rejected > 100
+    for cut in (len(data) - 8, len(data) // 2, 20):
+        p = tmp_path / "short.hbjt"
+        p.write_bytes(data[:cut])
+        with pytest.raises(hb.HbError) as e:
+            hb.JunctionTree.load(p, net, device=None)
+        assert e.value.code == _lib.HB_E_IO
+
+
+def test_on_chip_kernel_source_compiles_for_sm_100a(tmp_path):
+    """csrc/jit.cpp hb_tree: one kernel for changeEvidence + collect + distribute + all posteriors, per-row
+    tables in shared memory.  Deterministic source, every per-row step present, and it compiles for sm_100a with the
+    shared-memory loads the design relies on (nvcc here; numerics are checked on the GPU, tests/test_gpu_onchip.py)."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    for name, pnet, observed in (("cancer", hb.importBayesianGraph(os.path.join(G, "cancer.net")), [0]),
+                                 ("rand", None, [1, 4])):
+        if pnet is None:
+            net = random_net(11, n=10, states=(2, 3), max_parents=3)
+            pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+        jt = hb.JunctionTree(pnet, device=None)
+        src = jt.tree_source(observed)
+        assert src == hb.JunctionTree(pnet, device=None).tree_source(observed)
+        prog = jt.program(observed)
+        row_steps = [i for i, s in enumerate(prog["physical"]) if s["kind"] == 0 and not s["shared"]]
+        assert [int(x.split(":")[0]) for x in src.split("// step ")[1:]] and \
+            sorted(int(x.split(":")[0]) for x in src.split("// step ")[1:]) == row_steps
+        assert "hb_tree" in src and "__syncthreads" in src and "__dmul_rn" in src and "__dadd_rn" in src
+        if not os.path.exists(nvcc):
+            continue
+        cu = tmp_path / (name + ".cu")
+        cu.write_text(src)
+        cubin = tmp_path / (name + ".cubin")
+        r = subprocess.run([nvcc, "--fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-cubin", str(cu), "-o", str(cubin)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        sass = subprocess.run(["cuobjdump", "-sass", str(cubin)], capture_output=True, text=True).stdout
+        # (the only DFMAs are the Newton steps of the correctly rounded 1.0 / norm)
+        assert "LDS" in sass and "DMUL" in sass and "DADD" in sass and sass.count("DFMA") < sass.count("DMUL")
+    # a program whose per-row tables cannot fit shared memory has no on-chip kernel: the call says so
+    net, observed = synth.config_c3()
+    cnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    with pytest.raises(hb.HbError) as e:
+        hb.JunctionTree(cnet, device=None).tree_source(observed)
+    assert e.value.code == _lib.HB_E_UNSUPPORTED
