@@ -49,6 +49,7 @@ SIGNATURES = {
     "hb_jt_jit_source": (C.c_int, [vp, i32, i32p, cpp]),
     "hb_jt_tree_source": (C.c_int, [vp, i32, i32p, cpp]),
     "hb_jt_kernel_info": (C.c_int, [vp, i64p]),
+    "hb_jt_tree_profile": (C.c_int, [vp, i64p]),
     "hb_jt_specialise": (C.c_int, [vp, i32, i32p, i32p]),
     "hb_jt_specialised_kernels": (C.c_int, [vp, i32p]),
     "hb_jt_change_factor": (C.c_int, [vp, i32, i32p, f64p, i32p]),

@@ -287,6 +287,12 @@ class JunctionTree(_Batched):
                 "fp64_mul_per_row", "fp64_add_per_row", "on_chip", "origin"]
         return dict(zip(keys, out.tolist()))
 
+    def tree_profile(self):
+        """SM cycles per phase of the on-chip kernel since the last call (HB_TREE_PROFILE=1): list of 64 counters"""
+        out = np.zeros(64, np.int64)
+        check(lib().hb_jt_tree_profile(self._h, out.ctypes.data_as(i64p)))
+        return out.tolist()
+
     def tree_source(self, observed: Iterable[int] = ()) -> str:
         """CUDA source of the whole-schedule on-chip kernel for this observed list (raises HbError when there is none)"""
         oa, op = _i32(list(observed))

@@ -1143,6 +1143,12 @@ int hb_jt_kernel_info(const hb_jt* jt, int64_t* out10) {
   out10[9] = executor_jit_origin(jt->s.last_ex);
   return HB_OK;
 }
+int hb_jt_tree_profile(hb_jt* jt, int64_t* out64) {
+  return guarded([&] {
+    if (!jt || !out64 || !jt->s.last_ex) throw Error(HB_E_ARG, "no batch has run on this handle yet");
+    executor_tree_profile(jt->s.last_ex, jt->s.stream, out64);
+  });
+}
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream) {
   if (!jt) return HB_E_ARG;
   jt->s.stream = (cudaStream_t)cuda_stream;

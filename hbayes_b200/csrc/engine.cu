@@ -1352,8 +1352,9 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
   ex->d_sl_begin = upload(sl_begin);
   ex->d_sl_var = upload(sl_var);
   ex->d_sl_stride = upload(sl_stride);
-  HB_CUDA(cudaMalloc(&ex->d_flag, sizeof(int)));
-  HB_CUDA(cudaMemset(ex->d_flag, 0, sizeof(int)));
+  // the error flag, followed (8 bytes in) by 64 cycle counters of the on-chip kernel's HB_TREE_PROFILE instrumentation
+  HB_CUDA(cudaMalloc(&ex->d_flag, 8 + 64 * sizeof(unsigned long long)));
+  HB_CUDA(cudaMemset(ex->d_flag, 0, 8 + 64 * sizeof(unsigned long long)));
   if (workspace_bytes <= 0) {
     size_t free_b = 0, total_b = 0;
     HB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -1683,6 +1684,12 @@ int executor_specialised_kernels(const Executor* ex) {
   return n;
 }
 bool executor_on_chip(const Executor* ex) { return ex->tree_fn != nullptr; }
+void executor_tree_profile(Executor* ex, void* stream, int64_t out64[64]) {
+  HB_CUDA(cudaSetDevice(ex->device));
+  HB_CUDA(cudaMemcpyAsync(out64, (const char*)ex->d_flag + 8, 64 * sizeof(int64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  HB_CUDA(cudaMemsetAsync((char*)ex->d_flag + 8, 0, 64 * sizeof(int64_t), (cudaStream_t)stream));
+  HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+}
 int executor_jit_origin(const Executor* ex) { return ex->jit_origin; }
 const char* executor_jit_key(const Executor* ex) { return ex->jit ? jit_module_key(ex->jit).c_str() : ""; }
 void executor_set_fma(Executor* ex, bool on) { ex->fma = on; }

@@ -48,6 +48,9 @@ int executor_specialise(Executor* ex);
 int executor_specialised_kernels(const Executor* ex);
 // true when the program runs on the whole-schedule on-chip kernel (one launch per batch, per-row tables in shared memory)
 bool executor_on_chip(const Executor* ex);
+// HB_TREE_PROFILE=1 (read when the kernel is generated): SM cycles per phase of the on-chip kernel since the last call,
+// summed over all tiles -- [0] evidence preparation, [1 + l] dependency level l, [1 + levels] normalise + write-out
+void executor_tree_profile(Executor* ex, void* stream, int64_t out64[64]);
 // where the installed generated kernels came from: -1 none, 0 this process' registry, 1 disk cache, 2 compiled now
 int executor_jit_origin(const Executor* ex);
 const char* executor_jit_key(const Executor* ex);  // cache key of the installed cubin ("" when none)

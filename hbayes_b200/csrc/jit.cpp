@@ -161,8 +161,10 @@ struct Gen {
       o << "    const double " << name << "s = " << ld << q << " + " << off << "); const double2 " << name << " = make_double2(" << name << "s, "
         << name << "s);\n";
     loaded[key] = name;
+    ++n_loads;
     return name;
   }
+  int64_t n_loads = 0;  // load instructions emitted so far (one per distinct address of a group body)
   std::string mul(const std::string& a, const std::string& b) {
     std::string n = "m" + std::to_string(++tmp);
     o << "    const " << DV() << " " << n << " = hb_mul(" << a << ", " << b << ");\n";
@@ -267,7 +269,7 @@ struct Gen {
   }
 
   // row pointers that do not depend on the group (needs `row`, `arena`, `arena_out`, `pots`, `shared`, `rowoff`, `RT` in scope)
-  void emit_bases(const char* ind) {
+  void emit_bases(const char* ind, bool with_outp = true) {
     const Table& out = P.tables[st.out];
     for (const In& x : ins) {
       const Table& t = *x.t;
@@ -308,12 +310,13 @@ struct Gen {
       }
     }
     scalar_product = ps;
-    o << ind << "double* const outp = arena_out + (size_t)" << row_off(out) << " * RT + row;\n";  // same arena: the output region is never read here
+    if (with_outp) o << ind << "double* const outp = arena_out + (size_t)" << row_off(out) << " * RT + row;\n";  // same arena: the output region is never read here
   }
   std::string scalar_product;  // name of ps, empty when the step has no structural scalars
 
   // the body of one group `g` of output entries: digits, per-input pointers, the unrolled nest, the stores
-  void emit_group(bool streaming_store) {
+  enum { STORE_STREAMING = 0, STORE_PLAIN = 1, STORE_RESULT = 2 };  // __stcs to HBM / plain store / res[u] = value
+  void emit_group(int store) {
     const Network& net = *P.net;
     loaded.clear();
     if (!red.empty()) o << "    unsigned rem = g;\n";
@@ -339,7 +342,9 @@ struct Gen {
     std::vector<int> bound(st.levels.size(), 0);
     const std::vector<std::string> res = level(0, bound);
     for (int u = 0; u < U; ++u) {
-      if (streaming_store)
+      if (store == STORE_RESULT)
+        o << "    res[" << u << "] = " << res[u] << ";\n";
+      else if (store == STORE_STREAMING)
         o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT), " << res[u] << ");\n";
       else if (V == 2)
         o << "    *reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT) = " << res[u] << ";\n";
@@ -361,7 +366,7 @@ struct Gen {
     o << "  const double2 zero = make_double2(0.0, 0.0);\n";
     emit_bases("  ");
     o << "  for (unsigned g = lane * per; g < g_end; ++g) {\n";
-    emit_group(true);
+    emit_group(STORE_STREAMING);
     o << "  }\n}\n\n";
     return o.str();
   }
@@ -377,18 +382,53 @@ struct Gen {
     if (*items >= T) return;
     *V = 1, *items = st.n_out * R;
   }
+  // The step as a device function of one item (inlined at its call sites) and the loop that deals the items to the
+  // threads.  A thread with several items evaluates `ni` of them together: the bodies are independent and no store
+  // separates them, so their shared-memory loads and fp64 chains overlap.
+  std::string call;  // filled by tree_step: the loop inside hb_tree
   void tree_step(int si, int R, int T, int rot) {
     int64_t items = 0;
     tree_mode(st, R, T, &V, &no_block, &items);
     prepare();
     const int64_t rows = V == 2 ? R / 2 : R;
-    o << "    {  // step " << si << ": " << items / rows << (no_block ? " entries" : " groups of " + std::to_string(U)) << " x " << rows
-      << (V == 2 ? " row pairs\n" : " rows\n");
-    o << "    for (unsigned it = (tid + " << (T - rot % T) % T << "u) % " << T << "u; it < " << items << "u; it += " << T << "u) {\n";
-    o << "    const unsigned g = it / " << rows << "u, row = (it % " << rows << "u)" << (V == 2 ? " * 2u" : "") << ";\n";
-    emit_bases("    ");
-    emit_group(false);
-    o << "    }\n    }\n";
+    const std::string fn = "hb_s" + std::to_string(si);
+    o << "__device__ __forceinline__ void " << fn << "(const double* __restrict__ arena, const double* __restrict__ pots,\n"
+         "    const double* __restrict__ shared, const int* __restrict__ rowoff, const unsigned g, const unsigned row, " << DV() << "* __restrict__ res) {\n";
+    o << "    constexpr unsigned RT = " << R << "u;\n";
+    if (V == 2) o << "    const double2 zero = make_double2(0.0, 0.0);\n";
+    emit_bases("    ", false);
+    emit_group(STORE_RESULT);
+    o << "}\n\n";
+    int ni = 1;
+    static const int max_ni = getenv("HB_TREE_INTERLEAVE") ? std::max(1, std::min(4, atoi(getenv("HB_TREE_INTERLEAVE")))) : 2;
+    while (ni < max_ni && items >= (int64_t)2 * ni * T && n_loads * 2 * ni <= 96) ni *= 2;
+    std::ostringstream c;
+    c << "    {  // step " << si << ": " << items / rows << (no_block ? " entries" : " groups of " + std::to_string(U)) << " x " << rows
+      << (V == 2 ? " row pairs" : " rows") << (ni > 1 ? ", " + std::to_string(ni) + " items at a time\n" : "\n");
+    c << "    double* const outb = arena_out + " << row_off(P.tables[st.out]) * R << "u;\n";
+    c << "    for (unsigned it = (tid + " << (T - rot % T) % T << "u) % " << T << "u; it < " << items << "u; it += " << ni * T << "u) {\n";
+    for (int k = 0; k < ni; ++k) {
+      if (k == 0)
+        c << "      const unsigned it0 = it;\n";
+      else
+        c << "      const bool has" << k << " = it + " << k * T << "u < " << items << "u;\n      const unsigned it" << k << " = has" << k << " ? it + " << k * T << "u : it;\n";
+      c << "      const unsigned g" << k << " = it" << k << " / " << rows << "u, row" << k << " = (it" << k << " % " << rows << "u)" << (V == 2 ? " * 2u" : "") << ";\n";
+      c << "      " << DV() << " r" << k << "[" << U << "];\n";
+      c << "      " << fn << "(arena, pots, shared, rowoff, g" << k << ", row" << k << ", r" << k << ");\n";
+    }
+    for (int k = 0; k < ni; ++k) {
+      if (k > 0) c << "      if (has" << k << ") {\n";
+      for (int u = 0; u < U; ++u) {
+        const std::string at = "outb + (g" + std::to_string(k) + " * " + std::to_string(U) + "u + " + std::to_string(u) + "u) * RT + row" + std::to_string(k);
+        if (V == 2)
+          c << "      *reinterpret_cast<double2*>(" << at << ") = r" << k << "[" << u << "];\n";
+        else
+          c << "      *(" << at << ") = r" << k << "[" << u << "];\n";
+      }
+      if (k > 0) c << "      }\n";
+    }
+    c << "    }\n    }\n";
+    call = c.str();
   }
 };
 
@@ -862,6 +902,8 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   table("int", "Q", q);
   table("int", "QOBS", qobs);
   table("unsigned", "QMAP", qmap);
+  std::ostringstream fns;  // one device function per step, defined before the kernel
+  o << "@@STEP_FUNCTIONS@@";
   const int64_t inv_at = plan.arena_entries * R * 8, rowoff_at = inv_at + plan.invariant_entries * 8, stage_at = rowoff_at + round8(NS * R * 4),
                 ev_at = stage_at + (WP ? R * WP * 8 : 0);
   o << "extern \"C\" __global__ void __launch_bounds__(" << T << ", " << plan.min_blocks << ") hb_tree(const double* __restrict__ g_pots,\n"
@@ -885,6 +927,7 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   o << "  const double2 zero = make_double2(0.0, 0.0);\n";
   o << "  for (long long tile = blockIdx.x; tile * " << R << " < n_rows; tile += gridDim.x) {\n";
   o << "    const long long row0 = tile * " << R << ";\n";
+  if (getenv("HB_TREE_PROFILE") && atoi(getenv("HB_TREE_PROFILE")) != 0) o << "    long long t0 = clock64();\n";
   o << "    const int nr = (int)(n_rows - row0 < " << R << " ? n_rows - row0 : " << R << ");\n";
   // evidence tile -> shared memory (pad rows of the last tile: unobserved everywhere, slice 0, results never written)
   o << "    for (unsigned i = tid; i < " << R * NV << "u; i += " << T << "u) evs[i] = i < (unsigned)nr * " << NV << "u ? ev[row0 * " << NV << " + i] : (signed char)-1;\n";
@@ -903,6 +946,13 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
          "        off += SL_STRIDE[t] * s;\n      }\n"
          "      rowoff[i] = off;\n    }\n";
   o << "    __syncthreads();\n";
+  int64_t stat_loads = 0, stat_items = 0;  // shared-memory loads per evidence row; work items per tile
+  static const bool profile = getenv("HB_TREE_PROFILE") && atoi(getenv("HB_TREE_PROFILE")) != 0;
+  auto lap = [&](int slot) {  // HB_TREE_PROFILE=1: cycles per phase, summed over the CTAs' tiles, behind the error flag
+    if (profile) o << "    if (tid == 0) { const long long t1 = clock64(); atomicAdd(reinterpret_cast<unsigned long long*>(flag + 2) + " << slot
+                   << ", (unsigned long long)(t1 - t0)); t0 = t1; }\n";
+  };
+  lap(0);
   for (int lv = 0; lv < plan.n_levels; ++lv) {
     o << "    // ---- dependency level " << lv << " ----\n";
     int64_t rot = 0;
@@ -911,14 +961,18 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
       Gen g(P, P.steps[si]);
       g.tree_off = &plan.off;
       g.tree_step((int)si, R, T, (int)(rot % T));
-      o << g.o.str();
+      fns << g.o.str();
+      o << g.call;
       int v = 2;
       bool nb = false;
       int64_t items = 0;
       Gen::tree_mode(P.steps[si], R, T, &v, &nb, &items);
       rot += items;
+      stat_loads += g.n_loads * (items / (v == 2 ? R / 2 : R));
+      stat_items += items;
     }
     o << "    __syncthreads();\n";
+    lap(1 + lv);
   }
   // factorNorm + factorDivide + expansion to the query scope (the output_kernel of engine.cu, reading shared memory)
   o << "    for (unsigned i = tid; i < " << (int64_t)nq * R << "u; i += " << T << "u) {\n"
@@ -950,8 +1004,14 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
     o << "    for (unsigned i = tid; i < (unsigned)nr * " << W << "u; i += " << T << "u) out[row0 * " << W << "ll + i] = stage[(i / " << W << "u) * " << WP << "u + i % " << W
       << "u];\n";
   }
+  lap(1 + plan.n_levels);
   o << "  }\n}\n";
-  return o.str();
+  o << "// per evidence row: " << stat_loads << " table loads, " << plan.ops_mul << " fp64 multiplies, " << plan.ops_add << " fp64 adds; " << stat_items
+    << " work items per tile of " << R << " rows\n";
+  std::string src = o.str();
+  const size_t at = src.find("@@STEP_FUNCTIONS@@");
+  src.replace(at, strlen("@@STEP_FUNCTIONS@@"), fns.str());
+  return src;
 }
 
 void jit_destroy(JitModule* m) { delete m; }

@@ -124,6 +124,10 @@ int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n);
  * installed and used, [9] origin of the installed generated kernels: -1 none, 0 this process (incl. hb_jt_load),
  * 1 the disk cache, 2 compiled by NVRTC now. */
 int hb_jt_kernel_info(const hb_jt* jt, int64_t* out10);
+/* Tuning hook (HB_TREE_PROFILE=1 in the environment when the on-chip kernel is generated): SM cycles per phase of the
+ * on-chip kernel since the previous call, summed over all tiles: out64[0] evidence preparation, out64[1 + l] dependency
+ * level l, out64[1 + levels] normalise + write-out; zeros when the instrumentation is off. */
+int hb_jt_tree_profile(hb_jt* jt, int64_t* out64);
 /* changeEvidence (Bayes/FactorElimination/JTree.hs:454-466); list order is preserved */
 int hb_jt_set_evidence(hb_jt* jt, int32_t n, const int32_t* vars, const int32_t* states);
 /* posterior jt q_vars (Bayes/FactorElimination.hs:314-327).  out_scope receives the variable order of the

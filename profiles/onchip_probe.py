@@ -47,3 +47,11 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print(json.dumps({"rows": rows, "ms_per_pass": ms, "Mq_per_s": rows / ms / 1e3, "info": jt.kernel_info(), "stats": jt.last_stats()}))
+if os.environ.get("HB_TREE_PROFILE"):
+    jt.tree_profile()
+    jt.posteriors_batch(d_ev, d_out)
+    torch.cuda.synchronize()
+    prof = jt.tree_profile()
+    n = jt.kernel_info()["levels"] + 2
+    tot = float(sum(prof[:n])) or 1.0
+    print("phase cycles %:", " ".join("%.1f" % (100.0 * x / tot) for x in prof[:n]), "| cycles per tile:", tot / jt.last_stats()["tiles"])
