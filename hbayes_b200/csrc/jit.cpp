@@ -376,10 +376,12 @@ struct Gen {
   // items the step is cut into for a tile of R rows and T threads: groups of all states of the blocking variable x row
   // pairs when that already feeds every thread, else single output entries, else single entries x single rows
   static void tree_mode(const Step& st, int R, int T, int* V, bool* no_block, int64_t* items) {
+    static const double grain = getenv("HB_TREE_GRAIN") ? atof(getenv("HB_TREE_GRAIN")) : 1.0;  // tuning: items wanted per thread
+    const double want = grain * T;
     *V = 2, *no_block = false, *items = st.n_red * (R / 2);
-    if (*items >= T) return;
+    if (*items >= want) return;
     *no_block = true, *items = st.n_out * (R / 2);
-    if (*items >= T) return;
+    if (*items >= want) return;
     *V = 1, *items = st.n_out * R;
   }
   // The step as a device function of one item (inlined at its call sites) and the loop that deals the items to the
@@ -857,7 +859,7 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   std::ostringstream o;
   o << kPreamble;
   auto table = [&](const char* type, const char* name, const std::vector<int64_t>& v) {
-    o << "__constant__ " << type << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
+    o << "__device__ const " << type << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";  // read with divergent indices: L1, not the constant bank
     for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << v[i];
     if (v.empty()) o << "0";
     o << "};\n";
@@ -868,11 +870,14 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
     for (size_t j = 0; j < sl.vars.size(); ++j) sl_var.push_back(sl.vars[j]), sl_stride.push_back(sl.strides[j]);
     sl_begin.push_back((int64_t)sl_var.size());
   }
-  table("signed char", "OBS", obs);
-  table("signed char", "DIMS", dims);
-  table("int", "SL_BEGIN", sl_begin);
-  table("short", "SL_VAR", sl_var);
-  table("int", "SL_STRIDE", sl_stride);
+  {  // valid states of every variable in a row of this program: unobserved -> must be negative, observed -> 0..dim-1,
+     // fixed (split clique) -> exactly that state
+    std::vector<int64_t> chk;
+    for (int v = 0; v < NV; ++v) chk.push_back(obs[v] == 0 ? -128 : obs[v] == 1 ? 0 : obs[v] - 2);
+    for (int v = 0; v < NV; ++v) chk.push_back(obs[v] == 0 ? -1 : obs[v] == 1 ? dims[v] - 1 : obs[v] - 2);
+    table("signed char", "CHK", chk);
+  }
+  o << "__device__ __forceinline__ int hb_state(int s, int dim) { return (unsigned)s < (unsigned)dim ? s : 0; }\n";
   // queries: Q = {kind (0 one, 1 potential pool, 2 shared arena, 3 per-row table), base, slice, n_phys, n_full, column,
   // map offset, order offset, n_obs}, then per observed query variable (var, stride, dim)
   std::vector<int64_t> q, qobs, qmap;
@@ -925,26 +930,43 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   o << "  constexpr unsigned RT = " << R << "u;\n";
   o << "  const unsigned tid = threadIdx.x;\n";
   o << "  const double2 zero = make_double2(0.0, 0.0);\n";
+  const int64_t ept = (R * NV + T - 1) / T;  // evidence bytes per thread and tile
+  for (int64_t k = 0; k < ept; ++k)
+    o << "  signed char pre" << k << " = (tid + " << k * T << "u < " << R * NV << "u && (long long)blockIdx.x * " << R * NV << "ll + tid + " << k * T << "u < n_rows * " << NV
+      << "ll) ? ev[(long long)blockIdx.x * " << R * NV << "ll + tid + " << k * T << "u] : (signed char)-1;\n";
   o << "  for (long long tile = blockIdx.x; tile * " << R << " < n_rows; tile += gridDim.x) {\n";
   o << "    const long long row0 = tile * " << R << ";\n";
   if (getenv("HB_TREE_PROFILE") && atoi(getenv("HB_TREE_PROFILE")) != 0) o << "    long long t0 = clock64();\n";
   o << "    const int nr = (int)(n_rows - row0 < " << R << " ? n_rows - row0 : " << R << ");\n";
-  // evidence tile -> shared memory (pad rows of the last tile: unobserved everywhere, slice 0, results never written)
-  o << "    for (unsigned i = tid; i < " << R * NV << "u; i += " << T << "u) evs[i] = i < (unsigned)nr * " << NV << "u ? ev[row0 * " << NV << " + i] : (signed char)-1;\n";
+  // Evidence of this tile -> shared memory.  It was loaded into registers while the previous tile was computed (the CTA is
+  // persistent), so its HBM latency is hidden.  Pad rows of the last tile: unobserved everywhere, slice 0, never written.
+  for (int64_t k = 0; k < ept; ++k)
+    o << "    if (tid + " << k * T << "u < " << R * NV << "u) evs[tid + " << k * T << "u] = pre" << k << ";\n";
   o << "    __syncthreads();\n";
+  o << "    {\n      const long long nt = (tile + gridDim.x) * " << R * NV << "ll;\n";
+  for (int64_t k = 0; k < ept; ++k)
+    o << "      pre" << k << " = (tid + " << k * T << "u < " << R * NV << "u && nt + tid + " << k * T << "u < n_rows * " << NV << "ll) ? ev[nt + tid + " << k * T
+      << "u] : (signed char)-1;\n";
+  o << "    }\n";
+  // consistency of every row with the compiled observed set: state in [CHK[v], CHK[NV + v]]
   o << "    for (unsigned i = tid; i < (unsigned)nr * " << NV << "u; i += " << T << "u) {\n"
-       "      const int s = evs[i], ob = OBS[i % " << NV << "u];\n"
-       "      const bool bad = ob == 0 ? (s >= 0) : (ob == 1 ? (s < 0 || s >= DIMS[i % " << NV << "u]) : (s != ob - 2));\n"
-       "      if (bad) atomicOr(flag, 1);\n    }\n";
-  if (NS > 0)
+       "      const int s = evs[i];\n"
+       "      if (s < CHK[i % " << NV << "u] || s > CHK[" << NV << "u + i % " << NV << "u]) atomicOr(flag, 1);\n    }\n";
+  if (NS > 0) {  // per-row entry offset of every sliced potential (factorFromInstantiation folded into the addressing)
     o << "    for (unsigned i = tid; i < " << NS * R << "u; i += " << T << "u) {\n"
          "      const unsigned j = i / " << R << "u, r = i % " << R << "u;\n"
+         "      const signed char* const e = evs + r * " << NV << "u;\n"
          "      int off = 0;\n"
-         "      for (int t = SL_BEGIN[j]; t < SL_BEGIN[j + 1]; ++t) {\n"
-         "        int s = evs[r * " << NV << "u + SL_VAR[t]];\n"
-         "        s = s < 0 ? 0 : (s >= DIMS[SL_VAR[t]] ? 0 : s);\n"
-         "        off += SL_STRIDE[t] * s;\n      }\n"
-         "      rowoff[i] = off;\n    }\n";
+         "      switch (j) {\n";
+    for (int64_t j = 0; j < NS; ++j) {
+      const Slice& sl = P.slices[(size_t)j];
+      o << "        case " << j << ": off = ";
+      for (size_t t = 0; t < sl.vars.size(); ++t)
+        o << (t ? " + " : "") << sl.strides[t] << " * hb_state(e[" << sl.vars[t] << "], " << net.dims[sl.vars[t]] << ")";
+      o << "; break;\n";
+    }
+    o << "      }\n      rowoff[i] = off;\n    }\n";
+  }
   o << "    __syncthreads();\n";
   int64_t stat_loads = 0, stat_items = 0;  // shared-memory loads per evidence row; work items per tile
   static const bool profile = getenv("HB_TREE_PROFILE") && atoi(getenv("HB_TREE_PROFILE")) != 0;
@@ -974,31 +996,93 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
     o << "    __syncthreads();\n";
     lap(1 + lv);
   }
-  // factorNorm + factorDivide + expansion to the query scope (the output_kernel of engine.cu, reading shared memory)
+  // factorNorm + factorDivide + expansion to the query scope (what output_kernel of engine.cu does, reading shared
+  // memory): thread = (query, row), specialised per query -- norm = 0 + x0 + x1 + ... over the layout order, every entry
+  // (1.0 / norm) * value, 0.0 where the entry contradicts the evidence.
   o << "    for (unsigned i = tid; i < " << (int64_t)nq * R << "u; i += " << T << "u) {\n"
        "      const unsigned r = i % " << R << "u, qi = i / " << R << "u;\n"
-       "      const int* const d = Q + qi * 9;\n"
-       "      const int kind = d[0], n_phys = d[3], n_full = d[4], n_obs = d[8];\n"
-       "      const double* gp = nullptr;\n"
-       "      if (kind == 1) gp = pots + d[1] + (d[2] >= 0 ? rowoff[d[2] * " << R << " + r] : 0);\n"
-       "      else if (kind == 2) gp = shared + d[1];\n"
-       "      const double* const sp = sm + (size_t)d[1] * RT + r;\n"
-       "      const unsigned* const order = QMAP + d[7];\n"
-       "      const unsigned* const fmap = QMAP + d[6];\n"
-       "      double norm = 0.0;\n"
-       "      for (int j = 0; j < n_phys; ++j) norm = __dadd_rn(norm, kind == 3 ? sp[(size_t)order[j] * RT] : (kind == 0 ? 1.0 : gp[order[j]]));\n"
-       "      const double inv = normalise ? __ddiv_rn(1.0, norm) : 1.0;\n"
-       "      int st[8];\n"
-       "      for (int j = 0; j < n_obs; ++j) st[j] = evs[r * " << NV << "u + QOBS[qi * 24 + j * 3]];\n";
+       "      const signed char* const e = evs + r * " << NV << "u;\n";
   if (WP)
-    o << "      double* const op = stage + r * " << WP << "u + d[5];\n";
+    o << "      double* const op = stage + r * " << WP << "u;\n";
   else
-    o << "      double* const op = out + (row0 + r) * " << W << "ll + d[5];\n      if ((int)r >= nr) continue;\n";
-  o << "      for (int f = 0; f < n_full; ++f) {\n"
-       "        bool match = true;\n"
-       "        for (int j = 0; j < n_obs; ++j) match &= ((f / QOBS[qi * 24 + j * 3 + 1]) % QOBS[qi * 24 + j * 3 + 2]) == st[j];\n"
-       "        const double v = match ? (kind == 3 ? sp[(size_t)fmap[f] * RT] : (kind == 0 ? 1.0 : gp[fmap[f]])) : 0.0;\n"
-       "        op[f] = __dmul_rn(inv, v);\n      }\n    }\n";
+    o << "      if ((int)r >= nr) continue;\n      double* const op = out + (row0 + r) * " << W << "ll;\n";
+  o << "      switch (qi) {\n";
+  {
+    int qi = 0;
+    bool any_generic = false;
+    for (const Step& st : P.steps) {
+      if (st.kind != STEP_OUTPUT) continue;
+      const int this_q = qi++;
+      if (st.n_full > 64) {
+        any_generic = true;
+        continue;
+      }
+      const Table& t = P.tables[st.result];
+      o << "        case " << this_q << ": {\n";
+      auto value = [&](int64_t k) -> std::string {  // stored entry k of the result
+        if (t.kind == T_ONE) return "1.0";
+        if (t.kind == T_ROW) return "sm[(size_t)" + std::to_string(plan.off[st.result] + k) + " * RT + r]";
+        if (t.kind == T_SHARED) return "shared[" + std::to_string(t.off + k) + "]";
+        return "gp[" + std::to_string(k) + "]";
+      };
+      if (t.kind == T_POT) {
+        o << "          const double* const gp = pots + " << t.off;
+        if (t.slice_slot >= 0) o << " + rowoff[" << t.slice_slot * R << "u + r]";
+        o << ";\n";
+      }
+      std::map<int64_t, std::string> have;
+      auto use = [&](int64_t k) {
+        auto it = have.find(k);
+        if (it != have.end()) return it->second;
+        const std::string n = "v" + std::to_string(k);
+        o << "          const double " << n << " = " << value(k) << ";\n";
+        return have[k] = n;
+      };
+      std::string norm = "0.0";
+      int n_terms = 0;
+      for (int64_t f = 0; f < st.n_full; ++f) {
+        bool first_state = true;
+        for (size_t j = 0; j < st.obs_var.size(); ++j) first_state &= ((f / st.obs_stride[j]) % st.obs_dim[j]) == 0;
+        if (!first_state) continue;
+        const std::string v = use(st.full_map[(size_t)f]);
+        const std::string n = "n" + std::to_string(n_terms++);
+        o << "          const double " << n << " = __dadd_rn(" << norm << ", " << v << ");\n";
+        norm = n;
+      }
+      o << "          const double inv = normalise ? __ddiv_rn(1.0, " << norm << ") : 1.0;\n";
+      for (int64_t f = 0; f < st.n_full; ++f) {
+        std::string match;
+        for (size_t j = 0; j < st.obs_var.size(); ++j)
+          match += (match.empty() ? "" : " && ") + ("e[" + std::to_string(st.obs_var[j]) + "] == " + std::to_string((f / st.obs_stride[j]) % st.obs_dim[j]));
+        const std::string v = use(st.full_map[(size_t)f]);
+        o << "          op[" << st.out_col + f << "] = __dmul_rn(inv, " << (match.empty() ? v : "(" + match + ") ? " + v + " : 0.0") << ");\n";
+      }
+      o << "        } break;\n";
+    }
+    if (any_generic) {  // very wide queries (joint family posteriors): descriptor-driven
+      o << "        default: {\n"
+           "          const int* const d = Q + qi * 9;\n"
+           "          const int kind = d[0], n_phys = d[3], n_full = d[4], n_obs = d[8];\n"
+           "          const double* gp = nullptr;\n"
+           "          if (kind == 1) gp = pots + d[1] + (d[2] >= 0 ? rowoff[d[2] * " << R << " + r] : 0);\n"
+           "          else if (kind == 2) gp = shared + d[1];\n"
+           "          const double* const sp = sm + (size_t)d[1] * RT + r;\n"
+           "          const unsigned* const order = QMAP + d[7];\n"
+           "          const unsigned* const fmap = QMAP + d[6];\n"
+           "          double norm = 0.0;\n"
+           "          for (int j = 0; j < n_phys; ++j) norm = __dadd_rn(norm, kind == 3 ? sp[(size_t)order[j] * RT] : (kind == 0 ? 1.0 : gp[order[j]]));\n"
+           "          const double inv = normalise ? __ddiv_rn(1.0, norm) : 1.0;\n"
+           "          int st[8];\n"
+           "          for (int j = 0; j < n_obs; ++j) st[j] = e[QOBS[qi * 24 + j * 3]];\n"
+           "          for (int f = 0; f < n_full; ++f) {\n"
+           "            bool match = true;\n"
+           "            for (int j = 0; j < n_obs; ++j) match &= ((f / QOBS[qi * 24 + j * 3 + 1]) % QOBS[qi * 24 + j * 3 + 2]) == st[j];\n"
+           "            const double v = match ? (kind == 3 ? sp[(size_t)fmap[f] * RT] : (kind == 0 ? 1.0 : gp[fmap[f]])) : 0.0;\n"
+           "            op[d[5] + f] = __dmul_rn(inv, v);\n          }\n"
+           "        } break;\n";
+    }
+  }
+  o << "      }\n    }\n";
   if (WP) {
     o << "    __syncthreads();\n";
     o << "    for (unsigned i = tid; i < (unsigned)nr * " << W << "u; i += " << T << "u) out[row0 * " << W << "ll + i] = stage[(i / " << W << "u) * " << WP << "u + i % " << W
