@@ -117,6 +117,8 @@ int64_t stride_in(const Table& t, int v) {
   return 0;
 }
 
+int loop_levels_for(const Step& st, int64_t U);  // defined below
+
 struct Gen {
   const Program& P;
   const Step& st;
@@ -134,6 +136,13 @@ struct Gen {
   // per item instead of a group of all states of the blocking variable (finer items for the narrow steps of hb_tree).
   int V = 2;
   bool no_block = false;
+  // Register block: the output variables a thread enumerates itself (U = product of their dimensions entries evaluated in
+  // lock-step, every load emitted once per distinct address); the others index the item.  Default: the step's blocking
+  // variable w alone.  `custom_block` = a caller-chosen set (hb_tree picks it per step by the loads it saves).
+  std::vector<int> blocked;
+  bool custom_block = false;
+  std::vector<std::vector<int>> udig;  // per lock-step entry: state of every blocked variable
+  std::vector<int64_t> uoff;           // per lock-step entry: offset in the stored output layout
   Gen(const Program& p, const Step& s) : P(p), st(s) {}
   const char* DV() const { return V == 2 ? "double2" : "double"; }
   const char* zero() const { return V == 2 ? "zero" : "0.0"; }
@@ -181,7 +190,8 @@ struct Gen {
     for (size_t k = ins.size(); k-- > 0;) {
       const In& x = ins[k];
       if (x.level != (int)li) continue;
-      int64_t off = no_block ? 0 : (int64_t)u * x.in->wstride;
+      int64_t off = 0;
+      for (size_t j = 0; j < blocked.size(); ++j) off += (int64_t)udig[u][j] * stride_in(*x.t, blocked[j]);
       for (size_t m = (size_t)n_loop; m <= li; ++m) off += (int64_t)bound[m] * x.in->lstride[m];  // looped levels live in the pointer
       const std::string v = load(x, off);
       chain = chain.empty() ? v : mul(v, chain);
@@ -256,16 +266,40 @@ struct Gen {
     ins.clear();
     for (size_t l = 0; l < st.levels.size(); ++l)
       for (const StepInput& in : st.levels[l].in) ins.push_back(In{id++, (int)l, &P.tables[in.table], &in});
-    n_loop = std::max(0, jit_loop_levels(st));
     ptr.clear();
     for (const In& x : ins) ptr.push_back("p" + std::to_string(x.id));
+    if (!custom_block) {
+      blocked.clear();
+      if (!no_block && st.w_var >= 0) blocked.push_back(st.w_var);
+    }
     red.clear();
     for (int v : out.pscope)
-      if (v != st.w_var) red.push_back(v);
-    if (no_block) {  // the stored layout is row-major over `red`, then w fastest: entry index = digits over red ++ [w]
-      if (st.w_var >= 0) red.push_back(st.w_var);
-      U = 1;
+      if (std::find(blocked.begin(), blocked.end(), v) == blocked.end()) red.push_back(v);
+    U = 1;
+    for (int v : blocked) U *= P.net->dims[v];
+    auto out_stride = [&](int v) {
+      for (size_t i = 0; i < out.pscope.size(); ++i)
+        if (out.pscope[i] == v) return out.pstride[i];
+      return (int64_t)0;
+    };
+    udig.assign(U, std::vector<int>(blocked.size(), 0));
+    uoff.assign(U, 0);
+    for (int u = 0; u < U; ++u) {
+      int rem = u;
+      for (size_t j = blocked.size(); j-- > 0;) udig[u][j] = rem % P.net->dims[blocked[j]], rem /= P.net->dims[blocked[j]];
+      for (size_t j = 0; j < blocked.size(); ++j) uoff[u] += udig[u][j] * out_stride(blocked[j]);
     }
+    n_loop = std::max(0, loop_levels_for(st, U));
+  }
+  // offset of the item's first entry in the stored output layout, as an expression of the digits d<v> of `red`
+  std::string out_base() const {
+    const Table& out = P.tables[st.out];
+    std::string base;
+    for (int v : red)
+      for (size_t i = 0; i < out.pscope.size(); ++i)
+        if (out.pscope[i] == v && out.pstride[i])
+          base += (base.empty() ? "" : " + ") + ("d" + std::to_string(v)) + " * " + std::to_string(out.pstride[i]) + "u";
+    return base.empty() ? "0u" : base;
   }
 
   // row pointers that do not depend on the group (needs `row`, `arena`, `arena_out`, `pots`, `shared`, `rowoff`, `RT` in scope)
@@ -339,17 +373,19 @@ struct Gen {
       } else
         o << "    const double* const p" << x.id << " = b" << x.id << " + (" << base << ");\n";
     }
+    o << "    const unsigned ob = " << out_base() << ";\n";
     std::vector<int> bound(st.levels.size(), 0);
     const std::vector<std::string> res = level(0, bound);
+    if (store == STORE_RESULT) o << "    *ob_out = ob;\n";
     for (int u = 0; u < U; ++u) {
       if (store == STORE_RESULT)
         o << "    res[" << u << "] = " << res[u] << ";\n";
       else if (store == STORE_STREAMING)
-        o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT), " << res[u] << ");\n";
+        o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(ob + " << uoff[u] << "u) * RT), " << res[u] << ");\n";
       else if (V == 2)
-        o << "    *reinterpret_cast<double2*>(outp + (size_t)(g * " << U << "u + " << u << "u) * RT) = " << res[u] << ";\n";
+        o << "    *reinterpret_cast<double2*>(outp + (size_t)(ob + " << uoff[u] << "u) * RT) = " << res[u] << ";\n";
       else
-        o << "    outp[(size_t)(g * " << U << "u + " << u << "u) * RT] = " << res[u] << ";\n";
+        o << "    outp[(size_t)(ob + " << uoff[u] << "u) * RT] = " << res[u] << ";\n";
     }
   }
 
@@ -375,27 +411,24 @@ struct Gen {
   // `rot` first, so that the small steps of one dependency level land on different warps.
   // items the step is cut into for a tile of R rows and T threads: groups of all states of the blocking variable x row
   // pairs when that already feeds every thread, else single output entries, else single entries x single rows
-  static void tree_mode(const Step& st, int R, int T, int* V, bool* no_block, int64_t* items) {
-    static const double grain = getenv("HB_TREE_GRAIN") ? atof(getenv("HB_TREE_GRAIN")) : 1.0;  // tuning: items wanted per thread
-    const double want = grain * T;
-    *V = 2, *no_block = false, *items = st.n_red * (R / 2);
-    if (*items >= want) return;
-    *no_block = true, *items = st.n_out * (R / 2);
-    if (*items >= want) return;
-    *V = 1, *items = st.n_out * R;
-  }
   // The step as a device function of one item (inlined at its call sites) and the loop that deals the items to the
   // threads.  A thread with several items evaluates `ni` of them together: the bodies are independent and no store
   // separates them, so their shared-memory loads and fp64 chains overlap.
   std::string call;  // filled by tree_step: the loop inside hb_tree
-  void tree_step(int si, int R, int T, int rot) {
-    int64_t items = 0;
-    tree_mode(st, R, T, &V, &no_block, &items);
+  int64_t tree_items = 0;  // filled by tree_step
+  // `block` = the register block chosen for this step, v = rows per thread
+  void tree_step(int si, int R, int T, int rot, const std::vector<int>& block, int v) {
+    V = v;
+    custom_block = true;
+    blocked = block;
     prepare();
     const int64_t rows = V == 2 ? R / 2 : R;
+    const int64_t items = st.n_out / U * rows;
+    tree_items = items;
     const std::string fn = "hb_s" + std::to_string(si);
     o << "__device__ __forceinline__ void " << fn << "(const double* __restrict__ arena, const double* __restrict__ pots,\n"
-         "    const double* __restrict__ shared, const int* __restrict__ rowoff, const unsigned g, const unsigned row, " << DV() << "* __restrict__ res) {\n";
+         "    const double* __restrict__ shared, const int* __restrict__ rowoff, const unsigned g, const unsigned row, " << DV()
+      << "* __restrict__ res, unsigned* __restrict__ ob_out) {\n";
     o << "    constexpr unsigned RT = " << R << "u;\n";
     if (V == 2) o << "    const double2 zero = make_double2(0.0, 0.0);\n";
     emit_bases("    ", false);
@@ -405,8 +438,8 @@ struct Gen {
     static const int max_ni = getenv("HB_TREE_INTERLEAVE") ? std::max(1, std::min(4, atoi(getenv("HB_TREE_INTERLEAVE")))) : 2;
     while (ni < max_ni && items >= (int64_t)2 * ni * T && n_loads * 2 * ni <= 96) ni *= 2;
     std::ostringstream c;
-    c << "    {  // step " << si << ": " << items / rows << (no_block ? " entries" : " groups of " + std::to_string(U)) << " x " << rows
-      << (V == 2 ? " row pairs" : " rows") << (ni > 1 ? ", " + std::to_string(ni) + " items at a time\n" : "\n");
+    c << "    {  // step " << si << ": " << items / rows << " blocks of " << U << " x " << rows << (V == 2 ? " row pairs" : " rows")
+      << (ni > 1 ? ", " + std::to_string(ni) + " items at a time\n" : "\n");
     c << "    double* const outb = arena_out + " << row_off(P.tables[st.out]) * R << "u;\n";
     c << "    for (unsigned it = (tid + " << (T - rot % T) % T << "u) % " << T << "u; it < " << items << "u; it += " << ni * T << "u) {\n";
     for (int k = 0; k < ni; ++k) {
@@ -415,13 +448,13 @@ struct Gen {
       else
         c << "      const bool has" << k << " = it + " << k * T << "u < " << items << "u;\n      const unsigned it" << k << " = has" << k << " ? it + " << k * T << "u : it;\n";
       c << "      const unsigned g" << k << " = it" << k << " / " << rows << "u, row" << k << " = (it" << k << " % " << rows << "u)" << (V == 2 ? " * 2u" : "") << ";\n";
-      c << "      " << DV() << " r" << k << "[" << U << "];\n";
-      c << "      " << fn << "(arena, pots, shared, rowoff, g" << k << ", row" << k << ", r" << k << ");\n";
+      c << "      " << DV() << " r" << k << "[" << U << "];\n      unsigned ob" << k << ";\n";
+      c << "      " << fn << "(arena, pots, shared, rowoff, g" << k << ", row" << k << ", r" << k << ", &ob" << k << ");\n";
     }
     for (int k = 0; k < ni; ++k) {
       if (k > 0) c << "      if (has" << k << ") {\n";
       for (int u = 0; u < U; ++u) {
-        const std::string at = "outb + (g" + std::to_string(k) + " * " + std::to_string(U) + "u + " + std::to_string(u) + "u) * RT + row" + std::to_string(k);
+        const std::string at = "outb + (ob" + std::to_string(k) + " + " + std::to_string(uoff[u]) + "u) * RT + row" + std::to_string(k);
         if (V == 2)
           c << "      *reinterpret_cast<double2*>(" << at << ") = r" << k << "[" << u << "];\n";
         else
@@ -438,26 +471,29 @@ struct Gen {
 
 // chain evaluations in the generated body of a group when the `n_loop` outermost levels stay run-time loops
 // (about 150 bytes of source each)
-static int64_t body_ops(const Step& st, int n_loop) {
+static int64_t body_ops(const Step& st, int n_loop, int64_t U) {
   int64_t ops = 0, terms = 1;
   for (size_t l = 0; l < st.levels.size(); ++l) {
     if ((int)l >= n_loop) terms *= st.levels[l].d;
     ops += terms * (int64_t)std::max<size_t>(1, st.levels[l].in.size());
   }
-  return ops * st.U;
+  return ops * U;
 }
 constexpr int64_t MAX_BODY_OPS = 600;  // compile time grows faster than linearly with the size of a straight-line kernel
 
 // how many outermost levels stay run-time loops so that the unrolled rest fits MAX_BODY_OPS (-1: not even the
 // innermost level alone fits)
-int jit_loop_levels(const Step& st) {
+namespace {
+int loop_levels_for(const Step& st, int64_t U) {
   for (int n = 0; n < (int)st.levels.size(); ++n)
-    if (body_ops(st, n) <= MAX_BODY_OPS) return n;
+    if (body_ops(st, n, U) <= MAX_BODY_OPS) return n;
   return -1;
 }
+}  // namespace
+int jit_loop_levels(const Step& st) { return loop_levels_for(st, st.U); }
 int64_t jit_unrolled_ops(const Step& st) {
   const int n = jit_loop_levels(st);
-  return n < 0 ? -1 : body_ops(st, n);
+  return n < 0 ? -1 : body_ops(st, n, st.U);
 }
 
 bool jit_eligible(const Program& P, const Step& st) {
@@ -852,6 +888,57 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   return true;
 }
 
+namespace {
+// fp64 operations of one row of a step (multiplies + adds, as the reference performs them)
+int64_t step_ops(const Step& st) {
+  int64_t ops = 0, terms = st.n_out;
+  for (size_t l = 0; l < st.levels.size(); ++l) {
+    terms *= st.levels[l].d;
+    const int64_t k = (int64_t)st.levels[l].in.size() + (l + 1 < st.levels.size() ? 1 : 0) + (l == 0 && !st.scalars.empty() ? 1 : 0);
+    ops += terms * std::max<int64_t>(1, k);
+  }
+  return ops;
+}
+
+// table loads of one row of a step when the output variables in `block` are enumerated inside an item
+int64_t block_loads(const Program& P, const Step& st, const std::vector<int>& block) {
+  const Network& net = *P.net;
+  int64_t items = st.n_out;
+  for (int v : block) items /= net.dims[v];
+  std::vector<int> inner = block;  // variables an item runs over: the block, then the summed variables level by level
+  int64_t per_item = 0;
+  for (const Level& l : st.levels) {
+    if (l.sum_var >= 0 && l.d > 1) inner.push_back(l.sum_var);
+    for (const StepInput& in : l.in) {
+      int64_t n = 1;
+      for (int v : P.tables[in.table].pscope)
+        if (std::find(inner.begin(), inner.end(), v) != inner.end()) n *= net.dims[v];
+      per_item += n;
+    }
+  }
+  return items * per_item;
+}
+
+// the register block of at most `cap` entries that needs the fewest loads (ties: the smaller block)
+std::vector<int> choose_block(const Program& P, const Step& st, int64_t cap) {
+  const Network& net = *P.net;
+  std::vector<int> vars = P.tables[st.out].pscope;
+  if (vars.size() > 12) vars.resize(12);
+  std::vector<int> best;
+  int64_t best_loads = block_loads(P, st, best), best_size = 1;
+  for (unsigned mask = 1; mask < (1u << vars.size()); ++mask) {
+    std::vector<int> b;
+    int64_t size = 1;
+    for (size_t i = 0; i < vars.size(); ++i)
+      if (mask >> i & 1) b.push_back(vars[i]), size *= net.dims[vars[i]];
+    if (size > cap || loop_levels_for(st, size) < 0) continue;
+    const int64_t loads = block_loads(P, st, b);
+    if (loads < best_loads || (loads == best_loads && size < best_size)) best = b, best_loads = loads, best_size = size;
+  }
+  return best;
+}
+}  // namespace
+
 std::string tree_source(const Program& P, const TreePlan& plan) {
   const Network& net = *P.net;
   const int R = plan.R, T = plan.T;
@@ -975,23 +1062,32 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
                    << ", (unsigned long long)(t1 - t0)); t0 = t1; }\n";
   };
   lap(0);
+  // Items of equal work: a level's fp64 operations are dealt to the T threads, so a step that holds the share f of them
+  // is cut into about f * T items -- register blocks of up to 16 output entries (every input value loaded once per
+  // block: shared-memory bandwidth is what bounds the wide levels) x row pairs, single entries x single rows where the
+  // level is narrow (there latency is the bound and every thread should have something to do).
+  static const double grain = getenv("HB_TREE_GRAIN") ? atof(getenv("HB_TREE_GRAIN")) : 1.0;
+  static const int64_t block_cap = getenv("HB_TREE_BLOCK") ? std::max(1, atoi(getenv("HB_TREE_BLOCK"))) : 16;
   for (int lv = 0; lv < plan.n_levels; ++lv) {
     o << "    // ---- dependency level " << lv << " ----\n";
-    int64_t rot = 0;
+    int64_t rot = 0, level_ops = 0;
+    for (size_t si = 0; si < P.steps.size(); ++si)
+      if (plan.level[si] == lv) level_ops += step_ops(P.steps[si]);
     for (size_t si = 0; si < P.steps.size(); ++si) {
       if (plan.level[si] != lv) continue;
-      Gen g(P, P.steps[si]);
+      const Step& st = P.steps[si];
+      const double want = std::max(1.0, grain * T * (double)step_ops(st) / (double)std::max<int64_t>(level_ops, 1));
+      const int64_t fit = (int64_t)((double)(st.n_out * (R / 2)) / want);  // entries per block that still give `want` items
+      const int v = fit >= 1 ? 2 : 1;
+      const std::vector<int> block = choose_block(P, st, std::max<int64_t>(1, std::min(fit, block_cap)));
+      Gen g(P, st);
       g.tree_off = &plan.off;
-      g.tree_step((int)si, R, T, (int)(rot % T));
+      g.tree_step((int)si, R, T, (int)(rot % T), block, v);
       fns << g.o.str();
       o << g.call;
-      int v = 2;
-      bool nb = false;
-      int64_t items = 0;
-      Gen::tree_mode(P.steps[si], R, T, &v, &nb, &items);
-      rot += items;
-      stat_loads += g.n_loads * (items / (v == 2 ? R / 2 : R));
-      stat_items += items;
+      rot += g.tree_items;
+      stat_loads += g.n_loads * (g.tree_items / (v == 2 ? R / 2 : R));
+      stat_items += g.tree_items;
     }
     o << "    __syncthreads();\n";
     lap(1 + lv);
