@@ -434,27 +434,37 @@ struct Gen {
     emit_bases("    ", false);
     emit_group(STORE_RESULT);
     o << "}\n\n";
+    // A thread keeps its row (pair) for the whole kernel: rowA / slotA (two rows per thread) or rowB / slotB (one row) are
+    // computed once at kernel start; the blocks of a step go to the slots round robin, slot `rot` first.
+    const int64_t n_blocks = items / rows, n_slots = T / rows;
+    const char* rw = V == 2 ? "rowA" : "rowB";
+    const char* sl = V == 2 ? "slotA" : "slotB";
+    const int64_t first = (n_slots - (rot / rows) % n_slots) % n_slots;
     int ni = 1;
     static const int max_ni = getenv("HB_TREE_INTERLEAVE") ? std::max(1, std::min(4, atoi(getenv("HB_TREE_INTERLEAVE")))) : 2;
-    while (ni < max_ni && items >= (int64_t)2 * ni * T && n_loads * 2 * ni <= 96) ni *= 2;
+    while (ni < max_ni && n_blocks >= (int64_t)2 * ni * n_slots && n_loads * 2 * ni <= 96) ni *= 2;
     std::ostringstream c;
-    c << "    {  // step " << si << ": " << items / rows << " blocks of " << U << " x " << rows << (V == 2 ? " row pairs" : " rows")
+    c << "    {  // step " << si << ": " << n_blocks << " blocks of " << U << " x " << rows << (V == 2 ? " row pairs" : " rows")
       << (ni > 1 ? ", " + std::to_string(ni) + " items at a time\n" : "\n");
-    c << "    double* const outb = arena_out + " << row_off(P.tables[st.out]) * R << "u;\n";
-    c << "    for (unsigned it = (tid + " << (T - rot % T) % T << "u) % " << T << "u; it < " << items << "u; it += " << ni * T << "u) {\n";
+    c << "    double* const outb = arena_out + " << row_off(P.tables[st.out]) * R << "u + " << rw << ";\n";
+    const std::string g_first = first ? "(" + std::string(sl) + " + " + std::to_string(first) + "u) % " + std::to_string(n_slots) + "u" : std::string(sl);
+    if (n_blocks <= n_slots)
+      c << "    { const unsigned g = " << g_first << ";\n    if (g < " << n_blocks << "u) {\n";
+    else
+      c << "    for (unsigned g = " << g_first << "; g < " << n_blocks << "u; g += " << ni * n_slots << "u) {{\n";
     for (int k = 0; k < ni; ++k) {
       if (k == 0)
-        c << "      const unsigned it0 = it;\n";
+        c << "      const unsigned g0 = g;\n";
       else
-        c << "      const bool has" << k << " = it + " << k * T << "u < " << items << "u;\n      const unsigned it" << k << " = has" << k << " ? it + " << k * T << "u : it;\n";
-      c << "      const unsigned g" << k << " = it" << k << " / " << rows << "u, row" << k << " = (it" << k << " % " << rows << "u)" << (V == 2 ? " * 2u" : "") << ";\n";
+        c << "      const bool has" << k << " = g + " << k * n_slots << "u < " << n_blocks << "u;\n      const unsigned g" << k << " = has" << k << " ? g + " << k * n_slots
+          << "u : g;\n";
       c << "      " << DV() << " r" << k << "[" << U << "];\n      unsigned ob" << k << ";\n";
-      c << "      " << fn << "(arena, pots, shared, rowoff, g" << k << ", row" << k << ", r" << k << ", &ob" << k << ");\n";
+      c << "      " << fn << "(arena, pots, shared, rowoff, g" << k << ", " << rw << ", r" << k << ", &ob" << k << ");\n";
     }
     for (int k = 0; k < ni; ++k) {
       if (k > 0) c << "      if (has" << k << ") {\n";
       for (int u = 0; u < U; ++u) {
-        const std::string at = "outb + (ob" + std::to_string(k) + " + " + std::to_string(uoff[u]) + "u) * RT + row" + std::to_string(k);
+        const std::string at = "outb + (ob" + std::to_string(k) + " + " + std::to_string(uoff[u]) + "u) * RT";
         if (V == 2)
           c << "      *reinterpret_cast<double2*>(" << at << ") = r" << k << "[" << u << "];\n";
         else
@@ -462,7 +472,7 @@ struct Gen {
       }
       if (k > 0) c << "      }\n";
     }
-    c << "    }\n    }\n";
+    c << "    }}\n    }\n";
     call = c.str();
   }
 };
@@ -1016,7 +1026,7 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   o << "  signed char* const evs = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n";
   o << "  constexpr unsigned RT = " << R << "u;\n";
   o << "  const unsigned tid = threadIdx.x;\n";
-  o << "  const double2 zero = make_double2(0.0, 0.0);\n";
+  o << "  const unsigned rowA = (tid % " << R / 2 << "u) * 2u, slotA = tid / " << R / 2 << "u, rowB = tid % " << R << "u, slotB = tid / " << R << "u;\n";
   const int64_t ept = (R * NV + T - 1) / T;  // evidence bytes per thread and tile
   for (int64_t k = 0; k < ept; ++k)
     o << "  signed char pre" << k << " = (tid + " << k * T << "u < " << R * NV << "u && (long long)blockIdx.x * " << R * NV << "ll + tid + " << k * T << "u < n_rows * " << NV
@@ -1076,10 +1086,21 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
     for (size_t si = 0; si < P.steps.size(); ++si) {
       if (plan.level[si] != lv) continue;
       const Step& st = P.steps[si];
-      const double want = std::max(1.0, grain * T * (double)step_ops(st) / (double)std::max<int64_t>(level_ops, 1));
-      const int64_t fit = (int64_t)((double)(st.n_out * (R / 2)) / want);  // entries per block that still give `want` items
-      const int v = fit >= 1 ? 2 : 1;
-      const std::vector<int> block = choose_block(P, st, std::max<int64_t>(1, std::min(fit, block_cap)));
+      static const int policy = getenv("HB_TREE_POLICY") ? atoi(getenv("HB_TREE_POLICY")) : 0;
+      int v = 2;
+      std::vector<int> block;
+      if (policy == 1) {  // equal work
+        const double want = std::max(1.0, grain * T * (double)step_ops(st) / (double)std::max<int64_t>(level_ops, 1));
+        const int64_t fit = (int64_t)((double)(st.n_out * (R / 2)) / want);  // entries per block that still give `want` items
+        v = fit >= 1 ? 2 : 1;
+        block = choose_block(P, st, std::max<int64_t>(1, std::min(fit, block_cap)));
+      } else {  // every step on its own: the coarsest cut that still gives every thread an item
+        const double want = grain * T;
+        if (st.w_var >= 0 && st.n_red * (R / 2) >= want)
+          block = {st.w_var};
+        else if (st.n_out * (R / 2) < want)
+          v = 1;
+      }
       Gen g(P, st);
       g.tree_off = &plan.off;
       g.tree_step((int)si, R, T, (int)(rot % T), block, v);
