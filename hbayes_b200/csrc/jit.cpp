@@ -875,8 +875,8 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
       if (plan.level[si] >= 0) items[plan.level[si]] += P.steps[si].n_out * (R / 2);
     for (int64_t x : items) widest = std::max(widest, x);
   }
-  int T = 64;
-  while (T < 256 && T < widest) T *= 2;
+  int T = 64;  // measured on C2 (profiles/README.md): 256, 384 and 512 threads are within 3 %; 384 is the best
+  while (T < 384 && T < widest) T = T < 256 ? T * 2 : 384;
   if (const char* env = getenv("HB_TREE_THREADS")) T = std::max(32, std::min(1024, atoi(env) / 32 * 32));
   plan.T = T;
   int minb = (int)std::min<int64_t>(TREE_SMEM_MAX / (int64_t)plan.smem_bytes, 2048 / T);

@@ -65,7 +65,9 @@ def run(tmp_path, name, env):
 def test_specialised_kernels_bit_identical_to_oracle_and_to_the_templated_kernels(tmp_path):
     import numpy as np
 
-    jit, log = run(tmp_path, "jit", {"HB_JIT": "1", "HB_JIT_MIN_WORK": "1", "HB_JIT_VERBOSE": "1"})
+    # HB_TREE=0: programs this small would otherwise run on the on-chip kernel (tests/test_gpu_onchip.py)
+    jit, log = run(tmp_path, "jit", {"HB_JIT": "1", "HB_TREE": "0", "HB_JIT_MIN_WORK": "1", "HB_JIT_SYNC": "1", "HB_JIT_VERBOSE": "1",
+                                     "HB_CACHE_DIR": str(tmp_path / "cache")})
     assert "specialised kernels" in log, log[-2000:]  # they were really built and used
     assert int(log.rsplit("specialise ->", 1)[1].split()[0]) > 0
     plain, plain_log = run(tmp_path, "plain", {"HB_JIT": "0"})

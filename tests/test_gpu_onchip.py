@@ -1,0 +1,126 @@
+"""Whole-schedule on-chip kernel hb_tree (csrc/jit.cpp): changeEvidence + collect + distribute + every
+posterior of a tile of evidence rows in ONE launch, per-row tables in shared memory.  Forced for every program that
+qualifies (HB_JIT_MIN_WORK=1, HB_JIT_SYNC=1: read once per process -> a subprocess) and compared bit for bit with the oracle
+and with the templated kernels (HB_JIT=0) on the same inputs: junction trees with evidence on random networks incl. shuffled
+ids, family queries (wide results), variable elimination, zero-probability evidence (NaN rows), ragged batches (1..67 rows),
+the single-row stateful API, a split handle (unnormalised results) and C2 itself."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import numpy as np
+import hbayes_b200 as hb
+from hbayes_b200 import synth
+from oracle import OracleJT, OracleNet
+from helpers import G, random_net, same_bits
+
+out = {}
+on_chip = 0
+for seed, rows in ((5, 257), (9, 64), (12, 1000), (21, 33), (30, 1)):
+    net = random_net(seed, n=12 + seed %% 5, states=(2, 4), max_parents=3, shuffle=seed %% 2 == 1)
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    onet = OracleNet.from_arrays(net.dims, net.scopes, net.values)
+    rng = np.random.RandomState(seed)
+    observed = sorted(rng.permutation(net.n)[:3].tolist())
+    ev = np.full((rows, net.n), -1, np.int8)
+    for v in observed:
+        ev[:, v] = rng.randint(0, net.dims[v], size=rows)
+    jt = hb.JunctionTree(pnet)
+    got = jt.posteriors_batch(ev)
+    on_chip += jt.kernel_info()["on_chip"]
+    out["jt%%d" %% seed] = got
+    assert same_bits(got, OracleJT(onet).posteriors_batch(ev)), ("jt", seed)
+    fam = jt.queries_batch([net.scopes[v] for v in range(net.n)], ev)
+    on_chip += jt.kernel_info()["on_chip"]
+    out["fam%%d" %% seed] = np.concatenate([f[2] for f in fam], axis=1)
+    order = hb.minFillOrder(pnet)
+    r = [order[-1]]
+    p = [v for v in order if v not in r]
+    if not set(r) & set(observed):
+        ve = hb.VariableElimination(pnet, p, r).posterior_batch(ev)
+        out["ve%%d" %% seed] = ve
+        assert same_bits(ve, onet.posterior_marginal_batch(p, r, ev)), ("ve", seed)
+    # every batch length around the tile height: partial last tiles, single rows
+    for m in (1, 2, 3, 15, 16, 17, 31, 32, 33, 67):
+        if m <= rows:
+            assert same_bits(jt.posteriors_batch(ev[:m]), got[:m]), ("ragged", seed, m)
+# golden networks through the stateful single-row API, incl. zero-probability evidence (NaN like the reference)
+for name in ("cancer.net", "asia.net", "sprinkler.net"):
+    pnet = hb.importBayesianGraph(G + "/" + name)
+    onet = OracleNet.load_hugin(G + "/" + name)
+    jt, ojt = hb.JunctionTree(pnet), OracleJT(onet)
+    for evidence in ([], [(0, 0)], [(1, 1), (0, 0)]):
+        jt.changeEvidence(evidence); ojt.change_evidence(evidence)
+        for v in range(pnet.n):
+            a, b = jt.posterior([v]).values, ojt.posterior([v])[1]
+            assert same_bits(a, b), (name, evidence, v, a, b)
+        on_chip += jt.kernel_info()["on_chip"]
+net = synth.SynthNet([2, 2], [[], [0]], [np.array([1.0, 0.0]), np.array([0.5, 0.5, 0.5, 0.5])])
+pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+nan = hb.JunctionTree(pnet).posteriors_batch(np.array([[1, -1], [0, -1]], np.int8))
+assert np.isnan(nan[0]).all() and not np.isnan(nan[1]).any()
+assert same_bits(nan, OracleJT(OracleNet.from_arrays(net.dims, net.scopes, net.values)).posteriors_batch(np.array([[1, -1], [0, -1]], np.int8)))
+out["nan"] = nan
+# split handle: results stay unnormalised, the sum over the slices normalised == the unsplit engine (1e-12)
+net = random_net(41, n=9, states=(2, 3), max_parents=3)
+pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+ev = np.full((40, net.n), -1, np.int8)
+ev[:, 2] = np.arange(40) %% net.dims[2]
+whole = hb.JunctionTree(pnet).posteriors_batch(ev)
+total = np.zeros_like(whole)
+for s in range(net.dims[5]):
+    part = hb.JunctionTree(pnet, split=[(5, s)])
+    e = ev.copy(); e[:, 5] = s
+    total += part.posteriors_batch(e)
+    on_chip += part.kernel_info()["on_chip"]
+last = part.normalise_batch(total)
+cols = np.r_[0, np.cumsum(net.dims)]
+keep = [c for v in range(net.n) if v != 5 for c in range(cols[v], cols[v + 1])]
+assert np.abs(last[:, keep] - whole[:, keep]).max() < 1e-12
+out["split"] = last
+# C2 itself: a prefix against the oracle
+net, observed = synth.config_c2()
+pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+ev = synth.config_c2_evidence(net, observed, 3000)
+jt = hb.JunctionTree(pnet)
+n = jt.specialise(observed)
+got = jt.posteriors_batch(ev)
+info = jt.kernel_info()
+on_chip += info["on_chip"]
+assert same_bits(got[:512], OracleJT(OracleNet.from_arrays(net.dims, net.scopes, net.values)).posteriors_batch(ev[:512], n_threads=8))
+out["c2"] = got
+print("on_chip programs ->", on_chip, "c2 info", info, "specialise ->", n)
+np.savez(sys.argv[1], **out)
+'''
+
+
+def run(tmp_path, name, env):
+    path = str(tmp_path / (name + ".npz"))
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}, path], capture_output=True, text=True, env=e, timeout=1800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return path, r.stderr + r.stdout
+
+
+def test_on_chip_kernel_bit_identical_to_oracle_and_to_the_templated_kernels(tmp_path):
+    import numpy as np
+
+    chip, log = run(tmp_path, "chip", {"HB_JIT": "1", "HB_JIT_MIN_WORK": "1", "HB_JIT_SYNC": "1", "HB_JIT_VERBOSE": "1",
+                                       "HB_CACHE_DIR": str(tmp_path / "cache")})
+    assert "on-chip kernel hb_tree" in log, log[-2000:]  # really built and used
+    assert int(log.rsplit("on_chip programs ->", 1)[1].split()[0]) >= 15
+    assert "'on_chip': 1" in log.rsplit("c2 info", 1)[1]
+    plain, plain_log = run(tmp_path, "plain", {"HB_JIT": "0"})
+    assert int(plain_log.rsplit("on_chip programs ->", 1)[1].split()[0]) == 0
+    a, b = np.load(chip), np.load(plain)
+    assert sorted(a.files) == sorted(b.files) and len(a.files) >= 12
+    for k in a.files:
+        assert a[k].tobytes() == b[k].tobytes(), k
