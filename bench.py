@@ -31,10 +31,7 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line.  NCCL prints its banner ("NCCL version ...") to stdout at NCCL_DEBUG=VERSION, and
-# only honours NCCL_DEBUG_FILE above that level: raise VERSION to WARN (same banner, no more) and send it to stderr.
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL's own messages go to stderr (NCCL_DEBUG itself is left as the caller set it)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -61,7 +58,8 @@ def config_dict(n_gpus, rows_per_gpu):
         "n_vars": 37,
         "out_doubles_per_row": 107,
         "sharding": "rows x%d, no collective" % n_gpus,
-        "l2_policy": "working set per step >> L2 (row arena 21 GB, output 0.9 GB per GPU): no flush needed",
+        "l2_policy": "inputs larger than L2: every pass reads 38.8 MB of evidence and writes 0.9 GB of posteriors per GPU (L2 = 126 MB); "
+                     "nothing else goes through HBM (per-row tables live in shared memory): no flush needed",
     }
 
 
@@ -164,7 +162,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * rows / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus, ROWS_PER_GPU),
+        "dtype": "f64", "data": "synthetic", "config": dict(config_dict(args.gpus, ROWS_PER_GPU), sample_rows_per_step=rows),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d rows of the C2 evidence matrix per step, rows split over %d threads; C++ restatement of "
                                    "the reference algorithm (oracle/), not GHC" % (rows, threads)},
@@ -172,6 +170,41 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def pcie_peaks(pinned_out, d_out, pinned_ev, d_ev, stream):
+    """pinned host<->device copy bandwidth of the very buffers the e2e step moves (GB/s, best of 3, CUDA events)"""
+    import torch
+
+    def best(fn, nbytes):
+        ms = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return nbytes / (min(ms) / 1e3) / 1e9
+
+    return {"d2h_GBps": best(lambda: pinned_out.copy_(d_out, non_blocking=True), pinned_out.numel() * 8),
+            "h2d_GBps": best(lambda: d_ev.copy_(pinned_ev, non_blocking=True), pinned_ev.numel())}
+
+
+def other_configs():
+    """short runs of the other BASELINE.json configs on this GPU (bench/configs.py): C1 latency and batch, C3, C5"""
+    sys.path.insert(0, os.path.join(ROOT, "bench"))
+    import configs
+
+    res = {}
+    for name, fn in (("C1", configs.c1), ("C3", configs.c3), ("C5", lambda: configs.c5(64))):
+        t = time.perf_counter()
+        try:
+            res[name] = fn()
+        except Exception as e:  # a secondary measurement must never cost the headline line
+            res[name] = {"error": repr(e)[:300]}
+        res[name]["wall_s"] = time.perf_counter() - t
+    return res
 
 
 def main():
@@ -182,6 +215,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="evidence rows per GPU (default: the named workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -191,13 +225,18 @@ def main():
 
     import hbayes_b200 as hb
     from hbayes_b200 import synth
-    from hbayes_b200.dist import max_over_ranks, whole_job_rate
+    from hbayes_b200.dist import max_over_ranks, shard_rows, whole_job_rate
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    # stdout carries exactly one JSON line: whatever a library prints there meanwhile (NCCL's version banner at
+    # NCCL_DEBUG=VERSION, for one) is sent to stderr at the file-descriptor level; the environment is left alone
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -210,6 +249,12 @@ def main():
     stream = torch.cuda.current_stream()
     jt.set_stream(stream.cuda_stream)
     jt.set_timing(True)
+    # The kernels generated for this (network, observed set) are built here, next to createJunctionTree, not inside a timed
+    # step: NVRTC the first time on a box, the cubin cache (~/.cache/hbayes_b200) afterwards.
+    t0 = time.perf_counter()
+    n_spec = jt.specialise(observed)
+    specialise_s = time.perf_counter() - t0
+    info = jt.kernel_info()
     # every rank draws its own rows from the same stream of evidence (seed offset by rank)
     ev_host = synth.evidence_matrix(net, rows, observed, 37003 + rank)
     ev_pinned = torch.from_numpy(ev_host).pin_memory()
@@ -245,13 +290,28 @@ def main():
     ms = timed(dev_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     stats = jt.last_stats()
-    # kernel-family timing of one more (untimed) pass, CUDA events inside the library on the same stream
+    # kernel timing of one more (untimed) pass, CUDA events inside the library on the same stream
     dev_step()
     tm = jt.last_timing()
+    # strong scaling: the SAME 2^20 rows sharded over the ranks (BASELINE config 2 as written); weak scaling is `value`
+    lo, hi = shard_rows(rows, rank, world)
+    d_ev_s, d_out_s = d_ev[: hi - lo], d_out[: hi - lo]
+    strong_step = lambda: jt.posteriors_batch(d_ev_s, d_out_s)
+    for _ in range(W):
+        strong_step()
+    ms_strong = timed(strong_step, args.steps)
+    dev_step()  # d_out holds the full batch again for the parity check below
     for _ in range(2):
         e2e_step()
     e2e_steps = max(2, min(args.steps, 5))
     ms_e2e = timed(e2e_step, e2e_steps)
+    pcie = pcie_peaks(out_pinned, d_out, ev_pinned, d_ev, stream)
+    jt.posteriors_batch(ev_pinned, out_pinned)  # out_pinned holds this rank's answers again (the copy test overwrote it)
+    torch.cuda.synchronize()
+    # the same call from ordinary (pageable) host memory: what a caller that did not pin its buffers gets
+    out_pageable = np.empty((rows, pnet.width), np.float64)
+    jt.posteriors_batch(ev_host, out_pageable)
+    ms_pageable = timed(lambda: jt.posteriors_batch(ev_host, out_pageable), 2)
 
     if rank == 0:
         value = whole_job_rate([rows] * world, args.steps, ms)
@@ -262,52 +322,97 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        algo_bytes = 8.0 * (stats["row_read_per_row"] + stats["row_write_per_row"]) * rows
-        achieved = algo_bytes / (tm["prodsum_ms"] / 1e3) / 1e9
-        n_prodsum = stats["launches"] - 2 * stats["tiles"]
+        kernel_ms = tm["prodsum_ms"]
+        on_chip = bool(info["on_chip"])
+        if on_chip:  # one launch per pass; HBM sees the evidence rows and the posteriors only
+            algo_bytes = float(rows) * (len(net.dims) + 8.0 * pnet.width)
+            kernel_name = ("hb_tree (generated with NVRTC, csrc/jit.cpp): changeEvidence + collect + distribute + posterior of all 37 variables "
+                           "for tiles of %d rows, per-row tables in shared memory; 1 launch per pass" % info["rows_per_cta"])
+        else:
+            algo_bytes = 8.0 * (stats["row_read_per_row"] + stats["row_write_per_row"]) * rows
+            kernel_name = "the product/sum-out launches of one pass (per-step kernels)"
+        achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
         traffic, traffic_note = None, "no ncu capture for this row count"
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches (ncu, profiles/r1_traffic.json)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if rows == ROWS_PER_GPU and abs(tj["algorithmic_bytes"] - algo_bytes) < 1e-6 * algo_bytes:
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu --set full, profiles/r2_traffic.json)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if rows == tj["rows"] and on_chip == bool(tj["on_chip"]):
                 traffic, traffic_note = tj["traffic_bytes"], tj["source"]
         except Exception:
             pass
+        sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(world, rows),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ev_host.nbytes), "d2h_bytes_per_step": int(out_pinned.nbytes),
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "roofline": {"bound": "pcie d2h", "achieved": out_pinned.nbytes / (ms_e2e / e2e_steps / 1e3) / 1e9, "peak": pcie["d2h_GBps"],
+                                 "unit": "GB/s", "frac": out_pinned.nbytes / (ms_e2e / e2e_steps / 1e3) / 1e9 / pcie["d2h_GBps"],
+                                 "peak_source": "pinned cudaMemcpyAsync of the same %d-byte result matrix in this run, best of 3; H2D %.1f GB/s"
+                                                % (out_pinned.nbytes, pcie["h2d_GBps"])},
+                    "pageable": {"value": whole_job_rate([rows] * world, 2, ms_pageable), "ms_per_step": ms_pageable / 2,
+                                 "note": "same call, caller buffers NOT pinned (numpy arrays)"}},
             "gpu_launches": int(stats["launches"]) * args.steps,
-            "specialised_kernels": jt.specialised_kernels(),
+            "specialised_kernels": n_spec, "specialise_s": specialise_s,
+            "kernel_origin": {-1: "none", 0: "process", 1: "disk cache", 2: "nvrtc"}.get(info["origin"], "?"),
+            "scaling_strong": {"value": float(rows) * args.steps / (ms_strong / 1e3), "unit": UNIT, "rows_total": rows, "rows_per_gpu": hi - lo,
+                               "ms_per_step": ms_strong / args.steps,
+                               "note": "BASELINE config 2 as written: the same 2^20 rows sharded over the ranks (total work fixed); `value` is the weak-scaling figure"},
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm",
-                "kernel": "the %d product/sum-out launches of one pass (per-step specialised kernels hb_step_<i> compiled with NVRTC on "
-                          "the first warm-up pass, prodsum_kernel<K,V,D> / fused_kernel<KO,KI,V,DI> for the rest; 93%% of the pass; "
-                          "aggregated: one launch = one schedule step over all rows)" % n_prodsum,
+                "bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_pass": algo_bytes, "prodsum_ms_per_pass": tm["prodsum_ms"], "traffic": traffic,
-                "traffic_note": traffic_note,
-                "per_row": {"entries_read": stats["row_read_per_row"], "entries_written": stats["row_write_per_row"],
-                            "product_entries": stats["prod_per_row"], "arena_entries": stats["row_entries"]},
+                "algorithmic_bytes_per_pass": algo_bytes, "kernel_ms_per_pass": kernel_ms, "traffic": traffic, "traffic_note": traffic_note,
                 "pass_ms": tm,
             },
         }
+        if on_chip:
+            # HBM is no longer what binds this path: per row the kernel moves smem_loads + smem_stores table entries through
+            # shared memory and does fp64_mul + fp64_add operations; both against this GPU's nominal rates at the SM clock
+            # sampled during the timed region
+            smem_bytes = 8.0 * (info["smem_loads_per_row"] + info["smem_stores_per_row"]) * rows
+            smem_peak = 128.0 * n_sm * sm_mhz * 1e6 / 1e9
+            flops = float(info["fp64_mul_per_row"] + info["fp64_add_per_row"]) * rows
+            fp64_peak = 64.0 * n_sm * sm_mhz * 1e6 / 1e12
+            line["roofline"]["note"] = ("this kernel keeps every per-row table on chip: its HBM fraction is small by design (round 1 moved "
+                                        "61.7 KB per query through HBM, this one %.2f KB); the binding resources are below" % (algo_bytes / rows / 1e3))
+            line["roofline"]["binding"] = {
+                "shared_memory": {"achieved": smem_bytes / (kernel_ms / 1e3) / 1e9, "peak": smem_peak, "unit": "GB/s",
+                                  "frac": smem_bytes / (kernel_ms / 1e3) / 1e9 / smem_peak,
+                                  "per_row": {"loads": info["smem_loads_per_row"], "stores": info["smem_stores_per_row"]},
+                                  "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz (sampled)" % (n_sm, sm_mhz)},
+                "fp64": {"achieved": flops / (kernel_ms / 1e3) / 1e12, "peak": fp64_peak, "unit": "Tflop/s (separate multiply and add, no FMA)",
+                         "frac": flops / (kernel_ms / 1e3) / 1e12 / fp64_peak,
+                         "per_row": {"mul": info["fp64_mul_per_row"], "add": info["fp64_add_per_row"]},
+                         "peak_source": "64 fp64 lanes/clk/SM x %d SMs x %.0f MHz (sampled)" % (n_sm, sm_mhz)},
+                "kernel": {k: info[k] for k in ("rows_per_cta", "threads_per_cta", "levels", "smem_entries_per_row", "smem_bytes")},
+            }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = int(min(1 << 16, max(1024, threads * 330 * 12)))
             rate, want = cpu_port_rate(sample, threads, want_posteriors=True)
-            # the rows the CPU port just answered double as a full-size parity check of the timed GPU path (same engine
-            # state as the timed steps: specialised kernels, CUDA graph): bit for bit, NaN == NaN
-            got = d_out[:sample].cpu().numpy()
-            same = bool(np.array_equal(np.isnan(got), np.isnan(want)) and got[~np.isnan(got)].tobytes() == want[~np.isnan(want)].tobytes())
-            line["parity"] = {"rows_checked": sample, "bit_identical_to_cpu_port": same}
+            # the rows the CPU port just answered double as a full-size parity check of BOTH timed paths (same engine state as
+            # the timed steps): the device-resident output and the host buffer the e2e call filled, bit for bit, NaN == NaN
+
+            def same(got):
+                return bool(np.array_equal(np.isnan(got), np.isnan(want)) and got[~np.isnan(got)].tobytes() == want[~np.isnan(want)].tobytes())
+
+            line["parity"] = {"rows_checked": sample, "bit_identical_to_cpu_port": same(d_out[:sample].cpu().numpy()),
+                              "e2e_host_buffer_bit_identical_to_cpu_port": same(out_pinned[:sample].numpy()),
+                              "e2e_pageable_buffer_bit_identical_to_cpu_port": same(out_pageable[:sample]),
+                              "e2e_equals_device_path_all_rows": bool(torch.equal(out_pinned, d_out.cpu()))}
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "first %d rows of the same evidence matrix, rows split over %d host threads; C++ "
                                               "restatement of the reference algorithm (oracle/), not GHC" % (sample, threads)}
-        print(json.dumps(line))
+        if world == 1 and not args.no_other_configs:
+            del d_out, d_ev, out_pinned, ev_pinned
+            torch.cuda.empty_cache()
+            line["other_configs"] = other_configs()
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

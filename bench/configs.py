@@ -58,7 +58,8 @@ def c1():
     jt = hb.createJunctionTree(hb.nodeComparisonForTriangulation, net)
     ojt = OracleJT(OracleNet.load_hugin(path))
     sets = [[], [(0, 0)], [(0, 1)]]
-    for ev in sets:  # compile once per observed set
+    for ev in sets:  # compile once per observed set; the on-chip kernel of each is built here, not inside the timed loop
+        jt.specialise([v for v, _ in ev])
         jt.changeEvidence(ev)
     t = time.perf_counter()
     n = 0
@@ -82,7 +83,22 @@ def c1():
     rows[:, 0] = np.arange(1 << 16) % 2
     _, r = time_batch(jt, jt.posteriors_batch, rows)
     r.update(config="C1 cancer.net", single_query_latency_us=lat * 1e6, oracle_single_query_latency_us=olat * 1e6,
-             note="latency = changeEvidence + 5 posteriors through the stateful C-ABI calls (one 1-row pass, H2D+D2H+sync)")
+             note="latency = changeEvidence + 5 posteriors through the stateful calls (one launch + one synchronisation; evidence and "
+                  "result in mapped pinned memory); single_query_latency_us goes through the Python binding (6 ctypes calls), "
+                  "c_abi_single_query_latency_us is the same loop in plain C (bench/latency.c)")
+    try:  # the same loop from plain C: the library's own latency, without the Python binding
+        import subprocess
+        import tempfile
+
+        from hbayes_b200 import _lib
+
+        exe = os.path.join(tempfile.mkdtemp(), "latency")
+        libdir = os.path.dirname(_lib.LIB_PATH)
+        subprocess.run(["gcc", "-std=c99", "-O2", os.path.join(ROOT, "bench", "latency.c"), "-o", exe, "-L" + libdir, "-lhbayes_cuda",
+                        "-Wl,-rpath," + libdir], check=True, capture_output=True)
+        r.update(json.loads(subprocess.run([exe, path, "3000"], check=True, capture_output=True, text=True).stdout))
+    except Exception as e:
+        r["c_abi_latency_error"] = repr(e)[:200]
     return r
 
 
@@ -90,8 +106,10 @@ def c3():
     net, observed = synth.config_c3()
     pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
     jt = hb.JunctionTree(pnet)
+    jt.specialise(observed)  # generated kernels built up front (NVRTC or the cubin cache), not inside a timed pass
     ev = synth.config_c3_evidence(net, observed, 4096)
     out, r = time_batch(jt, jt.posteriors_batch, ev)
+    r["specialised_kernels"] = jt.specialised_kernels()
     ojt = OracleJT(OracleNet.from_arrays(net.dims, net.scopes, net.values))
     t = time.perf_counter()
     want = ojt.posteriors_batch(ev[:512], n_threads=THREADS)
@@ -106,6 +124,7 @@ def c5(rows):
     pnet = hb.BayesianNetwork.from_tables(g.dims, g.scopes, g.values)
     p, rr, observed = synth.config_c5_query(g, hb.minFillOrder(pnet))
     ve = hb.VariableElimination(pnet, p, rr)
+    ve.specialise(observed)
     ev = synth.evidence_matrix(g, rows, observed, 400003)
     out, r = time_batch(ve, ve.posterior_batch, ev, reps=2)
     onet = OracleNet.from_arrays(g.dims, g.scopes, g.values)

@@ -281,10 +281,10 @@ class JunctionTree(_Batched):
 
     def kernel_info(self):
         """what the program of the last batch / specialise call runs on (hb_jt_kernel_info)"""
-        out = np.zeros(10, np.int64)
+        out = np.zeros(12, np.int64)
         check(lib().hb_jt_kernel_info(self._h, out.ctypes.data_as(i64p)))
         keys = ["on_chip_eligible", "rows_per_cta", "threads_per_cta", "levels", "smem_entries_per_row", "smem_bytes",
-                "fp64_mul_per_row", "fp64_add_per_row", "on_chip", "origin"]
+                "fp64_mul_per_row", "fp64_add_per_row", "smem_loads_per_row", "smem_stores_per_row", "on_chip", "origin"]
         return dict(zip(keys, out.tolist()))
 
     def tree_profile(self):
@@ -439,6 +439,13 @@ class VariableElimination(_Batched):
                                     self.width, C.byref(n)))
         sc = scope.tolist()
         return Factor(sc, [self.net.dims[v] for v in sc], out[: n.value])
+
+    def specialise(self, observed: Iterable[int] = ()) -> int:
+        """build the kernels generated for this observed list now rather than inside the first large batch"""
+        oa, op = _i32(list(observed))
+        n = C.c_int32()
+        check(lib().hb_ve_specialise(self._h, len(oa), op, C.byref(n)))
+        return n.value
 
     def posterior_batch(self, evidence, out=None):
         return self._run_matrix(lib().hb_ve_posterior_batch, evidence, out, self.width)

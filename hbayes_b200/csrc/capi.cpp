@@ -84,6 +84,21 @@ struct Session {
   int8_t* d_ev = nullptr;
   double* d_out = nullptr;
   size_t ev_cap = 0, out_cap = 0;
+  // single-row calls: pinned host buffers mapped into the device address space (h_* host side, d_* device side)
+  void *h_one_ev = nullptr, *h_one_out = nullptr, *d_one_ev = nullptr, *d_one_out = nullptr;
+  size_t one_ev_cap = 0, one_out_cap = 0;
+  void reserve_mapped(size_t ev_bytes, size_t out_bytes) {
+    auto grow = [](void*& h, void*& d, size_t& cap, size_t bytes) {
+      if (bytes <= cap) return;
+      if (h) cudaFreeHost(h), h = nullptr;
+      bytes = std::max<size_t>(bytes * 2, 256);
+      cuda_ok(cudaHostAlloc(&h, bytes, cudaHostAllocMapped), "cudaHostAlloc(single-row staging)");
+      cuda_ok(cudaHostGetDevicePointer(&d, h, 0), "cudaHostGetDevicePointer");
+      cap = bytes;
+    };
+    grow(h_one_ev, d_one_ev, one_ev_cap, ev_bytes);
+    grow(h_one_out, d_one_out, one_out_cap, out_bytes);
+  }
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool timing = false;
   Executor* last_ex = nullptr;  // executor of the last batch call (for hb_*_last_timing)
@@ -125,6 +140,8 @@ struct Session {
     cache.clear();
     if (d_ev) cudaFree(d_ev);
     if (d_out) cudaFree(d_out);
+    if (h_one_ev) cudaFreeHost(h_one_ev);
+    if (h_one_out) cudaFreeHost(h_one_out);
     for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
     if (rest_uploaded) cudaEventDestroy(rest_uploaded);
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -347,20 +364,25 @@ struct hb_jt {
     c->prog.reset(compile_jt(s.net, *tree, observed, qs, opt));
     return *(s.cache[key] = std::move(c));
   }
+  // One evidence row through the program (the stateful single-row API).  Latency path: the row and the result live in
+  // pinned host memory mapped into the device's address space, so the call is one launch and one synchronisation -- the
+  // kernels read the few evidence bytes and write the few result doubles over PCIe themselves.  The evidence list was
+  // validated on the host (check_evidence_list) and the program was compiled for exactly its variables, so the device-side
+  // consistency flag cannot be raised here and is not read back.
   void run_one(Compiled& c, std::vector<double>& out) {
     if (!s.fixed.empty()) throw Error(HB_E_UNSUPPORTED, "the single-row calls are not available on a split handle: use the batch call");
     s.call_start = s.tick;
-    std::vector<int8_t> row(s.net.n(), -1);
+    const size_t n_vars = (size_t)s.net.n(), width = (size_t)c.prog->out_width;
+    Executor* ex = s.executor(c);  // sets the device
+    s.reserve_mapped(n_vars, width * sizeof(double));
+    int8_t* row = (int8_t*)s.h_one_ev;
+    memset(row, -1, n_vars);
     for (size_t i = 0; i < ev_vars.size(); ++i) row[ev_vars[i]] = (int8_t)ev_states[i];
-    out.assign((size_t)c.prog->out_width, 0.0);
-    s.reserve(row.size(), out.size() * sizeof(double));
-    cuda_ok(cudaMemcpyAsync(s.d_ev, row.data(), row.size(), cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
     RunStats rs;
-    executor_run(s.executor(c), 1, s.d_ev, s.d_out, s.stream, &rs);
+    executor_run(ex, 1, (const int8_t*)s.d_one_ev, (double*)s.d_one_out, s.stream, &rs);
     s.note(c, rs, false);
-    executor_check(s.executor(c), s.stream);
-    cuda_ok(cudaMemcpyAsync(out.data(), s.d_out, out.size() * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
     cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    out.assign((const double*)s.h_one_out, (const double*)s.h_one_out + width);
   }
 };
 
@@ -1133,14 +1155,14 @@ int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n) {
   *n = jt->s.last_ex ? executor_specialised_kernels(jt->s.last_ex) : 0;
   return HB_OK;
 }
-int hb_jt_kernel_info(const hb_jt* jt, int64_t* out10) {
-  if (!jt || !out10) return HB_E_ARG;
-  for (int i = 0; i < 10; ++i) out10[i] = 0;
-  out10[9] = -1;
+int hb_jt_kernel_info(const hb_jt* jt, int64_t* out12) {
+  if (!jt || !out12) return HB_E_ARG;
+  for (int i = 0; i < 12; ++i) out12[i] = 0;
+  out12[11] = -1;
   if (!jt->s.last_ex) return HB_OK;
-  executor_tree_info(jt->s.last_ex, out10);
-  out10[8] = executor_on_chip(jt->s.last_ex) ? 1 : 0;
-  out10[9] = executor_jit_origin(jt->s.last_ex);
+  executor_tree_info(jt->s.last_ex, out12);
+  out12[10] = executor_on_chip(jt->s.last_ex) ? 1 : 0;
+  out12[11] = executor_jit_origin(jt->s.last_ex);
   return HB_OK;
 }
 int hb_jt_tree_profile(hb_jt* jt, int64_t* out64) {
@@ -1405,6 +1427,14 @@ int hb_ve_change_factor(hb_ve* ve, int32_t n_scope, const int32_t* scope, const 
     if (!ve) throw Error(HB_E_ARG, "null handle");
     const bool hit = change_factor(ve->s, n_scope, scope, values);
     if (replaced) *replaced = hit ? 1 : 0;
+  });
+}
+int hb_ve_specialise(hb_ve* ve, int32_t n_observed, const int32_t* observed, int32_t* n_kernels) {
+  return guarded([&] {
+    if (!ve || n_observed < 0 || (n_observed > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
+    Compiled& c = ve->program(std::vector<int>(observed, observed + n_observed));
+    const int n = executor_specialise(ve->s.executor(c));
+    if (n_kernels) *n_kernels = n;
   });
 }
 int hb_ve_set_stream(hb_ve* ve, void* cuda_stream) {

@@ -700,6 +700,7 @@ struct Executor {
   bool tree_eligible = false;
   void* tree_fn = nullptr;
   int tree_grid = 0;
+  int64_t tree_loads = 0, tree_stores = 0;  // shared-memory table entries read / written per evidence row
   bool fma = false;  // 1e-12 mode: generated kernels are compiled with multiply-add contraction (never bit-exact)
   // NVRTC runs on a background thread (host-only work); the cubin is installed by the next call that finds it ready,
   // so a stream of batches never stalls on a compilation.
@@ -1427,7 +1428,7 @@ static void start_specialise(Executor* ex) {
   std::string src;
   if (ex->tree_eligible && tree_enabled()) {
     pend->is_tree = true;
-    src = tree_source(P, ex->tree);
+    src = tree_source(P, ex->tree, &ex->tree_loads, &ex->tree_stores);
   } else {
     pend->steps = steps_to_specialise(P);
     if (pend->steps.empty()) return;
@@ -1693,10 +1694,11 @@ void executor_tree_profile(Executor* ex, void* stream, int64_t out64[64]) {
 int executor_jit_origin(const Executor* ex) { return ex->jit_origin; }
 const char* executor_jit_key(const Executor* ex) { return ex->jit ? jit_module_key(ex->jit).c_str() : ""; }
 void executor_set_fma(Executor* ex, bool on) { ex->fma = on; }
-void executor_tree_info(const Executor* ex, int64_t out8[8]) {
+void executor_tree_info(const Executor* ex, int64_t out10[10]) {
   const TreePlan& t = ex->tree;
-  const int64_t v[8] = {ex->tree_eligible ? 1 : 0, t.R, t.T, t.n_levels, t.arena_entries, (int64_t)t.smem_bytes, t.ops_mul, t.ops_add};
-  for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  const int64_t v[10] = {ex->tree_eligible ? 1 : 0, t.R, t.T, t.n_levels, t.arena_entries, (int64_t)t.smem_bytes, t.ops_mul, t.ops_add,
+                         ex->tree_loads, ex->tree_stores};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
 }
 
 void executor_last_timing(Executor* ex, void* stream, double out4[4]) {

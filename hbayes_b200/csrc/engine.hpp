@@ -57,8 +57,9 @@ const char* executor_jit_key(const Executor* ex);  // cache key of the installed
 // 1e-12 mode: kernels generated AFTER this call are compiled with multiply-add contraction (not bit-exact)
 void executor_set_fma(Executor* ex, bool on);
 // on-chip plan: [0] eligible, [1] rows per tile, [2] threads per CTA, [3] dependency levels, [4] arena entries per row,
-// [5] shared-memory bytes per CTA, [6] fp64 multiplies per row, [7] fp64 adds per row
-void executor_tree_info(const Executor* ex, int64_t out8[8]);
+// [5] shared-memory bytes per CTA, [6] fp64 multiplies per row, [7] fp64 adds per row, [8] / [9] shared-memory table
+// entries read / written per row by the generated kernel (0 until it has been generated)
+void executor_tree_info(const Executor* ex, int64_t out10[10]);
 
 // CUDA-event timing of the kernel groups on the launching stream (off by default).  After a run,
 // executor_last_timing synchronises the stream and returns milliseconds summed over the row tiles:

@@ -949,7 +949,7 @@ std::vector<int> choose_block(const Program& P, const Step& st, int64_t cap) {
 }
 }  // namespace
 
-std::string tree_source(const Program& P, const TreePlan& plan) {
+std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_per_row, int64_t* stores_per_row) {
   const Network& net = *P.net;
   const int R = plan.R, T = plan.T;
   const int64_t NV = net.n(), NS = (int64_t)P.slices.size(), W = P.out_width, WP = plan.stage_pitch;
@@ -1209,6 +1209,12 @@ std::string tree_source(const Program& P, const TreePlan& plan) {
   o << "  }\n}\n";
   o << "// per evidence row: " << stat_loads << " table loads, " << plan.ops_mul << " fp64 multiplies, " << plan.ops_add << " fp64 adds; " << stat_items
     << " work items per tile of " << R << " rows\n";
+  if (loads_per_row) *loads_per_row = stat_loads;
+  if (stores_per_row) {
+    *stores_per_row = 0;
+    for (size_t si = 0; si < P.steps.size(); ++si)
+      if (plan.level[si] >= 0) *stores_per_row += P.steps[si].n_out;
+  }
   std::string src = o.str();
   const size_t at = src.find("@@STEP_FUNCTIONS@@");
   src.replace(at, strlen("@@STEP_FUNCTIONS@@"), fns.str());

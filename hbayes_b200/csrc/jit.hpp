@@ -54,7 +54,8 @@ struct TreePlan {
 };
 // false (reason in *why) when the program does not qualify: maximisation steps, tables too large for shared memory, ...
 bool tree_plan(const Program& P, TreePlan& plan, std::string* why);
-std::string tree_source(const Program& P, const TreePlan& plan);
+// loads_per_row / stores_per_row (optional): shared-memory table entries one evidence row reads / writes in the kernel
+std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_per_row = nullptr, int64_t* stores_per_row = nullptr);
 // kernel parameters of hb_tree: (const double* pots, const double* shared, const int8* evidence, double* out,
 //                                long long n_rows, int* flag, int normalise)
 bool jit_launch_smem(void* fn, unsigned grid, unsigned block, unsigned smem_bytes, void** params, void* stream);

@@ -120,10 +120,11 @@ int hb_jt_specialise(hb_jt* jt, int32_t n_observed, const int32_t* observed, int
 int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n);
 /* What the last batch call's (or hb_jt_specialise's) program runs on: [0] 1 if the program qualifies for the on-chip kernel,
  * [1] evidence rows per CTA tile, [2] threads per CTA, [3] dependency levels, [4] shared-memory arena entries per row,
- * [5] shared-memory bytes per CTA, [6] fp64 multiplies per row, [7] fp64 adds per row, [8] 1 if the on-chip kernel is
- * installed and used, [9] origin of the installed generated kernels: -1 none, 0 this process (incl. hb_jt_load),
- * 1 the disk cache, 2 compiled by NVRTC now. */
-int hb_jt_kernel_info(const hb_jt* jt, int64_t* out10);
+ * [5] shared-memory bytes per CTA, [6] fp64 multiplies per row, [7] fp64 adds per row, [8] / [9] shared-memory table
+ * entries read / written per row by the generated kernel, [10] 1 if the on-chip kernel is installed and used,
+ * [11] origin of the installed generated kernels: -1 none, 0 this process (incl. hb_jt_load), 1 the disk cache,
+ * 2 compiled by NVRTC now. */
+int hb_jt_kernel_info(const hb_jt* jt, int64_t* out12);
 /* Tuning hook (HB_TREE_PROFILE=1 in the environment when the on-chip kernel is generated): SM cycles per phase of the
  * on-chip kernel since the previous call, summed over all tiles: out64[0] evidence preparation, out64[1 + l] dependency
  * level l, out64[1 + levels] normalise + write-out; zeros when the instrumentation is off. */
@@ -228,6 +229,8 @@ int hb_ve_mpe_batch(hb_ve* ve, int64_t n_rows, const int8_t* evidence, int8_t* o
 int hb_ve_mpe_order(hb_ve* ve, int32_t n_obs, const int32_t* observed, int32_t* order_out, int32_t* n_out);
 /* changeFactor f g on the network behind a variable-elimination handle (Bayes/Factor.hs:66-81); see hb_jt_change_factor */
 int hb_ve_change_factor(hb_ve* ve, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced);
+/* builds the kernels generated for this observed list now (see hb_jt_specialise) */
+int hb_ve_specialise(hb_ve* ve, int32_t n_observed, const int32_t* observed, int32_t* n_kernels);
 int hb_ve_set_stream(hb_ve* ve, void* cuda_stream);
 int hb_ve_set_workspace(hb_ve* ve, int64_t bytes);
 int hb_ve_last_stats(const hb_ve* ve, int64_t* out8);
