@@ -56,6 +56,7 @@ SIGNATURES = {
     "hb_jt_em_step": (C.c_int, [vp, i64, vp, f64p, i32p, i32]),
     "hb_jt_set_split": (C.c_int, [vp, i32, i32p, i32p]),
     "hb_jt_normalise_batch": (C.c_int, [vp, i64, vp, i32]),
+    "hb_jt_set_precision": (C.c_int, [vp, i32]),
     "hb_jt_set_stream": (C.c_int, [vp, vp]),
     "hb_jt_set_workspace": (C.c_int, [vp, i64]),
     "hb_jt_last_stats": (C.c_int, [vp, i64p]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "hb_ve_mpe_order": (C.c_int, [vp, i32, i32p, i32p, i32p]),
     "hb_ve_change_factor": (C.c_int, [vp, i32, i32p, f64p, i32p]),
     "hb_ve_specialise": (C.c_int, [vp, i32, i32p, i32p]),
+    "hb_ve_set_precision": (C.c_int, [vp, i32]),
     "hb_ve_set_stream": (C.c_int, [vp, vp]),
     "hb_ve_set_workspace": (C.c_int, [vp, i64]),
     "hb_ve_last_stats": (C.c_int, [vp, i64p]),

@@ -167,6 +167,10 @@ class _Batched:
     def set_stream(self, cuda_stream: int):
         check(self._fn("set_stream")(self._h, C.c_void_p(cuda_stream)))
 
+    def set_precision(self, mode: str):
+        """"exact" (default: bit-identical to the reference) or "contract" (generated kernels may fuse multiply-add: ~1e-15)"""
+        check(self._fn("set_precision")(self._h, {"exact": 0, "contract": 1}[mode]))
+
     def set_workspace(self, nbytes: int):
         check(self._fn("set_workspace")(self._h, int(nbytes)))
 

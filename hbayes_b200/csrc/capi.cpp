@@ -1171,6 +1171,24 @@ int hb_jt_tree_profile(hb_jt* jt, int64_t* out64) {
     executor_tree_profile(jt->s.last_ex, jt->s.stream, out64);
   });
 }
+// precision mode of the kernels GENERATED from now on; device-resident programs are dropped so that they are rebuilt
+static int set_precision(Session& s, int32_t mode) {
+  return guarded([&] {
+    if (mode != HB_PRECISION_EXACT && mode != HB_PRECISION_CONTRACT) throw Error(HB_E_ARG, "unknown precision mode");
+    const bool fma = mode == HB_PRECISION_CONTRACT;
+    if (fma == s.fma) return;
+    s.fma = fma;
+    if (s.device >= 0) {
+      cuda_ok(cudaSetDevice(s.device), "cudaSetDevice");
+      cudaDeviceSynchronize();
+    }
+    for (auto& kv : s.cache)
+      if (kv.second->ex) executor_destroy(kv.second->ex), kv.second->ex = nullptr;
+    s.last_ex = s.last_post_ex = nullptr;
+  });
+}
+int hb_jt_set_precision(hb_jt* jt, int32_t mode) { return jt ? set_precision(jt->s, mode) : HB_E_ARG; }
+int hb_ve_set_precision(hb_ve* ve, int32_t mode) { return ve ? set_precision(ve->s, mode) : HB_E_ARG; }
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream) {
   if (!jt) return HB_E_ARG;
   jt->s.stream = (cudaStream_t)cuda_stream;

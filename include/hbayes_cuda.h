@@ -44,6 +44,14 @@ extern "C" {
 #define HB_HOST_PTRS 0    /* evidence / out are host buffers: copies are part of the call */
 #define HB_DEVICE_PTRS 1  /* evidence / out are device buffers on the handle's GPU */
 
+/* hb_*_set_precision: EXACT (default) = every multiply and add rounded separately, in the reference's association order:
+ * results are bit-identical to the reference's Double arithmetic.  CONTRACT = the kernels generated with NVRTC may
+ * contract `acc + a * b` into one fused multiply-add (one rounding instead of two, half the fp64 instructions):
+ * results agree with the reference to ~1e-15 relative (the north star's bar is 1e-12), not bit for bit.  The
+ * precompiled kernels are always exact. */
+#define HB_PRECISION_EXACT 0
+#define HB_PRECISION_CONTRACT 1
+
 typedef struct hb_net hb_net;
 typedef struct hb_jt hb_jt;
 typedef struct hb_ve hb_ve;
@@ -171,6 +179,7 @@ int hb_jt_change_factor(hb_jt* jt, int32_t n_scope, const int32_t* scope, const 
  * CPT's own [child, parents] order (cptDivide's union [b, a], Bayes/Factor/CPT.hs:159-160).  evidence is a host or
  * device pointer according to flags; out_values and out_scopes are host pointers. */
 int hb_jt_em_step(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out_values, int32_t* out_scopes, int32_t flags);
+int hb_jt_set_precision(hb_jt* jt, int32_t mode);
 /* CUDA stream (a cudaStream_t) the handle launches on; NULL = the default stream */
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream);
 /* bytes of device workspace the row arena may use (0 = default) */
@@ -231,6 +240,7 @@ int hb_ve_mpe_order(hb_ve* ve, int32_t n_obs, const int32_t* observed, int32_t* 
 int hb_ve_change_factor(hb_ve* ve, int32_t n_scope, const int32_t* scope, const double* values, int32_t* replaced);
 /* builds the kernels generated for this observed list now (see hb_jt_specialise) */
 int hb_ve_specialise(hb_ve* ve, int32_t n_observed, const int32_t* observed, int32_t* n_kernels);
+int hb_ve_set_precision(hb_ve* ve, int32_t mode);
 int hb_ve_set_stream(hb_ve* ve, void* cuda_stream);
 int hb_ve_set_workspace(hb_ve* ve, int64_t bytes);
 int hb_ve_last_stats(const hb_ve* ve, int64_t* out8);

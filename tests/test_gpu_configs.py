@@ -70,3 +70,55 @@ def test_c5_grid_16x16_properties():
     p2 = [v for v in hb.minDegreeOrder(pnet) if v not in r]
     out2 = hb.VariableElimination(pnet, p2, r).posterior_batch(ev)
     assert max_rel_err(out2, out) < 1e-9  # a different elimination order: same distribution, different rounding
+
+
+def test_c2_half_million_rows_from_host_buffers_equals_device_path_and_oracle():
+    """the host-pointer path whose chunk schedule (10/30/30/20/10 %, D2H overlapping the next chunk's kernels)
+    only engages from 2^19 rows is compared with the device-pointer path on ALL rows and with the oracle on a prefix --
+    on the precompiled kernels and on the generated on-chip kernel (the one bench.py times)."""
+    import torch
+
+    net, observed = synth.config_c2()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    rows = (1 << 19) + 77  # ragged: the last chunk and the last tile are partial
+    ev = synth.config_c2_evidence(net, observed, rows)
+    want = OracleJT(OracleNet.from_arrays(net.dims, net.scopes, net.values)).posteriors_batch(ev[:2048], n_threads=os.cpu_count() or 1)
+    for generated in (False, True):
+        os.environ["HB_JIT"] = "1" if generated else "0"
+        try:
+            jt = hb.JunctionTree(pnet)
+            if generated:
+                assert jt.specialise(observed) > 0 and jt.kernel_info()["on_chip_eligible"] == 1
+            host = jt.posteriors_batch(ev)  # numpy in, numpy out: HB_HOST_PTRS
+            assert bool(jt.kernel_info()["on_chip"]) == generated
+            dev = jt.posteriors_batch(torch.from_numpy(ev).cuda()).cpu().numpy()
+            assert same_bits(host, dev)
+            assert same_bits(host[:2048], want)
+            assert same_bits(host[-1:], OracleJT(OracleNet.from_arrays(net.dims, net.scopes, net.values)).posteriors_batch(ev[-1:]))
+            pinned_ev = torch.from_numpy(ev).pin_memory()
+            pinned_out = torch.empty((rows, pnet.width), dtype=torch.float64, pin_memory=True)
+            jt.posteriors_batch(pinned_ev, pinned_out)
+            assert same_bits(pinned_out.numpy(), host)
+        finally:
+            os.environ["HB_JIT"] = "0"
+
+
+def test_c3_generated_step_kernels_bitexact():
+    """the per-step generated kernels (hb_step_<i>, what C3 runs on in bench.py) against the oracle, in the
+    suite's own process: hb_jt_specialise builds them for C3's program (too large for the on-chip kernel)."""
+    net, observed = synth.config_c3()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    ev = synth.config_c3_evidence(net, observed, 192)
+    os.environ["HB_JIT"] = "1"
+    try:
+        jt = hb.JunctionTree(pnet)
+        n = jt.specialise(observed)
+        got = jt.posteriors_batch(ev)
+        info = jt.kernel_info()
+    finally:
+        os.environ["HB_JIT"] = "0"
+    assert n >= 20 and jt.specialised_kernels() == n and not info["on_chip"] and not info["on_chip_eligible"]
+    want = OracleJT(OracleNet.from_arrays(net.dims, net.scopes, net.values)).posteriors_batch(ev[:64], n_threads=os.cpu_count() or 1)
+    assert same_bits(got[:64], want)
+    plain = hb.JunctionTree(pnet).posteriors_batch(ev)  # HB_JIT=0: the precompiled kernels
+    assert same_bits(got, plain)

@@ -124,3 +124,34 @@ def test_on_chip_kernel_bit_identical_to_oracle_and_to_the_templated_kernels(tmp
     assert sorted(a.files) == sorted(b.files) and len(a.files) >= 12
     for k in a.files:
         assert a[k].tobytes() == b[k].tobytes(), k
+
+
+def test_contract_mode_agrees_to_1e_12_and_is_not_the_default():
+    """HB_PRECISION_CONTRACT (north star: marginals within 1e-12 relative, 1e-15 absolute floor): the generated kernels fuse
+    multiply-add; the default stays bit-exact."""
+    import numpy as np
+
+    import hbayes_b200 as hb
+    from hbayes_b200 import synth
+    from helpers import max_rel_err
+
+    net, observed = synth.config_c2()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    ev = synth.config_c2_evidence(net, observed, 20000)
+    exact = hb.JunctionTree(pnet).posteriors_batch(ev)  # HB_JIT=0 in this process: precompiled kernels
+    os.environ["HB_JIT"] = "1"
+    try:
+        jt = hb.JunctionTree(pnet)
+        assert jt.specialise(observed) > 0
+        assert jt.posteriors_batch(ev).tobytes() == exact.tobytes()  # default mode: exact
+        jt.set_precision("contract")
+        assert jt.specialise(observed) > 0
+        fast = jt.posteriors_batch(ev)
+        assert jt.kernel_info()["on_chip"] == 1
+        jt.set_precision("exact")
+        jt.specialise(observed)
+        assert jt.posteriors_batch(ev).tobytes() == exact.tobytes()
+    finally:
+        os.environ["HB_JIT"] = "0"
+    assert max_rel_err(fast, exact, floor=1e-15) < 1e-12
+    assert fast.tobytes() != exact.tobytes()  # the contracted kernel really ran

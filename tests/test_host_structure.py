@@ -47,6 +47,18 @@ def test_hugin_loader_matches_oracle():
     assert hb.importBayesianGraph(os.path.join(G, "missing.net")) is None
 
 
+def test_gui_export_dialect_loads_like_the_plain_file():
+    """a Hugin / SamIam GUI export -- `net { HR_... }` property header, node attributes, tab-indented nested data blocks, the
+    dialect of the reference's bundled cancer.net (/root/reference/cancer.net:1-128) -- gives exactly the network of the plain
+    file, in the product's loader and in the oracle's"""
+    plain = hb.importBayesianGraph(os.path.join(G, "sprinkler.net"))
+    for loader in (hb.importBayesianGraph, OracleNet.load_hugin):
+        gui = loader(os.path.join(G, "sprinkler_gui.net"))
+        assert (gui.names, gui.dims, gui.scopes, gui.values) == (plain.names, plain.dims, plain.scopes, plain.values)
+    text = open(os.path.join(G, "sprinkler_gui.net")).read()
+    assert "HR_Compile_TriangMethod" in text and "\tposition = (" in text and "data = (((" in text
+
+
 def test_bad_arguments_are_status_codes():
     with pytest.raises(hb.HbError) as e:
         hb.BayesianNetwork.from_tables([2, 2], [[0], [1, 0]], [[0.5, 0.5], [0.1, 0.9, 0.3]])
