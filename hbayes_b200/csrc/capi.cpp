@@ -67,6 +67,7 @@ struct Compiled {
   std::unique_ptr<Program> prog;
   Executor* ex = nullptr;
   bool stale = false;  // the network's CPT values changed after `ex` uploaded them (changeFactor)
+  bool warm = false;       // loaded from a saved handle that had generated kernels: rebuilt (from the saved cubin) with the executor
   uint64_t last_used = 0;  // Session::tick of the last call that ran it (executors are evicted least recently used first)
   ~Compiled() {
     if (ex) executor_destroy(ex);
@@ -183,6 +184,7 @@ struct Session {
       }
       executor_set_fma(c.ex, fma);
       c.stale = false;
+      if (c.warm) executor_specialise(c.ex);  // the cubin came with the file: no compilation
     }
     if (c.stale) executor_refresh_potentials(c.ex), c.stale = false;
     executor_set_timing(c.ex, timing);
@@ -551,7 +553,8 @@ int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const
 }
 // ---- persistence: network + junction-tree structure in one little-endian binary file -----------------------
 namespace {
-const char JT_MAGIC[8] = {'H', 'B', 'J', 'T', 'r', '0', '1', '\0'};
+const char JT_MAGIC[8] = {'H', 'B', 'J', 'T', 'r', '0', '2', '\0'};     // r02 = r01 + compiled programs and their cubins
+const char JT_MAGIC_R01[8] = {'H', 'B', 'J', 'T', 'r', '0', '1', '\0'};
 
 struct Writer {
   FILE* f;
@@ -701,6 +704,30 @@ int hb_jt_save(const hb_jt* jt, const char* path) {
     w.lists(t.children);
     w.lists(t.factors);
     w.ints(t.by_rank);
+    // compiled programs: the (observed list, queries) each was compiled for -- the step list and its index maps are a
+    // deterministic function of network + tree + this key and are rebuilt in milliseconds -- and the cubin of the
+    // kernels generated for it (seconds of NVRTC), keyed by the hash of their source
+    std::vector<int> fixed;
+    for (auto& f : jt->s.fixed) fixed.push_back(f.first), fixed.push_back(f.second);
+    w.ints(fixed);
+    std::vector<std::pair<std::string, std::shared_ptr<const std::string>>> cubins;
+    w.i64((int64_t)jt->s.cache.size());
+    for (auto& kv : jt->s.cache) {
+      w.ints(kv.first);
+      std::string key = kv.second->ex ? executor_jit_key(kv.second->ex) : "";
+      std::shared_ptr<const std::string> cubin = key.empty() ? nullptr : jit_registry_get(key);
+      if (!cubin) key.clear();
+      w.i64((int64_t)key.size());
+      if (!key.empty() && fwrite(key.data(), 1, key.size(), f) != key.size()) throw Error(HB_E_IO, "write failed");
+      if (cubin) cubins.push_back({key, cubin});
+    }
+    w.i64((int64_t)cubins.size());
+    for (auto& c : cubins) {
+      w.i64((int64_t)c.first.size());
+      w.i64((int64_t)c.second->size());
+      if (fwrite(c.first.data(), 1, c.first.size(), f) != c.first.size() || fwrite(c.second->data(), 1, c.second->size(), f) != c.second->size())
+        throw Error(HB_E_IO, "write failed");
+    }
   });
 }
 
@@ -711,7 +738,9 @@ int hb_jt_load(const char* path, const int32_t* devices, int32_t n_devices, hb_j
     if (!f) throw Error(HB_E_IO, std::string("cannot open ") + path);
     std::unique_ptr<FILE, int (*)(FILE*)> guard(f, fclose);
     char magic[8];
-    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, JT_MAGIC, 8) != 0) throw Error(HB_E_IO, "not a libhbayes_cuda junction-tree file");
+    if (fread(magic, 1, 8, f) != 8 || (memcmp(magic, JT_MAGIC, 8) != 0 && memcmp(magic, JT_MAGIC_R01, 8) != 0))
+      throw Error(HB_E_IO, "not a libhbayes_cuda junction-tree file");
+    const bool has_programs = memcmp(magic, JT_MAGIC, 8) == 0;
     Reader r(f);
     auto jt = std::make_unique<hb_jt>();
     Network& net = jt->s.net;
@@ -765,8 +794,50 @@ int hb_jt_load(const char* path, const int32_t* devices, int32_t n_devices, hb_j
     jt->s.device = pick_device(devices, n_devices);
     jt->post_off.assign(1, 0);
     for (int d : net.dims) jt->post_off.push_back(jt->post_off.back() + d);
-    Compiled& prior = jt->program({}, {});
-    if (jt->s.device >= 0) jt->run_one(prior, jt->posts);
+    if (has_programs) {
+      const std::vector<int> fixed = r.ints();
+      if (fixed.size() % 2) throw Error(HB_E_IO, "corrupt file: split list");
+      for (size_t i = 0; i < fixed.size(); i += 2) {
+        if (fixed[i] < 0 || fixed[i] >= n || fixed[i + 1] < 0 || fixed[i + 1] >= net.dims[fixed[i]]) throw Error(HB_E_IO, "corrupt file: split list");
+        jt->s.fixed.push_back({fixed[i], fixed[i + 1]});
+      }
+      const int64_t n_prog = r.count(1 << 20);
+      std::vector<std::pair<std::vector<int>, std::string>> programs;
+      for (int64_t i = 0; i < n_prog; ++i) {
+        std::vector<int> key = r.ints();
+        std::string ck((size_t)r.count(64), ' ');
+        if (!ck.empty() && fread(&ck[0], 1, ck.size(), f) != ck.size()) throw Error(HB_E_IO, "truncated file");
+        programs.push_back({std::move(key), std::move(ck)});
+      }
+      const int64_t n_cubin = r.count(1 << 20);
+      for (int64_t i = 0; i < n_cubin; ++i) {
+        std::string ck((size_t)r.count(64), ' ');
+        std::string blob((size_t)r.count((int64_t)1 << 30), '\0');
+        if (fread(&ck[0], 1, ck.size(), f) != ck.size() || fread(&blob[0], 1, blob.size(), f) != blob.size()) throw Error(HB_E_IO, "truncated file");
+        // a cubin is only ever used under the key of the source this process generates itself: a damaged or foreign blob
+        // under a wrong key is never looked up, one under the right key fails cuModuleLoadData and is ignored
+        if (blob.size() > 64 && blob.compare(0, 4, "\x7f" "ELF") == 0) jit_registry_put(ck, blob);
+      }
+      for (auto& pr : programs) {  // key = observed..., -1, queries (separated by -1)..., -1, fixed pairs
+        const std::vector<int>& key = pr.first;
+        if (key.size() < 2 + fixed.size()) throw Error(HB_E_IO, "corrupt file: program key");
+        const size_t q_end = key.size() - fixed.size() - 1;
+        size_t o_end = 0;
+        while (o_end < q_end && key[o_end] != -1) ++o_end;
+        if (o_end >= q_end || key[q_end] != -1) throw Error(HB_E_IO, "corrupt file: program key");
+        const std::vector<int> observed(key.begin(), key.begin() + o_end), query(key.begin() + o_end + 1, key.begin() + q_end);
+        try {
+          Compiled& c = jt->program(observed, query);
+          c.warm = !pr.second.empty();
+        } catch (const Error& e) {
+          throw Error(HB_E_IO, std::string("corrupt file: saved program does not compile: ") + e.what());
+        }
+      }
+    }
+    if (jt->s.fixed.empty()) {
+      Compiled& prior = jt->program({}, {});
+      if (jt->s.device >= 0) jt->run_one(prior, jt->posts);
+    }
     *out = jt.release();
   });
 }

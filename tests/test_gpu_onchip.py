@@ -155,3 +155,51 @@ def test_contract_mode_agrees_to_1e_12_and_is_not_the_default():
         os.environ["HB_JIT"] = "0"
     assert max_rel_err(fast, exact, floor=1e-15) < 1e-12
     assert fast.tobytes() != exact.tobytes()  # the contracted kernel really ran
+
+
+PERSIST = r'''
+import sys, time
+sys.path.insert(0, %(root)r)
+import numpy as np
+import hbayes_b200 as hb
+from hbayes_b200 import synth
+net, observed = synth.config_c2()
+pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+ev = synth.config_c2_evidence(net, observed, 4096)
+path, mode = sys.argv[1], sys.argv[2]
+if mode == "save":
+    jt = hb.JunctionTree(pnet)
+    t = time.perf_counter(); n = jt.specialise(observed); dt = time.perf_counter() - t
+    out = jt.posteriors_batch(ev)
+    jt.save(path)
+else:
+    jt = hb.JunctionTree.load(path, pnet)
+    jt.posteriors_batch(ev[:2])  # creates the device-resident program (context, potentials) outside the timed call
+    t = time.perf_counter(); n = jt.specialise(observed); dt = time.perf_counter() - t
+    out = jt.posteriors_batch(ev)
+np.save(path + "." + mode + ".npy", out)
+print("RESULT", n, "%%.6f" %% dt, jt.kernel_info()["origin"], jt.kernel_info()["on_chip"])
+'''
+
+
+def test_saved_handle_carries_its_compiled_kernels_to_the_next_process(tmp_path):
+    """f3 (the counterpart of saving a CALIBRATED tree, Bayes/ImportExport.hs:36-46,52-102): hb_jt_save writes the compiled
+    programs' keys and the cubins of their generated kernels; a second process that loads the file runs on them without
+    NVRTC (disk cache off here: the file alone carries them) -- specialise in well under 100 ms -- and answers bit for bit."""
+    import numpy as np
+
+    path = str(tmp_path / "c2.hbjt")
+    env = dict(os.environ, HB_JIT="1", HB_JIT_CACHE="0")
+    res = {}
+    for mode in ("save", "load"):
+        r = subprocess.run([sys.executable, "-c", PERSIST % {"root": ROOT}, path, mode], capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        res[mode] = r.stdout.rsplit("RESULT", 1)[1].split()
+    n0, t0, origin0, chip0 = res["save"]
+    n1, t1, origin1, chip1 = res["load"]
+    assert int(n0) == int(n1) > 0 and chip0 == chip1 == "1"
+    assert origin0 == "2"  # first process: compiled by NVRTC
+    assert origin1 == "0"  # second process: the cubin came with the file
+    assert float(t1) < 0.1 < float(t0)
+    assert np.load(path + ".save.npy").tobytes() == np.load(path + ".load.npy").tobytes()
+    assert os.path.getsize(path) > 100000  # the cubin is in there
