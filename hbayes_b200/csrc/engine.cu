@@ -1675,10 +1675,10 @@ void executor_normalise(Executor* ex, int64_t n_rows, double* d_out, void* strea
 void executor_set_timing(Executor* ex, bool on) { ex->timing = on; }
 
 int executor_specialised_kernels(const Executor* ex) {
-  if (ex->tree_fn) {  // the on-chip kernel covers every per-row step
-    int n = 0;
+  if (ex->tree_fn) {  // the on-chip kernel covers every per-row step (a program without evidence has none: everything is
+    int n = 0;        // batch-invariant and the kernel only normalises and writes -- still one generated kernel)
     for (int lv : ex->tree.level) n += lv >= 0;
-    return n;
+    return std::max(n, 1);
   }
   int n = 0;
   for (void* f : ex->jit_fn) n += f != nullptr;
