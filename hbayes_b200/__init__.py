@@ -29,6 +29,7 @@ from .api import (  # noqa: F401
     factorProduct,
     factorProjectOut,
     factorProjectTo,
+    host_alloc,
     marginalizeOneVariable,
     importBayesianGraph,
     learnEM,

@@ -24,6 +24,11 @@ SIGNATURES = {
     "hb_last_error": (C.c_char_p, []),
     "hb_string_free": (None, [vp]),
     "hb_device_count": (C.c_int, []),
+    "hb_host_alloc": (C.c_int, [i64, vpp]),
+    "hb_host_free": (None, [vp]),
+    "hb_host_register": (C.c_int, [vp, i64]),
+    "hb_host_unregister": (C.c_int, [vp]),
+    "hb_jt_n_devices": (C.c_int, [vp]),
     "hb_net_create": (C.c_int, [i32, i32p, i64p, i32p, i64p, f64p, vpp]),
     "hb_net_create_procedural": (C.c_int, [i32, i32p, i64p, i32p, i64p, f64p, C.POINTER(C.c_uint64), vpp]),
     "hb_net_cpt_values": (C.c_int, [vp, i32, i64, i64, f64p]),

@@ -152,8 +152,22 @@ def minFillOrder(net):
 def _device_args(device):
     if device is None:  # structure only: parity hooks work, compute calls fail loudly
         return None, HB_STRUCTURE_ONLY, None
-    a, p = _i32([device])
-    return p, 1, a
+    a, p = _i32([device] if isinstance(device, (int, np.integer)) else list(device))  # a list: host batches are sharded over them
+    return p, len(a), a
+
+
+def host_alloc(shape, dtype):
+    """a numpy array over page-locked host memory from hb_host_alloc (freed when the array is collected)"""
+    import weakref
+
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    check(lib().hb_host_alloc(n, C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib().hb_host_free, p)
+    return arr
 
 
 class _Batched:
@@ -234,6 +248,10 @@ class JunctionTree(_Batched):
         else:
             check(lib().hb_jt_compile(net._h, int(cmp), dp, nd, C.byref(h)))
         self._h = h
+
+    @property
+    def n_devices(self):
+        return int(lib().hb_jt_n_devices(self._h))
 
     def describe(self):
         p = C.c_void_p()

@@ -11,6 +11,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hbayes_cuda.h"
@@ -60,6 +61,11 @@ int pick_device(const int32_t* devices, int32_t n_devices) {
   int dev = 0;
   if (devices && n_devices > 0) dev = devices[0];
   if (dev < 0 || dev >= count) throw Error(HB_E_ARG, "device ordinal out of range");
+  for (int i = 1; devices && i < n_devices; ++i) {
+    if (devices[i] < 0 || devices[i] >= count) throw Error(HB_E_ARG, "device ordinal out of range");
+    for (int j = 0; j < i; ++j)
+      if (devices[j] == devices[i]) throw Error(HB_E_ARG, "a device is listed twice");
+  }
   return dev;
 }
 
@@ -334,6 +340,10 @@ struct hb_net {
 struct hb_jt {
   Session s;
   std::unique_ptr<Tree> tree;
+  // devices[1..] of the compile call: one replica of the handle per further GPU (same network, same tree, own programs
+  // and device state).  Host-buffer batch calls shard their rows over self + peers, one host thread per GPU, no
+  // communication between them; everything else runs on this handle's own device.
+  std::vector<std::unique_ptr<hb_jt>> peers;
   std::vector<int> ev_vars, ev_states;  // current changeEvidence list
   std::vector<double> posts;            // posterior [v] for every v under the current evidence
   bool posts_stale = false;             // a changeFactor happened since `posts` was computed
@@ -523,6 +533,14 @@ static int jt_compile(const hb_net* net, int32_t cmp, const int32_t* order, cons
     for (int d : jt->s.net.dims) jt->post_off.push_back(jt->post_off.back() + d);
     Compiled& prior = jt->program({}, {});
     if (jt->s.device >= 0) jt->run_one(prior, jt->posts);  // createJunctionTree calibrates the tree (distribute . collect)
+    for (int i = 1; jt->s.device >= 0 && devices && i < n_devices; ++i) {
+      auto peer = std::make_unique<hb_jt>();
+      peer->s.net = jt->s.net;
+      peer->tree = std::make_unique<Tree>(*jt->tree);
+      peer->s.device = devices[i];
+      peer->post_off = jt->post_off;
+      jt->peers.push_back(std::move(peer));
+    }
     *out = jt.release();
   });
 }
@@ -915,11 +933,64 @@ int hb_jt_posterior(hb_jt* jt, int32_t n_q, const int32_t* q_vars, int32_t* out_
     if (n_written) *n_written = c.prog->out_width;
   });
 }
+// rows below which a host-buffer batch is not worth spreading over the handle's other GPUs
+static constexpr int64_t kMinRowsPerDevice = 4096;
+
 int hb_jt_posteriors_batch(hb_jt* jt, int64_t n_rows, const int8_t* evidence, double* out, int32_t flags) {
   return guarded([&] {
     if (!jt) throw Error(HB_E_ARG, "null handle");
+    const int64_t width = jt->s.net.width();
+    const int n_vars = jt->s.net.n();
+    const size_t n_dev = 1 + jt->peers.size();
+    if (n_dev > 1 && !(flags & HB_DEVICE_PTRS) && n_rows >= (int64_t)n_dev * kMinRowsPerDevice && evidence && out) {
+      // evidence rows are independent: contiguous slices, one host thread and one GPU each, no communication
+      std::vector<int> codes(n_dev, HB_OK);
+      std::vector<std::string> messages(n_dev);
+      std::vector<std::thread> threads;
+      for (size_t d = 0; d < n_dev; ++d) {
+        const int64_t lo = n_rows * (int64_t)d / (int64_t)n_dev, hi = n_rows * (int64_t)(d + 1) / (int64_t)n_dev;
+        hb_jt* h = d == 0 ? jt : jt->peers[d - 1].get();
+        threads.emplace_back([=, &codes, &messages] {
+          codes[d] = guarded([&] {
+            run_matrix(h->s, [&](const std::vector<int>& obs) -> Compiled& { return h->program(obs, {}); }, hi - lo, evidence + lo * n_vars,
+                       out + lo * width, flags);
+            h->s.last_post_ex = h->s.last_ex;
+          });
+          if (codes[d] != HB_OK) messages[d] = g_error;  // thread-local: carried back to the caller's thread
+        });
+      }
+      for (std::thread& t : threads) t.join();
+      for (size_t d = 0; d < n_dev; ++d)
+        if (codes[d] != HB_OK) throw Error(codes[d], "device " + std::to_string(d == 0 ? jt->s.device : jt->peers[d - 1]->s.device) + ": " + messages[d]);
+      return;
+    }
     run_matrix(jt->s, [&](const std::vector<int>& obs) -> Compiled& { return jt->program(obs, {}); }, n_rows, evidence, out, flags);
     jt->s.last_post_ex = jt->s.last_ex;  // every program of this call has the all-posteriors layout
+  });
+}
+int hb_jt_n_devices(const hb_jt* jt) { return jt ? (int)(1 + jt->peers.size()) : HB_E_ARG; }
+
+int hb_host_alloc(int64_t bytes, void** out) {
+  return guarded([&] {
+    if (!out || bytes < 0) throw Error(HB_E_ARG, "null out or negative size");
+    void* p = nullptr;
+    cuda_ok(cudaHostAlloc(&p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable), "cudaHostAlloc");
+    *out = p;
+  });
+}
+void hb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int hb_host_register(void* p, int64_t bytes) {
+  return guarded([&] {
+    if (!p || bytes <= 0) throw Error(HB_E_ARG, "null buffer");
+    cuda_ok(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable), "cudaHostRegister");
+  });
+}
+int hb_host_unregister(void* p) {
+  return guarded([&] {
+    if (!p) throw Error(HB_E_ARG, "null buffer");
+    cuda_ok(cudaHostUnregister(p), "cudaHostUnregister");
   });
 }
 int hb_jt_queries_batch(hb_jt* jt, int32_t n_queries, const int32_t* query_off, const int32_t* query_vars, int64_t n_rows,
@@ -967,6 +1038,7 @@ int hb_jt_change_factor(hb_jt* jt, int32_t n_scope, const int32_t* scope, const 
     const bool hit = change_factor(jt->s, n_scope, scope, values);
     if (replaced) *replaced = hit ? 1 : 0;
     if (hit) jt->posts_stale = true;  // recalibrated under the kept evidence when the next posterior is asked for
+    for (auto& peer : jt->peers) change_factor(peer->s, n_scope, scope, values);
   });
 }
 
@@ -1216,9 +1288,14 @@ int hb_jt_normalise_batch(hb_jt* jt, int64_t n_rows, double* out, int32_t flags)
 int hb_jt_specialise(hb_jt* jt, int32_t n_observed, const int32_t* observed, int32_t* n_kernels) {
   return guarded([&] {
     if (!jt || n_observed < 0 || (n_observed > 0 && !observed)) throw Error(HB_E_ARG, "null argument");
-    Compiled& c = jt->program(std::vector<int>(observed, observed + n_observed), {});
+    const std::vector<int> obs(observed, observed + n_observed);
+    Compiled& c = jt->program(obs, {});
     const int n = executor_specialise(jt->s.executor(c));
     if (n_kernels) *n_kernels = n;
+    for (auto& peer : jt->peers) {  // the cubin is in this process' registry by now: the peers only load it
+      Compiled& pc = peer->program(obs, {});
+      executor_specialise(peer->s.executor(pc));
+    }
   });
 }
 int hb_jt_specialised_kernels(const hb_jt* jt, int32_t* n) {
@@ -1258,7 +1335,11 @@ static int set_precision(Session& s, int32_t mode) {
     s.last_ex = s.last_post_ex = nullptr;
   });
 }
-int hb_jt_set_precision(hb_jt* jt, int32_t mode) { return jt ? set_precision(jt->s, mode) : HB_E_ARG; }
+int hb_jt_set_precision(hb_jt* jt, int32_t mode) {
+  if (!jt) return HB_E_ARG;
+  for (auto& peer : jt->peers) set_precision(peer->s, mode);
+  return set_precision(jt->s, mode);
+}
 int hb_ve_set_precision(hb_ve* ve, int32_t mode) { return ve ? set_precision(ve->s, mode) : HB_E_ARG; }
 int hb_jt_set_stream(hb_jt* jt, void* cuda_stream) {
   if (!jt) return HB_E_ARG;
@@ -1270,6 +1351,7 @@ int hb_jt_set_workspace(hb_jt* jt, int64_t bytes) {
   jt->s.workspace = bytes;
   jt->s.cache.clear();
   jt->s.last_ex = jt->s.last_post_ex = nullptr;
+  for (auto& peer : jt->peers) peer->s.workspace = bytes, peer->s.cache.clear(), peer->s.last_ex = peer->s.last_post_ex = nullptr;
   return HB_OK;
 }
 int hb_jt_set_timing(hb_jt* jt, int32_t on) {
