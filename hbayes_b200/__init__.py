@@ -30,6 +30,7 @@ from .api import (  # noqa: F401
     factorProjectOut,
     factorProjectTo,
     host_alloc,
+    nccl_unique_id,
     marginalizeOneVariable,
     importBayesianGraph,
     learnEM,

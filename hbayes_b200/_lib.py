@@ -42,6 +42,8 @@ SIGNATURES = {
     "hb_jt_compile": (C.c_int, [vp, i32, i32p, i32, vpp]),
     "hb_jt_compile_with_order": (C.c_int, [vp, i32p, i32p, i32, vpp]),
     "hb_jt_compile_split": (C.c_int, [vp, i32, i32p, i32, i32, i32p, i32p, vpp]),
+    "hb_nccl_unique_id": (C.c_int, [vp]),
+    "hb_jt_compile_split_nccl": (C.c_int, [vp, i32, i32, i32, i32p, i32p, i32, i32, vp, vpp]),
     "hb_jt_save": (C.c_int, [vp, C.c_char_p]),
     "hb_jt_load": (C.c_int, [C.c_char_p, i32p, i32, vpp]),
     "hb_jt_describe_json": (C.c_int, [vp, cpp]),

@@ -156,6 +156,13 @@ def _device_args(device):
     return p, len(a), a
 
 
+def nccl_unique_id() -> bytes:
+    """128 bytes from ncclGetUniqueId: rank 0 creates it, every rank of a split clique passes it to JunctionTree(nccl=...)"""
+    buf = C.create_string_buffer(128)
+    check(lib().hb_nccl_unique_id(buf))
+    return buf.raw
+
+
 def host_alloc(shape, dtype):
     """a numpy array over page-locked host memory from hb_host_alloc (freed when the array is collected)"""
     import weakref
@@ -234,11 +241,18 @@ class JunctionTree(_Batched):
 
     _prefix = "hb_jt_"
 
-    def __init__(self, net: BayesianNetwork, cmp=nodeComparisonForTriangulation, order=None, device=0, split=None):
+    def __init__(self, net: BayesianNetwork, cmp=nodeComparisonForTriangulation, order=None, device=0, split=None, nccl=None):
         self.net = net
         dp, nd, self._keep = _device_args(device)
         h = C.c_void_p()
-        if split is not None:  # one slice of a split clique: [(vertex, state)], no calibration
+        if nccl is not None:  # (rank, world, unique id bytes): the slice `split` of a clique split over `world` GPUs, exchange inside the library
+            rank, world, uid = nccl
+            va, vp_ = _i32([e[0] for e in split])
+            sa, sp = _i32([e[1] for e in split])
+            buf = C.create_string_buffer(bytes(uid), 128) if uid is not None else None
+            check(lib().hb_jt_compile_split_nccl(net._h, int(cmp), HB_STRUCTURE_ONLY if device is None else int(device), len(split), vp_, sp,
+                                                 int(rank), int(world), buf, C.byref(h)))
+        elif split is not None:  # one slice of a split clique: [(vertex, state)], no calibration
             va, vp_ = _i32([e[0] for e in split])
             sa, sp = _i32([e[1] for e in split])
             check(lib().hb_jt_compile_split(net._h, int(cmp), dp, nd, len(split), vp_, sp, C.byref(h)))

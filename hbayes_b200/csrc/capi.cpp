@@ -18,6 +18,7 @@
 #include "engine.hpp"
 #include "jit.hpp"
 #include "model.hpp"
+#include "nccl_dyn.hpp"
 
 using namespace hb;
 
@@ -124,6 +125,10 @@ struct Session {
   int64_t chunk_rows = 1 << 18;
   // split clique: variables fixed to this handle's slice; batch results are then left unnormalised
   std::vector<std::pair<int, int>> fixed;
+  // split clique with the exchange inside the library (hb_jt_compile_split_nccl): this rank's communicator; programs are
+  // compiled with reduce points (CompileOptions::reduce_groups) and batch results come back complete and normalised
+  void* comm = nullptr;
+  int nccl_rank = 0, nccl_world = 1;
   // grow-only device scratch of hb_jt_em_step (result matrix of a chunk, group staging, evidence, row indices):
   // freeing gigabytes per call costs more than the step itself
   struct Scratch {
@@ -145,6 +150,12 @@ struct Session {
   ~Session() {
     if (device >= 0) cudaSetDevice(device);
     cache.clear();
+    if (comm) {
+      try {
+        nccl_comm_destroy(comm);
+      } catch (...) {
+      }
+    }
     if (d_ev) cudaFree(d_ev);
     if (d_out) cudaFree(d_out);
     if (h_one_ev) cudaFreeHost(h_one_ev);
@@ -189,6 +200,7 @@ struct Session {
         c.ex = executor_create(*c.prog, device, workspace);
       }
       executor_set_fma(c.ex, fma);
+      executor_set_comm(c.ex, comm);
       c.stale = false;
       if (c.warm) executor_specialise(c.ex);  // the cubin came with the file: no compilation
     }
@@ -247,9 +259,34 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
     std::vector<int8_t> first(n_vars);
     cuda_ok(cudaMemcpyAsync(first.data(), evidence, n_vars, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(first row)");
     cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    if (s.comm) {  // split clique over NCCL: the rows leave the split variables unobserved; this rank's states go into a copy
+      for (auto& f : s.fixed) first[f.first] = (int8_t)f.second;
+      Compiled& c = get(observed_of_row(first.data(), n_vars));
+      s.reserve((size_t)n_rows * n_vars, 0);
+      cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)n_rows * n_vars, cudaMemcpyDeviceToDevice, s.stream), "cudaMemcpy(evidence)");
+      executor_fill_fixed(s.executor(c), s.d_ev, n_rows, s.stream);
+      executor_run(s.executor(c), n_rows, s.d_ev, out, s.stream, &rs, true);
+      s.note(c, rs, false);
+      executor_check(s.executor(c), s.stream);
+      return;
+    }
     Compiled& c = get(observed_of_row(first.data(), n_vars));
     executor_run(s.executor(c), n_rows, evidence, out, s.stream, &rs, s.fixed.empty());
     s.note(c, rs, false);
+    executor_check(s.executor(c), s.stream);
+    return;
+  }
+  if (s.comm) {  // host buffers, split clique over NCCL: one upload, one pass (every rank must take the same path: no regrouping)
+    std::vector<int8_t> first(evidence, evidence + n_vars);
+    for (auto& f : s.fixed) first[f.first] = (int8_t)f.second;
+    Compiled& c = get(observed_of_row(first.data(), n_vars));
+    const int64_t w = c.prog->out_width;
+    s.reserve((size_t)n_rows * n_vars, (size_t)n_rows * w * sizeof(double));
+    cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)n_rows * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+    executor_fill_fixed(s.executor(c), s.d_ev, n_rows, s.stream);
+    executor_run(s.executor(c), n_rows, s.d_ev, s.d_out, s.stream, &rs, true);
+    s.note(c, rs, false);
+    cuda_ok(cudaMemcpyAsync(out, s.d_out, (size_t)n_rows * w * sizeof(double), cudaMemcpyDeviceToHost, s.stream), "cudaMemcpy(out)");
     executor_check(s.executor(c), s.stream);
     return;
   }
@@ -373,6 +410,7 @@ struct hb_jt {
     auto c = std::make_unique<Compiled>();
     CompileOptions opt;
     opt.fixed = s.fixed;
+    opt.reduce_groups = s.comm != nullptr || s.nccl_world < 0;  // nccl_world < 0: structure-only handle asking for the split program
     c->prog.reset(compile_jt(s.net, *tree, observed, qs, opt));
     return *(s.cache[key] = std::move(c));
   }
@@ -560,6 +598,40 @@ int hb_jt_compile_split(const hb_net* net, int32_t cmp, const int32_t* devices, 
     for (int d : jt->s.net.dims) jt->post_off.push_back(jt->post_off.back() + d);
     for (int i = 0; i < n_fixed; ++i) jt->s.fixed.push_back({vars[i], states[i]});
     *out = jt.release();  // no calibration: the unsplit tables may not fit one GPU
+  });
+}
+int hb_nccl_unique_id(void* out128) {
+  return guarded([&] {
+    if (!out128) throw Error(HB_E_ARG, "null out");
+    nccl_unique_id(out128);
+  });
+}
+int hb_jt_compile_split_nccl(const hb_net* net, int32_t cmp, int32_t device, int32_t n_fixed, const int32_t* vars, const int32_t* states,
+                             int32_t rank, int32_t world, const void* unique_id128, hb_jt** out) {
+  return guarded([&] {
+    if (!net || !out) throw Error(HB_E_ARG, "null argument");
+    check_evidence_list(net->net, n_fixed, vars, states);
+    if (world < 1 || rank < 0 || rank >= world) throw Error(HB_E_ARG, "rank outside the world");
+    auto jt = std::make_unique<hb_jt>();
+    jt->s.net = net->net;
+    jt->tree.reset(tree_build(jt->s.net, cmp, nullptr));
+    jt->post_off.assign(1, 0);
+    for (int d : jt->s.net.dims) jt->post_off.push_back(jt->post_off.back() + d);
+    for (int i = 0; i < n_fixed; ++i) jt->s.fixed.push_back({vars[i], states[i]});
+    jt->s.nccl_rank = rank;
+    if (device == HB_STRUCTURE_ONLY) {  // parity hook: the split program (reduce points) without a GPU or a communicator
+      jt->s.device = -1;
+      jt->s.nccl_world = -world;
+      *out = jt.release();
+      return;
+    }
+    if (!unique_id128) throw Error(HB_E_ARG, "null NCCL unique id");
+    int32_t dev_list[1] = {device};
+    jt->s.device = pick_device(dev_list, 1);
+    jt->s.nccl_world = world;
+    cuda_ok(cudaSetDevice(jt->s.device), "cudaSetDevice");
+    jt->s.comm = nccl_comm_init(world, rank, unique_id128);  // collective: every rank of the world is in this call now
+    *out = jt.release();
   });
 }
 int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const int32_t* devices, int32_t n_devices, hb_jt** out) {

@@ -42,8 +42,16 @@ struct Compiler {
   const Network& net;
   Program& P;
   int one = -1;  // the `Scalar 1.0` table
+  bool reduce_groups = false;
+  // split clique: the split (fixed) variables a table is still conditioned on -- it holds the term of THIS GPU's states
+  std::map<int, std::vector<int>> dep;
+  std::vector<int> dep_of(int id) const {
+    auto it = dep.find(id);
+    return it == dep.end() ? std::vector<int>{} : it->second;
+  }
 
   Compiler(const Network& n, Program& p, const std::vector<int>& observed, const CompileOptions& opt) : net(n), P(p) {
+    reduce_groups = opt.reduce_groups;
     P.net = &net;
     P.observed = observed;
     P.is_observed.assign(net.n(), 0);
@@ -121,7 +129,10 @@ struct Compiler {
       t.slice_slot = (int)P.slices.size();
       P.slices.push_back(sl);
     }
-    return add(t);
+    const int id = add(t);
+    for (int x : P.tables[id].scope)
+      if (P.fixed_state[x] >= 0) dep[id].push_back(x);
+    return id;
   }
 
   // a free-standing factor (hb_factor_*): values appended to the potential pool, reference layout
@@ -196,16 +207,22 @@ struct Compiler {
     }
     key.push_back(-2 - sum_var);
     if (is_max) key.push_back(-1);
-    auto memo = cse.find(key);
+    std::vector<int> conditioned;  // union of the inputs' split variables
+    for (int id : inputs)
+      for (int x : dep_of(id))
+        if (!contains(conditioned, x)) conditioned.push_back(x);
+    // a conditioned table may be all-reduced in place at the end of ITS group: it must not be shared with another group
+    auto memo = (reduce_groups && !conditioned.empty()) ? cse.end() : cse.find(key);
     if (memo != cse.end()) {
       tr.prod = memo->second.prod;
       tr.out = T(memo->second.table).scope;
       g.trace.push_back(tr);
       return memo->second.table;
     }
-    const int result = product_sumout_new(inputs, sum_var, tr, is_max);
+    const int result = product_sumout_new(inputs, sum_var, tr, is_max, reduce_groups && !conditioned.empty());
     g.trace.push_back(tr);
-    cse[key] = Memo{result, tr.prod};
+    if (!(reduce_groups && !conditioned.empty())) cse[key] = Memo{result, tr.prod};
+    if (!conditioned.empty() && result != one) dep[result] = conditioned;
     return result;
   }
 
@@ -215,7 +232,7 @@ struct Compiler {
   };
   std::map<std::vector<int>, Memo> cse;
 
-  int product_sumout_new(const std::vector<int>& inputs, int sum_var, Group::TraceStep& tr, bool is_max = false) {
+  int product_sumout_new(const std::vector<int>& inputs, int sum_var, Group::TraceStep& tr, bool is_max = false, bool per_row = false) {
     std::vector<int> naked = T(inputs.back()).scope;
     for (int i = (int)inputs.size() - 2; i >= 0; --i) naked = list_union(T(inputs[i]).scope, naked);
     std::vector<int> chain, scalars;  // structural partition isScalarFactor (PrivateCPT.hs:223)
@@ -256,6 +273,7 @@ struct Compiler {
       return add(out);
     }
     if (is_max && sums) shared = false;  // the argmax tables are per row
+    if (per_row) shared = false;         // conditioned on this GPU's slice and possibly all-reduced per batch: never hoisted
     out.kind = shared ? T_SHARED : T_ROW;
     set_physical(out);
     st.shared = shared;
@@ -327,6 +345,34 @@ struct Compiler {
     std::vector<int> fin;
     for (auto& kv : buckets) fin.insert(fin.end(), kv.second.begin(), kv.second.end());
     return product_sumout(fin, -1, g, mpe);
+  }
+
+  // Split clique, end of a message / posterior: the split variables the result is conditioned on but no longer mentions
+  // were eliminated inside this group -- from this GPU's slice only.  The result is linear in that partial sum, so the
+  // sum over the ranks is taken here, on |result| doubles per row.  Returns true when the result still mentions split
+  // variables (it stays one slice per GPU).
+  bool close_group(int res, bool is_query = false) {
+    if (!reduce_groups) return false;
+    const std::vector<int> d = dep_of(res);
+    if (d.empty()) return false;
+    std::vector<int> gone, kept;
+    for (int x : d) (contains(T(res).scope, x) ? kept : gone).push_back(x);
+    if (gone.empty()) return true;
+    // a query that keeps some split variables: every rank writes its term at its own states of the kept ones, zero
+    // elsewhere, and the sum of the expanded results over ALL ranks is also the sum over the eliminated ones
+    if (is_query && !kept.empty()) return true;
+    if (!kept.empty())
+      throw Error(HB_E_UNSUPPORTED, "split clique: a separator or query holds some of the split variables and eliminates others (needs a sub-communicator)");
+    const int rid = resolve(res);
+    if (P.tables[rid].kind != T_ROW)
+      throw Error(HB_E_UNSUPPORTED, "split clique: a message that is a bare slice of a potential cannot be reduced in place");
+    bool produced = false;
+    for (const Step& st : P.steps) produced = produced || (st.kind == STEP_PRODSUM && st.out == rid);
+    if (!produced) throw Error(HB_E_UNSUPPORTED, "split clique: the result of a message is not a table of its own");
+    P.tables[rid].reduce = true;
+    dep.erase(res);
+    dep.erase(rid);
+    return false;
   }
 
   std::vector<int> first_appearance(const std::vector<int>& factors) const {  // nub . concatMap factorVariables
@@ -413,7 +459,7 @@ struct Compiler {
         if (S.kind != STEP_PRODSUM || !S.scalars.empty() || S.levels[0].in.empty() || S.levels[0].is_max) continue;
         const int tid = S.levels[0].in[0].table;
         const int q = producer[tid];
-        if (q < 0 || uses[tid] != 1) continue;
+        if (q < 0 || uses[tid] != 1 || P.tables[tid].reduce) continue;
         const Step& Q = P.steps[q];
         if (Q.shared != S.shared || !Q.scalars.empty() || Q.levels[0].is_max) continue;
         const int q_inner = (int)Q.levels.back().in.size();
@@ -659,6 +705,7 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
     for (int v : C.first_appearance(all))
       if (!contains(keep, v)) remove.push_back(v);
     int res = C.marginal(all, remove, keep, {}, g);
+    C.close_group(res);
     g.out_scope = C.T(res).scope;
     g.result = res;
     prog->groups.push_back(std::move(g));
@@ -731,10 +778,16 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
     for (int v : C.first_appearance(all))
       if (!contains(q.vars, v)) remove.push_back(v);
     int res = C.marginal(all, remove, q.vars, {}, g);
+    const bool sliced = C.close_group(res, true);
     C.emit_output(res, g);
+    prog->steps.back().gather = sliced;
     prog->groups.push_back(std::move(g));
   }
   C.finish(opt);
+  for (const Step& st : prog->steps) {
+    if (st.kind == STEP_PRODSUM && prog->tables[st.out].reduce) ++prog->n_reduce;
+    if (st.kind == STEP_OUTPUT && st.gather) ++prog->n_gather;
+  }
   return prog.release();
 }
 
@@ -878,7 +931,7 @@ std::string describe_program(const Program& P) {
     if (s.kind == STEP_PRODSUM) {
       o << ",\"out_scope\":";
       js_list(o, P.tables[s.out].pscope);
-      o << ",\"out_off\":" << P.tables[s.out].off << ",\"scalars\":";
+      o << ",\"out_off\":" << P.tables[s.out].off << ",\"reduce\":" << (P.tables[s.out].reduce ? 1 : 0) << ",\"scalars\":";
       js_list(o, s.scalars);
       o << ",\"levels\":[";
       for (size_t l = 0; l < s.levels.size(); ++l) {
@@ -900,7 +953,7 @@ std::string describe_program(const Program& P) {
       }
       o << "]";
     } else
-      o << ",\"result\":" << s.result << ",\"out_col\":" << s.out_col << ",\"n_full\":" << s.n_full;
+      o << ",\"result\":" << s.result << ",\"out_col\":" << s.out_col << ",\"n_full\":" << s.n_full << ",\"gather\":" << (s.gather ? 1 : 0);
     o << "}";
   }
   o << "],\"mpe_order\":";

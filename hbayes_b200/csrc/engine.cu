@@ -43,6 +43,7 @@
 
 #include "engine.hpp"
 #include "jit.hpp"
+#include "nccl_dyn.hpp"
 #include "procedural.hpp"
 
 namespace hb {
@@ -516,6 +517,7 @@ struct OutDesc {
   int map_off, order_off;  // into the int32 map pool
   int n_obs;
   int obs_var[MAXOBS], obs_stride[MAXOBS], obs_dim[MAXOBS];
+  int gather;              // split clique: left unnormalised here, summed over the ranks and normalised afterwards
 };
 
 struct OutChunk {           // a run of consecutive queries whose columns fit one shared-memory tile
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(BLOCK) output_kernel(const OutArgs a) {
       const uint32_t* fmap = a.maps + d.map_off;
       double norm = 0.0;
       for (int j = 0; j < d.n_phys; ++j) norm = __dadd_rn(norm, p ? p[(long long)order[j] * m] : 1.0);
-      const double inv = a.normalise ? __ddiv_rn(1.0, norm) : 1.0;
+      const double inv = (a.normalise && !d.gather) ? __ddiv_rn(1.0, norm) : 1.0;
       int st[MAXOBS];
       for (int j = 0; j < d.n_obs; ++j) st[j] = e[d.obs_var[j]];
       double* o = ch.direct ? a.out + (long long)row * a.width + d.out_col : tile + r * pitch + (int)(d.out_col - ch.col_begin);
@@ -609,6 +611,56 @@ __global__ void __launch_bounds__(BLOCK) normalise_kernel(const NormArgs a) {
   for (int c = a.col_begin[b]; c < a.col_begin[b + 1]; ++c) norm = __dadd_rn(norm, p[c]);
   const double inv = __ddiv_rn(1.0, norm);
   for (int c = a.col_begin[b]; c < a.col_begin[b + 1]; ++c) p[c] = __dmul_rn(inv, p[c]);
+}
+
+// Split clique over NCCL, queries that mention a split variable: every rank has written its own slice of the unnormalised
+// result (zeros elsewhere).  forward: the blocks of those queries are packed into a contiguous matrix [rows][gw] for the
+// all-reduce; backward: the summed blocks are normalised (norm = 0 + x0 + x1 + ..., x * (1.0 / norm)) and written back.
+struct GatherArgs {
+  double* out;           // [n_rows][width]
+  double* tmp;           // [n_rows][gw]
+  const int* out_begin;  // [n_blocks + 1]: first column of each block in `out` (last entry unused)
+  const int* tmp_begin;  // [n_blocks + 1]: first column of each block in `tmp`
+  int n_blocks, backward, normalise;
+  long long n_rows, width, gw;
+};
+__global__ void __launch_bounds__(BLOCK) gather_blocks_kernel(const GatherArgs a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.n_rows * a.n_blocks) return;
+  const long long row = gid / a.n_blocks;
+  const int b = (int)(gid % a.n_blocks);
+  double* o = a.out + row * a.width + a.out_begin[b];
+  double* t = a.tmp + row * a.gw + a.tmp_begin[b];
+  const int n = a.tmp_begin[b + 1] - a.tmp_begin[b];
+  if (!a.backward) {
+    for (int c = 0; c < n; ++c) t[c] = o[c];
+    return;
+  }
+  double norm = 0.0;
+  for (int c = 0; c < n; ++c) norm = __dadd_rn(norm, t[c]);
+  const double inv = a.normalise ? __ddiv_rn(1.0, norm) : 1.0;
+  for (int c = 0; c < n; ++c) o[c] = __dmul_rn(inv, t[c]);
+}
+
+// Split clique over NCCL: the caller's rows leave the split variables unobserved (-1); every rank fills in the states of
+// ITS slice.  A row that observes a split variable at another state contradicts the slice: flagged.
+struct FillArgs {
+  int8_t* ev;               // [n_rows][n_vars]
+  const int8_t* observed;   // as PrepArgs::observed: 2 + s = fixed at state s
+  long long n_rows;
+  int n_vars;
+  int* flag;
+};
+__global__ void __launch_bounds__(BLOCK) fill_fixed_kernel(const FillArgs a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.n_rows * a.n_vars) return;
+  const int o = a.observed[gid % a.n_vars];
+  if (o < 2) return;
+  const int s = a.ev[gid];
+  if (s < 0)
+    a.ev[gid] = (int8_t)(o - 2);
+  else if (s != o - 2)
+    atomicOr(a.flag, 1);
 }
 
 // mpe traceback (mpeInstantiations, Bayes/Factor/MaxCPT.hs:73-75): the reference carries the maximising
@@ -696,6 +748,12 @@ struct Executor {
   double work_seen = 0;  // joint entries evaluated so far (rows x product entries per row)
   // Whole-schedule on-chip kernel (jit.cpp, hb_tree): when the per-row tables of a tile fit shared memory the whole pass
   // is ONE launch and the HBM row arena is not used at all.
+  // split clique over NCCL (Program::n_reduce / n_gather > 0): the communicator is the handle's, not the executor's
+  void* comm = nullptr;
+  double* d_gather = nullptr;  // [rows of a tile][gather width]
+  size_t gather_cap = 0;
+  int *d_gather_out = nullptr, *d_gather_tmp = nullptr;
+  int gather_width = 0, gather_blocks = 0;
   TreePlan tree;
   bool tree_eligible = false;
   void* tree_fn = nullptr;
@@ -738,7 +796,7 @@ struct Executor {
     for (cudaStream_t st : side_streams) cudaStreamDestroy(st);
     for (cudaEvent_t e : step_events) cudaEventDestroy(e);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
-    for (void* p : {(void*)d_args, (void*)d_trace, (void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
+    for (void* p : {(void*)d_gather, (void*)d_gather_out, (void*)d_gather_tmp, (void*)d_args, (void*)d_trace, (void*)d_pots, (void*)d_shared, (void*)d_arena, (void*)d_maps, (void*)d_maps_rt, (void*)d_rowoff, (void*)d_observed,
                     (void*)d_dims, (void*)d_sl_begin, (void*)d_sl_var, (void*)d_sl_stride, (void*)d_out_desc, (void*)d_out_chunks, (void*)d_norm_cols, (void*)d_gen_in,
                     (void*)d_gen_sc, (void*)d_flag})
       if (p) cudaFree(p);
@@ -1224,6 +1282,7 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
       }
       d.n_phys = n_phys;
       d.n_obs = (int)st.obs_var.size();
+      d.gather = st.gather ? 1 : 0;
       for (int j = 0; j < d.n_obs; ++j) d.obs_var[j] = st.obs_var[j], d.obs_stride[j] = (int)st.obs_stride[j], d.obs_dim[j] = (int)st.obs_dim[j];
       ex->out_desc.push_back(d);
       ex->out_steps.push_back((int)si);
@@ -1360,8 +1419,20 @@ Executor* executor_create(const Program& P, int device, int64_t workspace_bytes)
     size_t free_b = 0, total_b = 0;
     HB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     workspace_bytes = std::min<int64_t>((int64_t)(free_b * 0.6), (int64_t)24 << 30);
+    // the ranks of a split clique all-reduce whole tiles: they must cut a batch into the same tiles whatever memory each has free
+    if (P.n_reduce > 0 || P.n_gather > 0) workspace_bytes = (int64_t)8 << 30;
   }
   ex->workspace = workspace_bytes;
+  if (P.n_gather > 0) {
+    std::vector<int> ob, tb = {0};
+    for (const OutDesc& d : ex->out_desc)
+      if (d.gather) ob.push_back((int)d.out_col), tb.push_back(tb.back() + d.n_full);
+    ob.push_back(0);
+    ex->gather_blocks = (int)tb.size() - 1;
+    ex->gather_width = tb.back();
+    ex->d_gather_out = upload(ob);
+    ex->d_gather_tmp = upload(tb);
+  }
   run_shared_steps(*ex);
   {
     std::string why;
@@ -1507,6 +1578,8 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
   const Program& P = *ex->P;
   HB_CUDA(cudaSetDevice(ex->device));
   const int n_vars = P.net->n();
+  if ((P.n_reduce > 0 || P.n_gather > 0) && !ex->comm)
+    throw Error(HB_E_NCCL, "this program sums a split clique over the ranks: the handle has no communicator (hb_jt_compile_split_nccl)");
   {  // Kernels generated for this program (jit.cpp): the on-chip kernel, or per-step kernels for its heaviest steps.  NVRTC
      // takes seconds, so the compilation starts in the background once the program has seen >= 2^31 joint entries in one
      // call (C2: 140 K rows) or 2^35 in all, and is installed by the first later call that finds it finished; cached
@@ -1574,7 +1647,33 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
       for (const Executor::Node& n : nodes) launch_prodsum(*ex, P.steps[n.si], n.si, stride, nr, on);
     };
     static const bool graphs_on = !(getenv("HB_GRAPHS") && atoi(getenv("HB_GRAPHS")) == 0);
-    if (graphs_on && nodes.size() >= 16) {
+    if (P.n_reduce > 0) {
+      // Split clique: plain launches in dependency order, the same on every rank.  A table that holds this GPU's partial
+      // sum over the split variables is all-reduced right after the step that produces it -- one exchange of |table|
+      // doubles per row and per message -- unless only the final normalisation reads it: those (the posteriors' own
+      // results) are exchanged together at the end, as one NCCL group.
+      std::vector<const Table*> late;
+      for (const Executor::Node& n : nodes) {
+        const Step& st = P.steps[n.si];
+        launch_prodsum(*ex, st, n.si, stride, nr, stream);
+        const Table& t = P.tables[st.out];
+        if (!t.reduce) continue;
+        bool only_output = true;
+        for (const Step& other : P.steps)
+          if (other.kind == STEP_PRODSUM && !other.shared)
+            for (const Level& l : other.levels)
+              for (const StepInput& in : l.in) only_output = only_output && in.table != st.out;
+        if (only_output)
+          late.push_back(&t);
+        else
+          nccl_allreduce_sum(ex->comm, ex->d_arena + t.off * stride, (size_t)(t.size * stride), stream);
+      }
+      if (!late.empty()) {
+        nccl_group_start();
+        for (const Table* t : late) nccl_allreduce_sum(ex->comm, ex->d_arena + t->off * stride, (size_t)(t->size * stride), stream);
+        nccl_group_end();
+      }
+    } else if (graphs_on && nodes.size() >= 16) {
       auto it = ex->graphs.find(nr);
       if (it == ex->graphs.end()) {
         if (!ex->capture_stream) HB_CUDA(cudaStreamCreateWithFlags(&ex->capture_stream, cudaStreamNonBlocking));
@@ -1639,6 +1738,23 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
       dim3 grid((nr + OUT_ROWS - 1) / OUT_ROWS, (unsigned)ex->out_chunks.size());
       output_kernel<<<grid, BLOCK, ex->out_tile_bytes, stream>>>(oa);
       ++launches;
+      if (P.n_gather > 0) {  // queries that mention a split variable: sum the ranks' slices, then normalise
+        const size_t need = (size_t)nr * ex->gather_width;
+        if (need > ex->gather_cap) {
+          HB_CUDA(cudaStreamSynchronize(stream));
+          free_dev(ex->d_gather);
+          HB_CUDA(cudaMalloc(&ex->d_gather, need * sizeof(double)));
+          ex->gather_cap = need;
+        }
+        GatherArgs ga{d_out + r0 * P.out_width, ex->d_gather, ex->d_gather_out, ex->d_gather_tmp, ex->gather_blocks, 0, normalise ? 1 : 0,
+                      nr, P.out_width, ex->gather_width};
+        const unsigned gb = (unsigned)(((int64_t)nr * ex->gather_blocks + BLOCK - 1) / BLOCK);
+        gather_blocks_kernel<<<gb, BLOCK, 0, stream>>>(ga);
+        nccl_allreduce_sum(ex->comm, ex->d_gather, need, stream);
+        ga.backward = 1;
+        gather_blocks_kernel<<<gb, BLOCK, 0, stream>>>(ga);
+        launches += 2;
+      }
     }
     if (d_mpe_states && ex->n_trace > 0) {
       TraceArgs ta{ex->d_trace, ex->n_trace, (int)P.mpe_r.size(), nr, ex->d_args, stride, d_mpe_states + r0 * (int64_t)P.mpe_r.size()};
@@ -1685,6 +1801,15 @@ int executor_specialised_kernels(const Executor* ex) {
   return n;
 }
 bool executor_on_chip(const Executor* ex) { return ex->tree_fn != nullptr; }
+void executor_set_comm(Executor* ex, void* comm) { ex->comm = comm; }
+void executor_fill_fixed(Executor* ex, int8_t* d_evidence, int64_t n_rows, void* stream) {
+  if (n_rows <= 0) return;
+  HB_CUDA(cudaSetDevice(ex->device));
+  const int n_vars = ex->P->net->n();
+  FillArgs a{d_evidence, ex->d_observed, n_rows, n_vars, ex->d_flag};
+  fill_fixed_kernel<<<(unsigned)((n_rows * n_vars + BLOCK - 1) / BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  HB_CUDA(cudaGetLastError());
+}
 void executor_tree_profile(Executor* ex, void* stream, int64_t out64[64]) {
   HB_CUDA(cudaSetDevice(ex->device));
   HB_CUDA(cudaMemcpyAsync(out64, (const char*)ex->d_flag + 8, 64 * sizeof(int64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));

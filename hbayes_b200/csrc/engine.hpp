@@ -48,6 +48,11 @@ int executor_specialise(Executor* ex);
 int executor_specialised_kernels(const Executor* ex);
 // true when the program runs on the whole-schedule on-chip kernel (one launch per batch, per-row tables in shared memory)
 bool executor_on_chip(const Executor* ex);
+// the NCCL communicator (an ncclComm_t, owned by the handle) a split-clique program exchanges its partial sums over
+void executor_set_comm(Executor* ex, void* comm);
+// writes the states of this rank's slice into the split variables' columns of a (device) evidence matrix; a row that
+// observes a split variable at another state raises the executor's error flag
+void executor_fill_fixed(Executor* ex, int8_t* d_evidence, int64_t n_rows, void* stream);
 // HB_TREE_PROFILE=1 (read when the kernel is generated): SM cycles per phase of the on-chip kernel since the last call,
 // summed over all tiles -- [0] evidence preparation, [1 + l] dependency level l, [1 + levels] normalise + write-out
 void executor_tree_profile(Executor* ex, void* stream, int64_t out64[64]);

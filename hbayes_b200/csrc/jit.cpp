@@ -751,6 +751,7 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   };
   plan = TreePlan();
   if (!P.max_steps.empty() || !P.mpe_r.empty()) return fail("maximisation steps");
+  if (P.n_reduce > 0 || P.n_gather > 0) return fail("split clique with exchange steps");
   const size_t ns = P.steps.size();
   plan.level.assign(ns, -1);
   plan.off.assign(P.tables.size(), -1);

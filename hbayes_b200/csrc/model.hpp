@@ -93,6 +93,8 @@ struct Table {
   int64_t size = 1;              // physical entries
   int64_t off = 0;               // entry offset in its pool (potential pool / shared arena / row arena)
   int slice_slot = -1;           // T_POT mentioning observed variables: index into Program::slices
+  bool reduce = false;           // split clique over NCCL: the stored table is this GPU's partial sum over the split variables;
+                                 // it is all-reduced (sum over the ranks) right after the step that produces it
   int alias_of = -1;             // a final product of a single table is that table
   int def_step = -1, last_use = -1;
 };
@@ -137,6 +139,8 @@ struct Step {
   std::vector<int32_t> full_map;               // full entry -> physical entry of `result` (ignoring observed vars)
   std::vector<int> obs_var;                    // observed query variables ...
   std::vector<int64_t> obs_stride, obs_dim;    // ... their stride and dimension in the full layout
+  bool gather = false;                         // STEP_OUTPUT, split clique over NCCL: the query holds a split variable -- every rank fills
+                                               // its own slice of the (unnormalised) result, the ranks' matrices are summed, then normalised
   int group = -1;                              // provenance: index into Program::groups (first emitter)
   int64_t arg_off = -1;                        // max step: entry offset of its argmax table in the argmax arena
   int n_inputs() const {
@@ -199,6 +203,7 @@ struct Program {
   std::vector<int> mpe_r;        // variables to maximise, caller's order
   std::vector<int> mpe_order;    // variable order of the reference's instantiation list (structural)
   int64_t arg_entries = 0;       // per-row argmax arena size (int8 entries)
+  int n_reduce = 0, n_gather = 0;  // tables all-reduced / queries gathered across the ranks of a split clique (0: no communication)
 };
 
 struct Query {
@@ -208,6 +213,11 @@ struct CompileOptions {
   // variables with a state known at compile time (the slice of a split clique this GPU owns): treated like
   // observed variables, and potentials mentioning them are stored restricted to that state
   std::vector<std::pair<int, int>> fixed;
+  // Split clique with the sum over the split variables taken where it belongs: every message / posterior
+  // that eliminates the split variables is computed from this GPU's slice and all-reduced over the ranks (|result| doubles
+  // per row); what follows is no longer conditioned on the slice.  false: the whole program stays conditioned and the
+  // caller sums the result matrices (cutset conditioning, hb_jt_set_split).
+  bool reduce_groups = false;
   bool fuse = true;    // chain a step into its only consumer (the intermediate table stays in registers)
   bool block = true;   // choose the blocking variable of each step by the loads it saves (false: the last variable)
   int max_levels = 4;  // levels per fused step

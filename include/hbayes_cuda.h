@@ -115,6 +115,22 @@ int hb_jt_compile_with_order(const hb_net* net, const int32_t* elim_order, const
  * nothing is calibrated (the unsplit tables may not fit one GPU). */
 int hb_jt_compile_split(const hb_net* net, int32_t cmp, const int32_t* devices, int32_t n_devices, int32_t n_fixed,
                         const int32_t* vars, const int32_t* states, hb_jt** out);
+/* Split clique with the exchange step INSIDE the library (BASELINE config C4): one process per GPU, `world`
+ * of them, each owning the slice vars[i] = states[i] of the tables that mention the split variables (the state
+ * combinations are dealt one per rank: world = prod dims(vars)).  rank 0 obtains a 128-byte id with hb_nccl_unique_id and
+ * hands it to the others by whatever channel the host program has (MPI, torch.distributed, a file); the compile call is
+ * collective (ncclCommInitRank).  Programs compiled on the handle sum over the split variables where the reference's
+ * elimination does: every message that leaves the split clique and every posterior inside it is computed from the
+ * rank's slice and summed over the ranks with ncclAllReduce(ncclDouble, ncclSum) on the handle's stream -- |separator|
+ * (or |query|) doubles per row; everything downstream of such a message is no longer conditioned on the slice and is
+ * computed once, not once per slice.  Batch calls are collective too (same rows on every rank, split variables
+ * unobserved = -1) and return complete, normalised posteriors on every rank.  Agreement with the unsplit engine:
+ * ~1e-15 relative (the sum over the split variables is reassociated), tests use 1e-12.  HB_E_NCCL: libnccl missing, or
+ * an NCCL call failed.  HB_E_UNSUPPORTED: a separator holds some split variables and eliminates others.
+ * device = HB_STRUCTURE_ONLY gives a handle that only answers hb_jt_program_json (no GPU, no communicator). */
+int hb_nccl_unique_id(void* out128);
+int hb_jt_compile_split_nccl(const hb_net* net, int32_t cmp, int32_t device, int32_t n_fixed, const int32_t* vars,
+                             const int32_t* states, int32_t rank, int32_t world, const void* unique_id128, hb_jt** out);
 /* Persistence (the counterpart of the Binary save/load of a junction tree, Bayes/ImportExport.hs:36-46): the network
  * and the tree structure in one binary file.  Loading skips moralisation / triangulation / spanning tree; schedules
  * are recompiled on demand (milliseconds) and the tree is re-calibrated on the GPU. */

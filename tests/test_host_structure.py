@@ -357,3 +357,12 @@ def test_on_chip_kernel_source_compiles_for_sm_100a(tmp_path):
     with pytest.raises(hb.HbError) as e:
         hb.JunctionTree(cnet, device=None).tree_source(observed)
     assert e.value.code == _lib.HB_E_UNSUPPORTED
+
+
+def test_split_program_exchange_steps_are_structural():
+    """the program compiled for one slice of a split clique marks every table that holds a partial sum over the
+    split variable (messages leaving the split clique, posteriors inside it) for an all-reduce and every query that
+    mentions the split variable for a gather -- decided on the host, no GPU or communicator needed"""
+    from test_gpu_split_nccl import test_split_program_has_its_exchange_steps
+
+    test_split_program_has_its_exchange_steps()
