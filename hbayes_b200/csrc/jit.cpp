@@ -849,7 +849,7 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   const int64_t inv_entries = P.pot_entries + P.shared_entries;
   plan.invariant_entries = inv_entries * 8 <= TREE_INVARIANT_MAX ? inv_entries : 0;
   auto bytes = [&](int64_t R, bool staged) {
-    return plan.arena_entries * R * 8 + plan.invariant_entries * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + 2 * round8(R * NV);
+    return plan.arena_entries * R * 8 + plan.invariant_entries * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV);
   };
   int R = 0;
   if (const char* env = getenv("HB_TREE_ROWS")) R = std::max(2, atoi(env) / 2 * 2);
@@ -1005,9 +1005,6 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
   table("int", "Q", q);
   table("int", "QOBS", qobs);
   table("unsigned", "QMAP", qmap);
-  // With a staging tile and at least two levels the write-out of a tile's posteriors is deferred into the next tile's first
-  // level and the evidence tile is double-buffered: no barrier is spent on the output at all.
-  const bool deferred = WP > 0 && plan.n_levels >= 2;
   std::ostringstream fns;  // one device function per step, defined before the kernel
   o << "@@STEP_FUNCTIONS@@";
   const int64_t inv_at = plan.arena_entries * R * 8, rowoff_at = inv_at + plan.invariant_entries * 8, stage_at = rowoff_at + round8(NS * R * 4),
@@ -1027,10 +1024,7 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
     o << "  const double* const pots = g_pots;\n  const double* const shared = g_shared;\n";
   o << "  int* const rowoff = reinterpret_cast<int*>(smem_raw + " << rowoff_at << ");\n";
   if (WP) o << "  double* const stage = reinterpret_cast<double*>(smem_raw + " << stage_at << ");\n";
-  if (deferred)
-    o << "  signed char* const evs_base = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n  long long prow0 = -1;\n  int pnr = 0;\n  unsigned par = 0u;\n";
-  else
-    o << "  signed char* const evs = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n";
+  o << "  signed char* const evs = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n";
   o << "  constexpr unsigned RT = " << R << "u;\n";
   o << "  const unsigned tid = threadIdx.x;\n";
   o << "  const unsigned rowA = (tid % " << R / 2 << "u) * 2u, slotA = tid / " << R / 2 << "u, rowB = tid % " << R << "u, slotB = tid / " << R << "u;\n";
@@ -1040,7 +1034,6 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
       << "ll) ? ev[(long long)blockIdx.x * " << R * NV << "ll + tid + " << k * T << "u] : (signed char)-1;\n";
   o << "  for (long long tile = blockIdx.x; tile * " << R << " < n_rows; tile += gridDim.x) {\n";
   o << "    const long long row0 = tile * " << R << ";\n";
-  if (deferred) o << "    signed char* const evs = evs_base + par * " << round8(R * NV) << "u;\n";
   if (getenv("HB_TREE_PROFILE") && atoi(getenv("HB_TREE_PROFILE")) != 0) o << "    long long t0 = clock64();\n";
   o << "    const int nr = (int)(n_rows - row0 < " << R << " ? n_rows - row0 : " << R << ");\n";
   // Evidence of this tile -> shared memory.  It was loaded into registers while the previous tile was computed (the CTA is
@@ -1073,112 +1066,6 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
     o << "      }\n      rowoff[i] = off;\n    }\n";
   }
   o << "    __syncthreads();\n";
-  // factorNorm + factorDivide + expansion to the query scope (what output_kernel of engine.cu does, reading shared
-  // memory): thread = (query, row), specialised per query -- norm = 0 + x0 + x1 + ... over the layout order, every entry
-  // (1.0 / norm) * value, 0.0 where the entry contradicts the evidence.  A query is normalised in the level AFTER the one
-  // that produced its result (between the same barriers as that level's steps), so the division's latency hides behind
-  // real work and only the last level's queries are left for the end of the tile.
-  std::vector<int> qlevel;
-  {
-    std::vector<int> producer_level(P.tables.size(), -1);
-    for (size_t si = 0; si < P.steps.size(); ++si)
-      if (plan.level[si] >= 0) producer_level[P.steps[si].out] = plan.level[si];
-    for (const Step& st : P.steps)
-      if (st.kind == STEP_OUTPUT) qlevel.push_back(std::max(deferred ? 1 : 0, producer_level[st.result] + 1));
-  }
-  auto emit_normalise = [&](int lv, int64_t rot) {
-    std::vector<std::pair<int, const Step*>> mine;  // (query index, output step)
-    {
-      int qi = 0;
-      for (const Step& st : P.steps)
-        if (st.kind == STEP_OUTPUT) {
-          if (qlevel[(size_t)qi] == lv) mine.push_back({qi, &st});
-          ++qi;
-        }
-    }
-    if (mine.empty()) return;
-    o << "    for (unsigned i = (tid + " << (T - rot % T) % T << "u) % " << T << "u; i < " << (int64_t)mine.size() * R << "u; i += " << T << "u) {\n"
-         "      const unsigned r = i % " << R << "u, ql = i / " << R << "u;\n"
-         "      const signed char* const e = evs + r * " << NV << "u;\n";
-    if (WP)
-      o << "      double* const op = stage + r * " << WP << "u;\n";
-    else
-      o << "      if ((int)r >= nr) continue;\n      double* const op = out + (row0 + r) * " << W << "ll;\n";
-    o << "      switch (ql) {\n";
-    for (size_t k = 0; k < mine.size(); ++k) {
-      const int this_q = mine[k].first;
-      const Step& st = *mine[k].second;
-      o << "        case " << k << ": {  // query " << this_q << "\n";
-      if (st.n_full > 64) {  // very wide queries (joint family posteriors): descriptor-driven
-        o << "          const unsigned qi = " << this_q << "u;\n"
-             "          const int* const d = Q + qi * 9;\n"
-             "          const int kind = d[0], n_phys = d[3], n_full = d[4], n_obs = d[8];\n"
-             "          const double* gp = nullptr;\n"
-             "          if (kind == 1) gp = pots + d[1] + (d[2] >= 0 ? rowoff[d[2] * " << R << " + r] : 0);\n"
-             "          else if (kind == 2) gp = shared + d[1];\n"
-             "          const double* const sp = sm + (size_t)d[1] * RT + r;\n"
-             "          const unsigned* const order = QMAP + d[7];\n"
-             "          const unsigned* const fmap = QMAP + d[6];\n"
-             "          double norm = 0.0;\n"
-             "          for (int j = 0; j < n_phys; ++j) norm = __dadd_rn(norm, kind == 3 ? sp[(size_t)order[j] * RT] : (kind == 0 ? 1.0 : gp[order[j]]));\n"
-             "          const double inv = normalise ? __drcp_rn(norm) : 1.0;\n"
-             "          int st[8];\n"
-             "          for (int j = 0; j < n_obs; ++j) st[j] = e[QOBS[qi * 24 + j * 3]];\n"
-             "          for (int f = 0; f < n_full; ++f) {\n"
-             "            bool match = true;\n"
-             "            for (int j = 0; j < n_obs; ++j) match &= ((f / QOBS[qi * 24 + j * 3 + 1]) % QOBS[qi * 24 + j * 3 + 2]) == st[j];\n"
-             "            const double v = match ? (kind == 3 ? sp[(size_t)fmap[f] * RT] : (kind == 0 ? 1.0 : gp[fmap[f]])) : 0.0;\n"
-             "            op[d[5] + f] = __dmul_rn(inv, v);\n          }\n"
-             "        } break;\n";
-        continue;
-      }
-      const Table& t = P.tables[st.result];
-      auto value = [&](int64_t k2) -> std::string {  // stored entry k2 of the result
-        if (t.kind == T_ONE) return "1.0";
-        if (t.kind == T_ROW) return "sm[(size_t)" + std::to_string(plan.off[st.result] + k2) + " * RT + r]";
-        if (t.kind == T_SHARED) return "shared[" + std::to_string(t.off + k2) + "]";
-        return "gp[" + std::to_string(k2) + "]";
-      };
-      if (t.kind == T_POT) {
-        o << "          const double* const gp = pots + " << t.off;
-        if (t.slice_slot >= 0) o << " + rowoff[" << t.slice_slot * R << "u + r]";
-        o << ";\n";
-      }
-      std::map<int64_t, std::string> have;
-      auto use = [&](int64_t k2) {
-        auto it = have.find(k2);
-        if (it != have.end()) return it->second;
-        const std::string n = "v" + std::to_string(k2);
-        o << "          const double " << n << " = " << value(k2) << ";\n";
-        return have[k2] = n;
-      };
-      std::string norm = "0.0";
-      int n_terms = 0;
-      for (int64_t f = 0; f < st.n_full; ++f) {
-        bool first_state = true;
-        for (size_t j = 0; j < st.obs_var.size(); ++j) first_state &= ((f / st.obs_stride[j]) % st.obs_dim[j]) == 0;
-        if (!first_state) continue;
-        const std::string v = use(st.full_map[(size_t)f]);
-        const std::string n = "n" + std::to_string(n_terms++);
-        o << "          const double " << n << " = __dadd_rn(" << norm << ", " << v << ");\n";
-        norm = n;
-      }
-      // 1.0 / norm, correctly rounded: __drcp_rn gives the same bits as __ddiv_rn(1.0, norm) without the division's slow path
-      o << "          const double inv = normalise ? __drcp_rn(" << norm << ") : 1.0;\n";
-      for (int64_t f = 0; f < st.n_full; ++f) {
-        std::string match;
-        for (size_t j = 0; j < st.obs_var.size(); ++j)
-          match += (match.empty() ? "" : " && ") + ("e[" + std::to_string(st.obs_var[j]) + "] == " + std::to_string((f / st.obs_stride[j]) % st.obs_dim[j]));
-        const std::string v = use(st.full_map[(size_t)f]);
-        o << "          op[" << st.out_col + f << "] = __dmul_rn(inv, " << (match.empty() ? v : "(" + match + ") ? " + v + " : 0.0") << ");\n";
-      }
-      o << "        } break;\n";
-    }
-    o << "      }\n    }\n";
-  };
-  if (deferred)  // the previous tile's posteriors: shared memory -> HBM while the first (narrow) level runs; nobody writes the staging tile before level 1
-    o << "    if (prow0 >= 0)\n      for (unsigned i = tid; i < (unsigned)pnr * " << W << "u; i += " << T << "u) out[prow0 * " << W << "ll + i] = stage[(i / " << W << "u) * " << WP
-      << "u + i % " << W << "u];\n";
   int64_t stat_loads = 0, stat_items = 0;  // shared-memory loads per evidence row; work items per tile
   static const bool profile = getenv("HB_TREE_PROFILE") && atoi(getenv("HB_TREE_PROFILE")) != 0;
   auto lap = [&](int slot) {  // HB_TREE_PROFILE=1: cycles per phase, summed over the CTAs' tiles, behind the error flag
@@ -1224,25 +1111,103 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
       stat_loads += g.n_loads * (g.tree_items / (v == 2 ? R / 2 : R));
       stat_items += g.tree_items;
     }
-    emit_normalise(lv, rot);
     o << "    __syncthreads();\n";
     lap(1 + lv);
   }
-  emit_normalise(plan.n_levels, 0);  // the queries whose result the last level produced
-  if (WP && !deferred) {
+  // factorNorm + factorDivide + expansion to the query scope (what output_kernel of engine.cu does, reading shared
+  // memory): thread = (query, row), specialised per query -- norm = 0 + x0 + x1 + ... over the layout order, every entry
+  // (1.0 / norm) * value, 0.0 where the entry contradicts the evidence.
+  o << "    for (unsigned i = tid; i < " << (int64_t)nq * R << "u; i += " << T << "u) {\n"
+       "      const unsigned r = i % " << R << "u, qi = i / " << R << "u;\n"
+       "      const signed char* const e = evs + r * " << NV << "u;\n";
+  if (WP)
+    o << "      double* const op = stage + r * " << WP << "u;\n";
+  else
+    o << "      if ((int)r >= nr) continue;\n      double* const op = out + (row0 + r) * " << W << "ll;\n";
+  o << "      switch (qi) {\n";
+  {
+    int qi = 0;
+    bool any_generic = false;
+    for (const Step& st : P.steps) {
+      if (st.kind != STEP_OUTPUT) continue;
+      const int this_q = qi++;
+      if (st.n_full > 64) {
+        any_generic = true;
+        continue;
+      }
+      const Table& t = P.tables[st.result];
+      o << "        case " << this_q << ": {\n";
+      auto value = [&](int64_t k) -> std::string {  // stored entry k of the result
+        if (t.kind == T_ONE) return "1.0";
+        if (t.kind == T_ROW) return "sm[(size_t)" + std::to_string(plan.off[st.result] + k) + " * RT + r]";
+        if (t.kind == T_SHARED) return "shared[" + std::to_string(t.off + k) + "]";
+        return "gp[" + std::to_string(k) + "]";
+      };
+      if (t.kind == T_POT) {
+        o << "          const double* const gp = pots + " << t.off;
+        if (t.slice_slot >= 0) o << " + rowoff[" << t.slice_slot * R << "u + r]";
+        o << ";\n";
+      }
+      std::map<int64_t, std::string> have;
+      auto use = [&](int64_t k) {
+        auto it = have.find(k);
+        if (it != have.end()) return it->second;
+        const std::string n = "v" + std::to_string(k);
+        o << "          const double " << n << " = " << value(k) << ";\n";
+        return have[k] = n;
+      };
+      std::string norm = "0.0";
+      int n_terms = 0;
+      for (int64_t f = 0; f < st.n_full; ++f) {
+        bool first_state = true;
+        for (size_t j = 0; j < st.obs_var.size(); ++j) first_state &= ((f / st.obs_stride[j]) % st.obs_dim[j]) == 0;
+        if (!first_state) continue;
+        const std::string v = use(st.full_map[(size_t)f]);
+        const std::string n = "n" + std::to_string(n_terms++);
+        o << "          const double " << n << " = __dadd_rn(" << norm << ", " << v << ");\n";
+        norm = n;
+      }
+      o << "          const double inv = normalise ? __ddiv_rn(1.0, " << norm << ") : 1.0;\n";
+      for (int64_t f = 0; f < st.n_full; ++f) {
+        std::string match;
+        for (size_t j = 0; j < st.obs_var.size(); ++j)
+          match += (match.empty() ? "" : " && ") + ("e[" + std::to_string(st.obs_var[j]) + "] == " + std::to_string((f / st.obs_stride[j]) % st.obs_dim[j]));
+        const std::string v = use(st.full_map[(size_t)f]);
+        o << "          op[" << st.out_col + f << "] = __dmul_rn(inv, " << (match.empty() ? v : "(" + match + ") ? " + v + " : 0.0") << ");\n";
+      }
+      o << "        } break;\n";
+    }
+    if (any_generic) {  // very wide queries (joint family posteriors): descriptor-driven
+      o << "        default: {\n"
+           "          const int* const d = Q + qi * 9;\n"
+           "          const int kind = d[0], n_phys = d[3], n_full = d[4], n_obs = d[8];\n"
+           "          const double* gp = nullptr;\n"
+           "          if (kind == 1) gp = pots + d[1] + (d[2] >= 0 ? rowoff[d[2] * " << R << " + r] : 0);\n"
+           "          else if (kind == 2) gp = shared + d[1];\n"
+           "          const double* const sp = sm + (size_t)d[1] * RT + r;\n"
+           "          const unsigned* const order = QMAP + d[7];\n"
+           "          const unsigned* const fmap = QMAP + d[6];\n"
+           "          double norm = 0.0;\n"
+           "          for (int j = 0; j < n_phys; ++j) norm = __dadd_rn(norm, kind == 3 ? sp[(size_t)order[j] * RT] : (kind == 0 ? 1.0 : gp[order[j]]));\n"
+           "          const double inv = normalise ? __ddiv_rn(1.0, norm) : 1.0;\n"
+           "          int st[8];\n"
+           "          for (int j = 0; j < n_obs; ++j) st[j] = e[QOBS[qi * 24 + j * 3]];\n"
+           "          for (int f = 0; f < n_full; ++f) {\n"
+           "            bool match = true;\n"
+           "            for (int j = 0; j < n_obs; ++j) match &= ((f / QOBS[qi * 24 + j * 3 + 1]) % QOBS[qi * 24 + j * 3 + 2]) == st[j];\n"
+           "            const double v = match ? (kind == 3 ? sp[(size_t)fmap[f] * RT] : (kind == 0 ? 1.0 : gp[fmap[f]])) : 0.0;\n"
+           "            op[d[5] + f] = __dmul_rn(inv, v);\n          }\n"
+           "        } break;\n";
+    }
+  }
+  o << "      }\n    }\n";
+  if (WP) {
     o << "    __syncthreads();\n";
     o << "    for (unsigned i = tid; i < (unsigned)nr * " << W << "u; i += " << T << "u) out[row0 * " << W << "ll + i] = stage[(i / " << W << "u) * " << WP << "u + i % " << W
       << "u];\n";
   }
-  if (deferred) o << "    prow0 = row0; pnr = nr; par ^= 1u;\n";
   lap(1 + plan.n_levels);
-  o << "  }\n";
-  if (deferred) {
-    o << "  __syncthreads();\n";
-    o << "  if (prow0 >= 0)\n    for (unsigned i = tid; i < (unsigned)pnr * " << W << "u; i += " << T << "u) out[prow0 * " << W << "ll + i] = stage[(i / " << W << "u) * " << WP
-      << "u + i % " << W << "u];\n";
-  }
-  o << "}\n";
+  o << "  }\n}\n";
   o << "// per evidence row: " << stat_loads << " table loads, " << plan.ops_mul << " fp64 multiplies, " << plan.ops_add << " fp64 adds; " << stat_items
     << " work items per tile of " << R << " rows\n";
   if (loads_per_row) *loads_per_row = stat_loads;
