@@ -1167,7 +1167,8 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
         o << "          const double " << n << " = __dadd_rn(" << norm << ", " << v << ");\n";
         norm = n;
       }
-      o << "          const double inv = normalise ? __ddiv_rn(1.0, " << norm << ") : 1.0;\n";
+      // 1.0 / norm, correctly rounded: __drcp_rn gives the same bits as __ddiv_rn(1.0, norm) without the division's slow path
+      o << "          const double inv = normalise ? __drcp_rn(" << norm << ") : 1.0;\n";
       for (int64_t f = 0; f < st.n_full; ++f) {
         std::string match;
         for (size_t j = 0; j < st.obs_var.size(); ++j)
@@ -1189,7 +1190,7 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
            "          const unsigned* const fmap = QMAP + d[6];\n"
            "          double norm = 0.0;\n"
            "          for (int j = 0; j < n_phys; ++j) norm = __dadd_rn(norm, kind == 3 ? sp[(size_t)order[j] * RT] : (kind == 0 ? 1.0 : gp[order[j]]));\n"
-           "          const double inv = normalise ? __ddiv_rn(1.0, norm) : 1.0;\n"
+           "          const double inv = normalise ? __drcp_rn(norm) : 1.0;\n"
            "          int st[8];\n"
            "          for (int j = 0; j < n_obs; ++j) st[j] = e[QOBS[qi * 24 + j * 3]];\n"
            "          for (int f = 0; f < n_full; ++f) {\n"
