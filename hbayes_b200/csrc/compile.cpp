@@ -211,8 +211,7 @@ struct Compiler {
     for (int id : inputs)
       for (int x : dep_of(id))
         if (!contains(conditioned, x)) conditioned.push_back(x);
-    // a conditioned table may be all-reduced in place at the end of ITS group: it must not be shared with another group
-    auto memo = (reduce_groups && !conditioned.empty()) ? cse.end() : cse.find(key);
+    auto memo = cse.find(key);
     if (memo != cse.end()) {
       tr.prod = memo->second.prod;
       tr.out = T(memo->second.table).scope;
@@ -221,7 +220,7 @@ struct Compiler {
     }
     const int result = product_sumout_new(inputs, sum_var, tr, is_max, reduce_groups && !conditioned.empty());
     g.trace.push_back(tr);
-    if (!(reduce_groups && !conditioned.empty())) cse[key] = Memo{result, tr.prod};
+    cse[key] = Memo{result, tr.prod};
     if (!conditioned.empty() && result != one) dep[result] = conditioned;
     return result;
   }
@@ -351,28 +350,45 @@ struct Compiler {
   // were eliminated inside this group -- from this GPU's slice only.  The result is linear in that partial sum, so the
   // sum over the ranks is taken here, on |result| doubles per row.  Returns true when the result still mentions split
   // variables (it stays one slice per GPU).
-  bool close_group(int res, bool is_query = false) {
-    if (!reduce_groups) return false;
+  // Returns the table that now stands for the group's result; *sliced = the result still mentions split variables (it
+  // stays one slice per GPU).  The all-reduce runs in place on a private copy of the result (|result| entries per row):
+  // the result itself may be shared, through common-subexpression elimination, with groups that still use it as this
+  // GPU's partial sum.
+  int close_group(int res, bool is_query, bool* sliced) {
+    *sliced = false;
+    if (!reduce_groups) return res;
     const std::vector<int> d = dep_of(res);
-    if (d.empty()) return false;
+    if (d.empty()) return res;
     std::vector<int> gone, kept;
     for (int x : d) (contains(T(res).scope, x) ? kept : gone).push_back(x);
-    if (gone.empty()) return true;
+    *sliced = !kept.empty();
+    if (gone.empty()) return res;
     // a query that keeps some split variables: every rank writes its term at its own states of the kept ones, zero
     // elsewhere, and the sum of the expanded results over ALL ranks is also the sum over the eliminated ones
-    if (is_query && !kept.empty()) return true;
+    if (is_query && !kept.empty()) return res;
     if (!kept.empty())
-      throw Error(HB_E_UNSUPPORTED, "split clique: a separator or query holds some of the split variables and eliminates others (needs a sub-communicator)");
+      throw Error(HB_E_UNSUPPORTED, "split clique: a separator holds some of the split variables and eliminates others (needs a sub-communicator)");
     const int rid = resolve(res);
-    if (P.tables[rid].kind != T_ROW)
-      throw Error(HB_E_UNSUPPORTED, "split clique: a message that is a bare slice of a potential cannot be reduced in place");
-    bool produced = false;
-    for (const Step& st : P.steps) produced = produced || (st.kind == STEP_PRODSUM && st.out == rid);
-    if (!produced) throw Error(HB_E_UNSUPPORTED, "split clique: the result of a message is not a table of its own");
-    P.tables[rid].reduce = true;
-    dep.erase(res);
-    dep.erase(rid);
-    return false;
+    if (P.tables[rid].kind == T_ONE) return res;
+    Table out;  // the copy: 0 + 1.0 * x, exact
+    out.scalar = T(res).scalar;
+    out.scope = T(res).scope;
+    out.kind = T_ROW;
+    set_physical(out);
+    Step st;
+    st.group = (int)P.groups.size();
+    st.shared = false;
+    Level lv;
+    StepInput in;
+    in.table = rid;
+    lv.in.push_back(in);
+    st.levels.push_back(std::move(lv));
+    st.n_out = out.size;
+    out.reduce = true;
+    const int id = add(out);
+    st.out = id;
+    P.steps.push_back(std::move(st));
+    return id;
   }
 
   std::vector<int> first_appearance(const std::vector<int>& factors) const {  // nub . concatMap factorVariables
@@ -705,7 +721,8 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
     for (int v : C.first_appearance(all))
       if (!contains(keep, v)) remove.push_back(v);
     int res = C.marginal(all, remove, keep, {}, g);
-    C.close_group(res);
+    bool sliced = false;
+    res = C.close_group(res, false, &sliced);
     g.out_scope = C.T(res).scope;
     g.result = res;
     prog->groups.push_back(std::move(g));
@@ -778,7 +795,8 @@ Program* compile_jt(const Network& net, const Tree& tree, const std::vector<int>
     for (int v : C.first_appearance(all))
       if (!contains(q.vars, v)) remove.push_back(v);
     int res = C.marginal(all, remove, q.vars, {}, g);
-    const bool sliced = C.close_group(res, true);
+    bool sliced = false;
+    res = C.close_group(res, true, &sliced);
     C.emit_output(res, g);
     prog->steps.back().gather = sliced;
     prog->groups.push_back(std::move(g));
