@@ -830,8 +830,11 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   // the batch-invariant tables (potential pool, shared arena) are copied to shared memory once per CTA when they are small
   const int64_t inv_entries = P.pot_entries + P.shared_entries;
   plan.invariant_entries = inv_entries * 8 <= TREE_INVARIANT_MAX ? inv_entries : 0;
+  int64_t n_row_steps = 0;
+  for (size_t si = 0; si < ns; ++si) n_row_steps += plan.level[si] >= 0;
+  plan.range_bytes = round8(n_row_steps * 16 * 2 * 2);  // per step and warp (at most 16 warps): first and end block, 16 bits each
   auto bytes = [&](int64_t R, bool staged) {
-    return plan.arena_entries * R * 8 + plan.invariant_entries * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV);
+    return plan.arena_entries * R * 8 + plan.invariant_entries * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV) + plan.range_bytes;
   };
   int R = 0;
   if (const char* env = getenv("HB_TREE_ROWS")) R = std::max(2, atoi(env) / 2 * 2);
@@ -860,7 +863,7 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   }
   int T = 64;  // measured on C2 (profiles/README.md): 256, 384 and 512 threads are within 3 %; 384 is the best
   while (T < 384 && T < widest) T = T < 256 ? T * 2 : 384;
-  if (const char* env = getenv("HB_TREE_THREADS")) T = std::max(32, std::min(1024, atoi(env) / 32 * 32));
+  if (const char* env = getenv("HB_TREE_THREADS")) T = std::max(32, std::min(512, atoi(env) / 32 * 32));
   plan.T = T;
   int minb = (int)std::min<int64_t>(TREE_SMEM_MAX / (int64_t)plan.smem_bytes, 2048 / T);
   minb = std::max(1, std::min(minb, 65536 / (T * 128)));  // leave at least 128 registers per thread
@@ -990,7 +993,7 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
   std::ostringstream fns;  // one device function per step, defined before the kernel
   o << "@@STEP_FUNCTIONS@@";
   const int64_t inv_at = plan.arena_entries * R * 8, rowoff_at = inv_at + plan.invariant_entries * 8, stage_at = rowoff_at + round8(NS * R * 4),
-                ev_at = stage_at + (WP ? R * WP * 8 : 0);
+                ev_at = stage_at + (WP ? R * WP * 8 : 0), rng_at = ev_at + round8(R * NV);
   o << "extern \"C\" __global__ void __launch_bounds__(" << T << ", " << plan.min_blocks << ") hb_tree(const double* __restrict__ g_pots,\n"
        "    const double* __restrict__ g_shared, const signed char* __restrict__ ev, double* __restrict__ out, long long n_rows,\n"
        "    int* __restrict__ flag, int normalise) {\n";
@@ -1007,6 +1010,9 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
   o << "  int* const rowoff = reinterpret_cast<int*>(smem_raw + " << rowoff_at << ");\n";
   if (WP) o << "  double* const stage = reinterpret_cast<double*>(smem_raw + " << stage_at << ");\n";
   o << "  signed char* const evs = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n";
+  // the warps' block ranges: read at the top of every step by every warp -- shared memory, not the (small, thrashing) constant cache
+  o << "  unsigned short* const RNG = reinterpret_cast<unsigned short*>(smem_raw + " << rng_at << ");\n";
+  o << "  for (unsigned i = threadIdx.x; i < @@N_RANGES@@u; i += " << T << "u) RNG[i] = RNG_TABLE[i];\n";
   o << "  constexpr unsigned RT = " << R << "u;\n";
   o << "  const unsigned tid = threadIdx.x;\n";
   o << "  const unsigned warp = tid >> 5, lane = tid & 31u;\n";
@@ -1247,11 +1253,13 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
   std::string src = o.str();
   const size_t at = src.find("@@STEP_FUNCTIONS@@");
   std::ostringstream tab;
-  tab << "__constant__ unsigned short RNG[" << std::max<size_t>(rng.size(), 1) << "] = {";
+  tab << "__device__ const unsigned short RNG_TABLE[" << std::max<size_t>(rng.size(), 1) << "] = {";
   for (size_t i = 0; i < rng.size(); ++i) tab << (i ? "," : "") << rng[i];
   if (rng.empty()) tab << "0";
   tab << "};\n";
   src.replace(at, strlen("@@STEP_FUNCTIONS@@"), tab.str() + fns.str());
+  const size_t at2 = src.find("@@N_RANGES@@");
+  src.replace(at2, strlen("@@N_RANGES@@"), std::to_string(rng.size()));
   return src;
 }
 
