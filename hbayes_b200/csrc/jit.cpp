@@ -417,7 +417,7 @@ struct Gen {
   std::string call;  // filled by tree_step: the loop inside hb_tree
   int64_t tree_items = 0;  // filled by tree_step
   // `block` = the register block chosen for this step, v = rows per thread
-  void tree_step(int si, int R, int T, int range_index, const std::vector<int>& block, int v) {
+  void tree_step(int si, int R, int T, int rot, const std::vector<int>& block, int v) {
     V = v;
     custom_block = true;
     blocked = block;
@@ -434,27 +434,45 @@ struct Gen {
     emit_bases("    ", false);
     emit_group(STORE_RESULT);
     o << "}\n\n";
-    // A thread keeps its row (pair) and its warp for the whole kernel.  Every warp owns a contiguous range of the step's
-    // blocks, [RNG[2 * (range_index * n_warps + warp)], RNG[... + 1]): the ranges of a level are cut on the host so that
-    // all warps get the same amount of work (tree_source); the slots of a warp (lanes / rows) take neighbouring blocks.
-    const int64_t n_blocks = items / rows, spw = 32 / rows;  // blocks a warp evaluates side by side
+    // A thread keeps its row (pair) for the whole kernel: rowA / slotA (two rows per thread) or rowB / slotB (one row) are
+    // computed once at kernel start; the blocks of a step go to the slots round robin, slot `rot` first.
+    const int64_t n_blocks = items / rows, n_slots = T / rows;
     const char* rw = V == 2 ? "rowA" : "rowB";
-    const char* sw = V == 2 ? "swA" : "swB";
+    const char* sl = V == 2 ? "slotA" : "slotB";
+    const int64_t first = (n_slots - (rot / rows) % n_slots) % n_slots;
+    int ni = 1;
+    static const int max_ni = getenv("HB_TREE_INTERLEAVE") ? std::max(1, std::min(4, atoi(getenv("HB_TREE_INTERLEAVE")))) : 2;
+    while (ni < max_ni && n_blocks >= (int64_t)2 * ni * n_slots && n_loads * 2 * ni <= 96) ni *= 2;
     std::ostringstream c;
-    c << "    {  // step " << si << ": " << n_blocks << " blocks of " << U << " x " << rows << (V == 2 ? " row pairs\n" : " rows\n");
+    c << "    {  // step " << si << ": " << n_blocks << " blocks of " << U << " x " << rows << (V == 2 ? " row pairs" : " rows")
+      << (ni > 1 ? ", " + std::to_string(ni) + " items at a time\n" : "\n");
     c << "    double* const outb = arena_out + " << row_off(P.tables[st.out]) * R << "u + " << rw << ";\n";
-    c << "    const unsigned hi = RNG[" << 2 * range_index * (T / 32) << "u + 2u * warp + 1u];\n";
-    c << "    for (unsigned g = RNG[" << 2 * range_index * (T / 32) << "u + 2u * warp] + " << sw << "; g < hi; g += " << spw << "u) {\n";
-    c << "      " << DV() << " r0[" << U << "];\n      unsigned ob0;\n";
-    c << "      " << fn << "(arena, pots, shared, rowoff, g, " << rw << ", r0, &ob0);\n";
-    for (int u = 0; u < U; ++u) {
-      const std::string at = "outb + (ob0 + " + std::to_string(uoff[u]) + "u) * RT";
-      if (V == 2)
-        c << "      *reinterpret_cast<double2*>(" << at << ") = r0[" << u << "];\n";
+    const std::string g_first = first ? "(" + std::string(sl) + " + " + std::to_string(first) + "u) % " + std::to_string(n_slots) + "u" : std::string(sl);
+    if (n_blocks <= n_slots)
+      c << "    { const unsigned g = " << g_first << ";\n    if (g < " << n_blocks << "u) {\n";
+    else
+      c << "    for (unsigned g = " << g_first << "; g < " << n_blocks << "u; g += " << ni * n_slots << "u) {{\n";
+    for (int k = 0; k < ni; ++k) {
+      if (k == 0)
+        c << "      const unsigned g0 = g;\n";
       else
-        c << "      *(" << at << ") = r0[" << u << "];\n";
+        c << "      const bool has" << k << " = g + " << k * n_slots << "u < " << n_blocks << "u;\n      const unsigned g" << k << " = has" << k << " ? g + " << k * n_slots
+          << "u : g;\n";
+      c << "      " << DV() << " r" << k << "[" << U << "];\n      unsigned ob" << k << ";\n";
+      c << "      " << fn << "(arena, pots, shared, rowoff, g" << k << ", " << rw << ", r" << k << ", &ob" << k << ");\n";
     }
-    c << "    }\n    }\n";
+    for (int k = 0; k < ni; ++k) {
+      if (k > 0) c << "      if (has" << k << ") {\n";
+      for (int u = 0; u < U; ++u) {
+        const std::string at = "outb + (ob" + std::to_string(k) + " + " + std::to_string(uoff[u]) + "u) * RT";
+        if (V == 2)
+          c << "      *reinterpret_cast<double2*>(" << at << ") = r" << k << "[" << u << "];\n";
+        else
+          c << "      *(" << at << ") = r" << k << "[" << u << "];\n";
+      }
+      if (k > 0) c << "      }\n";
+    }
+    c << "    }}\n    }\n";
     call = c.str();
   }
 };
@@ -749,7 +767,7 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
     }
     if (st.shared) continue;
     if (st.levels.empty() || st.levels[0].is_max || P.tables[st.out].kind != T_ROW) return fail("unsupported step");
-    if (st.U > 32 || st.n_out >= 65536) return fail("step too large");
+    if (st.U > 32 || st.n_red >= ((int64_t)1 << 24)) return fail("step too large");
     const int64_t ops = jit_unrolled_ops(st);
     if (ops < 0) return fail("step body too large to unroll");
     body += ops;
@@ -830,11 +848,8 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   // the batch-invariant tables (potential pool, shared arena) are copied to shared memory once per CTA when they are small
   const int64_t inv_entries = P.pot_entries + P.shared_entries;
   plan.invariant_entries = inv_entries * 8 <= TREE_INVARIANT_MAX ? inv_entries : 0;
-  int64_t n_row_steps = 0;
-  for (size_t si = 0; si < ns; ++si) n_row_steps += plan.level[si] >= 0;
-  plan.range_bytes = round8(n_row_steps * 16 * 2 * 2);  // per step and warp (at most 16 warps): first and end block, 16 bits each
   auto bytes = [&](int64_t R, bool staged) {
-    return plan.arena_entries * R * 8 + plan.invariant_entries * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV) + plan.range_bytes;
+    return plan.arena_entries * R * 8 + plan.invariant_entries * 8 + round8(NS * R * 4) + (staged ? R * (W | 1) * 8 : 0) + round8(R * NV);
   };
   int R = 0;
   if (const char* env = getenv("HB_TREE_ROWS")) R = std::max(2, atoi(env) / 2 * 2);
@@ -863,7 +878,7 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   }
   int T = 64;  // measured on C2 (profiles/README.md): 256, 384 and 512 threads are within 3 %; 384 is the best
   while (T < 384 && T < widest) T = T < 256 ? T * 2 : 384;
-  if (const char* env = getenv("HB_TREE_THREADS")) T = std::max(32, std::min(512, atoi(env) / 32 * 32));
+  if (const char* env = getenv("HB_TREE_THREADS")) T = std::max(32, std::min(1024, atoi(env) / 32 * 32));
   plan.T = T;
   int minb = (int)std::min<int64_t>(TREE_SMEM_MAX / (int64_t)plan.smem_bytes, 2048 / T);
   minb = std::max(1, std::min(minb, 65536 / (T * 128)));  // leave at least 128 registers per thread
@@ -993,7 +1008,7 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
   std::ostringstream fns;  // one device function per step, defined before the kernel
   o << "@@STEP_FUNCTIONS@@";
   const int64_t inv_at = plan.arena_entries * R * 8, rowoff_at = inv_at + plan.invariant_entries * 8, stage_at = rowoff_at + round8(NS * R * 4),
-                ev_at = stage_at + (WP ? R * WP * 8 : 0), rng_at = ev_at + round8(R * NV);
+                ev_at = stage_at + (WP ? R * WP * 8 : 0);
   o << "extern \"C\" __global__ void __launch_bounds__(" << T << ", " << plan.min_blocks << ") hb_tree(const double* __restrict__ g_pots,\n"
        "    const double* __restrict__ g_shared, const signed char* __restrict__ ev, double* __restrict__ out, long long n_rows,\n"
        "    int* __restrict__ flag, int normalise) {\n";
@@ -1010,13 +1025,9 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
   o << "  int* const rowoff = reinterpret_cast<int*>(smem_raw + " << rowoff_at << ");\n";
   if (WP) o << "  double* const stage = reinterpret_cast<double*>(smem_raw + " << stage_at << ");\n";
   o << "  signed char* const evs = reinterpret_cast<signed char*>(smem_raw + " << ev_at << ");\n";
-  // the warps' block ranges: read at the top of every step by every warp -- shared memory, not the (small, thrashing) constant cache
-  o << "  unsigned short* const RNG = reinterpret_cast<unsigned short*>(smem_raw + " << rng_at << ");\n";
-  o << "  for (unsigned i = threadIdx.x; i < @@N_RANGES@@u; i += " << T << "u) RNG[i] = RNG_TABLE[i];\n";
   o << "  constexpr unsigned RT = " << R << "u;\n";
   o << "  const unsigned tid = threadIdx.x;\n";
-  o << "  const unsigned warp = tid >> 5, lane = tid & 31u;\n";
-  o << "  const unsigned rowA = (lane % " << R / 2 << "u) * 2u, swA = lane / " << R / 2 << "u, rowB = lane % " << R << "u, swB = lane / " << R << "u;\n";
+  o << "  const unsigned rowA = (tid % " << R / 2 << "u) * 2u, slotA = tid / " << R / 2 << "u, rowB = tid % " << R << "u, slotB = tid / " << R << "u;\n";
   const int64_t ept = (R * NV + T - 1) / T;  // evidence bytes per thread and tile
   for (int64_t k = 0; k < ept; ++k)
     o << "  signed char pre" << k << " = (tid + " << k * T << "u < " << R * NV << "u && (long long)blockIdx.x * " << R * NV << "ll + tid + " << k * T << "u < n_rows * " << NV
@@ -1062,86 +1073,42 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
                    << ", (unsigned long long)(t1 - t0)); t0 = t1; }\n";
   };
   lap(0);
-  // Work distribution inside a level.  Every step is cut into register blocks of output entries (all values a block needs
-  // are loaded once: shared-memory bandwidth is what bounds the wide levels, profiles/README.md) x rows; a warp evaluates
-  // 32 / rows blocks side by side.  Block shape and rows per thread are chosen per step -- the coarsest cut whose single
-  // warp pass stays below half a warp's share of the level, so that (a) narrow levels are cut finely enough to occupy every
-  // warp and (b) wide levels move as little as possible through shared memory -- and then the passes of the level are
-  // dealt to the warps as contiguous ranges of equal cost (RNG table, constant memory).
+  // Items of equal work: a level's fp64 operations are dealt to the T threads, so a step that holds the share f of them
+  // is cut into about f * T items -- register blocks of up to 16 output entries (every input value loaded once per
+  // block: shared-memory bandwidth is what bounds the wide levels) x row pairs, single entries x single rows where the
+  // level is narrow (there latency is the bound and every thread should have something to do).
+  static const double grain = getenv("HB_TREE_GRAIN") ? atof(getenv("HB_TREE_GRAIN")) : 1.0;
   static const int64_t block_cap = getenv("HB_TREE_BLOCK") ? std::max(1, atoi(getenv("HB_TREE_BLOCK"))) : 16;
-  static const double grain = getenv("HB_TREE_GRAIN") ? atof(getenv("HB_TREE_GRAIN")) : 2.0;  // passes per warp and level aimed at
-  const int NW = T / 32;
-  std::vector<int64_t> rng;  // per (step in emission order, warp): first block, end block
-  int range_index = 0;
   for (int lv = 0; lv < plan.n_levels; ++lv) {
     o << "    // ---- dependency level " << lv << " ----\n";
-    struct Choice {
-      size_t si;
-      std::vector<int> block;
-      int v;
-      int64_t n_blocks, spw;
-      double pass_cost;  // instructions of one warp pass (fp64 + loads)
-    };
-    std::vector<Choice> chosen;
-    double level_fp64 = 0;  // fp64 warp instructions of the level (the same for every cut)
+    int64_t rot = 0, level_ops = 0;
     for (size_t si = 0; si < P.steps.size(); ++si)
-      if (plan.level[si] == lv) level_fp64 += (double)step_ops(P.steps[si]) * R / 32.0;
-    const double pass_budget = std::max(48.0, level_fp64 / NW / grain);
+      if (plan.level[si] == lv) level_ops += step_ops(P.steps[si]);
     for (size_t si = 0; si < P.steps.size(); ++si) {
       if (plan.level[si] != lv) continue;
       const Step& st = P.steps[si];
-      const double ops_entry = (double)step_ops(st) / (double)st.n_out;
-      Choice best{si, {}, 1, st.n_out, 32 / R, 0.0};
-      double best_loads = -1;
-      for (int v : {2, 1}) {
-        if (v == 2 && R < 2) continue;
-        for (int64_t cap = block_cap; cap >= 1; cap /= 2) {
-          const std::vector<int> block = choose_block(P, st, cap);
-          int64_t U = 1;
-          for (int x : block) U *= net.dims[x];
-          const double loads_block = (double)block_loads(P, st, block) / (double)(st.n_out / U);
-          const double pass = v * ops_entry * U + loads_block * v;  // per thread: V instructions per operation, V (scalar) or 1 (vector) per load: upper bound
-          if (pass > pass_budget && !(v == 1 && cap == 1)) continue;
-          const double loads = (double)block_loads(P, st, block);  // per row
-          if (best_loads < 0 || loads < best_loads) {
-            best_loads = loads;
-            best = Choice{si, block, v, st.n_out / U, 32 / (v == 2 ? R / 2 : R), pass};
-          }
-        }
-        if (best_loads >= 0) break;  // two rows per thread whenever some block fits the budget: half the instructions per flop
+      static const int policy = getenv("HB_TREE_POLICY") ? atoi(getenv("HB_TREE_POLICY")) : 0;
+      int v = 2;
+      std::vector<int> block;
+      if (policy == 1) {  // equal work
+        const double want = std::max(1.0, grain * T * (double)step_ops(st) / (double)std::max<int64_t>(level_ops, 1));
+        const int64_t fit = (int64_t)((double)(st.n_out * (R / 2)) / want);  // entries per block that still give `want` items
+        v = fit >= 1 ? 2 : 1;
+        block = choose_block(P, st, std::max<int64_t>(1, std::min(fit, block_cap)));
+      } else {  // every step on its own: the coarsest cut that still gives every thread an item
+        const double want = grain * T;
+        if (st.w_var >= 0 && st.n_red * (R / 2) >= want)
+          block = {st.w_var};
+        else if (st.n_out * (R / 2) < want)
+          v = 1;
       }
-      chosen.push_back(best);
-    }
-    // equal-cost contiguous ranges: walk the passes of the level in order, moving to the next warp whenever its share is full
-    double total = 0;
-    for (const Choice& c : chosen) total += (double)((c.n_blocks + c.spw - 1) / c.spw) * std::max(c.pass_cost, 1.0);
-    const double share = total / NW;
-    int w = 0;
-    double acc = 0;
-    for (const Choice& c : chosen) {
-      const Step& st = P.steps[c.si];
-      std::vector<int64_t> lo(NW, 0), hi(NW, 0);
-      const double cost = std::max(c.pass_cost, 1.0);
-      int64_t at = 0;
-      while (at < c.n_blocks) {
-        const int64_t left_passes = (c.n_blocks - at + c.spw - 1) / c.spw;
-        int64_t take = (int64_t)((share * (w + 1) - acc) / cost + 0.5);
-        if (w == NW - 1) take = left_passes;
-        take = std::max<int64_t>(1, std::min(take, left_passes));
-        const int64_t end = std::min(c.n_blocks, at + take * c.spw);
-        if (hi[w] == lo[w]) lo[w] = at;
-        hi[w] = end;
-        acc += (double)take * cost;
-        at = end;
-        if (acc >= share * (w + 1) - 0.5 * cost && w < NW - 1) ++w;
-      }
-      for (int k = 0; k < NW; ++k) rng.push_back(lo[k]), rng.push_back(hi[k]);
       Gen g(P, st);
       g.tree_off = &plan.off;
-      g.tree_step((int)c.si, R, T, range_index++, c.block, c.v);
+      g.tree_step((int)si, R, T, (int)(rot % T), block, v);
       fns << g.o.str();
       o << g.call;
-      stat_loads += g.n_loads * (g.tree_items / (c.v == 2 ? R / 2 : R));
+      rot += g.tree_items;
+      stat_loads += g.n_loads * (g.tree_items / (v == 2 ? R / 2 : R));
       stat_items += g.tree_items;
     }
     o << "    __syncthreads();\n";
@@ -1252,14 +1219,7 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
   }
   std::string src = o.str();
   const size_t at = src.find("@@STEP_FUNCTIONS@@");
-  std::ostringstream tab;
-  tab << "__device__ const unsigned short RNG_TABLE[" << std::max<size_t>(rng.size(), 1) << "] = {";
-  for (size_t i = 0; i < rng.size(); ++i) tab << (i ? "," : "") << rng[i];
-  if (rng.empty()) tab << "0";
-  tab << "};\n";
-  src.replace(at, strlen("@@STEP_FUNCTIONS@@"), tab.str() + fns.str());
-  const size_t at2 = src.find("@@N_RANGES@@");
-  src.replace(at2, strlen("@@N_RANGES@@"), std::to_string(rng.size()));
+  src.replace(at, strlen("@@STEP_FUNCTIONS@@"), fns.str());
   return src;
 }
 

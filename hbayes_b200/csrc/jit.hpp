@@ -48,7 +48,6 @@ struct TreePlan {
   std::vector<int64_t> off;    // per table: entry offset of a per-row table in the shared-memory arena, -1 otherwise
   int64_t arena_entries = 0;   // per row, with reuse of dead tables from one level to the next
   int64_t invariant_entries = 0;  // potential pool + shared arena entries staged in shared memory (0: read through L1/L2)
-  int64_t range_bytes = 0;     // shared memory reserved for the warps' block ranges
   int64_t stage_pitch = 0;     // doubles per row of the output staging tile (0: results are written straight to HBM)
   size_t smem_bytes = 0;
   int64_t ops_mul = 0, ops_add = 0;  // fp64 multiplies / adds per row (what the reference does, no more)
