@@ -340,12 +340,25 @@ class JunctionTree(_Batched):
 
     def changeEvidence(self, evidence: Sequence[tuple]):
         """evidence = [(vertex, state)], order kept (it decides the reference's operation order)."""
-        va, vp_ = _i32([e[0] for e in evidence])
-        sa, sp = _i32([e[1] for e in evidence])
-        check(lib().hb_jt_set_evidence(self._h, len(evidence), vp_, sp))
+        n = len(evidence)
+        vs = (C.c_int32 * max(n, 1))(*[int(e[0]) for e in evidence])
+        ss = (C.c_int32 * max(n, 1))(*[int(e[1]) for e in evidence])
+        check(lib().hb_jt_set_evidence(self._h, n, vs, ss))
         return self
 
     def posterior(self, variables: Sequence[int]):
+        if len(variables) == 1:  # the common case (posterior jt [v]): no numpy round trips on the latency path
+            v = int(variables[0])
+            if not 0 <= v < self.net.n:
+                raise HbError(_lib.HB_E_ARG, "query on unknown vertex")
+            size = self.net.dims[v]
+            out = (C.c_double * size)()
+            q, scope, n = (C.c_int32 * 1)(v), (C.c_int32 * 1)(), C.c_int64()
+            code = lib().hb_jt_posterior(self._h, 1, q, scope, out, size, C.byref(n))
+            if code == HB_E_NO_CLUSTER:
+                return None
+            check(code)
+            return Factor([v], [size], np.frombuffer(out, np.float64, n.value))
         qa, qp = _i32(list(variables))
         size = int(np.prod([self.net.dims[v] for v in variables]))
         out = np.zeros(size, np.float64)
