@@ -441,7 +441,9 @@ struct Gen {
     const char* sl = V == 2 ? "slotA" : "slotB";
     const int64_t first = (n_slots - (rot / rows) % n_slots) % n_slots;
     int ni = 1;
-    static const int max_ni = getenv("HB_TREE_INTERLEAVE") ? std::max(1, std::min(4, atoi(getenv("HB_TREE_INTERLEAVE")))) : 2;
+    // items evaluated together by one thread: measured on C2, 1 -> 6.41 ms, 2 -> 6.78 ms, 4 -> 6.78 ms per 2^20 rows (the larger
+    // bodies cost more in instruction fetch and registers than the overlap gains)
+    static const int max_ni = getenv("HB_TREE_INTERLEAVE") ? std::max(1, std::min(4, atoi(getenv("HB_TREE_INTERLEAVE")))) : 1;
     while (ni < max_ni && n_blocks >= (int64_t)2 * ni * n_slots && n_loads * 2 * ni <= 96) ni *= 2;
     std::ostringstream c;
     c << "    {  // step " << si << ": " << n_blocks << " blocks of " << U << " x " << rows << (V == 2 ? " row pairs" : " rows")
@@ -489,7 +491,8 @@ static int64_t body_ops(const Step& st, int n_loop, int64_t U) {
   }
   return ops * U;
 }
-constexpr int64_t MAX_BODY_OPS = 600;  // compile time grows faster than linearly with the size of a straight-line kernel
+// compile time grows faster than linearly with the size of a straight-line kernel (HB_JIT_BODY: tuning override)
+static const int64_t MAX_BODY_OPS = getenv("HB_JIT_BODY") ? std::max(8, atoi(getenv("HB_JIT_BODY"))) : 600;
 
 // how many outermost levels stay run-time loops so that the unrolled rest fits MAX_BODY_OPS (-1: not even the
 // innermost level alone fits)
