@@ -1087,8 +1087,17 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
     int64_t rot = 0, level_ops = 0;
     for (size_t si = 0; si < P.steps.size(); ++si)
       if (plan.level[si] == lv) level_ops += step_ops(P.steps[si]);
-    for (size_t si = 0; si < P.steps.size(); ++si) {
-      if (plan.level[si] != lv) continue;
+    // order of the steps inside a level (HB_TREE_ORDER: 0 program order, 1 most operations per output entry first, 2 last)
+    static const int order = getenv("HB_TREE_ORDER") ? atoi(getenv("HB_TREE_ORDER")) : 0;
+    std::vector<size_t> in_level;
+    for (size_t si = 0; si < P.steps.size(); ++si)
+      if (plan.level[si] == lv) in_level.push_back(si);
+    if (order)
+      std::stable_sort(in_level.begin(), in_level.end(), [&](size_t a, size_t b) {
+        const double ca = (double)step_ops(P.steps[a]) / (double)P.steps[a].n_out, cb = (double)step_ops(P.steps[b]) / (double)P.steps[b].n_out;
+        return order == 1 ? ca > cb : ca < cb;
+      });
+    for (size_t si : in_level) {
       const Step& st = P.steps[si];
       static const int policy = getenv("HB_TREE_POLICY") ? atoi(getenv("HB_TREE_POLICY")) : 0;
       int v = 2;
