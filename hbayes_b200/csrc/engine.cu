@@ -1647,31 +1647,31 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
       for (const Executor::Node& n : nodes) launch_prodsum(*ex, P.steps[n.si], n.si, stride, nr, on);
     };
     static const bool graphs_on = !(getenv("HB_GRAPHS") && atoi(getenv("HB_GRAPHS")) == 0);
-    if (P.n_reduce > 0) {
-      // Split clique: plain launches in dependency order, the same on every rank.  A table that holds this GPU's partial
-      // sum over the split variables is all-reduced right after the step that produces it -- one exchange of |table|
-      // doubles per row and per message -- unless only the final normalisation reads it: those (the posteriors' own
-      // results) are exchanged together at the end, as one NCCL group.
-      std::vector<const Table*> late;
+    // Split clique: a table that holds this GPU's partial sum over the split variables is all-reduced right after the step
+    // that produces it -- one exchange of |table| doubles per row and per message -- unless only the final normalisation
+    // reads it: those (the posteriors' own results) are exchanged together after the last step, as one NCCL group.
+    std::vector<const Table*> late;
+    bool early_reduce = false;
+    for (const Executor::Node& n : nodes) {
+      const Table& t = P.tables[P.steps[n.si].out];
+      if (!t.reduce) continue;
+      bool only_output = true;
+      for (const Step& other : P.steps)
+        if (other.kind == STEP_PRODSUM && !other.shared)
+          for (const Level& l : other.levels)
+            for (const StepInput& in : l.in) only_output = only_output && in.table != P.steps[n.si].out;
+      if (only_output)
+        late.push_back(&t);
+      else
+        early_reduce = true;
+    }
+    if (early_reduce) {  // exchanges between the steps: plain launches in dependency order, the same on every rank
       for (const Executor::Node& n : nodes) {
         const Step& st = P.steps[n.si];
         launch_prodsum(*ex, st, n.si, stride, nr, stream);
         const Table& t = P.tables[st.out];
-        if (!t.reduce) continue;
-        bool only_output = true;
-        for (const Step& other : P.steps)
-          if (other.kind == STEP_PRODSUM && !other.shared)
-            for (const Level& l : other.levels)
-              for (const StepInput& in : l.in) only_output = only_output && in.table != st.out;
-        if (only_output)
-          late.push_back(&t);
-        else
+        if (t.reduce && std::find(late.begin(), late.end(), &t) == late.end())
           nccl_allreduce_sum(ex->comm, ex->d_arena + t.off * stride, (size_t)(t.size * stride), stream);
-      }
-      if (!late.empty()) {
-        nccl_group_start();
-        for (const Table* t : late) nccl_allreduce_sum(ex->comm, ex->d_arena + t->off * stride, (size_t)(t->size * stride), stream);
-        nccl_group_end();
       }
     } else if (graphs_on && nodes.size() >= 16) {
       auto it = ex->graphs.find(nr);
@@ -1729,6 +1729,11 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
       HB_CUDA(cudaGraphLaunch(it->second, stream));
     } else {
       launch_steps(stream);
+    }
+    if (!late.empty()) {
+      nccl_group_start();
+      for (const Table* t : late) nccl_allreduce_sum(ex->comm, ex->d_arena + t->off * stride, (size_t)(t->size * stride), stream);
+      nccl_group_end();
     }
     launches += (int64_t)nodes.size();
     mark();
