@@ -874,10 +874,10 @@ struct Reuse {
 };
 LaunchShape launch_shape(int row_threads, int rows_per_thread, int64_t n_out, const Reuse& reuse = Reuse()) {
   LaunchShape s;
-  static const bool reuse_on = !(getenv("HB_REUSE_TILE") && atoi(getenv("HB_REUSE_TILE")) == 0);
-  static const int reuse_bx = getenv("HB_REUSE_BX") ? atoi(getenv("HB_REUSE_BX")) : 32;          // row-threads per block
-  static const int reuse_kb = getenv("HB_REUSE_KB") ? atoi(getenv("HB_REUSE_KB")) : 96;          // tile budget
-  static const int reuse_min = getenv("HB_REUSE_MIN") ? atoi(getenv("HB_REUSE_MIN")) : 3;        // minimum re-read factor
+  constexpr bool reuse_on = true;
+  constexpr int reuse_bx = 32;   // row-threads per block
+  constexpr int reuse_kb = 96;   // tile budget, KB
+  constexpr int reuse_min = 3;   // minimum re-read factor
   const int64_t tile_bytes = reuse.row_entries * reuse_bx * rows_per_thread * 8;
   if (reuse_on && row_threads >= 64 && n_out >= 32 && reuse.row_entries > 0 && reuse.row_loads >= reuse_min * reuse.row_entries &&
       tile_bytes <= (int64_t)reuse_kb * 1024) {

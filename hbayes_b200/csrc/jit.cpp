@@ -440,11 +440,9 @@ struct Gen {
     const char* rw = V == 2 ? "rowA" : "rowB";
     const char* sl = V == 2 ? "slotA" : "slotB";
     const int64_t first = (n_slots - (rot / rows) % n_slots) % n_slots;
-    int ni = 1;
-    // items evaluated together by one thread: measured on C2, 1 -> 6.41 ms, 2 -> 6.78 ms, 4 -> 6.78 ms per 2^20 rows (the larger
-    // bodies cost more in instruction fetch and registers than the overlap gains)
-    static const int max_ni = getenv("HB_TREE_INTERLEAVE") ? std::max(1, std::min(4, atoi(getenv("HB_TREE_INTERLEAVE")))) : 1;
-    while (ni < max_ni && n_blocks >= (int64_t)2 * ni * n_slots && n_loads * 2 * ni <= 96) ni *= 2;
+    // one item per thread at a time: evaluating two or four together (no store between their bodies) measured 6 % slower on
+    // C2 -- larger bodies cost more in registers and instruction fetch than the overlap gains
+    const int ni = 1;
     std::ostringstream c;
     c << "    {  // step " << si << ": " << n_blocks << " blocks of " << U << " x " << rows << (V == 2 ? " row pairs" : " rows")
       << (ni > 1 ? ", " + std::to_string(ni) + " items at a time\n" : "\n");
@@ -491,8 +489,8 @@ static int64_t body_ops(const Step& st, int n_loop, int64_t U) {
   }
   return ops * U;
 }
-// compile time grows faster than linearly with the size of a straight-line kernel (HB_JIT_BODY: tuning override)
-static const int64_t MAX_BODY_OPS = getenv("HB_JIT_BODY") ? std::max(8, atoi(getenv("HB_JIT_BODY"))) : 600;
+// compile time grows faster than linearly with the size of a straight-line kernel; 100 .. 600 measured the same on C2
+constexpr int64_t MAX_BODY_OPS = 600;
 
 // how many outermost levels stay run-time loops so that the unrolled rest fits MAX_BODY_OPS (-1: not even the
 // innermost level alone fits)
@@ -516,12 +514,9 @@ bool jit_eligible(const Program& P, const Step& st) {
   for (const Level& l : st.levels)
     for (const StepInput& in : l.in)
       if (P.tables[in.table].kind == T_ONE) return false;
-  // Steps whose body only fits with run-time loops around it can be generated too (HB_JIT_LOOPS=1; parity-checked on
-  // C3), but at two CTAs per SM they spill and measured no faster than the templated kernels (C3: 6.6 vs 6.2 ms), so
-  // by default only fully unrolled steps are specialised.
-  static const bool loops_on = getenv("HB_JIT_LOOPS") && atoi(getenv("HB_JIT_LOOPS")) != 0;
-  const int n_loop = jit_loop_levels(st);
-  return n_loop == 0 || (loops_on && n_loop > 0);
+  // A step whose body only fits with run-time loops around it stays on the precompiled kernels: as a kernel of its own it
+  // spilled at two CTAs per SM and measured no faster (C3: 6.6 vs 6.2 ms).  (Inside hb_tree such steps do use the loops.)
+  return jit_loop_levels(st) == 0;
 }
 
 // loads per row (8-byte slots, one row) the specialised kernel issues for the step / the templated kernels issue
@@ -902,57 +897,6 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
   return true;
 }
 
-namespace {
-// fp64 operations of one row of a step (multiplies + adds, as the reference performs them)
-int64_t step_ops(const Step& st) {
-  int64_t ops = 0, terms = st.n_out;
-  for (size_t l = 0; l < st.levels.size(); ++l) {
-    terms *= st.levels[l].d;
-    const int64_t k = (int64_t)st.levels[l].in.size() + (l + 1 < st.levels.size() ? 1 : 0) + (l == 0 && !st.scalars.empty() ? 1 : 0);
-    ops += terms * std::max<int64_t>(1, k);
-  }
-  return ops;
-}
-
-// table loads of one row of a step when the output variables in `block` are enumerated inside an item
-int64_t block_loads(const Program& P, const Step& st, const std::vector<int>& block) {
-  const Network& net = *P.net;
-  int64_t items = st.n_out;
-  for (int v : block) items /= net.dims[v];
-  std::vector<int> inner = block;  // variables an item runs over: the block, then the summed variables level by level
-  int64_t per_item = 0;
-  for (const Level& l : st.levels) {
-    if (l.sum_var >= 0 && l.d > 1) inner.push_back(l.sum_var);
-    for (const StepInput& in : l.in) {
-      int64_t n = 1;
-      for (int v : P.tables[in.table].pscope)
-        if (std::find(inner.begin(), inner.end(), v) != inner.end()) n *= net.dims[v];
-      per_item += n;
-    }
-  }
-  return items * per_item;
-}
-
-// the register block of at most `cap` entries that needs the fewest loads (ties: the smaller block)
-std::vector<int> choose_block(const Program& P, const Step& st, int64_t cap) {
-  const Network& net = *P.net;
-  std::vector<int> vars = P.tables[st.out].pscope;
-  if (vars.size() > 12) vars.resize(12);
-  std::vector<int> best;
-  int64_t best_loads = block_loads(P, st, best), best_size = 1;
-  for (unsigned mask = 1; mask < (1u << vars.size()); ++mask) {
-    std::vector<int> b;
-    int64_t size = 1;
-    for (size_t i = 0; i < vars.size(); ++i)
-      if (mask >> i & 1) b.push_back(vars[i]), size *= net.dims[vars[i]];
-    if (size > cap || loop_levels_for(st, size) < 0) continue;
-    const int64_t loads = block_loads(P, st, b);
-    if (loads < best_loads || (loads == best_loads && size < best_size)) best = b, best_loads = loads, best_size = size;
-  }
-  return best;
-}
-}  // namespace
-
 std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_per_row, int64_t* stores_per_row) {
   const Network& net = *P.net;
   const int R = plan.R, T = plan.T;
@@ -1076,47 +1020,24 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
                    << ", (unsigned long long)(t1 - t0)); t0 = t1; }\n";
   };
   lap(0);
-  // Items of equal work: a level's fp64 operations are dealt to the T threads, so a step that holds the share f of them
-  // is cut into about f * T items -- register blocks of up to 16 output entries (every input value loaded once per
-  // block: shared-memory bandwidth is what bounds the wide levels) x row pairs, single entries x single rows where the
-  // level is narrow (there latency is the bound and every thread should have something to do).
-  static const double grain = getenv("HB_TREE_GRAIN") ? atof(getenv("HB_TREE_GRAIN")) : 1.0;
-  static const int64_t block_cap = getenv("HB_TREE_BLOCK") ? std::max(1, atoi(getenv("HB_TREE_BLOCK"))) : 16;
+  static const double grain = getenv("HB_TREE_GRAIN") ? atof(getenv("HB_TREE_GRAIN")) : 1.0;  // tuning: items wanted per thread
   for (int lv = 0; lv < plan.n_levels; ++lv) {
     o << "    // ---- dependency level " << lv << " ----\n";
-    int64_t rot = 0, level_ops = 0;
-    for (size_t si = 0; si < P.steps.size(); ++si)
-      if (plan.level[si] == lv) level_ops += step_ops(P.steps[si]);
-    // order of the steps inside a level (HB_TREE_ORDER: 0 program order, 1 most operations per output entry first, 2 last)
-    static const int order = getenv("HB_TREE_ORDER") ? atoi(getenv("HB_TREE_ORDER")) : 0;
-    std::vector<size_t> in_level;
-    for (size_t si = 0; si < P.steps.size(); ++si)
-      if (plan.level[si] == lv) in_level.push_back(si);
-    if (order)
-      std::stable_sort(in_level.begin(), in_level.end(), [&](size_t a, size_t b) {
-        const double ca = (double)step_ops(P.steps[a]) / (double)P.steps[a].n_out, cb = (double)step_ops(P.steps[b]) / (double)P.steps[b].n_out;
-        return order == 1 ? ca > cb : ca < cb;
-      });
-    for (size_t si : in_level) {
+    int64_t rot = 0;
+    for (size_t si = 0; si < P.steps.size(); ++si) {
+      if (plan.level[si] != lv) continue;
       const Step& st = P.steps[si];
-      static const int policy = getenv("HB_TREE_POLICY") ? atoi(getenv("HB_TREE_POLICY")) : 0;
+      // the coarsest cut of the step that still keeps the threads busy: blocks of all states of w x row pairs when they give
+      // at least half the threads an item (measured on C2: threshold 1.0 T -> 6.40 ms, 0.5 T -> 6.32 ms, 0.25 T -> 9.66 ms
+      // per 2^20 rows: few long items cost more than the loads they save), else single entries x row pairs, else single
+      // entries x single rows (narrow steps: latency is the bound and every thread should have something to do)
+      static const double group_grain = getenv("HB_TREE_GROUP_GRAIN") ? atof(getenv("HB_TREE_GROUP_GRAIN")) : 0.5;
       int v = 2;
       std::vector<int> block;
-      if (policy == 1) {  // equal work
-        const double want = std::max(1.0, grain * T * (double)step_ops(st) / (double)std::max<int64_t>(level_ops, 1));
-        const int64_t fit = (int64_t)((double)(st.n_out * (R / 2)) / want);  // entries per block that still give `want` items
-        v = fit >= 1 ? 2 : 1;
-        block = choose_block(P, st, std::max<int64_t>(1, std::min(fit, block_cap)));
-      } else {  // every step on its own: the coarsest cut that still gives every thread an item
-        // blocks of all states of w when they give at least half the threads an item (measured on C2: 1.0 -> 6.40 ms, 0.5 -> 6.32 ms,
-        // 0.25 -> 9.66 ms per 2^20 rows: the few, long items of a coarser cut cost more than the loads they save)
-        static const double group_grain = getenv("HB_TREE_GROUP_GRAIN") ? atof(getenv("HB_TREE_GROUP_GRAIN")) : 0.5;
-        const double want = grain * T;
-        if (st.w_var >= 0 && st.n_red * (R / 2) >= group_grain * T)
-          block = {st.w_var};
-        else if (st.n_out * (R / 2) < want)
-          v = 1;
-      }
+      if (st.w_var >= 0 && st.n_red * (R / 2) >= group_grain * T)
+        block = {st.w_var};
+      else if (st.n_out * (R / 2) < grain * T)
+        v = 1;
       Gen g(P, st);
       g.tree_off = &plan.off;
       g.tree_step((int)si, R, T, (int)(rot % T), block, v);
