@@ -363,6 +363,7 @@ def main():
         e2e_step()
     e2e_steps = max(2, min(args.steps, 5))
     ms_e2e = timed(e2e_step, e2e_steps)
+    barrier()  # every rank measures its copies at the same time: the denominator is the rate the box sustains for N concurrent transfers
     pcie = pcie_peaks(out_pinned, d_out, ev_pinned, d_ev, stream)
     jt.posteriors_batch(ev_pinned, out_pinned)  # out_pinned holds this rank's answers again (the copy test overwrote it)
     torch.cuda.synchronize()
@@ -418,8 +419,8 @@ def main():
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "roofline": {"bound": "pcie d2h", "achieved": out_pinned.nbytes / (ms_e2e / e2e_steps / 1e3) / 1e9, "peak": pcie["d2h_GBps"],
                                  "unit": "GB/s", "frac": out_pinned.nbytes / (ms_e2e / e2e_steps / 1e3) / 1e9 / pcie["d2h_GBps"],
-                                 "peak_source": "pinned cudaMemcpyAsync of the same %d-byte result matrix in this run, best of 3; H2D %.1f GB/s"
-                                                % (out_pinned.nbytes, pcie["h2d_GBps"])},
+                                 "peak_source": "pinned cudaMemcpyAsync of the same %d-byte result matrix in this run (rank 0, all %d ranks copying at the "
+                                                "same time), best of 3; H2D %.1f GB/s" % (out_pinned.nbytes, world, pcie["h2d_GBps"])},
                     "pageable": {"value": whole_job_rate([rows] * world, 2, ms_pageable), "ms_per_step": ms_pageable / 2,
                                  "note": "same call, caller buffers NOT pinned (numpy arrays)"}},
             "gpu_launches": int(stats["launches"]) * args.steps,
