@@ -395,8 +395,10 @@ struct Gen {
     o << "extern \"C\" __global__ void __launch_bounds__(256, " << (getenv("HB_JIT_MINBLOCKS") ? atoi(getenv("HB_JIT_MINBLOCKS")) : 2) << ") " << name
       << "(const double* __restrict__ arena, double* __restrict__ arena_out, const double* __restrict__ pots,\n"
          "    const double* __restrict__ shared, const int* __restrict__ rowoff, int nr, long long RT) {\n";
-    o << "  const int row = (blockIdx.x * blockDim.x + threadIdx.x) * 2;\n  if (row >= nr) return;\n";
-    o << "  const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;\n";
+    // strips of groups along blockIdx.x (the fast axis of the block scheduler), row blocks along blockIdx.y: the CTAs that are
+    // resident together work on the SAME rows, so a step that enumerates its inputs many times finds them in L2
+    o << "  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * 2;\n  if (row >= nr) return;\n";
+    o << "  const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;\n";
     o << "  const unsigned per = (" << st.n_red << "u + lanes - 1) / lanes;\n";
     o << "  const unsigned g_end = min(" << st.n_red << "u, lane * per + per);\n";
     o << "  const double2 zero = make_double2(0.0, 0.0);\n";
