@@ -182,7 +182,7 @@ struct Strip {
   __device__ __forceinline__ bool init(unsigned n_red, unsigned U, unsigned C) {
     nch = (U + 1) >> 1;
     const unsigned n_items = n_red * nch;
-    const unsigned lanes = gridDim.y * blockDim.y, lane = blockIdx.y * blockDim.y + threadIdx.y;
+    const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;  // strips: the fast grid axis
     const unsigned per = (n_items + lanes - 1) / lanes;
     it = lane * per;
     it_end = min(n_items, it + per);
@@ -213,7 +213,7 @@ struct Strip {
 template <int K, int V, int D, int MASK, bool MAXM = false>
 __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ StepArgs<K> a) {
   typedef Rows<V> R;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (row >= a.nr) return;  // V == 2: the pad row after an odd tile exists in the arena and in rowoff
   const double* p0[K];
   const double* p1[K];
@@ -313,7 +313,7 @@ template <int KO, int KI, int V, int DI, int MASK>
 __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __grid_constant__ FusedArgs<KO + KI> a) {
   constexpr int K = KO + KI;
   typedef Rows<V> R;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
   if (row >= a.nr) return;
   const double* p0[K];
   const double* p1[K];
@@ -416,13 +416,13 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
 // Any number of inputs and scalars (descriptors in global memory), one row per thread.  Rare: buckets
 // with more than MAXK tables, or steps made of scalars only.
 __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArgs a) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y * blockDim.x + threadIdx.x;
   if (row >= a.nr) return;
   const double ps = a.n_sc > 0 ? fold_scalars(a.sc, a.n_sc, row) : 1.0;
   double* outp = a.out + (a.out_is_row ? row : 0);
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
-  const unsigned step = gridDim.y * blockDim.y;
-  for (unsigned o = blockIdx.y * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
+  const unsigned step = gridDim.x * blockDim.y;
+  for (unsigned o = blockIdx.x * blockDim.y + threadIdx.y; o < a.n_out; o += step) {
     const unsigned op = o / a.U, u = o - op * a.U;
     const unsigned hiI = op / a.C, loI = op - hiI * a.C;
     double acc = 0.0;
@@ -863,7 +863,7 @@ struct LaunchShape {
   dim3 grid, block;
 };
 // Launch shapes.  Rows run along x (blocks of up to BLOCK row-threads), output entries are cut into
-// contiguous strips along threadIdx.y / blockIdx.y.
+// contiguous strips along threadIdx.y / blockIdx.x.
 //  * streaming shape: a block is as wide in rows as possible; strips only to fill the machine.
 //  * reuse shape: when a step enumerates small per-row inputs many times, a block owns just 32 row-threads
 //    (one warp wide) and ALL output entries, so the rows of its inputs (`tile_bytes`) stay in L1 while the
@@ -882,17 +882,22 @@ LaunchShape launch_shape(int row_threads, int rows_per_thread, int64_t n_out, co
   if (reuse_on && row_threads >= 64 && n_out >= 32 && reuse.row_entries > 0 && reuse.row_loads >= reuse_min * reuse.row_entries &&
       tile_bytes <= (int64_t)reuse_kb * 1024) {
     s.block = dim3(reuse_bx, BLOCK / reuse_bx);
-    s.grid = dim3((row_threads + reuse_bx - 1) / reuse_bx, 1);
+    s.grid = dim3(1, (row_threads + reuse_bx - 1) / reuse_bx);
     return s;
   }
+  // grid.x = strips of output entries (the fast axis of the block scheduler), grid.y = row blocks: CTAs that are resident
+  // together work on the same rows.  A step that re-reads its per-row inputs (too large for the L1 shape above) gets row
+  // blocks one warp wide so that the strips of a row block find those rows in L2.
+  int cap = reuse_on && reuse.row_entries > 0 && reuse.row_loads >= reuse_min * reuse.row_entries ? 32 : BLOCK;
+  while ((row_threads + cap - 1) / cap > 65535) cap <<= 1;  // gridDim.y limit
   int bx = 1;
-  while (bx < row_threads && bx < BLOCK) bx <<= 1;
-  const int by = BLOCK / bx;
+  while (bx < row_threads && bx < cap) bx <<= 1;
+  const int by = std::max(1, BLOCK / bx);
   s.block = dim3(bx, by);
-  s.grid.x = (row_threads + bx - 1) / bx;
-  const int64_t max_y = (n_out + 2 * by - 1) / (2 * by);  // at least two entries per thread (U = 2)
-  const int64_t want = (148 * 8 * 2 + s.grid.x - 1) / s.grid.x;
-  s.grid.y = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_y, want), 65535));
+  s.grid.y = (row_threads + bx - 1) / bx;
+  const int64_t max_x = (n_out + 2 * by - 1) / (2 * by);  // at least two entries per thread (U = 2)
+  const int64_t want = (148 * 8 * 2 + s.grid.y - 1) / s.grid.y;
+  s.grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_x, want), 65535));
   return s;
 }
 
