@@ -896,7 +896,12 @@ LaunchShape launch_shape(int row_threads, int rows_per_thread, int64_t n_out, co
   s.block = dim3(bx, by);
   s.grid.y = (row_threads + bx - 1) / bx;
   const int64_t max_x = (n_out + 2 * by - 1) / (2 * by);  // at least two entries per thread (U = 2)
-  const int64_t want = (148 * 8 * 2 + s.grid.y - 1) / s.grid.y;
+  int64_t want = (148 * 8 * 2 + s.grid.y - 1) / s.grid.y;
+  if (cap == 32) {  // a re-reading step: so many strips per row block that one wave of CTAs touches about 64 MB of rows (they stay in L2)
+    const int64_t slab = (reuse.row_entries + n_out) * bx * rows_per_thread * 8;
+    const int64_t blocks_per_wave = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max<int64_t>(slab, 1));
+    want = std::max(want, (296 + blocks_per_wave - 1) / blocks_per_wave);
+  }
   s.grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_x, want), 65535));
   return s;
 }
@@ -1071,6 +1076,19 @@ void launch_fused_ki(const Executor& ex, const Step& st, int si, int64_t RT, int
 
 }  // namespace
 
+// Strips of groups per row block for a generated step kernel: enough CTAs to fill the machine twice, and for a step that
+// re-reads its per-row inputs so many that ONE wave of resident CTAs (296) covers only as many row blocks as fit ~64 MB of
+// tables -- those rows then stay in L2 while their strips sweep them (C3's largest step read 9.4 GB for 1.2 GB of tables).
+static unsigned strips_for(const Reuse& reuse, int64_t out_entries, unsigned bx, unsigned by, unsigned row_blocks, int64_t n_red) {
+  int64_t want = (296 + row_blocks - 1) / row_blocks;
+  if (reuse.row_entries > 0 && reuse.row_loads >= 3 * reuse.row_entries) {
+    const int64_t slab = (reuse.row_entries + out_entries) * bx * 2 * 8;
+    const int64_t blocks_per_wave = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max<int64_t>(slab, 1));
+    want = std::max(want, (296 + blocks_per_wave - 1) / blocks_per_wave);
+  }
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, (n_red + by - 1) / by), 65535));
+}
+
 static bool is_generic(const Step& st) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
   if (st.levels.size() > 1) return false;  // the compiler only fuses within MAXL levels / MAXK inputs, without scalars
@@ -1112,7 +1130,7 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
     while ((row_threads + bx - 1) / bx > 65535u) bx *= 2;  // gridDim.y limit
     const unsigned by = (unsigned)std::max<int64_t>(1, std::min<int64_t>(256 / bx, st.n_red));
     const unsigned gy = (row_threads + bx - 1) / bx;  // row blocks
-    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((296 + gy - 1) / gy, (st.n_red + by - 1) / by));  // strips
+    const unsigned gx = strips_for(reuse, ex.P->tables[st.out].size, bx, by, gy, st.n_red);
     const double *arena = ex.d_arena, *pots = ex.d_pots, *shared = ex.d_shared;
     double* arena_out = ex.d_arena;
     const int32_t* rowoff = ex.d_rowoff;
