@@ -899,7 +899,7 @@ LaunchShape launch_shape(int row_threads, int rows_per_thread, int64_t n_out, co
   int64_t want = (148 * 8 * 2 + s.grid.y - 1) / s.grid.y;
   if (cap == 32) {  // a re-reading step: so many strips per row block that one wave of CTAs touches about 64 MB of rows (they stay in L2)
     const int64_t slab = (reuse.row_entries + n_out) * bx * rows_per_thread * 8;
-    const int64_t blocks_per_wave = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max<int64_t>(slab, 1));
+    const int64_t blocks_per_wave = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max<int64_t>(slab, 1));  // 16 .. 96 MB measured the same on C3
     want = std::max(want, (296 + blocks_per_wave - 1) / blocks_per_wave);
   }
   s.grid.x = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_x, want), 65535));
@@ -1083,7 +1083,7 @@ static unsigned strips_for(const Reuse& reuse, int64_t out_entries, unsigned bx,
   int64_t want = (296 + row_blocks - 1) / row_blocks;
   if (reuse.row_entries > 0 && reuse.row_loads >= 3 * reuse.row_entries) {
     const int64_t slab = (reuse.row_entries + out_entries) * bx * 2 * 8;
-    const int64_t blocks_per_wave = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max<int64_t>(slab, 1));
+    const int64_t blocks_per_wave = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max<int64_t>(slab, 1));  // 16 .. 96 MB measured the same on C3
     want = std::max(want, (296 + blocks_per_wave - 1) / blocks_per_wave);
   }
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, (n_red + by - 1) / by), 65535));
