@@ -482,22 +482,27 @@ struct PrepArgs {
   int* flag;
 };
 
+// thread = row; blockIdx.y = a chunk of PREP_CHUNK variables (consistency check) and of PREP_CHUNK slices: a network with
+// hundreds of sliced potentials and few thousand rows would otherwise run this on a handful of CTAs (C3: 168 us of a 4.7 ms pass)
+constexpr int PREP_CHUNK = 32;
 __global__ void __launch_bounds__(BLOCK) prep_rows_kernel(const PrepArgs a) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j0 = blockIdx.y * PREP_CHUNK, j1 = min(a.n_slices, j0 + PREP_CHUNK);
   if (row >= a.nr) {  // pad rows up to the next multiple of 64 read slice 0 (their results are never used)
     if (row < ((a.nr + 63) & ~63) && row < a.RT)
-      for (int j = 0; j < a.n_slices; ++j) a.rowoff[(long long)j * a.RT + row] = 0;
+      for (int j = j0; j < j1; ++j) a.rowoff[(long long)j * a.RT + row] = 0;
     return;
   }
   const int8_t* e = a.ev + (long long)row * a.n_vars;
   bool bad = false;
-  for (int v = 0; v < a.n_vars; ++v) {
-    const int s = e[v];
-    const int o = a.observed[v];
-    bad |= o == 0 ? (s >= 0) : (o == 1 ? (s < 0 || s >= a.dims[v]) : (s != o - 2));
-  }
+  for (int v = blockIdx.y * PREP_CHUNK; v < a.n_vars; v += gridDim.y * PREP_CHUNK)
+    for (int k = v; k < min(a.n_vars, v + PREP_CHUNK); ++k) {
+      const int s = e[k];
+      const int o = a.observed[k];
+      bad |= o == 0 ? (s >= 0) : (o == 1 ? (s < 0 || s >= a.dims[k]) : (s != o - 2));
+    }
   if (bad) atomicOr(a.flag, 1);
-  for (int j = 0; j < a.n_slices; ++j) {
+  for (int j = j0; j < j1; ++j) {
     int off = 0;
     for (int t = a.sl_begin[j]; t < a.sl_begin[j + 1]; ++t) {
       int s = e[a.sl_var[t]];
@@ -1668,7 +1673,10 @@ void executor_run(Executor* ex, int64_t n_rows, const int8_t* d_evidence, double
     mark();
     PrepArgs pa{d_evidence + r0 * n_vars, nr, n_vars, (int)P.slices.size(), stride, ex->d_observed, ex->d_dims,
                 ex->d_sl_begin, ex->d_sl_var, ex->d_sl_stride, ex->d_rowoff, ex->d_flag};
-    prep_rows_kernel<<<(((nr + 63) & ~63) + BLOCK - 1) / BLOCK, BLOCK, 0, stream>>>(pa);
+    {
+      const dim3 pgrid((((nr + 63) & ~63) + BLOCK - 1) / BLOCK, (unsigned)std::max<size_t>(1, (P.slices.size() + PREP_CHUNK - 1) / PREP_CHUNK));
+      prep_rows_kernel<<<pgrid, BLOCK, 0, stream>>>(pa);
+    }
     ++launches;
     mark();
     const std::vector<Executor::Node>& nodes = ex->nodes;

@@ -517,7 +517,8 @@ bool jit_eligible(const Program& P, const Step& st) {
     for (const StepInput& in : l.in)
       if (P.tables[in.table].kind == T_ONE) return false;
   // A step whose body only fits with run-time loops around it stays on the precompiled kernels: as a kernel of its own it
-  // spilled at two CTAs per SM and measured no faster (C3: 6.6 vs 6.2 ms).  (Inside hb_tree such steps do use the loops.)
+  // measured no faster (C3 with every such step generated: 6.6 vs 6.2 ms; with only one looped level allowed: 4.91 vs 4.72 ms).
+  // (Inside hb_tree such steps do use the loops.)
   return jit_loop_levels(st) == 0;
 }
 
