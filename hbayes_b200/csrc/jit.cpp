@@ -117,7 +117,7 @@ int64_t stride_in(const Table& t, int v) {
   return 0;
 }
 
-int loop_levels_for(const Step& st, int64_t U);  // defined below
+int loop_levels_for(const Step& st, int64_t U, int64_t max_ops);  // defined below
 
 struct Gen {
   const Program& P;
@@ -141,6 +141,7 @@ struct Gen {
   // variable w alone.  `custom_block` = a caller-chosen set (hb_tree picks it per step by the loads it saves).
   std::vector<int> blocked;
   bool custom_block = false;
+  int64_t body_budget = 600;           // chain evaluations unrolled per item; outer levels beyond it become run-time loops
   std::vector<std::vector<int>> udig;  // per lock-step entry: state of every blocked variable
   std::vector<int64_t> uoff;           // per lock-step entry: offset in the stored output layout
   Gen(const Program& p, const Step& s) : P(p), st(s) {}
@@ -289,7 +290,7 @@ struct Gen {
       for (size_t j = blocked.size(); j-- > 0;) udig[u][j] = rem % P.net->dims[blocked[j]], rem /= P.net->dims[blocked[j]];
       for (size_t j = 0; j < blocked.size(); ++j) uoff[u] += udig[u][j] * out_stride(blocked[j]);
     }
-    n_loop = std::max(0, loop_levels_for(st, U));
+    n_loop = std::max(0, loop_levels_for(st, U, body_budget));
   }
   // offset of the item's first entry in the stored output layout, as an expression of the digits d<v> of `red`
   std::string out_base() const {
@@ -497,13 +498,14 @@ constexpr int64_t MAX_BODY_OPS = 600;
 // how many outermost levels stay run-time loops so that the unrolled rest fits MAX_BODY_OPS (-1: not even the
 // innermost level alone fits)
 namespace {
-int loop_levels_for(const Step& st, int64_t U) {
+int loop_levels_for(const Step& st, int64_t U, int64_t max_ops) {
   for (int n = 0; n < (int)st.levels.size(); ++n)
-    if (body_ops(st, n, U) <= MAX_BODY_OPS) return n;
-  return -1;
+    if (body_ops(st, n, U) <= max_ops) return n;
+  // even the innermost level alone exceeds the budget: acceptable as long as it stays below the hard limit
+  return body_ops(st, (int)st.levels.size() - 1, U) <= MAX_BODY_OPS ? (int)st.levels.size() - 1 : -1;
 }
 }  // namespace
-int jit_loop_levels(const Step& st) { return loop_levels_for(st, st.U); }
+int jit_loop_levels(const Step& st) { return loop_levels_for(st, st.U, MAX_BODY_OPS); }
 int64_t jit_unrolled_ops(const Step& st) {
   const int n = jit_loop_levels(st);
   return n < 0 ? -1 : body_ops(st, n, st.U);
