@@ -794,6 +794,10 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
     plan.n_levels = std::max(plan.n_levels, lv + 1);
   }
   if (n_out_steps == 0) return fail("no query");
+  // Results wider than this per row are not worth the on-chip kernel: they cannot be staged for coalesced rows (measured on
+  // the learnEM family-query program of C2, 1226 doubles per sample: 11.7 ms per 2^18 samples against 10.2 ms on the
+  // precompiled and 8.9 ms on the per-step generated kernels -- that pass is bound by writing its 2.6 GB result matrix)
+  if (P.out_width > 512) return fail("result rows too wide");
   if (body > TREE_MAX_BODY) return fail("program too large for one kernel");
   // liveness at level granularity: a table may be overwritten from the level AFTER its last reader's
   for (size_t si = 0; si < ns; ++si) {
