@@ -435,7 +435,10 @@ struct Compiler {
       return;
     }
     for (const Level& l : st.levels)
-      for (const StepInput& in : l.in) f(in.table);
+      for (const StepInput& in : l.in) {
+        f(in.table);
+        for (int id : in.scales) f(id);
+      }
     for (int id : st.scalars) f(id);
   }
 
@@ -460,6 +463,68 @@ struct Compiler {
     }
     for (const Step& st : P.steps)
       if (st.kind == STEP_PRODSUM && !st.shared) ++P.stat_ops;
+    // ---- 1b. scale steps ----
+    // A per-row step that only multiplies a table by a ONE-ENTRY table and sums nothing -- T * c, c the prior of an observed
+    // or fixed root restricted to its state -- is not materialised for the product steps that read it: they read T and
+    // multiply every loaded entry by c themselves.  Same operands, same single rounding (IEEE multiplication commutes), so
+    // the values are those the stored table would have held; what disappears is one write and one read of the whole table
+    // per reader (C4: three 2^26-entry copies per row, 40 % of the pass' traffic).
+    if (opt.fuse) {
+      auto unit = [&](int id) {
+        const Table& t = P.tables[id];
+        return t.size == 1 && (t.kind == T_POT || t.kind == T_SHARED) && !t.scalar;
+      };
+      for (size_t q = 0; q < P.steps.size(); ++q) {
+        const Step& Q = P.steps[q];
+        if (Q.kind != STEP_PRODSUM || Q.shared || !Q.scalars.empty() || Q.levels.size() != 1) continue;
+        const Level& lq = Q.levels[0];
+        if (lq.is_max || lq.sum_var >= 0 || lq.d != 1 || lq.in.size() != 2) continue;
+        const int big_at = unit(lq.in[1].table) ? 0 : (unit(lq.in[0].table) ? 1 : -1);
+        if (big_at < 0) continue;
+        const StepInput& big = lq.in[(size_t)big_at];
+        const int c = lq.in[(size_t)(1 - big_at)].table;
+        if (!lq.in[(size_t)(1 - big_at)].scales.empty() || (int)big.scales.size() >= MAX_SCALES) continue;
+        const Table& T = P.tables[big.table];
+        std::vector<int> a = T.pscope, b = P.tables[Q.out].pscope;
+        std::sort(a.begin(), a.end());
+        std::sort(b.begin(), b.end());
+        if (a != b) continue;  // the product must be entry for entry over T's scope
+        std::vector<int> scales = big.scales;
+        scales.push_back(c);
+        for (size_t r = q + 1; r < P.steps.size(); ++r) {
+          Step& S = P.steps[r];
+          if (S.kind != STEP_PRODSUM || S.levels.empty() || S.levels[0].is_max) continue;
+          bool other_scaled = false, reads = false;
+          for (const Level& l : S.levels)
+            for (const StepInput& in : l.in) {
+              if (in.table == Q.out) reads = true;
+              else if (!in.scales.empty()) other_scaled = true;
+            }
+          if (!reads || other_scaled) continue;
+          int hits = 0;
+          for (const Level& l : S.levels)
+            for (const StepInput& in : l.in) hits += in.table == Q.out;
+          if (hits != 1) continue;
+          for (Level& l : S.levels)
+            for (StepInput& in : l.in)
+              if (in.table == Q.out) in.table = big.table, in.scales = scales;
+        }
+      }
+      // the scale steps nobody reads any more
+      const int ns = (int)P.steps.size();
+      std::vector<char> live_t(P.tables.size(), 0), live_s(ns, 0);
+      for (int s2 = ns - 1; s2 >= 0; --s2) {
+        const Step& st = P.steps[s2];
+        if (st.kind == STEP_OUTPUT || live_t[st.out]) {
+          live_s[s2] = 1;
+          for_each_input(st, [&](int id) { live_t[id] = 1; });
+        }
+      }
+      std::vector<Step> kept;
+      for (int s2 = 0; s2 < ns; ++s2)
+        if (live_s[s2]) kept.push_back(std::move(P.steps[s2]));
+      P.steps.swap(kept);
+    }
     // ---- 2. fusion ----
     // Consumer S whose FIRST chain input T is produced by step Q, read by nobody else, and whose scope is
     // exactly S's product scope (every entry of T is used once): Q's levels are appended below S's and T
@@ -478,6 +543,15 @@ struct Compiler {
         if (q < 0 || uses[tid] != 1 || P.tables[tid].reduce) continue;
         const Step& Q = P.steps[q];
         if (Q.shared != S.shared || !Q.scalars.empty() || Q.levels[0].is_max) continue;
+        {  // the table read through scale factors must exist; and a step keeps at most one scaled input
+          if (!S.levels[0].in[0].scales.empty()) continue;
+          int scaled = 0;
+          const Step* both[2] = {&S, &Q};
+          for (const Step* x : both)
+            for (const Level& l : x->levels)
+              for (const StepInput& in : l.in) scaled += !in.scales.empty();
+          if (scaled > 1) continue;
+        }
         const int q_inner = (int)Q.levels.back().in.size();
         if ((int)(S.levels.size() + Q.levels.size()) > opt.max_levels || q_inner < 1 || q_inner > opt.max_inner ||
             S.n_inputs() - 1 + Q.n_inputs() - q_inner > opt.max_outer)
@@ -960,7 +1034,8 @@ std::string describe_program(const Program& P) {
           o << (k ? "," : "") << "{\"table\":" << lv.in[k].table << ",\"kind\":" << t.kind << ",\"pot\":" << t.pot << ",\"off\":" << t.off
             << ",\"size\":" << t.size << ",\"lstride\":";
           js_nums(o, lv.in[k].lstride);
-          o << ",\"wstride\":" << lv.in[k].wstride;
+          o << ",\"wstride\":" << lv.in[k].wstride << ",\"scales\":";
+          js_list(o, lv.in[k].scales);
           o << ",\"scope\":";
           js_list(o, t.pscope);
           o << ",\"strides\":";

@@ -100,6 +100,8 @@ struct StepArgs {
   int nr;                 // rows in this tile
   long long RT;           // row stride of the arena
   signed char* arg;       // maximisation step: argmax table [entry][RT]; nullptr otherwise
+  int scaled_in, n_scale; // input whose loaded entries are multiplied by the one-entry tables scale[0..n_scale) (-1: none)
+  TabRef scale[MAX_SCALES];
 };
 
 struct GenericArgs {      // any number of inputs / scalars, descriptors in global memory
@@ -111,6 +113,8 @@ struct GenericArgs {      // any number of inputs / scalars, descriptors in glob
   int out_is_row, nr;
   long long RT;
   signed char* arg;       // max step (MAXCPT): argmax table, [entry][RT] like the arena; nullptr for a sum step
+  int scaled_in, n_scale;
+  TabRef scale[MAX_SCALES];
 };
 
 __device__ __forceinline__ const double* row_ptr(const TabRef& t, int row) {
@@ -127,6 +131,22 @@ __device__ __forceinline__ double fold_scalars(const TabRef* sc, int n, int row)
 // V rows per thread: a pair of adjacent rows of a row table is one 16-byte access.
 template <int V>
 struct Rows;
+
+// the scale factors of a step's scaled input for this thread's rows (1.0 where there is none: never multiplied in)
+template <class R, int V>
+__device__ __forceinline__ void load_scales(const TabRef* scale, int n_scale, int row, R* sfac) {
+#pragma unroll
+  for (int j = 0; j < MAX_SCALES; ++j)
+    sfac[j] = j < n_scale ? R::splat(*row_ptr(scale[j], row), V == 2 ? *row_ptr(scale[j], row + 1) : 0.0) : R::splat(1.0, 1.0);
+}
+// x = ((x * s0) * s1) * ...
+template <class R>
+__device__ __forceinline__ R apply_scales(R x, const R* sfac, int n_scale) {
+#pragma unroll
+  for (int j = 0; j < MAX_SCALES; ++j)
+    if (j < n_scale) x = x.mul(sfac[j]);
+  return x;
+}
 template <>
 struct Rows<1> {
   double x;
@@ -232,6 +252,8 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
   double* outp = a.out + (a.out_is_row ? row : 0);
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
   const int d = D > 0 ? D : a.d;
+  R sfac[MAX_SCALES];
+  load_scales<R, V>(a.scale, a.n_scale, row, sfac);
   Strip sp;
   if (!sp.init(a.n_red, a.U, a.C)) return;
   for (; sp.it < sp.it_end; sp.next(a.C)) {
@@ -250,9 +272,11 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         x0[i] = R::load(p0[i], p1[i], isrow[i], off0[i] + s * ss[i]);
-        if ((MASK >> i) & 1)
+        if (i == a.scaled_in) x0[i] = apply_scales(x0[i], sfac, a.n_scale);
+        if ((MASK >> i) & 1) {
           x1[i] = R::load(p0[i], p1[i], isrow[i], off1[i] + s * ss[i]);
-        else
+          if (i == a.scaled_in) x1[i] = apply_scales(x1[i], sfac, a.n_scale);
+        } else
           x1[i] = x0[i];
       }
       R c0 = x0[K - 1], c1 = x1[K - 1];
@@ -297,6 +321,8 @@ struct FusedArgs {
   double* out;
   int out_is_row, nr;
   long long RT;
+  int scaled_in, n_scale;
+  TabRef scale[MAX_SCALES];
 };
 
 constexpr int FU = 2;  // output entries evaluated in lock-step by one thread of the fused kernel
@@ -328,6 +354,8 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
   const int inner = a.L - 1;
   const int d_inner = DI > 0 ? DI : a.d[inner];
+  R sfac[MAX_SCALES];
+  load_scales<R, V>(a.scale, a.n_scale, row, sfac);
   unsigned sti[KI];  // stride of the innermost summed variable in the innermost inputs
 #pragma unroll
   for (int i = 0; i < KI; ++i) sti[i] = a.st[KO + i][inner];
@@ -355,9 +383,11 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
 #pragma unroll
         for (int i = 0; i < KI; ++i) {
           x0[i] = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur0[KO + i] + q * sti[i]);
-          if ((MASK >> i) & 1)
+          if (KO + i == a.scaled_in) x0[i] = apply_scales(x0[i], sfac, a.n_scale);
+          if ((MASK >> i) & 1) {
             x1[i] = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur1[KO + i] + q * sti[i]);
-          else
+            if (KO + i == a.scaled_in) x1[i] = apply_scales(x1[i], sfac, a.n_scale);
+          } else
             x1[i] = x0[i];
         }
         R c0 = x0[KI - 1], c1 = x1[KI - 1];
@@ -381,8 +411,9 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
 #pragma unroll
           for (int i = KO - 1; i >= 0; --i) {
             if (a.lvl[i] == ll) {
-              const R x0 = R::load(p0[i], p1[i], isrow[i], cur0[i]);
-              const R x1 = R::load(p0[i], p1[i], isrow[i], cur1[i]);
+              R x0 = R::load(p0[i], p1[i], isrow[i], cur0[i]);
+              R x1 = R::load(p0[i], p1[i], isrow[i], cur1[i]);
+              if (i == a.scaled_in) x0 = apply_scales(x0, sfac, a.n_scale), x1 = apply_scales(x1, sfac, a.n_scale);
               r0 = have ? x0.mul(r0) : x0;
               r1 = have ? x1.mul(r1) : x1;
               have = true;
@@ -432,7 +463,9 @@ __global__ void __launch_bounds__(BLOCK) prodsum_generic_kernel(const GenericArg
       for (int i = a.k - 1; i >= 0; --i) {
         const InArg& in = a.in[i];
         const unsigned off = __ldg(in.hi + hiI) + __ldg(in.lo + loI) + u * in.wstride + s * in.sstride;
-        const double v = row_ptr(in.t, row)[off];
+        double v = row_ptr(in.t, row)[off];
+        if (i == a.scaled_in)
+          for (int j = 0; j < a.n_scale; ++j) v = __dmul_rn(v, *row_ptr(a.scale[j], row));
         c = (i == a.k - 1) ? v : __dmul_rn(v, c);
       }
       if (a.k > 0 && a.n_sc > 0) c = __dmul_rn(ps, c);
@@ -850,6 +883,23 @@ const StepInput& flat_input(const Step& st, int i, int* level = nullptr) {
   throw Error(HB_E_ARG, "input index out of range");
 }
 
+// the scaled input of a step (flat index, -1 if none) and its one-entry tables as the kernels see them
+static int scaled_input(const Executor& ex, const Step& st, int64_t RT, TabRef* scale, int* n_scale) {
+  int flat = 0;
+  *n_scale = 0;
+  for (const Level& l : st.levels)
+    for (const StepInput& in : l.in) {
+      if (!in.scales.empty()) {
+        if ((int)in.scales.size() > MAX_SCALES) throw Error(HB_E_UNSUPPORTED, "too many scale factors on one input");
+        *n_scale = (int)in.scales.size();
+        for (size_t j = 0; j < in.scales.size(); ++j) scale[j] = tab_ref(ex, ex.P->tables[in.scales[j]], RT);
+        return flat;
+      }
+      ++flat;
+    }
+  return -1;
+}
+
 InArg in_arg(const Executor& ex, const Step& st, int si, int i, int64_t RT) {
   int level = 0;
   const StepInput& in = flat_input(st, i, &level);
@@ -985,6 +1035,7 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
   a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
   a.nr = nr;
   a.RT = RT;
+  a.scaled_in = scaled_input(ex, st, RT, a.scale, &a.n_scale);
   const int64_t items2 = st.n_red * ((st.U + 1) / 2) * 2;
   if (st.levels[0].is_max) {  // maximisation step (mpe): run-time term count, every input loaded for both blocked states
     constexpr int FULL = (1 << K) - 1;
@@ -1061,6 +1112,7 @@ void launch_fused(const Executor& ex, const Step& st, int si, int64_t RT, int nr
   a.out = a.out_is_row ? ex.d_arena + out.off * RT : ex.d_shared + out.off;
   a.nr = nr;
   a.RT = RT;
+  a.scaled_in = scaled_input(ex, st, RT, a.scale, &a.n_scale);
   const int di = st.levels.back().d;
   const int64_t items2 = st.n_red * ((st.U + 1) / 2) * 2;
   if (two_rows_per_thread(nr))
@@ -1118,6 +1170,7 @@ static GenericArgs generic_args(const Executor& ex, const Step& st, int si, int6
   a.nr = nr;
   a.RT = RT;
   a.arg = st.levels[0].is_max ? ex.d_args + st.arg_off * RT : nullptr;
+  a.scaled_in = scaled_input(ex, st, RT, a.scale, &a.n_scale);
   return a;
 }
 

@@ -170,8 +170,13 @@ struct Gen {
     else
       o << "    const double " << name << "s = " << ld << q << " + " << off << "); const double2 " << name << " = make_double2(" << name << "s, "
         << name << "s);\n";
-    loaded[key] = name;
     ++n_loads;
+    for (size_t j = 0; j < x.in->scales.size(); ++j) {  // x = ((t[i] * s0) * s1) * ...: the scale step evaluated where it is read
+      const std::string scaled = name + "_s" + std::to_string(j);
+      o << "    const " << DV() << " " << scaled << " = hb_mul(" << name << ", scl" << j << ");\n";
+      name = scaled;
+    }
+    loaded[key] = name;
     return name;
   }
   int64_t n_loads = 0;  // load instructions emitted so far (one per distinct address of a group body)
@@ -316,6 +321,23 @@ struct Gen {
       } else
         o << ind << "const double* const b" << x.id << " = " << (t.kind == T_POT ? "pots" : "shared") << " + " << t.off << ";\n";
     }
+    // the one-entry tables the scaled input's entries are multiplied by
+    for (const In& x : ins)
+      for (size_t j = 0; j < x.in->scales.size(); ++j) {
+        const Table& t = P.tables[x.in->scales[j]];
+        const char* pool = t.kind == T_POT ? "pots" : "shared";
+        const std::string n = "scl" + std::to_string(j);
+        if (t.kind == T_POT && t.slice_slot >= 0) {
+          if (V == 2)
+            o << ind << "const double2 " << n << " = make_double2(pots[" << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row]], pots[" << t.off
+              << " + rowoff[(size_t)" << t.slice_slot << " * RT + row + 1]]);\n";
+          else
+            o << ind << "const double " << n << " = pots[" << t.off << " + rowoff[(size_t)" << t.slice_slot << " * RT + row]];\n";
+        } else if (V == 2)
+          o << ind << "const double2 " << n << " = make_double2(" << pool << "[" << t.off << "], " << pool << "[" << t.off << "]);\n";
+        else
+          o << ind << "const double " << n << " = " << pool << "[" << t.off << "];\n";
+      }
     // structural scalars of level 0: ps = s1 * (s2 * ...), applied as ps * chain (PrivateCPT.hs:225-227)
     std::string ps;
     for (size_t k = st.scalars.size(); k-- > 0;) {

@@ -104,7 +104,12 @@ struct StepInput {
   std::vector<int64_t> lstride;  // stride (entries) along the summed variable of level 0..own level (0 if absent)
   int64_t wstride = 0;           // stride along the step's blocking variable (0: the input does not depend on it)
   std::vector<uint32_t> hi, lo;  // entry offset of reduced output index o': hi[o' / C] + lo[o' % C]
+  // One-entry tables every loaded entry is multiplied by, in this order: x = ((t[i] * s0) * s1) * ...  (compile.cpp "scale
+  // steps": a step that only multiplies a table by the restricted prior of an observed / fixed variable is evaluated where
+  // its result is read instead of being stored).  At most one input of a step carries scales, at most MAX_SCALES of them.
+  std::vector<int> scales;
 };
+constexpr int MAX_SCALES = 3;
 
 // One reference operation (itemProduct of a bucket + itemProjectOut of one variable).  A step holds a
 // chain of them, level 0 outermost: the table a level produces is consumed only by the level above it,
