@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -123,6 +124,15 @@ struct Session {
   std::vector<cudaEvent_t> chunk_done;
   cudaEvent_t rest_uploaded = nullptr;
   int64_t chunk_rows = 1 << 18;
+  // Pageable caller buffers (a numpy array, a Haskell mallocForeignPtrBytes block): the handle owns a ring of page-locked
+  // bounce buffers; the copy engine fills one while host threads drain the others into the caller's matrix (Bounce below).
+  // A direct cudaMemcpyAsync to pageable memory is staged by the driver on the calling thread at ~15 GB/s.
+  std::vector<void*> ring;
+  std::vector<cudaEvent_t> ring_copied;
+  size_t ring_bytes = 0;
+  void* h_ev_stage = nullptr;  // page-locked copy of a pageable evidence matrix (grow-only)
+  size_t ev_stage_cap = 0;
+  int copy_thread_share = 1;  // handles that run at the same time on this host (devices of one multi-GPU handle)
   // split clique: variables fixed to this handle's slice; batch results are then left unnormalised
   std::vector<std::pair<int, int>> fixed;
   // split clique with the exchange inside the library (hb_jt_compile_split_nccl): this rank's communicator; programs are
@@ -163,6 +173,9 @@ struct Session {
     for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
     if (rest_uploaded) cudaEventDestroy(rest_uploaded);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (void* b : ring) cudaFreeHost(b);
+    for (cudaEvent_t e : ring_copied) cudaEventDestroy(e);
+    if (h_ev_stage) cudaFreeHost(h_ev_stage);
   }
   // the device-resident form of a compiled program, created on first use
   void evict(Compiled* keep, size_t leave) {  // destroys least recently used executors until at most `leave` others remain
@@ -242,6 +255,105 @@ std::vector<int> observed_of_row(const int8_t* row, int n_vars) {
     if (row[v] >= 0) obs.push_back(v);
   return obs;
 }
+
+// true when `p` is ordinary pageable host memory (neither cudaHostAlloc'ed nor cudaHostRegister'ed nor device memory)
+bool is_pageable(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();  // older drivers report plain malloc memory as an error
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Device -> pageable host memory through the handle's ring of page-locked buffers.  The caller enqueues pieces (at most
+// ring_bytes each) in order with `copy`; piece i goes to ring[i % NB] on the copy stream as soon as the host threads have
+// drained piece i - NB; W host threads each copy their 1/W of every piece into the destination once its event has fired.
+// So the PCIe transfer of a piece overlaps the host copies of the pieces before it, and the host copy runs on W cores.
+struct Bounce {
+  static constexpr int NB = 4;
+  static constexpr size_t PIECE = (size_t)16 << 20;
+  Session& s;
+  int W = 1;
+  struct Piece {
+    char* dst;
+    size_t bytes;
+  };
+  std::vector<Piece> pieces;  // reserved up front: workers read entries below `issued` only
+  std::atomic<int> issued{0};
+  std::atomic<bool> abort{false};
+  std::unique_ptr<std::atomic<int>[]> drained;
+  std::vector<std::thread> workers;
+  int n_issued = 0;
+
+  Bounce(Session& session, size_t max_pieces) : s(session) {
+    if (s.ring.empty()) {
+      for (int i = 0; i < NB; ++i) {
+        void* b = nullptr;
+        cuda_ok(cudaHostAlloc(&b, PIECE, cudaHostAllocDefault), "cudaHostAlloc(bounce ring)");
+        s.ring.push_back(b);
+        cudaEvent_t e;
+        cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        s.ring_copied.push_back(e);
+      }
+      s.ring_bytes = PIECE;
+    }
+    const int hw = (int)std::thread::hardware_concurrency();
+    W = std::max(1, std::min(8, hw / 2 / std::max(1, s.copy_thread_share)));
+    if (const char* env = getenv("HB_COPY_THREADS")) W = std::max(1, std::min(64, atoi(env)));
+    pieces.resize(max_pieces);
+    drained.reset(new std::atomic<int>[max_pieces]);
+    for (size_t i = 0; i < max_pieces; ++i) drained[i].store(0, std::memory_order_relaxed);
+    for (int j = 0; j < W; ++j) workers.emplace_back([this, j] { drain(j); });
+  }
+  static size_t pieces_for(size_t bytes) { return (bytes + PIECE - 1) / PIECE; }
+  void drain(int j) {
+    cudaSetDevice(s.device);
+    for (size_t i = 0; i < pieces.size(); ++i) {
+      while (issued.load(std::memory_order_acquire) <= (int)i) {
+        if (abort.load(std::memory_order_relaxed)) return;
+        std::this_thread::yield();
+      }
+      if (cudaEventSynchronize(s.ring_copied[i % NB]) != cudaSuccess) {
+        abort.store(true);
+        return;
+      }
+      const Piece& p = pieces[i];
+      const size_t a = p.bytes * (size_t)j / (size_t)W / 64 * 64, b = j + 1 == W ? p.bytes : p.bytes * (size_t)(j + 1) / (size_t)W / 64 * 64;
+      if (b > a) memcpy(p.dst + a, (const char*)s.ring[i % NB] + a, b - a);
+      drained[i].fetch_add(1, std::memory_order_release);
+    }
+  }
+  void wait_drained(int i) {
+    while (drained[i].load(std::memory_order_acquire) < W) {
+      if (abort.load(std::memory_order_relaxed)) throw Error(HB_E_CUDA, "device-to-host copy failed");
+      std::this_thread::yield();
+    }
+  }
+  // enqueue src[0, bytes) -> dst on the copy stream (which already waits for the kernels that produce src)
+  void copy(char* dst, const char* src, size_t bytes) {
+    for (size_t off = 0; off < bytes; off += PIECE) {
+      const size_t m = std::min(PIECE, bytes - off);
+      const int i = n_issued;
+      if (i >= NB) wait_drained(i - NB);
+      cuda_ok(cudaMemcpyAsync(s.ring[i % NB], src + off, m, cudaMemcpyDeviceToHost, s.copy_stream), "cudaMemcpy(out)");
+      cuda_ok(cudaEventRecord(s.ring_copied[i % NB], s.copy_stream), "cudaEventRecord");
+      pieces[(size_t)i] = Piece{dst + off, m};
+      issued.store(++n_issued, std::memory_order_release);
+    }
+  }
+  void finish() {  // every enqueued piece is in the caller's buffer when this returns
+    for (int i = std::max(0, n_issued - NB); i < n_issued; ++i) wait_drained(i);
+    stop();
+  }
+  void stop() {
+    abort.store(true);
+    for (std::thread& t : workers)
+      if (t.joinable()) t.join();
+    workers.clear();
+  }
+  ~Bounce() { stop(); }
+};
 
 // Runs `get(observed)`'s program over an evidence matrix.  Host buffers: rows are assumed to share the
 // observed set of row 0 (the device checks every row); if they do not, they are grouped by observed set
@@ -335,9 +447,26 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
   }
   cuts.push_back(n_rows);
   Executor* ex0 = s.executor(c0);
+  // pageable caller buffers go through page-locked staging owned by the handle (HB_BOUNCE=0: plain cudaMemcpyAsync)
+  const bool bounce_on = !(getenv("HB_BOUNCE") && atoi(getenv("HB_BOUNCE")) == 0);
+  const size_t out_bytes = (size_t)n_rows * width * sizeof(double), ev_bytes = (size_t)n_rows * n_vars;
+  const bool out_bounce = bounce_on && out_bytes >= ((size_t)4 << 20) && is_pageable(out);
+  const bool ev_bounce = bounce_on && ev_bytes >= ((size_t)1 << 20) && is_pageable(evidence);
+  std::unique_ptr<Bounce> bounce;
+  if (out_bounce) {
+    size_t np = 0;
+    int64_t b0 = 0;
+    for (int64_t cut : cuts) np += Bounce::pieces_for((size_t)std::max<int64_t>(0, cut - b0) * width * sizeof(double)), b0 = cut;
+    bounce.reset(new Bounce(s, np));
+  }
+  if (ev_bounce && ev_bytes > s.ev_stage_cap) {
+    if (s.h_ev_stage) cudaFreeHost(s.h_ev_stage), s.h_ev_stage = nullptr, s.ev_stage_cap = 0;
+    cuda_ok(cudaHostAlloc(&s.h_ev_stage, ev_bytes, cudaHostAllocDefault), "cudaHostAlloc(evidence staging)");
+    s.ev_stage_cap = ev_bytes;
+  }
   // evidence: the first chunk's rows on the compute stream, the rest on the (still idle) copy stream meanwhile
-  const int64_t first_rows = cuts[0] > 0 ? cuts[0] : n_rows;
-  cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)first_rows * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+  const int64_t first_rows = ev_bounce ? n_rows : (cuts[0] > 0 ? cuts[0] : n_rows);
+  if (!ev_bounce) cuda_ok(cudaMemcpyAsync(s.d_ev, evidence, (size_t)first_rows * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
   if (first_rows < n_rows) {
     if (!s.rest_uploaded) cuda_ok(cudaEventCreateWithFlags(&s.rest_uploaded, cudaEventDisableTiming), "cudaEventCreate");
     cuda_ok(cudaMemcpyAsync(s.d_ev + first_rows * n_vars, evidence + first_rows * n_vars, (size_t)(n_rows - first_rows) * n_vars,
@@ -350,6 +479,11 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
     const int64_t m = cuts[c] - r0;
     if (m <= 0) continue;
     if (r0 == first_rows && first_rows < n_rows) cuda_ok(cudaStreamWaitEvent(s.stream, s.rest_uploaded, 0), "cudaStreamWaitEvent");
+    if (ev_bounce) {  // this chunk's rows: host copy into the page-locked stage (overlaps the GPU work already queued), then upload
+      int8_t* const stage = (int8_t*)s.h_ev_stage + r0 * n_vars;
+      memcpy(stage, evidence + r0 * n_vars, (size_t)m * n_vars);
+      cuda_ok(cudaMemcpyAsync(s.d_ev + r0 * n_vars, stage, (size_t)m * n_vars, cudaMemcpyHostToDevice, s.stream), "cudaMemcpy(evidence)");
+    }
     executor_run(ex0, m, s.d_ev + r0 * n_vars, s.d_out + r0 * width, s.stream, &rs, s.fixed.empty());
     s.note(c0, rs, !first_chunk);
     first_chunk = false;
@@ -360,8 +494,11 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
     }
     cuda_ok(cudaEventRecord(s.chunk_done[c], s.stream), "cudaEventRecord");
     cuda_ok(cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c], 0), "cudaStreamWaitEvent");
-    cuda_ok(cudaMemcpyAsync(out + r0 * width, s.d_out + r0 * width, (size_t)m * width * sizeof(double), cudaMemcpyDeviceToHost, s.copy_stream),
-            "cudaMemcpy(out)");
+    if (bounce)
+      bounce->copy((char*)(out + r0 * width), (const char*)(s.d_out + r0 * width), (size_t)m * width * sizeof(double));
+    else
+      cuda_ok(cudaMemcpyAsync(out + r0 * width, s.d_out + r0 * width, (size_t)m * width * sizeof(double), cudaMemcpyDeviceToHost, s.copy_stream),
+              "cudaMemcpy(out)");
   }
   bool uniform = true;
   try {
@@ -370,6 +507,7 @@ void run_matrix(Session& s, GetProgram&& get, int64_t n_rows, const int8_t* evid
     if (e.code != HB_E_ARG) throw;
     uniform = false;
   }
+  if (bounce) bounce->finish(), bounce.reset();
   cuda_ok(cudaStreamSynchronize(s.copy_stream), "cudaStreamSynchronize");
   if (uniform) return;
   // mixed observed sets: group rows on the host
@@ -606,6 +744,8 @@ static int jt_compile(const hb_net* net, int32_t cmp, const int32_t* order, cons
       peer->post_off = jt->post_off;
       jt->peers.push_back(std::move(peer));
     }
+    jt->s.copy_thread_share = (int)(1 + jt->peers.size());
+    for (auto& peer : jt->peers) peer->s.copy_thread_share = jt->s.copy_thread_share;
     *out = jt.release();
   });
 }

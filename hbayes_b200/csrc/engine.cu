@@ -230,7 +230,10 @@ struct Strip {
 // of the warp is one contiguous 256*V-byte segment.  D = terms per entry (0: run-time count).
 // MASK: bit i set = input i depends on the blocking variable (two loads per item); clear = one load serves both
 // blocked states.  The mask is a template parameter so that the loads stay unconditional, back to back.
-template <int K, int V, int D, int MASK, bool MAXM = false>
+// SC: one input is read through scale factors (compile.cpp "scale steps"); a template parameter so that every other
+// instantiation is the code it was without them (as run-time tests they cost registers and spills in all 400 kernels:
+// C3 4.7 -> 7.1 ms, C5 24.2 -> 28.7 ms).  Scaled steps without a generated kernel run the <D = 0, full MASK> variants.
+template <int K, int V, int D, int MASK, bool MAXM = false, bool SC = false>
 __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ StepArgs<K> a) {
   typedef Rows<V> R;
   const int row = (blockIdx.y * blockDim.x + threadIdx.x) * V;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
   const size_t om = a.out_is_row ? (size_t)a.RT : 1;
   const int d = D > 0 ? D : a.d;
   R sfac[MAX_SCALES];
-  load_scales<R, V>(a.scale, a.n_scale, row, sfac);
+  if constexpr (SC) load_scales<R, V>(a.scale, a.n_scale, row, sfac);
   Strip sp;
   if (!sp.init(a.n_red, a.U, a.C)) return;
   for (; sp.it < sp.it_end; sp.next(a.C)) {
@@ -272,10 +275,12 @@ __global__ void __launch_bounds__(BLOCK) prodsum_kernel(const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         x0[i] = R::load(p0[i], p1[i], isrow[i], off0[i] + s * ss[i]);
-        if (i == a.scaled_in) x0[i] = apply_scales(x0[i], sfac, a.n_scale);
+        if constexpr (SC)
+          if (i == a.scaled_in) x0[i] = apply_scales(x0[i], sfac, a.n_scale);
         if ((MASK >> i) & 1) {
           x1[i] = R::load(p0[i], p1[i], isrow[i], off1[i] + s * ss[i]);
-          if (i == a.scaled_in) x1[i] = apply_scales(x1[i], sfac, a.n_scale);
+          if constexpr (SC)
+            if (i == a.scaled_in) x1[i] = apply_scales(x1[i], sfac, a.n_scale);
         } else
           x1[i] = x0[i];
       }
@@ -335,7 +340,7 @@ constexpr int FU = 2;  // output entries evaluated in lock-step by one thread of
 #ifndef HB_FUSED_MINB
 #define HB_FUSED_MINB 2
 #endif
-template <int KO, int KI, int V, int DI, int MASK>
+template <int KO, int KI, int V, int DI, int MASK, bool SC = false>
 __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __grid_constant__ FusedArgs<KO + KI> a) {
   constexpr int K = KO + KI;
   typedef Rows<V> R;
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
   const int inner = a.L - 1;
   const int d_inner = DI > 0 ? DI : a.d[inner];
   R sfac[MAX_SCALES];
-  load_scales<R, V>(a.scale, a.n_scale, row, sfac);
+  if constexpr (SC) load_scales<R, V>(a.scale, a.n_scale, row, sfac);
   unsigned sti[KI];  // stride of the innermost summed variable in the innermost inputs
 #pragma unroll
   for (int i = 0; i < KI; ++i) sti[i] = a.st[KO + i][inner];
@@ -383,10 +388,12 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
 #pragma unroll
         for (int i = 0; i < KI; ++i) {
           x0[i] = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur0[KO + i] + q * sti[i]);
-          if (KO + i == a.scaled_in) x0[i] = apply_scales(x0[i], sfac, a.n_scale);
+          if constexpr (SC)
+            if (KO + i == a.scaled_in) x0[i] = apply_scales(x0[i], sfac, a.n_scale);
           if ((MASK >> i) & 1) {
             x1[i] = R::load(p0[KO + i], p1[KO + i], isrow[KO + i], cur1[KO + i] + q * sti[i]);
-            if (KO + i == a.scaled_in) x1[i] = apply_scales(x1[i], sfac, a.n_scale);
+            if constexpr (SC)
+              if (KO + i == a.scaled_in) x1[i] = apply_scales(x1[i], sfac, a.n_scale);
           } else
             x1[i] = x0[i];
         }
@@ -413,7 +420,8 @@ __global__ void __launch_bounds__(BLOCK, HB_FUSED_MINB) fused_kernel(const __gri
             if (a.lvl[i] == ll) {
               R x0 = R::load(p0[i], p1[i], isrow[i], cur0[i]);
               R x1 = R::load(p0[i], p1[i], isrow[i], cur1[i]);
-              if (i == a.scaled_in) x0 = apply_scales(x0, sfac, a.n_scale), x1 = apply_scales(x1, sfac, a.n_scale);
+              if constexpr (SC)
+                if (i == a.scaled_in) x0 = apply_scales(x0, sfac, a.n_scale), x1 = apply_scales(x1, sfac, a.n_scale);
               r0 = have ? x0.mul(r0) : x0;
               r1 = have ? x1.mul(r1) : x1;
               have = true;
@@ -1049,6 +1057,17 @@ void launch_k(const Executor& ex, const Step& st, int si, int64_t RT, int nr, cu
     }
     return;
   }
+  if (a.scaled_in >= 0) {  // scaled input, no generated kernel: the general variant (run-time term count, every input loaded twice)
+    constexpr int FULL = (1 << K) - 1;
+    if (two_rows_per_thread(nr)) {
+      const LaunchShape sh = launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st));
+      prodsum_kernel<K, 2, 0, FULL, false, true><<<sh.grid, sh.block, 0, stream>>>(a);
+    } else {
+      const LaunchShape sh = launch_shape(nr, 1, items2);
+      prodsum_kernel<K, 1, 0, FULL, false, true><<<sh.grid, sh.block, 0, stream>>>(a);
+    }
+    return;
+  }
   if (two_rows_per_thread(nr))
     launch_kv<K, 2>(a, a.d, mask, launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st)), stream);
   else
@@ -1115,6 +1134,17 @@ void launch_fused(const Executor& ex, const Step& st, int si, int64_t RT, int nr
   a.scaled_in = scaled_input(ex, st, RT, a.scale, &a.n_scale);
   const int di = st.levels.back().d;
   const int64_t items2 = st.n_red * ((st.U + 1) / 2) * 2;
+  if (a.scaled_in >= 0) {  // as in launch_k
+    constexpr int FULL = (1 << KI) - 1;
+    if (two_rows_per_thread(nr)) {
+      const LaunchShape sh = launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st));
+      fused_kernel<KO, KI, 2, 0, FULL, true><<<sh.grid, sh.block, 0, stream>>>(a);
+    } else {
+      const LaunchShape sh = launch_shape(nr, 1, items2);
+      fused_kernel<KO, KI, 1, 0, FULL, true><<<sh.grid, sh.block, 0, stream>>>(a);
+    }
+    return;
+  }
   if (two_rows_per_thread(nr))
     launch_fused_d<KO, KI, 2>(a, di, mask, launch_shape((nr + 1) / 2, 2, items2, reuse_of(P, st)), stream);
   else

@@ -89,8 +89,16 @@ def test_c2_half_million_rows_from_host_buffers_equals_device_path_and_oracle():
             jt = hb.JunctionTree(pnet)
             if generated:
                 assert jt.specialise(observed) > 0 and jt.kernel_info()["on_chip_eligible"] == 1
-            host = jt.posteriors_batch(ev)  # numpy in, numpy out: HB_HOST_PTRS
+            host = jt.posteriors_batch(ev)  # numpy in, numpy out: pageable host memory -> the handle's page-locked bounce ring
             assert bool(jt.kernel_info()["on_chip"]) == generated
+            for knob, value in (("HB_COPY_THREADS", "3"), ("HB_BOUNCE", "0")):  # odd slice count; plain cudaMemcpyAsync
+                os.environ[knob] = value
+                try:
+                    again = np.full_like(host, -1.0)
+                    jt.posteriors_batch(ev, again)
+                finally:
+                    del os.environ[knob]
+                assert same_bits(again, host)
             dev = jt.posteriors_batch(torch.from_numpy(ev).cuda()).cpu().numpy()
             assert same_bits(host, dev)
             assert same_bits(host[:2048], want)
