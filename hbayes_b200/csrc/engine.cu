@@ -1167,8 +1167,11 @@ void launch_fused_ki(const Executor& ex, const Step& st, int si, int64_t RT, int
 // re-reads its per-row inputs so many that ONE wave of resident CTAs (296) covers only as many row blocks as fit ~64 MB of
 // tables -- those rows then stay in L2 while their strips sweep them (C3's largest step read 9.4 GB for 1.2 GB of tables).
 static unsigned strips_for(const Reuse& reuse, int64_t out_entries, unsigned bx, unsigned by, unsigned row_blocks, int64_t n_red) {
-  int64_t want = (296 + row_blocks - 1) / row_blocks;
-  if (reuse.row_entries > 0 && reuse.row_loads >= 3 * reuse.row_entries) {
+  // CTAs per SM a streaming step is cut into (HB_JIT_WAVES): its kernels are light in registers, more resident CTAs = more loads in flight
+  static const int64_t stream_ctas = 148 * (int64_t)std::max(1, getenv("HB_JIT_WAVES") ? atoi(getenv("HB_JIT_WAVES")) : 2);
+  const bool rereads = reuse.row_entries > 0 && reuse.row_loads >= 3 * reuse.row_entries;
+  int64_t want = ((rereads ? 296 : stream_ctas) + row_blocks - 1) / row_blocks;
+  if (rereads) {
     const int64_t slab = (reuse.row_entries + out_entries) * bx * 2 * 8;
     const int64_t blocks_per_wave = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max<int64_t>(slab, 1));  // 16 .. 96 MB measured the same on C3
     want = std::max(want, (296 + blocks_per_wave - 1) / blocks_per_wave);
@@ -1206,7 +1209,9 @@ static GenericArgs generic_args(const Executor& ex, const Step& st, int si, int6
 
 static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int nr, cudaStream_t stream) {
   const int k = st.n_inputs(), s = (int)st.scalars.size();
-  if (!ex.jit_fn.empty() && ex.jit_fn[si] && nr >= 64) {  // the step has a specialised kernel (rows along x: not for few-row tiles)
+  // the step has a specialised kernel: rows along x, so with one strip of groups per lane not for few-row tiles (a warp would
+  // touch 16 or 32 distant strips); with the groups dealt round robin the lanes of a warp sit on adjacent groups
+  if (!ex.jit_fn.empty() && ex.jit_fn[si] && (nr >= 64 || jit_step_shape(*ex.P, st).interleave)) {
     // Row threads (two rows each) along threadIdx.x, strips of groups along threadIdx.y / blockIdx.x, row blocks along
     // blockIdx.y; enough of both to fill 148 SMs twice.  A step that reads its per-row inputs several times over gets narrow
     // row blocks (one warp of row threads): the strips of one row block are scheduled together and share those rows in L2
@@ -1596,10 +1601,11 @@ static std::vector<int> steps_to_specialise(const Program& P) {
   }
   std::sort(cand.rbegin(), cand.rend());
   std::vector<int> steps;
-  int64_t budget = 8000;  // bounds the compilation time: C2 needs 4.6 K (49 kernels, 5.5 s)
+  int64_t budget = getenv("HB_JIT_BUDGET") ? atoll(getenv("HB_JIT_BUDGET")) : 8000;  // bounds the compilation time: C2 needs 4.6 K (49 kernels, 5.5 s)
+  const size_t max_kernels = getenv("HB_JIT_MAX_KERNELS") ? (size_t)atoll(getenv("HB_JIT_MAX_KERNELS")) : 96;
   for (auto& c : cand) {
     const int64_t ops = jit_unrolled_ops(P.steps[c.second]);
-    if (ops > budget || steps.size() >= 96) continue;
+    if (ops > budget || steps.size() >= max_kernels) continue;
     budget -= ops;
     steps.push_back(c.second);
   }

@@ -142,6 +142,10 @@ struct Gen {
   std::vector<int> blocked;
   bool custom_block = false;
   int64_t body_budget = 600;           // chain evaluations unrolled per item; outer levels beyond it become run-time loops
+  // hb_step_<i>: groups dealt round robin to the lanes (adjacent lanes, adjacent groups) instead of one contiguous strip per
+  // lane; `unroll` = groups of the strip loop the compiler may evaluate together (more loads in flight per thread)
+  bool interleave = false;
+  int unroll = 0;
   std::vector<std::vector<int>> udig;  // per lock-step entry: state of every blocked variable
   std::vector<int64_t> uoff;           // per lock-step entry: offset in the stored output layout
   Gen(const Program& p, const Step& s) : P(p), st(s) {}
@@ -263,6 +267,8 @@ struct Gen {
   // row stride RT is the compile-time tile height, so every address below folds into an immediate.
   const std::vector<int64_t>* tree_off = nullptr;
   std::vector<int> red;  // output variables other than the blocking one, stored row-major (last fastest), then w
+  std::vector<int64_t> rdim;  // states of each digit of `red` (a digit may stand for a run of merged variables)
+  bool merge_digits = !(getenv("HB_JIT_MERGE") && atoi(getenv("HB_JIT_MERGE")) == 0);
   int64_t row_off(const Table& t) const { return tree_off ? (*tree_off)[(size_t)(&t - &P.tables[0])] : t.off; }
 
   void prepare() {
@@ -279,8 +285,33 @@ struct Gen {
       if (!no_block && st.w_var >= 0) blocked.push_back(st.w_var);
     }
     red.clear();
-    for (int v : out.pscope)
-      if (std::find(blocked.begin(), blocked.end(), v) == blocked.end()) red.push_back(v);
+    rdim.clear();
+    auto pstride_of = [](const Table& t, int v) {
+      for (size_t i = 0; i < t.pscope.size(); ++i)
+        if (t.pscope[i] == v) return t.pstride[i];
+      return (int64_t)0;
+    };
+    for (int v : out.pscope) {
+      if (std::find(blocked.begin(), blocked.end(), v) != blocked.end()) continue;
+      // Adjacent digits a (slower), v (faster) that every table of the step walks as ONE mixed-radix digit -- stride(a) =
+      // stride(v) * dim(v) in the output and in every input (0 = 0 counts) -- are merged: one digit of dim(a) * dim(v) states
+      // with v's strides.  The 2^23 groups of a step over 23 binary variables then cost no index arithmetic at all.
+      const int64_t dv = P.net->dims[v];
+      bool merge = merge_digits && !red.empty() && rdim.back() * dv < ((int64_t)1 << 31);
+      if (merge) {
+        const int a = red.back();
+        merge = pstride_of(out, a) == pstride_of(out, v) * dv;
+        for (const In& x : ins)
+          if (pstride_of(*x.t, a) != pstride_of(*x.t, v) * dv) merge = false;
+      }
+      if (merge) {
+        red.back() = v;  // the run is named after its fastest variable
+        rdim.back() *= dv;
+      } else {
+        red.push_back(v);
+        rdim.push_back(dv);
+      }
+    }
     U = 1;
     for (int v : blocked) U *= P.net->dims[v];
     auto out_stride = [&](int v) {
@@ -374,11 +405,10 @@ struct Gen {
   // the body of one group `g` of output entries: digits, per-input pointers, the unrolled nest, the stores
   enum { STORE_STREAMING = 0, STORE_PLAIN = 1, STORE_RESULT = 2 };  // __stcs to HBM / plain store / res[u] = value
   void emit_group(int store) {
-    const Network& net = *P.net;
     loaded.clear();
     if (!red.empty()) o << "    unsigned rem = g;\n";
     for (size_t j = red.size(); j-- > 0;)
-      o << "    const unsigned d" << red[j] << " = rem % " << net.dims[red[j]] << "u;" << (j ? " rem /= " + std::to_string(net.dims[red[j]]) + "u;" : "")
+      o << "    const unsigned d" << red[j] << " = " << (j ? "rem % " + std::to_string(rdim[j]) + "u;" : "rem;") << (j ? " rem /= " + std::to_string(rdim[j]) + "u;" : "")
         << "\n";
     for (const In& x : ins) {
       std::string base;
@@ -422,11 +452,37 @@ struct Gen {
     // resident together work on the SAME rows, so a step that enumerates its inputs many times finds them in L2
     o << "  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * 2;\n  if (row >= nr) return;\n";
     o << "  const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;\n";
-    o << "  const unsigned per = (" << st.n_red << "u + lanes - 1) / lanes;\n";
-    o << "  const unsigned g_end = min(" << st.n_red << "u, lane * per + per);\n";
+    if (!interleave) {
+      o << "  const unsigned per = (" << st.n_red << "u + lanes - 1) / lanes;\n";
+      o << "  const unsigned g_end = min(" << st.n_red << "u, lane * per + per);\n";
+    }
     o << "  const double2 zero = make_double2(0.0, 0.0);\n";
     emit_bases("  ");
-    o << "  for (unsigned g = lane * per; g < g_end; ++g) {\n";
+    if (interleave && unroll > 1) {
+      // `unroll` groups at a time, all their loads ahead of the first store (the compiler does not move a load of the next
+      // group above the stores of this one): a light streaming step keeps several times the bytes in flight per thread
+      o << "  auto body = [&](const unsigned g, double2* __restrict__ res, unsigned* __restrict__ ob_out) {\n";
+      emit_group(STORE_RESULT);
+      o << "  };\n";
+      o << "  for (unsigned g = lane; g < " << st.n_red << "u; g += lanes * " << unroll << "u) {\n";
+      for (int k = 0; k < unroll; ++k) {
+        if (k) o << "    const bool has" << k << " = g + lanes * " << k << "u < " << st.n_red << "u;\n";
+        o << "    double2 r" << k << "[" << U << "]; unsigned ob" << k << ";\n";
+        o << "    body(" << (k ? "has" + std::to_string(k) + " ? g + lanes * " + std::to_string(k) + "u : g" : std::string("g")) << ", r" << k << ", &ob" << k << ");\n";
+      }
+      for (int k = 0; k < unroll; ++k) {
+        if (k) o << "    if (has" << k << ") {\n";
+        for (int u = 0; u < U; ++u)
+          o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(ob" << k << " + " << uoff[u] << "u) * RT), r" << k << "[" << u << "]);\n";
+        if (k) o << "    }\n";
+      }
+      o << "  }\n}\n\n";
+      return o.str();
+    }
+    if (interleave)  // the lanes that run together take adjacent groups: a streaming step touches HBM like a copy does
+      o << "  for (unsigned g = lane; g < " << st.n_red << "u; g += lanes) {\n";
+    else
+      o << "  for (unsigned g = lane * per; g < g_end; ++g) {\n";
     emit_group(STORE_STREAMING);
     o << "  }\n}\n\n";
     return o.str();
@@ -446,6 +502,7 @@ struct Gen {
     V = v;
     custom_block = true;
     blocked = block;
+    merge_digits = false;  // the blocks of a clique-sized step have two or three digits: nothing to gain (C2: same instruction count)
     prepare();
     const int64_t rows = V == 2 ? R / 2 : R;
     const int64_t items = st.n_out / U * rows;
@@ -581,10 +638,34 @@ static const char* const kPreamble =
     "__device__ __forceinline__ double2 hb_mul(double2 a, double2 b) { return make_double2(hb_mul(a.x, b.x), hb_mul(a.y, b.y)); }\n"
     "__device__ __forceinline__ double2 hb_add(double2 a, double2 b) { return make_double2(hb_add(a.x, b.x), hb_add(a.y, b.y)); }\n\n";
 
+// A step that enumerates its per-row inputs several times over (the message of a big clique built from small tables) keeps
+// one contiguous strip of groups per lane: the re-reads of a lane stay in L1 / L2 (launch_prodsum, engine.cu).  A streaming
+// step -- every per-row entry read about once -- deals its groups round robin.
+JitShape jit_step_shape(const Program& P, const Step& st) {
+  static const int mode = getenv("HB_JIT_INTERLEAVE") ? atoi(getenv("HB_JIT_INTERLEAVE")) : 1;  // 0 never, 1 streaming steps, 2 always
+  static const int unroll = getenv("HB_JIT_UNROLL") ? atoi(getenv("HB_JIT_UNROLL")) : 0;
+  int64_t terms = 1, row_entries = 0, row_loads = 0;
+  for (const Level& l : st.levels) {
+    terms *= l.d;
+    for (const StepInput& in : l.in)
+      if (P.tables[in.table].kind == T_ROW) row_entries += P.tables[in.table].size, row_loads += st.n_out * terms;
+  }
+  JitShape sh;
+  sh.rereads = row_entries > 0 && row_loads >= 3 * row_entries;
+  sh.interleave = mode == 2 || (mode == 1 && !sh.rereads);
+  if (sh.interleave && !sh.rereads)  // only light bodies: the registers of `unroll` groups are live together
+    for (int n = unroll; n > 1 && !sh.unroll; n /= 2)
+      if (jit_unrolled_ops(st) * n <= 96) sh.unroll = n;
+  return sh;
+}
+
 std::string jit_source(const Program& P, const std::vector<int>& steps) {
   std::string src = kPreamble;
   for (int si : steps) {
     Gen g(P, P.steps[si]);
+    const JitShape sh = jit_step_shape(P, P.steps[si]);
+    g.interleave = sh.interleave;
+    g.unroll = sh.unroll;
     src += g.kernel("hb_step_" + std::to_string(si));
   }
   return src;

@@ -19,6 +19,13 @@ int64_t jit_unrolled_ops(const Step& st);
 // Loads per row the specialised kernel of the step would issue, and what the templated kernels issue: a step is only
 // worth a specialised kernel when the first is clearly smaller.
 void jit_load_counts(const Program& P, const Step& st, int64_t* specialised, int64_t* templated);
+// How the kernel of a step walks its groups (part of the generated source, so the launch has to agree with it).
+struct JitShape {
+  bool rereads = false;     // the step reads its per-row inputs at least three times over
+  bool interleave = false;  // groups dealt round robin to the lanes instead of one contiguous strip per lane
+  int unroll = 0;           // groups of the loop evaluated together (0: left to the compiler)
+};
+JitShape jit_step_shape(const Program& P, const Step& st);
 // The CUDA source of the specialised kernels `hb_step_<si>` of the given steps (for tests and inspection).
 std::string jit_source(const Program& P, const std::vector<int>& steps);
 void jit_destroy(JitModule* m);

@@ -21,7 +21,7 @@ from oracle import OracleJT, OracleNet
 from helpers import random_net, same_bits
 
 out = {}
-for seed, rows in ((5, 257), (9, 64), (12, 1000)):
+for seed, rows in ((5, 257), (9, 64), (7, 3), (8, 18), (12, 1000)):  # incl. tiles of fewer than 64 rows
     net = random_net(seed, n=12 + seed %% 5, states=(2, 4), max_parents=3, shuffle=seed %% 2 == 1)
     pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
     onet = OracleNet.from_arrays(net.dims, net.scopes, net.values)
@@ -62,12 +62,14 @@ def run(tmp_path, name, env):
     return path, r.stderr + r.stdout
 
 
-def test_specialised_kernels_bit_identical_to_oracle_and_to_the_templated_kernels(tmp_path):
+@pytest.mark.parametrize("knobs", [{}, {"HB_JIT_INTERLEAVE": "2", "HB_JIT_UNROLL": "4"}, {"HB_JIT_INTERLEAVE": "0"}, {"HB_JIT_UNROLL": "2", "HB_JIT_MERGE": "0"}],
+                         ids=["default", "interleave-all-unroll4", "strips", "unroll2-no-digit-merge"])
+def test_specialised_kernels_bit_identical_to_oracle_and_to_the_templated_kernels(tmp_path, knobs):
     import numpy as np
 
     # HB_TREE=0: programs this small would otherwise run on the on-chip kernel (tests/test_gpu_onchip.py)
     jit, log = run(tmp_path, "jit", {"HB_JIT": "1", "HB_TREE": "0", "HB_JIT_MIN_WORK": "1", "HB_JIT_SYNC": "1", "HB_JIT_VERBOSE": "1",
-                                     "HB_CACHE_DIR": str(tmp_path / "cache")})
+                                     "HB_CACHE_DIR": str(tmp_path / "cache"), **knobs})
     assert "specialised kernels" in log, log[-2000:]  # they were really built and used
     assert int(log.rsplit("specialise ->", 1)[1].split()[0]) > 0
     plain, plain_log = run(tmp_path, "plain", {"HB_JIT": "0"})
