@@ -37,6 +37,7 @@ net, split = synth.config_c4(a.parents)
 pnet = hb.BayesianNetwork.from_tables_procedural(net.dims, net.scopes, net.values, net.proc_seed)
 t0 = time.perf_counter()
 sjt = SplitJunctionTree(pnet, split, rank=rank, world=world, device=local)
+sjt.specialise([net.n - 1])
 rng = np.random.RandomState(5)
 ev = np.full((a.rows, net.n), -1, np.int8)
 ev[:, net.n - 1] = rng.randint(0, 2, a.rows)  # the child is observed: every table of the query is per-row

@@ -42,6 +42,11 @@ class SplitJunctionTree:
         self.combos = combos[rank::world]
         self.slices = [JunctionTree(net, cmp=cmp, device=device, split=list(zip(self.split_vars, c))) for c in self.combos]
 
+    def specialise(self, observed) -> int:
+        """build the generated kernels of every slice for rows that observe `observed` (the split variables are added)"""
+        obs = sorted(set(observed) | set(self.split_vars))
+        return sum(jt.specialise(obs) for jt in self.slices)
+
     def partial_batch(self, evidence: np.ndarray):
         """cutset form: sum over this rank's slices of the unnormalised posteriors; a CUDA tensor [rows][sum dims]"""
         import torch

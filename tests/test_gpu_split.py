@@ -62,3 +62,35 @@ def test_few_rows_huge_tables_use_small_tiles():
         assert np.abs(out[:, off[v]:off[v + 1]].sum(1) - 1).max() < 1e-12
     sjt = SplitJunctionTree(proc, split)
     assert max_rel_err(sjt.posteriors_batch(ev).cpu().numpy(), out) <= 1e-12
+
+
+def test_few_rows_huge_tables_on_generated_kernels():
+    """C4's regime (a handful of rows, tables of millions of entries) on the generated step kernels: the groups of a streaming
+    step are dealt round robin, so a warp of a 4-row tile still reads contiguous memory (csrc/jit.cpp).  Same bits as the
+    precompiled kernels, for the unsplit handle and for one slice of the split clique (scaled one-entry tables)."""
+    net, split = synth.config_c4(20)
+    proc = hb.BayesianNetwork.from_tables_procedural(net.dims, net.scopes, net.values, net.proc_seed)
+    ev = np.full((5, net.n), -1, np.int8)
+    ev[:, net.n - 1] = [0, 1, 0, 1, 1]
+    jt = hb.JunctionTree(proc)
+    before = jt.posteriors_batch(ev)
+    assert jt.specialised_kernels() == 0
+    n = jt.specialise([net.n - 1])
+    after = jt.posteriors_batch(ev)
+    if n == 0:
+        pytest.skip("NVRTC is not available on this box")
+    assert jt.specialised_kernels() == n and jt.last_stats()["rows_per_tile"] == 6
+    assert same_bits(after, before)
+    combo = [(v, i % 2) for i, v in enumerate(split)]
+    ev2 = ev.copy()
+    for v, s in combo:
+        ev2[:, v] = s
+    observed = sorted(split + [net.n - 1])
+    sl = hb.JunctionTree(proc, split=combo)
+    import torch
+
+    d_ev = torch.from_numpy(ev2).cuda()
+    b = sl.posteriors_batch(d_ev).cpu().numpy()
+    assert sl.specialise(observed) > 0
+    a = sl.posteriors_batch(d_ev).cpu().numpy()
+    assert sl.specialised_kernels() > 0 and same_bits(a, b)
