@@ -790,6 +790,9 @@ struct Executor {
   // Kernels specialised per step (jit.cpp), built on the first pass over a large batch; jit_fn[si] = nullptr: templated kernel
   JitModule* jit = nullptr;
   std::vector<void*> jit_fn;
+  bool jit_elided = false;          // the generated kernels were built on the premise of jit_zero_add_elidable()
+  int jit_blocked = 0;              // how many of them use a register block over several output variables
+  std::vector<JitShape> jit_shape;  // of the steps that have a kernel: how it walks its groups (the launch has to agree with the source)
   bool jit_tried = false;
   double work_seen = 0;  // joint entries evaluated so far (rows x product entries per row)
   // Whole-schedule on-chip kernel (jit.cpp, hb_tree): when the per-row tables of a tile fit shared memory the whole pass
@@ -1211,19 +1214,21 @@ static void launch_prodsum(Executor& ex, const Step& st, int si, int64_t RT, int
   const int k = st.n_inputs(), s = (int)st.scalars.size();
   // the step has a specialised kernel: rows along x, so with one strip of groups per lane not for few-row tiles (a warp would
   // touch 16 or 32 distant strips); with the groups dealt round robin the lanes of a warp sit on adjacent groups
-  if (!ex.jit_fn.empty() && ex.jit_fn[si] && (nr >= 64 || jit_step_shape(*ex.P, st).interleave)) {
+  if (!ex.jit_fn.empty() && ex.jit_fn[si] && (nr >= 64 || ex.jit_shape[si].interleave)) {
+    const JitShape& shape = ex.jit_shape[si];
     // Row threads (two rows each) along threadIdx.x, strips of groups along threadIdx.y / blockIdx.x, row blocks along
     // blockIdx.y; enough of both to fill 148 SMs twice.  A step that reads its per-row inputs several times over gets narrow
     // row blocks (one warp of row threads): the strips of one row block are scheduled together and share those rows in L2
     // (C3's largest step: 9.4 GB of DRAM traffic for 1.2 GB of tables with 128-thread row blocks along the fast grid axis).
-    const unsigned row_threads = (unsigned)((nr + 1) / 2);
+    const unsigned row_threads = (unsigned)(shape.V == 1 ? nr : (nr + 1) / 2);
     const Reuse reuse = reuse_of(*ex.P, st);
     unsigned bx = reuse.row_entries > 0 && reuse.row_loads >= 3 * reuse.row_entries ? 32 : 128;
     while (bx > 1 && bx / 2 >= row_threads) bx /= 2;
     while ((row_threads + bx - 1) / bx > 65535u) bx *= 2;  // gridDim.y limit
-    const unsigned by = (unsigned)std::max<int64_t>(1, std::min<int64_t>(256 / bx, st.n_red));
+    const int64_t units = shape.groups / shape.inner;  // what the lanes share out: groups, or runs of `inner` groups
+    const unsigned by = (unsigned)std::max<int64_t>(1, std::min<int64_t>(256 / bx, units));
     const unsigned gy = (row_threads + bx - 1) / bx;  // row blocks
-    const unsigned gx = strips_for(reuse, ex.P->tables[st.out].size, bx, by, gy, st.n_red);
+    const unsigned gx = strips_for(reuse, ex.P->tables[st.out].size, bx, by, gy, units);
     const double *arena = ex.d_arena, *pots = ex.d_pots, *shared = ex.d_shared;
     double* arena_out = ex.d_arena;
     const int32_t* rowoff = ex.d_rowoff;
@@ -1578,6 +1583,18 @@ static void run_shared_steps(Executor& ex) {
 void executor_refresh_potentials(Executor* ex) {
   HB_CUDA(cudaSetDevice(ex->device));
   HB_CUDA(cudaDeviceSynchronize());
+  if (ex->jit_elided && !jit_zero_add_elidable(*ex->P)) {
+    // the generated kernels left out the `0 +` of every sum on the premise that no potential is negative, -0.0 or NaN
+    // (jit.cpp): the new factor breaks it, so they go and the next specialisation emits the adds
+    ex->pending.reset();
+    ex->tree_fn = nullptr;
+    ex->jit_fn.clear();
+    jit_destroy(ex->jit);
+    ex->jit = nullptr;
+    ex->drop_graphs();
+    ex->jit_tried = false;
+    ex->jit_elided = false;
+  }
   upload_potentials(*ex);  // same addresses: captured graphs stay valid
   run_shared_steps(*ex);
 }
@@ -1604,9 +1621,22 @@ static std::vector<int> steps_to_specialise(const Program& P) {
   int64_t budget = getenv("HB_JIT_BUDGET") ? atoll(getenv("HB_JIT_BUDGET")) : 8000;  // bounds the compilation time: C2 needs 4.6 K (49 kernels, 5.5 s)
   // C5 (340 light steps): 96 kernels 20.8 ms per pass, all 334 eligible steps 19.3 ms (12 s of NVRTC once, then the cubin cache)
   const size_t max_kernels = getenv("HB_JIT_MAX_KERNELS") ? (size_t)atoll(getenv("HB_JIT_MAX_KERNELS")) : 384;
+  // the steps with a register block over several output variables (re-reading steps, jit_step_shape) are the heaviest of a
+  // program and few: they do not draw on the budget of the others
+  int blocked_left = getenv("HB_JIT_MAX_BLOCKED") ? atoi(getenv("HB_JIT_MAX_BLOCKED")) : 24;
   for (auto& c : cand) {
-    const int64_t ops = jit_unrolled_ops(P.steps[c.second]);
-    if (ops > budget || steps.size() >= max_kernels) continue;
+    const JitShape sh = jit_step_shape(P, P.steps[c.second]);
+    if (steps.size() >= max_kernels) continue;
+    if (sh.custom) {
+      if (blocked_left <= 0 && sh.n_loop > 0) continue;
+      if (blocked_left > 0) {
+        --blocked_left;
+        steps.push_back(c.second);
+        continue;
+      }
+    }
+    const int64_t ops = sh.ops;
+    if (ops < 0 || ops > budget) continue;
     budget -= ops;
     steps.push_back(c.second);
   }
@@ -1620,6 +1650,7 @@ static void start_specialise(Executor* ex) {
   ex->jit_tried = true;
   const Program& P = *ex->P;
   auto pend = std::make_unique<Executor::Pending>();
+  ex->jit_elided = jit_zero_add_elidable(P);
   std::string src;
   if (ex->tree_eligible && tree_enabled()) {
     pend->is_tree = true;
@@ -1672,6 +1703,8 @@ static void finish_specialise(Executor* ex, bool wait) {
               ex->tree.R, ex->tree.T, per_sm, ex->tree.n_levels, (long long)ex->tree.arena_entries, ex->tree.smem_bytes);
   } else {
     ex->jit_fn.assign(P.steps.size(), nullptr);
+    ex->jit_shape.assign(P.steps.size(), JitShape());
+    int n_blocked = 0;
     for (int si : pend->steps) {
       void* fn = jit_function(mod, "hb_step_" + std::to_string(si));
       if (!fn) {
@@ -1680,8 +1713,12 @@ static void finish_specialise(Executor* ex, bool wait) {
         return;
       }
       ex->jit_fn[si] = fn;
+      ex->jit_shape[si] = jit_step_shape(P, P.steps[si]);
+      n_blocked += ex->jit_shape[si].custom;
     }
-    if (getenv("HB_JIT_VERBOSE") && atoi(getenv("HB_JIT_VERBOSE"))) fprintf(stderr, "[hbayes jit] %zu specialised kernels\n", pend->steps.size());
+    ex->jit_blocked = n_blocked;
+    if (getenv("HB_JIT_VERBOSE") && atoi(getenv("HB_JIT_VERBOSE")))
+      fprintf(stderr, "[hbayes jit] %zu specialised kernels, %d of them with a register block over several output variables\n", pend->steps.size(), n_blocked);
   }
   jit_destroy(ex->jit);
   ex->jit = mod;

@@ -23,7 +23,9 @@
 #include <cstdlib>
 #include <initializer_list>
 #include <map>
+#include <cmath>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <sstream>
@@ -146,6 +148,20 @@ struct Gen {
   // lane; `unroll` = groups of the strip loop the compiler may evaluate together (more loads in flight per thread)
   bool interleave = false;
   int unroll = 0;
+  // The reference starts every sum at 0 (`sum` = foldl (+) 0): 0 + x.  When no potential of the network is negative, -0.0 or
+  // NaN, no intermediate value can be -0.0 or a signalling NaN, so 0 + x == x bit for bit and the add is not emitted
+  // (jit_zero_add_elidable; a changeFactor that breaks the premise drops the kernels, engine.cu).
+  bool elide_zero_add = false;
+  // Re-reading steps: the digits of the output variables that the largest per-row input does not mention vary fastest along
+  // a lane's strip of groups, so consecutive groups re-read that input at the same addresses (L1 hits instead of L2 traffic).
+  bool reorder_digits = false;
+  // ... and the strip of a lane becomes two loops: `go` over the digits the largest input depends on, `gi` over the others,
+  // so that input's addresses (and, registers permitting, its values) are invariant in the inner loop.
+  bool split_loop = false;
+  size_t n_slow = 0;     // leading digits of `red` that index the largest per-row input (split_loop)
+  int64_t n_inner = 1;   // groups of the inner loop (split_loop), 1 otherwise
+  int min_blocks = 2;    // hb_step_<i>: CTAs per SM the kernel is bounded for (a large register block needs the registers of one)
+  int64_t n_groups = 1;  // n_out / U, set by prepare()
   std::vector<std::vector<int>> udig;  // per lock-step entry: state of every blocked variable
   std::vector<int64_t> uoff;           // per lock-step entry: offset in the stored output layout
   Gen(const Program& p, const Step& s) : P(p), st(s) {}
@@ -256,7 +272,7 @@ struct Gen {
       if (li + 1 < st.levels.size()) inner = level(li + 1, bound);
       for (int u = 0; u < U; ++u) {
         const std::string chain = term(li, u, bound, inner);
-        acc[u] = acc[u].empty() ? add(zero(), chain) : add(acc[u], chain);
+        acc[u] = acc[u].empty() ? (elide_zero_add ? chain : add(zero(), chain)) : add(acc[u], chain);
       }
     }
     return acc;
@@ -312,8 +328,28 @@ struct Gen {
         rdim.push_back(dv);
       }
     }
+    if (reorder_digits && red.size() > 1) {
+      const Table* big = nullptr;
+      for (const In& x : ins)
+        if (x.t->kind == T_ROW && (!big || x.t->size > big->size)) big = x.t;
+      if (big) {
+        std::vector<int> r2;
+        std::vector<int64_t> d2;
+        for (int pass = 0; pass < 2; ++pass)
+          for (size_t j = 0; j < red.size(); ++j)
+            if ((pstride_of(*big, red[j]) != 0) == (pass == 0)) r2.push_back(red[j]), d2.push_back(rdim[j]);
+        red = r2;
+        rdim = d2;
+        n_slow = 0;
+        for (int v : red) n_slow += pstride_of(*big, v) != 0;
+        n_inner = 1;
+        if (split_loop && n_slow > 0 && n_slow < red.size())
+          for (size_t j = n_slow; j < red.size(); ++j) n_inner *= rdim[j];
+      }
+    }
     U = 1;
     for (int v : blocked) U *= P.net->dims[v];
+    n_groups = st.n_out / U;
     auto out_stride = [&](int v) {
       for (size_t i = 0; i < out.pscope.size(); ++i)
         if (out.pscope[i] == v) return out.pstride[i];
@@ -406,10 +442,21 @@ struct Gen {
   enum { STORE_STREAMING = 0, STORE_PLAIN = 1, STORE_RESULT = 2 };  // __stcs to HBM / plain store / res[u] = value
   void emit_group(int store) {
     loaded.clear();
-    if (!red.empty()) o << "    unsigned rem = g;\n";
-    for (size_t j = red.size(); j-- > 0;)
-      o << "    const unsigned d" << red[j] << " = " << (j ? "rem % " + std::to_string(rdim[j]) + "u;" : "rem;") << (j ? " rem /= " + std::to_string(rdim[j]) + "u;" : "")
-        << "\n";
+    if (n_inner > 1) {  // the digits of `go` (slow) and of `gi` (fast) separately
+      o << "    unsigned rem = go;\n";
+      for (size_t j = n_slow; j-- > 0;)
+        o << "    const unsigned d" << red[j] << " = " << (j ? "rem % " + std::to_string(rdim[j]) + "u;" : "rem;") << (j ? " rem /= " + std::to_string(rdim[j]) + "u;" : "")
+          << "\n";
+      o << "    unsigned remi = gi;\n";
+      for (size_t j = red.size(); j-- > n_slow;)
+        o << "    const unsigned d" << red[j] << " = " << (j > n_slow ? "remi % " + std::to_string(rdim[j]) + "u;" : "remi;")
+          << (j > n_slow ? " remi /= " + std::to_string(rdim[j]) + "u;" : "") << "\n";
+    } else {
+      if (!red.empty()) o << "    unsigned rem = g;\n";
+      for (size_t j = red.size(); j-- > 0;)
+        o << "    const unsigned d" << red[j] << " = " << (j ? "rem % " + std::to_string(rdim[j]) + "u;" : "rem;") << (j ? " rem /= " + std::to_string(rdim[j]) + "u;" : "")
+          << "\n";
+    }
     for (const In& x : ins) {
       std::string base;
       for (int v : red) {
@@ -433,8 +480,10 @@ struct Gen {
     for (int u = 0; u < U; ++u) {
       if (store == STORE_RESULT)
         o << "    res[" << u << "] = " << res[u] << ";\n";
-      else if (store == STORE_STREAMING)
+      else if (store == STORE_STREAMING && V == 2)
         o << "    __stcs(reinterpret_cast<double2*>(outp + (size_t)(ob + " << uoff[u] << "u) * RT), " << res[u] << ");\n";
+      else if (store == STORE_STREAMING)
+        o << "    __stcs(outp + (size_t)(ob + " << uoff[u] << "u) * RT, " << res[u] << ");\n";
       else if (V == 2)
         o << "    *reinterpret_cast<double2*>(outp + (size_t)(ob + " << uoff[u] << "u) * RT) = " << res[u] << ";\n";
       else
@@ -445,18 +494,19 @@ struct Gen {
   std::string kernel(const std::string& name) {
     prepare();
     // two CTAs per SM (<= 128 registers): measured on C2, 1 -> 86.2, 2 -> 89.7, 3 -> 75.9 M queries/s
-    o << "extern \"C\" __global__ void __launch_bounds__(256, " << (getenv("HB_JIT_MINBLOCKS") ? atoi(getenv("HB_JIT_MINBLOCKS")) : 2) << ") " << name
+    o << "extern \"C\" __global__ void __launch_bounds__(256, " << (getenv("HB_JIT_MINBLOCKS") ? atoi(getenv("HB_JIT_MINBLOCKS")) : min_blocks) << ") " << name
       << "(const double* __restrict__ arena, double* __restrict__ arena_out, const double* __restrict__ pots,\n"
          "    const double* __restrict__ shared, const int* __restrict__ rowoff, int nr, long long RT) {\n";
     // strips of groups along blockIdx.x (the fast axis of the block scheduler), row blocks along blockIdx.y: the CTAs that are
     // resident together work on the SAME rows, so a step that enumerates its inputs many times finds them in L2
-    o << "  const int row = (blockIdx.y * blockDim.x + threadIdx.x) * 2;\n  if (row >= nr) return;\n";
+    o << "  const int row = (blockIdx.y * blockDim.x + threadIdx.x)" << (V == 2 ? " * 2" : "") << ";\n  if (row >= nr) return;\n";
     o << "  const unsigned lanes = gridDim.x * blockDim.y, lane = blockIdx.x * blockDim.y + threadIdx.y;\n";
+    const int64_t n_outer = n_groups / n_inner;
     if (!interleave) {
-      o << "  const unsigned per = (" << st.n_red << "u + lanes - 1) / lanes;\n";
-      o << "  const unsigned g_end = min(" << st.n_red << "u, lane * per + per);\n";
+      o << "  const unsigned per = (" << n_outer << "u + lanes - 1) / lanes;\n";
+      o << "  const unsigned g_end = min(" << n_outer << "u, lane * per + per);\n";
     }
-    o << "  const double2 zero = make_double2(0.0, 0.0);\n";
+    if (V == 2) o << "  const double2 zero = make_double2(0.0, 0.0);\n";
     emit_bases("  ");
     if (interleave && unroll > 1) {
       // `unroll` groups at a time, all their loads ahead of the first store (the compiler does not move a load of the next
@@ -464,9 +514,9 @@ struct Gen {
       o << "  auto body = [&](const unsigned g, double2* __restrict__ res, unsigned* __restrict__ ob_out) {\n";
       emit_group(STORE_RESULT);
       o << "  };\n";
-      o << "  for (unsigned g = lane; g < " << st.n_red << "u; g += lanes * " << unroll << "u) {\n";
+      o << "  for (unsigned g = lane; g < " << n_groups << "u; g += lanes * " << unroll << "u) {\n";
       for (int k = 0; k < unroll; ++k) {
-        if (k) o << "    const bool has" << k << " = g + lanes * " << k << "u < " << st.n_red << "u;\n";
+        if (k) o << "    const bool has" << k << " = g + lanes * " << k << "u < " << n_groups << "u;\n";
         o << "    double2 r" << k << "[" << U << "]; unsigned ob" << k << ";\n";
         o << "    body(" << (k ? "has" + std::to_string(k) + " ? g + lanes * " + std::to_string(k) + "u : g" : std::string("g")) << ", r" << k << ", &ob" << k << ");\n";
       }
@@ -480,11 +530,13 @@ struct Gen {
       return o.str();
     }
     if (interleave)  // the lanes that run together take adjacent groups: a streaming step touches HBM like a copy does
-      o << "  for (unsigned g = lane; g < " << st.n_red << "u; g += lanes) {\n";
+      o << "  for (unsigned g = lane; g < " << n_groups << "u; g += lanes) {\n";
+    else if (n_inner > 1)
+      o << "  for (unsigned go = lane * per; go < g_end; ++go) {\n#pragma unroll 1\n  for (unsigned gi = 0; gi < " << n_inner << "u; ++gi) {\n";
     else
       o << "  for (unsigned g = lane * per; g < g_end; ++g) {\n";
     emit_group(STORE_STREAMING);
-    o << "  }\n}\n\n";
+    o << (n_inner > 1 && !interleave ? "  }\n" : "") << "  }\n}\n\n";
     return o.str();
   }
 
@@ -590,17 +642,24 @@ int64_t jit_unrolled_ops(const Step& st) {
   return n < 0 ? -1 : body_ops(st, n, st.U);
 }
 
-bool jit_eligible(const Program& P, const Step& st) {
+static bool jit_basic(const Program& P, const Step& st) {
   if (st.kind != STEP_PRODSUM || st.shared || !st.scalars.empty() || st.levels.empty() || st.levels[0].is_max) return false;
   if (P.tables[st.out].kind != T_ROW || st.U > 8 || st.n_inputs() < 1) return false;
   if (st.n_red >= ((int64_t)1 << 31)) return false;
   for (const Level& l : st.levels)
     for (const StepInput& in : l.in)
       if (P.tables[in.table].kind == T_ONE) return false;
+  return true;
+}
+
+bool jit_eligible(const Program& P, const Step& st) {
+  if (!jit_basic(P, st)) return false;
   // A step whose body only fits with run-time loops around it stays on the precompiled kernels: as a kernel of its own it
   // measured no faster (C3 with every such step generated: 6.6 vs 6.2 ms; with only one looped level allowed: 4.91 vs 4.72 ms).
-  // (Inside hb_tree such steps do use the loops.)
-  return jit_loop_levels(st) == 0;
+  // (Inside hb_tree such steps do use the loops.)  The exception: a re-reading step with a register block over several
+  // output variables (jit_step_shape) -- there the loops buy a body with a fraction of the loads per entry.
+  if (jit_loop_levels(st) == 0) return true;
+  return jit_step_shape(P, st).eligible;
 }
 
 // loads per row (8-byte slots, one row) the specialised kernel issues for the step / the templated kernels issue
@@ -641,10 +700,40 @@ static const char* const kPreamble =
 // A step that enumerates its per-row inputs several times over (the message of a big clique built from small tables) keeps
 // one contiguous strip of groups per lane: the re-reads of a lane stay in L1 / L2 (launch_prodsum, engine.cu).  A streaming
 // step -- every per-row entry read about once -- deals its groups round robin.
+namespace {
+// loads one group executes when the output variables `block` are evaluated in lock step and the n_loop outermost levels are
+// run-time loops: per input one load per distinct address of the unrolled part (states of the block variables it mentions
+// x states of the summed variables it mentions), repeated by every looped level around it
+int64_t block_loads(const Program& P, const Step& st, const std::vector<int>& block, int n_loop) {
+  int64_t total = 0;
+  for (size_t l = 0; l < st.levels.size(); ++l)
+    for (const StepInput& in : st.levels[l].in) {
+      const Table& t = P.tables[in.table];
+      int64_t n = 1;
+      for (int v : block)
+        if (stride_in(t, v) != 0) n *= P.net->dims[v];
+      for (size_t m = 0; m <= l; ++m)
+        if ((int)m < n_loop || in.lstride[m] != 0) n *= st.levels[m].d;
+      total += n;
+    }
+  return total;
+}
+}  // namespace
+
 JitShape jit_step_shape(const Program& P, const Step& st) {
   static const int mode = getenv("HB_JIT_INTERLEAVE") ? atoi(getenv("HB_JIT_INTERLEAVE")) : 1;  // 0 never, 1 streaming steps, 2 always
   // measured (profiles/r2_step_probe.jsonl): C4, 4 rows: 2.64 ms per pass with one group per iteration, 2.34 ms with four; C5: 23.5 / 20.8 ms
   static const int unroll = getenv("HB_JIT_UNROLL") ? atoi(getenv("HB_JIT_UNROLL")) : 4;
+  // register blocks over several output variables for re-reading steps: at most this many entries in lock step (0 = off)
+  // measured on C3 (profiles/r2_step_block.jsonl, ms per pass): off 4.41 | 8 entries, two CTAs per SM, 320-evaluation bodies 3.85 |
+  // 16 entries, one CTA per SM (255 registers), 600-evaluation bodies 3.77 | 8, one, 600: 3.78 | 16, two, 320: 4.10
+  static const int block_u = getenv("HB_JIT_BLOCK_U") ? atoi(getenv("HB_JIT_BLOCK_U")) : 16;
+  static const int block_loops = getenv("HB_JIT_BLOCK_LOOPS") ? atoi(getenv("HB_JIT_BLOCK_LOOPS")) : 2;
+  static const int block_minb = getenv("HB_JIT_BLOCK_MINB") ? atoi(getenv("HB_JIT_BLOCK_MINB")) : 1;
+  static const int64_t block_body = getenv("HB_JIT_BLOCK_BODY") ? atoll(getenv("HB_JIT_BLOCK_BODY")) : MAX_BODY_OPS;  // unrolled chain evaluations per group
+  // one row per thread: half the registers of a row pair (measured on C3: 4.07 ms per pass against 4.31 with row pairs)
+  static const int block_v = getenv("HB_JIT_BLOCK_V") && atoi(getenv("HB_JIT_BLOCK_V")) == 2 ? 2 : 1;
+  static const int64_t block_min_joint = getenv("HB_JIT_BLOCK_MIN_JOINT") ? atoll(getenv("HB_JIT_BLOCK_MIN_JOINT")) : 8192;
   int64_t terms = 1, row_entries = 0, row_loads = 0;
   for (const Level& l : st.levels) {
     terms *= l.d;
@@ -654,19 +743,135 @@ JitShape jit_step_shape(const Program& P, const Step& st) {
   JitShape sh;
   sh.rereads = row_entries > 0 && row_loads >= 3 * row_entries;
   sh.interleave = mode == 2 || (mode == 1 && !sh.rereads);
-  if (sh.interleave && !sh.rereads)  // only light bodies: the registers of `unroll` groups are live together
+  if (st.w_var >= 0) sh.block.push_back(st.w_var);
+  sh.U = st.U;
+  sh.groups = st.n_red;
+  sh.n_loop = jit_loop_levels(st);
+  sh.ops = jit_unrolled_ops(st);
+  sh.eligible = jit_basic(P, st) && sh.n_loop == 0;
+  if (sh.interleave && !sh.rereads && sh.eligible)  // only light bodies: the registers of `unroll` groups are live together
     for (int n = unroll; n > 1 && !sh.unroll; n /= 2)
-      if (jit_unrolled_ops(st) * n <= 96) sh.unroll = n;
+      if (sh.ops * n <= 96) sh.unroll = n;
+  // a re-reading step walks its groups as (outer, inner): the inner groups leave the largest per-row input where it is
+  const auto set_inner = [&]() {
+    static const bool split = !(getenv("HB_JIT_SPLIT_LOOP") && atoi(getenv("HB_JIT_SPLIT_LOOP")) == 0);
+    static const bool reorder = !(getenv("HB_JIT_DIGIT_ORDER") && atoi(getenv("HB_JIT_DIGIT_ORDER")) == 0);
+    sh.inner = 1;
+    if (!split || !reorder || !sh.rereads || sh.interleave) return;
+    const Table* big = nullptr;
+    for (const Level& l : st.levels)
+      for (const StepInput& in : l.in)
+        if (P.tables[in.table].kind == T_ROW && (!big || P.tables[in.table].size > big->size)) big = &P.tables[in.table];
+    if (!big) return;
+    int64_t inner = 1, outer = 1;
+    for (int v : P.tables[st.out].pscope) {
+      if (std::find(sh.block.begin(), sh.block.end(), v) != sh.block.end()) continue;
+      (stride_in(*big, v) != 0 ? outer : inner) *= P.net->dims[v];
+    }
+    // the compiler hoists the loads of `big` out of the inner loop: only when they fit the registers (it spills otherwise)
+    int64_t big_loads = sh.V;
+    for (int v : sh.block)
+      if (stride_in(*big, v) != 0) big_loads *= P.net->dims[v];
+    for (size_t l = 0; l < st.levels.size(); ++l)
+      for (const StepInput& in : st.levels[l].in)
+        if (&P.tables[in.table] == big)
+          for (size_t m = 0; m <= l; ++m)
+            if (in.lstride[m] != 0) big_loads *= st.levels[m].d;
+    static const int64_t max_hoist = getenv("HB_JIT_SPLIT_MAX") ? atoll(getenv("HB_JIT_SPLIT_MAX")) : 32;  // doubles
+    if (inner > 1 && outer > 1 && big_loads <= max_hoist) sh.inner = inner;
+  };
+  set_inner();
+  if (!sh.rereads || sh.interleave || block_u <= st.U || !jit_basic(P, st) || st.n_out * terms < block_min_joint) return sh;
+  // the block with the fewest loads per output entry among the sets of output variables with at most block_u state
+  // combinations; ties go to the smaller block, then to the one that holds w
+  const Table& out = P.tables[st.out];
+  const std::vector<int>& cand = out.pscope;
+  if (cand.size() > 20) return sh;
+  const int base_loop = std::max(0, sh.n_loop);
+  const double base = (double)block_loads(P, st, sh.block, base_loop) / std::max(1, st.U);
+  std::vector<int> best;
+  double best_cost = base;
+  int64_t best_u = st.U;
+  int best_loop = base_loop;
+  std::vector<int> cur;
+  const auto consider = [&](int64_t u) {
+    const int n_loop = loop_levels_for(st, u, block_body);
+    if (n_loop < 0 || n_loop > block_loops || body_ops(st, n_loop, u) > MAX_BODY_OPS) return;
+    const double cost = (double)block_loads(P, st, cur, n_loop) / (double)u;
+    const bool has_w = std::find(cur.begin(), cur.end(), st.w_var) != cur.end();
+    const bool best_has_w = std::find(best.begin(), best.end(), st.w_var) != best.end();
+    if (cost < best_cost * (1 - 1e-9) || (cost <= best_cost * (1 + 1e-9) && !best.empty() && (u < best_u || (u == best_u && has_w && !best_has_w)))) {
+      best = cur;
+      best_cost = cost;
+      best_u = u;
+      best_loop = n_loop;
+    }
+  };
+  const std::function<void(size_t, int64_t)> walk = [&](size_t i, int64_t u) {
+    if (i == cand.size()) {
+      if (!cur.empty()) consider(u);
+      return;
+    }
+    walk(i + 1, u);
+    const int64_t d = P.net->dims[cand[i]];
+    if (u * d <= block_u) {
+      cur.push_back(cand[i]);
+      walk(i + 1, u * d);
+      cur.pop_back();
+    }
+  };
+  walk(0, 1);
+  // worth it from two thirds of the loads down (a larger block costs registers: one CTA per SM instead of two)
+  if (best.empty() || best_cost > base * 0.67) return sh;
+  sh.block = best;
+  sh.custom = true;
+  sh.U = (int)best_u;
+  sh.groups = st.n_out / best_u;
+  sh.n_loop = best_loop;
+  sh.ops = body_ops(st, best_loop, best_u);
+  sh.min_blocks = block_minb;
+  sh.body_budget = block_body;
+  sh.V = block_v;
+  sh.eligible = true;
+  set_inner();
   return sh;
 }
 
+bool jit_zero_add_elidable(const Program& P) {
+  static const bool off = getenv("HB_JIT_ZERO_ADD") && atoi(getenv("HB_JIT_ZERO_ADD")) != 0;  // 1: always emit 0 + x
+  if (off) return false;
+  const auto ok = [](double x) { return x >= 0.0 && !std::signbit(x); };  // false for NaN, negative values and -0.0
+  for (int v = 0; v < P.net->n(); ++v)
+    if (!P.net->procedural(v))  // a procedural CPT is a quotient of sums of values in [0.05, 1) (procedural.hpp): positive
+      for (double x : P.net->values[v])
+        if (!ok(x)) return false;
+  for (double x : P.extra_values)
+    if (!ok(x)) return false;
+  return true;
+}
+
 std::string jit_source(const Program& P, const std::vector<int>& steps) {
+  static const bool reorder = !(getenv("HB_JIT_DIGIT_ORDER") && atoi(getenv("HB_JIT_DIGIT_ORDER")) == 0);
   std::string src = kPreamble;
+  // measured on C3 (profiles/r2_step_block.jsonl): without the adds the pass is SLOWER (4.20 against 3.84 ms; the largest looped
+  // kernel, step 567, goes from 0.78 to 0.96 ms), while the on-chip kernel gains 4 % on C2 -- so only hb_tree leaves them out
+  static const bool step_elide = getenv("HB_JIT_STEP_ELIDE") && atoi(getenv("HB_JIT_STEP_ELIDE")) != 0;
+  const bool elide = step_elide && jit_zero_add_elidable(P);
   for (int si : steps) {
     Gen g(P, P.steps[si]);
     const JitShape sh = jit_step_shape(P, P.steps[si]);
     g.interleave = sh.interleave;
     g.unroll = sh.unroll;
+    g.elide_zero_add = elide;
+    g.reorder_digits = reorder && sh.rereads && !sh.interleave;
+    g.split_loop = sh.inner > 1;
+    if (sh.custom) {
+      g.custom_block = true;
+      g.blocked = sh.block;
+      g.body_budget = sh.body_budget;
+      g.min_blocks = sh.min_blocks;
+      g.V = sh.V;
+    }
     src += g.kernel("hb_step_" + std::to_string(si));
   }
   return src;
@@ -1011,6 +1216,7 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
 }
 
 std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_per_row, int64_t* stores_per_row) {
+  const bool elide = jit_zero_add_elidable(P);
   const Network& net = *P.net;
   const int R = plan.R, T = plan.T;
   const int64_t NV = net.n(), NS = (int64_t)P.slices.size(), W = P.out_width, WP = plan.stage_pitch;
@@ -1153,6 +1359,7 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
         v = 1;
       Gen g(P, st);
       g.tree_off = &plan.off;
+      g.elide_zero_add = elide;
       g.tree_step((int)si, R, T, (int)(rot % T), block, v);
       fns << g.o.str();
       o << g.call;
@@ -1212,6 +1419,11 @@ std::string tree_source(const Program& P, const TreePlan& plan, int64_t* loads_p
         for (size_t j = 0; j < st.obs_var.size(); ++j) first_state &= ((f / st.obs_stride[j]) % st.obs_dim[j]) == 0;
         if (!first_state) continue;
         const std::string v = use(st.full_map[(size_t)f]);
+        if (elide && n_terms == 0) {  // 0 + x == x (see Gen::elide_zero_add)
+          ++n_terms;
+          norm = v;
+          continue;
+        }
         const std::string n = "n" + std::to_string(n_terms++);
         o << "          const double " << n << " = __dadd_rn(" << norm << ", " << v << ");\n";
         norm = n;

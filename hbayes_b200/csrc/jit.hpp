@@ -24,8 +24,26 @@ struct JitShape {
   bool rereads = false;     // the step reads its per-row inputs at least three times over
   bool interleave = false;  // groups dealt round robin to the lanes instead of one contiguous strip per lane
   int unroll = 0;           // groups of the loop evaluated together (0: left to the compiler)
+  // Register block: the output variables whose states one thread evaluates in lock step (a group = all their state
+  // combinations, U entries).  Default: the step's blocking variable w alone.  A re-reading step gets the set of output
+  // variables that leaves the fewest loads per output entry (`custom`): an outer-product block over variables of DIFFERENT
+  // inputs uses every loaded value several times.  The arithmetic of an entry does not depend on the block.
+  std::vector<int> block;
+  bool custom = false;
+  int V = 2;                // evidence rows per thread (2: adjacent rows, 16-byte accesses)
+  int U = 1;                // entries per group
+  int64_t groups = 1;       // n_out / U
+  int64_t inner = 1;        // > 1: a lane's strip is cut in units of `inner` consecutive groups (groups / inner units in all)
+  int n_loop = 0;           // outermost levels that stay run-time loops in the generated body
+  int64_t body_budget = 600;  // ... so that the unrolled rest stays below this many chain evaluations
+  int64_t ops = 0;          // chain evaluations in the unrolled part of a group's body (-1: does not fit)
+  int min_blocks = 2;       // __launch_bounds__(256, min_blocks)
+  bool eligible = false;    // the body fits the limits
 };
 JitShape jit_step_shape(const Program& P, const Step& st);
+// May the generated kernels leave out the `0 +` every reference sum starts with?  Yes when no potential is negative, -0.0
+// or NaN: then 0 + x == x bit for bit for every intermediate value.  (HB_JIT_ZERO_ADD=1 keeps the adds.)
+bool jit_zero_add_elidable(const Program& P);
 // The CUDA source of the specialised kernels `hb_step_<si>` of the given steps (for tests and inspection).
 std::string jit_source(const Program& P, const std::vector<int>& steps);
 void jit_destroy(JitModule* m);

@@ -243,7 +243,16 @@ std::string describe_network(const Network& net) {
   o << "],\"values\":[";
   for (int v = 0; v < net.n(); ++v) {
     o << (v ? "," : "") << "[";
-    for (size_t i = 0; i < net.values[v].size(); ++i) o << (i ? "," : "") << net.values[v][i];  // procedural CPTs print as []
+    for (size_t i = 0; i < net.values[v].size(); ++i) {  // procedural CPTs print as []
+      const double x = net.values[v][i];
+      o << (i ? "," : "");
+      if (x != x)
+        o << "NaN";  // what Python's json module reads (and writes) for the non-finite doubles
+      else if (x - x != 0.0)
+        o << (x > 0 ? "Infinity" : "-Infinity");
+      else
+        o << x;
+    }
     o << "]";
   }
   o << "]}";

@@ -203,3 +203,48 @@ def test_saved_handle_carries_its_compiled_kernels_to_the_next_process(tmp_path)
     assert float(t1) < 0.1 < float(t0)
     assert np.load(path + ".save.npy").tobytes() == np.load(path + ".load.npy").tobytes()
     assert os.path.getsize(path) > 100000  # the cubin is in there
+
+
+def test_negative_zero_in_a_new_factor_brings_the_zero_adds_back():
+    """hb_tree leaves out the `0 +` every reference sum starts with as long as no potential is negative, -0.0 or NaN
+    (csrc/jit.cpp jit_zero_add_elidable).  changeFactor with a table that holds -0.0 breaks that premise: the handle drops the
+    kernel it had built (the precompiled kernels answer), the next specialisation emits the adds, and every answer is the
+    oracle's bit for bit -- +0.0 where the shortcut would have produced -0.0."""
+    import numpy as np
+
+    import hbayes_b200 as hb
+    from hbayes_b200 import synth
+    from oracle import OracleJT, OracleNet
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import same_bits
+
+    net, observed = synth.config_c2()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    ev = synth.config_c2_evidence(net, observed, 2048)
+    os.environ["HB_JIT"] = "1"
+    try:
+        jt = hb.JunctionTree(pnet)
+        assert jt.specialise(observed) > 0
+        before = jt.posteriors_batch(ev)
+        assert jt.kernel_info()["on_chip"] == 1
+        assert same_bits(before, OracleJT(OracleNet.from_arrays(net.dims, net.scopes, net.values)).posteriors_batch(ev, n_threads=8))
+        # an unobserved variable with parents: its first state gets probability -0.0 under every parent configuration
+        v = next(i for i in range(net.n) if i not in observed and len(net.scopes[i]) > 1)
+        values = [np.asarray(x, np.float64).copy() for x in net.values]
+        per_state = values[v].size // net.dims[v]
+        values[v][:per_state] = -0.0
+        assert jt.change_factor(hb.Factor(net.scopes[v], [net.dims[x] for x in net.scopes[v]], values[v]))
+        want = OracleJT(OracleNet.from_arrays(net.dims, net.scopes, values)).posteriors_batch(ev, n_threads=8)
+        col = int(sum(net.dims[:v]))
+        assert not np.signbit(want[:, col]).any() and (want[:, col] == 0).all()  # the reference's 0 + (-0.0) = +0.0
+        got = jt.posteriors_batch(ev)
+        assert jt.kernel_info()["on_chip"] == 0  # the kernel without the adds is gone
+        assert same_bits(got, want)
+        assert jt.specialise(observed) > 0  # rebuilt, now with the adds
+        again = jt.posteriors_batch(ev)
+        assert jt.kernel_info()["on_chip"] == 1
+        assert same_bits(again, want)
+        assert "hb_add(zero, " in jt.tree_source(observed) or "hb_add(0.0, " in jt.tree_source(observed)
+    finally:
+        os.environ["HB_JIT"] = "0"

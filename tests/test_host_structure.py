@@ -366,3 +366,75 @@ def test_split_program_exchange_steps_are_structural():
     from test_gpu_split_nccl import test_split_program_has_its_exchange_steps
 
     test_split_program_has_its_exchange_steps()
+
+
+def _kernels(src):
+    """{step: source} of the `hb_step_<i>` kernels in a generated translation unit"""
+    parts = re.split(r'(?=extern "C" __global__)', src)[1:]
+    return {int(re.search(r"hb_step_(\d+)\(", p).group(1)): p for p in parts}
+
+
+def test_rereading_steps_get_register_blocks_over_several_output_variables(tmp_path):
+    """csrc/jit.cpp jit_step_shape: a step that enumerates a big joint from small per-row tables (the messages around C3's
+    largest cluster) evaluates the states of SEVERAL output variables in lock step -- an outer-product block, every loaded
+    value used several times -- with one row per thread and the registers of a whole SM partition; the variables its largest
+    input does not mention vary fastest (an inner loop where that is worth it).  The choice is deterministic, HB_JIT_BLOCK_U=0
+    turns it off, and the blocked kernels compile for sm_100a without spilling much (numerics: tests/test_gpu_configs.py)."""
+    import shutil
+    import subprocess
+
+    net, observed = synth.config_c3()
+    pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)
+    src = hb.JunctionTree(pnet, device=None).jit_source(sorted(observed))
+    ks = _kernels(src)
+    blocked = {i: k for i, k in ks.items() if "__launch_bounds__(256, 1)" in k}
+    assert 4 <= len(blocked) <= 40, sorted(blocked)
+    prog = hb.JunctionTree(pnet, device=None).program(sorted(observed))
+    heaviest = max((i for i, s in enumerate(prog["physical"]) if s["kind"] == 0 and not s["shared"]),
+                   key=lambda i: prog["physical"][i]["n_out"] * int(np.prod([l["d"] for l in prog["physical"][i]["levels"]])))
+    assert heaviest in blocked
+    for i, k in blocked.items():
+        assert "double2" not in k.split("{", 1)[1], i  # one row per thread
+        st = prog["physical"][i]
+        stores = k.count("__stcs(")
+        assert stores > st["U"] and st["n_out"] % stores == 0, (i, stores)  # more entries in lock step than the states of w
+        # every `0 +` of the reference is there (the per-step kernels keep them, see jit_source)
+        assert "hb_add(0.0, " in k or "= 0.0;" in k, i
+    assert any("for (unsigned gi = 0;" in k for k in blocked.values())
+    off = subprocess.run([os.sys.executable, "-c", "import sys; sys.path.insert(0, %r)\n"
+                          "import hbayes_b200 as hb\nfrom hbayes_b200 import synth\n"
+                          "net, observed = synth.config_c3()\n"
+                          "pnet = hb.BayesianNetwork.from_tables(net.dims, net.scopes, net.values)\n"
+                          "src = hb.JunctionTree(pnet, device=None).jit_source(sorted(observed))\n"
+                          "print(src.count('__launch_bounds__(256, 1)'), src.count('hb_step_'))" % os.path.dirname(G.rstrip("/")).rsplit("/tests", 1)[0]],
+                         capture_output=True, text=True, env=dict(os.environ, HB_JIT_BLOCK_U="0"))
+    assert off.returncode == 0, off.stderr[-2000:]
+    n_blocked_off, n_kernels_off = map(int, off.stdout.split())
+    assert n_blocked_off == 0 and n_kernels_off < len(ks)  # the looped steps are only eligible with a block
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    cu = tmp_path / "blocked.cu"
+    cu.write_text(src.split('extern "C"', 1)[0] + "".join(blocked[i] for i in sorted(blocked)))
+    r = subprocess.run([nvcc, "--fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-cubin", "-Xptxas", "-v", str(cu), "-o", str(tmp_path / "blocked.cubin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    spills = [int(x) for x in re.findall(r"(\d+) bytes spill stores", r.stderr)]
+    assert len(spills) == len(blocked) and max(spills) <= 512, spills
+
+
+def test_on_chip_kernel_leaves_out_the_zero_adds_only_for_nonnegative_potentials():
+    """csrc/jit.cpp jit_zero_add_elidable: the reference starts every sum at 0 (`sum` = foldl (+) 0).  0 + x == x bit for bit
+    unless x is -0.0 (or a signalling NaN), and no intermediate can be either when no potential is negative, -0.0 or NaN:
+    then hb_tree leaves the adds out.  One -0.0 anywhere in a CPT and they are all back."""
+    net = random_net(11, n=10, states=(2, 3), max_parents=3)
+    values = [np.asarray(v, np.float64).copy() for v in net.values]
+    zero_adds = lambda s: s.count("hb_add(zero, ") + s.count("hb_add(0.0, ") + s.count("__dadd_rn(0.0, ")
+    plain = hb.JunctionTree(hb.BayesianNetwork.from_tables(net.dims, net.scopes, values), device=None).tree_source([1, 4])
+    assert zero_adds(plain) == 0
+    for bad in (-0.0, -0.25, float("nan")):
+        v2 = [v.copy() for v in values]
+        v2[3][0] = bad
+        src = hb.JunctionTree(hb.BayesianNetwork.from_tables(net.dims, net.scopes, v2), device=None).tree_source([1, 4])
+        assert zero_adds(src) > 20, bad
+        assert src.count("hb_add(") > plain.count("hb_add(")
