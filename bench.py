@@ -457,6 +457,8 @@ def main():
                 "fp64": {"achieved": flops / (kernel_ms / 1e3) / 1e12, "peak": fp64_peak, "unit": "Tflop/s (separate multiply and add, no FMA)",
                          "frac": flops / (kernel_ms / 1e3) / 1e12 / fp64_peak,
                          "per_row": {"mul": info["fp64_mul_per_row"], "add": info["fp64_add_per_row"]},
+                         "note": "operations the kernel executes: the `0 +` each reference sum starts with is left out while no "
+                                 "potential is negative, -0.0 or NaN (0 + x == x bit for bit; csrc/jit.cpp jit_zero_add_elidable)",
                          "peak_source": "64 fp64 lanes/clk/SM x %d SMs x %.0f MHz (sampled)" % (n_sm, sm_mhz)},
                 "kernel": {k: info[k] for k in ("rows_per_cta", "threads_per_cta", "levels", "smem_entries_per_row", "smem_bytes")},
             }

@@ -1057,6 +1057,7 @@ int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
 }  // namespace
 
 bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
+  const bool elide = jit_zero_add_elidable(P);
   auto fail = [&](const std::string& m) {
     if (why) *why = m;
     return false;
@@ -1208,7 +1209,9 @@ bool tree_plan(const Program& P, TreePlan& plan, std::string* why) {
       terms *= st.levels[l].d;
       const int64_t k = (int64_t)st.levels[l].in.size() + (l + 1 < st.levels.size() ? 1 : 0) + (l == 0 && !st.scalars.empty() ? 1 : 0);
       plan.ops_mul += terms * std::max<int64_t>(0, k - 1);
-      plan.ops_add += terms;
+      // the reference adds every term to a sum that starts at 0; without the `0 +` (jit_zero_add_elidable) a sum of d terms
+      // costs d - 1 adds -- counted as executed, so that the fp64 rate of the bench line is the kernel's
+      plan.ops_add += elide ? terms - terms / st.levels[l].d : terms;
     }
     if (st.scalars.size() > 1) plan.ops_mul += (int64_t)st.scalars.size() - 1;
   }

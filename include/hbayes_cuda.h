@@ -61,9 +61,9 @@ void hb_string_free(char* s);
 /* number of visible CUDA devices (0 when there is none); never fails */
 int hb_device_count(void);
 
-/* Page-locked host memory for evidence / result matrices.  The batch calls accept any host pointer, but only page-locked
- * buffers are moved by DMA while kernels run (measured on C2, 2^20 rows: 17 ms per call from page-locked buffers, 54 ms from
- * pageable ones).  A Haskell caller allocates its matrices here (mallocForeignPtrBytes memory is pageable) and frees
+/* Page-locked host memory for evidence / result matrices.  The batch calls accept any host pointer; pageable buffers are
+ * staged through a page-locked bounce ring inside the library, page-locked ones are moved by DMA directly (measured on C2,
+ * 2^20 rows: 17 ms per call from page-locked buffers, 19-30 ms from pageable ones).  A Haskell caller allocates its matrices here (mallocForeignPtrBytes memory is pageable) and frees
  * them with hb_host_free as the ForeignPtr finalizer; hb_host_register page-locks a buffer the caller already owns for as
  * long as it stays allocated (unregister BEFORE freeing it). */
 int hb_host_alloc(int64_t bytes, void** out);
