@@ -62,8 +62,11 @@ def run(tmp_path, name, env):
     return path, r.stderr + r.stdout
 
 
-@pytest.mark.parametrize("knobs", [{}, {"HB_JIT_INTERLEAVE": "2", "HB_JIT_UNROLL": "4"}, {"HB_JIT_INTERLEAVE": "0"}, {"HB_JIT_UNROLL": "2", "HB_JIT_MERGE": "0"}],
-                         ids=["default", "interleave-all-unroll4", "strips", "unroll2-no-digit-merge"])
+@pytest.mark.parametrize("knobs", [{}, {"HB_JIT_INTERLEAVE": "2", "HB_JIT_UNROLL": "4"}, {"HB_JIT_INTERLEAVE": "0"}, {"HB_JIT_UNROLL": "2", "HB_JIT_MERGE": "0"},
+                                   # register blocks over several output variables for EVERY re-reading step (by default only joints of
+                                   # >= 8192 entries, i.e. C3 in tests/test_gpu_configs.py), with bodies so small that some keep run-time loops
+                                   {"HB_JIT_BLOCK_MIN_JOINT": "1", "HB_JIT_BLOCK_BODY": "12"}],
+                         ids=["default", "interleave-all-unroll4", "strips", "unroll2-no-digit-merge", "blocks-everywhere"])
 def test_specialised_kernels_bit_identical_to_oracle_and_to_the_templated_kernels(tmp_path, knobs):
     import numpy as np
 
