@@ -47,8 +47,12 @@ def time_batch(obj, fn, ev, reps=5):
     ms = e0.elapsed_time(e1) / reps
     st, tm = obj.last_stats(), obj.last_timing()
     gbs = 8.0 * (st["row_read_per_row"] + st["row_write_per_row"]) * ev.shape[0] / max(tm["prodsum_ms"], 1e-9) / 1e6
+    try:  # the roofline denominator bench.py uses for its own `roofline` object
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        peak = 6650.0
     return out, {"rows": int(ev.shape[0]), "ms_per_pass": ms, "queries_per_s": ev.shape[0] / ms * 1e3, "launches": st["launches"],
-                 "tiles": st["tiles"], "prodsum_ms": tm["prodsum_ms"], "algorithmic_GBps": gbs,
+                 "tiles": st["tiles"], "prodsum_ms": tm["prodsum_ms"], "algorithmic_GBps": gbs, "hbm_frac": gbs / peak,
                  "per_row": {k: st[k] for k in ("row_entries", "prod_per_row", "row_read_per_row", "row_write_per_row")}}
 
 
