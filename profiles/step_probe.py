@@ -6,6 +6,9 @@ knobs come from the environment (they are read once per process):
   HB_JIT_UNROLL      groups evaluated together (loads of all of them ahead of the first store)
   HB_JIT_WAVES       CTAs per SM a streaming step is cut into
   HB_JIT_MAX_KERNELS / HB_JIT_BUDGET   how many steps of a program get a kernel of their own
+  HB_JIT_BLOCK_U / _V / _MINB / _BODY / _LOOPS / _MIN_JOINT   register blocks over several output variables for re-reading steps
+  HB_JIT_DIGIT_ORDER, HB_JIT_SPLIT_LOOP, HB_JIT_STEP_ELIDE, HB_JIT_ZERO_ADD   (profiles/step_block_matrix.sh, csrc/jit.cpp jit_step_shape)
+  HB_LANES           streams the steps of a pass overlap on inside the CUDA graph
   HB_JIT=0           precompiled kernels only
 
   python profiles/step_probe.py C3|C4|C5     -> one JSON line: ms per pass, algorithmic GB/s, sha1 of the result matrix
